@@ -1,0 +1,89 @@
+"""ctypes binding of the C-ABI shared library (include/fitv2_b200.h).
+
+The library is built in-tree by ``__graft_entry__.build()`` (nvcc, sm_100a).  There is NO fallback:
+if the shared object is missing or a call fails, the product path raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfitv2_b200.so")
+
+OPERAND_BF16, OPERAND_FP16 = 0, 1
+
+# enum fitv2_weight (include/fitv2_b200.h) — keep in the same order
+WEIGHT_SLOTS = [
+    "X_EMBED_W", "X_EMBED_B", "T_MLP0_W", "T_MLP0_B", "T_MLP2_W", "T_MLP2_B", "Y_TABLE",
+    "GLOBAL_ADALN_W", "GLOBAL_ADALN_B", "LORA_A_W", "LORA_A_B", "LORA_B_W", "LORA_B_B",
+    "FINAL_ADALN_W", "FINAL_ADALN_B", "FINAL_LINEAR_W", "FINAL_LINEAR_B",
+    "QKV_W", "QKV_B", "PROJ_W", "PROJ_B", "GATEUP_W", "GATEUP_B", "FC2_W", "FC2_B",
+    "ROPE_FREQS_H", "ROPE_FREQS_W",
+]
+SLOT = {n: i for i, n in enumerate(WEIGHT_SLOTS)}
+OP16_SLOTS = {"QKV_W", "PROJ_W", "GATEUP_W", "FC2_W"}
+
+TAPS = dict(c=0, gmod=1, mod=2, fmod=3, x_res=4, q=5, k=6, vt=7, attn_out=8, h=9, hidden=10,
+            rope_cos=11, rope_sin=12, seg_uniform=13)
+
+
+class FitV2Config(C.Structure):
+    _fields_ = [
+        ("hidden_size", C.c_int32), ("depth", C.c_int32), ("num_heads", C.c_int32), ("head_dim", C.c_int32),
+        ("mlp_hidden", C.c_int32), ("lora_dim", C.c_int32), ("token_channels", C.c_int32),
+        ("num_embeddings", C.c_int32), ("operand_dtype", C.c_int32), ("time_shifting", C.c_float),
+        ("rope_magnitude", C.c_float),
+    ]
+
+
+class FitV2Error(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load libfitv2_b200.so; raises FitV2Error (never falls back) when it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FitV2Error(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). fitv2_b200 has no CPU or PyTorch fallback.")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64, f32 = C.c_void_p, C.c_int, C.c_int64, C.c_float
+    lib.fitv2_last_error.restype = C.c_char_p
+    lib.fitv2_version.restype = C.c_char_p
+    lib.fitv2_create.argtypes = [C.POINTER(FitV2Config), C.POINTER(vp)]
+    lib.fitv2_destroy.argtypes = [vp]
+    lib.fitv2_destroy.restype = None
+    lib.fitv2_bind_weight.argtypes = [vp, i32, vp, i64]
+    lib.fitv2_workspace_bytes.argtypes = [vp, i32, i32]
+    lib.fitv2_workspace_bytes.restype = i64
+    lib.fitv2_set_workspace.argtypes = [vp, vp, i64]
+    lib.fitv2_forward.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp, i32, i32, vp]
+    lib.fitv2_cfg_combine.argtypes = [vp, vp, f32, i32, i32, i32, i32, vp]
+    lib.fitv2_cfg_euler.argtypes = [vp, vp, f32, f32, vp, i32, i32, i32, vp]
+    lib.fitv2_debug_gemm.argtypes = [vp, i32, vp, vp, vp, vp, i32, i32, i32, i32, vp]
+    lib.fitv2_debug_attention.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp]
+    lib.fitv2_debug_tap.argtypes = [vp, i32, vp, i64, vp]
+    lib.fitv2_kernel_launches.argtypes = [vp]
+    lib.fitv2_kernel_launches.restype = i64
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = load().fitv2_last_error().decode("utf-8", "replace")
+        raise FitV2Error(f"{what or 'fitv2 call'} failed ({rc}): {msg}")
+
+
+EXPORTED_SYMBOLS = [
+    "fitv2_last_error", "fitv2_version", "fitv2_create", "fitv2_destroy", "fitv2_bind_weight",
+    "fitv2_workspace_bytes", "fitv2_set_workspace", "fitv2_forward", "fitv2_cfg_combine", "fitv2_cfg_euler",
+    "fitv2_debug_gemm", "fitv2_debug_attention", "fitv2_debug_tap", "fitv2_kernel_launches",
+]

@@ -1,0 +1,245 @@
+// Masked flash attention over padded, variable-length / variable-aspect token sequences.
+//
+// Replaces fit/model/modules.py:176-204 of the reference:
+//     attn_mask[b,i,j] = (mask[b,i] == mask[b,j])                (segment-id equality, NOT a pad mask)
+//     o = softmax(q k^T / sqrt(dh) + attn_mask) v ;  o *= (mask != 0)
+//
+// One CTA = one (sample, head, 128-query tile).  Keys are consumed in tiles of 128 with an online
+// softmax.  Both contractions run on tcgen05:
+//     S = Q K^T   : M=128 queries, N=128 keys, K=DHP (head_dim padded to a multiple of 16)
+//     O = P V     : M=128 queries, N=DHP,      K=128 keys   (V arrives transposed, keys contiguous)
+// Q/K/V^T/P are staged in shared memory in the canonical K-major swizzled layouts (a 64-element
+// SWIZZLE_128B panel plus a 16/32-element SWIZZLE_32B/64B tail panel for head_dim 72/96),
+// accumulators live in TMEM, the softmax runs in registers in fp32 (exp2 with folded scale).
+// Two CTAs are resident per SM so one CTA's softmax overlaps the other's MMAs / loads.
+#pragma once
+#include "common.cuh"
+
+namespace fitv2 {
+
+template <int DH> struct AttnCfg {
+    static constexpr int kDHP = (DH + 15) / 16 * 16;          // 72 -> 80, 96 -> 96
+    static constexpr int kTail = kDHP - 64;                    // elements in the tail panel (16 or 32)
+    static constexpr int kTailBytes = kTail * 2;               // 32 or 64
+    static constexpr int kChunks = kDHP / 8;                   // 16-byte chunks per staged Q/K row
+    static constexpr int kRealChunks = DH / 8;
+    static constexpr int kQMain = 128 * 128, kQTail = 128 * kTailBytes;
+    static constexpr int kOffQ = 0;
+    static constexpr int kOffQT = kOffQ + kQMain;
+    static constexpr int kOffK = kOffQT + ((kQTail + 1023) / 1024) * 1024;
+    static constexpr int kOffKT = kOffK + kQMain;
+    static constexpr int kOffV = kOffKT + ((kQTail + 1023) / 1024) * 1024;
+    static constexpr int kVPanel = ((kDHP * 128 + 1023) / 1024) * 1024;   // one 64-key panel of V^T
+    static constexpr int kOffP = kOffV + 2 * kVPanel;
+    static constexpr int kPPanel = 128 * 128;
+    static constexpr int kOffSeg = kOffP + 2 * kPPanel;
+    static constexpr int kOffBar = kOffSeg + 128 * 4;
+    static constexpr int kSmemBytes = kOffBar + 64 + 1024;     // + alignment slack
+    static_assert(kTail == 16 || kTail == 32, "head_dim must be 72..80 or 88..96 (64 + 16/32 tail)");
+};
+
+template <typename OT, int DH>
+__global__ void __launch_bounds__(128, 2)
+attention_kernel(const OT* __restrict__ q, const OT* __restrict__ k, const OT* __restrict__ vt,
+                 const float* __restrict__ seg, const int* __restrict__ seg_uniform,
+                 OT* __restrict__ out, int heads, int tokens, int tokens_v, float scale_log2e,
+                 float* __restrict__ dbg_s, float* __restrict__ dbg_o)
+{
+    using C = AttnCfg<DH>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    float* seg_kv = reinterpret_cast<float*>(smem + C::kOffSeg);
+    uint64_t* bar_s = reinterpret_cast<uint64_t*>(smem + C::kOffBar);
+    uint64_t* bar_o = bar_s + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_s + 2);
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int q0 = blockIdx.x * 128, head = blockIdx.y, sample = blockIdx.z;
+    const size_t bh = (size_t)sample * heads + head;
+    const OT* qg = q + bh * tokens * DH;
+    const OT* kg = k + bh * tokens * DH;
+    const OT* vg = vt + bh * DH * tokens_v;
+    const float* segb = seg + (size_t)sample * tokens;
+    const bool uniform = seg_uniform[sample] != 0;
+
+    if (tid == 0) { mbar_init(bar_s, 1); mbar_init(bar_o, 1); mbar_fence_init(); }
+    if (warp == 0) { __syncwarp(); tmem_alloc(tmem_slot, 256); }
+
+    // ---- stage the Q tile (zero rows past the sequence end, zero pad columns) ----
+    for (int id = tid; id < 128 * C::kChunks; id += 128) {
+        const int r = id / C::kChunks, c = id % C::kChunks;
+        uint4 val = make_uint4(0, 0, 0, 0);
+        if (q0 + r < tokens && c < C::kRealChunks)
+            val = *reinterpret_cast<const uint4*>(qg + (size_t)(q0 + r) * DH + c * 8);
+        uint8_t* dst = c < 8 ? smem + C::kOffQ + swz_offset<128>(r, c)
+                             : smem + C::kOffQT + swz_offset<C::kTailBytes>(r, c - 8);
+        *reinterpret_cast<uint4*>(dst) = val;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t t_s = tmem_base + (uint32_t(warp * 32) << 16);        // S accumulator, columns [0,128)
+    const uint32_t t_o = t_s + 128;                                      // O accumulator, columns [128,128+DHP)
+
+    const int qi = q0 + tid;
+    const bool q_ok = qi < tokens;
+    const float my_seg = q_ok ? segb[qi] : 0.f;
+
+    float o_acc[C::kDHP];
+#pragma unroll
+    for (int j = 0; j < C::kDHP; ++j) o_acc[j] = 0.f;
+    float m_run = -INFINITY, l_run = 0.f;
+
+    constexpr uint32_t idesc_s = umma_idesc(Op16<OT>::kUmmaFormat, 128, 128);
+    constexpr uint32_t idesc_o = umma_idesc(Op16<OT>::kUmmaFormat, 128, C::kDHP);
+    const int kv_tiles = (tokens + 127) / 128;
+    uint32_t ph = 0;
+
+    for (int t = 0; t < kv_tiles; ++t, ph ^= 1) {
+        const int kv0 = t * 128;
+        // ---- stage K tile, V^T tile, key segment ids (previous tile's MMAs have retired: bar_o was awaited) ----
+        for (int id = tid; id < 128 * C::kChunks; id += 128) {
+            const int r = id / C::kChunks, c = id % C::kChunks;
+            uint4 val = make_uint4(0, 0, 0, 0);
+            if (kv0 + r < tokens && c < C::kRealChunks)
+                val = *reinterpret_cast<const uint4*>(kg + (size_t)(kv0 + r) * DH + c * 8);
+            uint8_t* dst = c < 8 ? smem + C::kOffK + swz_offset<128>(r, c)
+                                 : smem + C::kOffKT + swz_offset<C::kTailBytes>(r, c - 8);
+            *reinterpret_cast<uint4*>(dst) = val;
+        }
+        for (int id = tid; id < C::kDHP * 16; id += 128) {
+            const int d = id >> 4, c = id & 15;                        // row d of V^T, 8 keys per chunk
+            const int kv = kv0 + c * 8;
+            uint4 val = make_uint4(0, 0, 0, 0);
+            if (d < DH && kv < tokens) {
+                val = *reinterpret_cast<const uint4*>(vg + (size_t)d * tokens_v + kv);
+                if (kv + 8 > tokens) {                                 // boundary chunk: clear keys past the end
+                    uint16_t* h = reinterpret_cast<uint16_t*>(&val);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) if (kv + e >= tokens) h[e] = 0;
+                }
+            }
+            *reinterpret_cast<uint4*>(smem + C::kOffV + (c >> 3) * C::kVPanel + swz_offset<128>(d, c & 7)) = val;
+        }
+        seg_kv[tid] = (kv0 + tid < tokens) ? segb[kv0 + tid] : 0.f;
+        fence_proxy_async_smem();
+        __syncthreads();
+
+        // ---- S = Q K^T ----
+        if (tid == 0) {
+            tc_fence_after();
+            const uint64_t dq = umma_desc_kmajor(smem_u32(smem + C::kOffQ), 128);
+            const uint64_t dk = umma_desc_kmajor(smem_u32(smem + C::kOffK), 128);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) umma_ss(tmem_base, dq + 2 * kk, dk + 2 * kk, idesc_s, kk != 0);
+            const uint64_t dqt = umma_desc_kmajor(smem_u32(smem + C::kOffQT), C::kTailBytes);
+            const uint64_t dkt = umma_desc_kmajor(smem_u32(smem + C::kOffKT), C::kTailBytes);
+#pragma unroll
+            for (int kk = 0; kk < C::kTail / 16; ++kk) umma_ss(tmem_base, dqt + 2 * kk, dkt + 2 * kk, idesc_s, 1);
+            umma_commit(bar_s);
+        }
+        mbar_wait(bar_s, ph);
+        tc_fence_after();
+
+        // ---- online softmax, pass 1: masked row maximum ----
+        const int kv_valid = min(128, tokens - kv0);
+        float tmax = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            uint32_t v[32];
+            tmem_ld32(t_s + c * 32, v);
+            tmem_ld_wait();
+            if (dbg_s != nullptr && t == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) dbg_s[tid * 128 + c * 32 + j] = __uint_as_float(v[j]);   // raw S tile (debug)
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int col = c * 32 + j;
+                const bool ok = col < kv_valid && (uniform || seg_kv[col] == my_seg);
+                tmax = fmaxf(tmax, ok ? __uint_as_float(v[j]) : -INFINITY);
+            }
+        }
+        const float m_new = fmaxf(m_run, tmax);
+        const float m_scaled = (m_new == -INFINITY) ? 0.f : m_new * scale_log2e;
+        const float alpha = (m_run == -INFINITY) ? 0.f : exp2f(m_run * scale_log2e - m_scaled);
+        m_run = m_new;
+
+        // ---- pass 2: p = exp2(s*c - m*c), row sum of the ROUNDED p, P -> smem (A operand of P V) ----
+        float lsum = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            uint32_t v[32];
+            tmem_ld32(t_s + c * 32, v);
+            tmem_ld_wait();
+            uint32_t packed[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int col = c * 32 + 2 * j;
+                const bool ok0 = col < kv_valid && (uniform || seg_kv[col] == my_seg);
+                const bool ok1 = col + 1 < kv_valid && (uniform || seg_kv[col + 1] == my_seg);
+                const float p0 = ok0 ? exp2f(fmaf(__uint_as_float(v[2 * j]), scale_log2e, -m_scaled)) : 0.f;
+                const float p1 = ok1 ? exp2f(fmaf(__uint_as_float(v[2 * j + 1]), scale_log2e, -m_scaled)) : 0.f;
+                packed[j] = Op16<OT>::pack(p0, p1);
+                const float2 r = Op16<OT>::unpack(packed[j]);
+                lsum += r.x + r.y;
+            }
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {                              // 4 chunks of 8 keys per 32 columns
+                const int chunk = c * 4 + g;                            // 0..15 across the 128-key tile
+                *reinterpret_cast<uint4*>(smem + C::kOffP + (chunk >> 3) * C::kPPanel + swz_offset<128>(tid, chunk & 7)) =
+                    make_uint4(packed[g * 4], packed[g * 4 + 1], packed[g * 4 + 2], packed[g * 4 + 3]);
+            }
+        }
+        l_run = l_run * alpha + lsum;
+        tc_fence_before();
+        fence_proxy_async_smem();
+        __syncthreads();
+
+        // ---- O_tile = P V ----
+        if (tid == 0) {
+            tc_fence_after();
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) {
+                const uint64_t dp = umma_desc_kmajor(smem_u32(smem + C::kOffP + (kk >> 2) * C::kPPanel), 128) + 2 * (kk & 3);
+                const uint64_t dv = umma_desc_kmajor(smem_u32(smem + C::kOffV + (kk >> 2) * C::kVPanel), 128) + 2 * (kk & 3);
+                umma_ss(tmem_base + 128, dp, dv, idesc_o, kk != 0);
+            }
+            umma_commit(bar_o);
+        }
+        mbar_wait(bar_o, ph);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < C::kDHP / 16; ++c) {
+            uint32_t v[16];
+            tmem_ld16(t_o + c * 16, v);
+            tmem_ld_wait();
+            if (dbg_o != nullptr && t == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) dbg_o[tid * C::kDHP + c * 16 + j] = __uint_as_float(v[j]);  // raw P V tile (debug)
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) o_acc[c * 16 + j] = o_acc[c * 16 + j] * alpha + __uint_as_float(v[j]);
+        }
+        tc_fence_before();
+        __syncthreads();          // all TMEM reads + smem operand reads of this tile are done before restaging
+    }
+
+    // ---- normalise, zero padded queries (mask != 0), write (M, heads*DH) rows for the proj GEMM ----
+    if (q_ok) {
+        const float inv = (my_seg != 0.f && l_run > 0.f) ? 1.0f / l_run : 0.f;
+        OT* dst = out + ((size_t)sample * tokens + qi) * (heads * DH) + head * DH;
+#pragma unroll
+        for (int c = 0; c < DH / 8; ++c) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int p = 0; p < 4; ++p) pk[p] = Op16<OT>::pack(o_acc[c * 8 + 2 * p] * inv, o_acc[c * 8 + 2 * p + 1] * inv);
+            *reinterpret_cast<uint4*>(dst + c * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+    }
+    __syncthreads();
+    if (warp == 0) { __syncwarp(); tmem_dealloc(tmem_base, 256); }
+}
+
+}  // namespace fitv2

@@ -1,0 +1,220 @@
+// Blackwell (sm_100a) device primitives used by the FiTv2 hot-path kernels:
+// mbarrier, TMA (cp.async.bulk.tensor), tcgen05 (UMMA / TMEM) and small helpers.
+// Everything is inline PTX; there is no CUTLASS/CuTe dependency.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+namespace fitv2 {
+
+// --------------------------------------------------------------------------------------------
+// 16-bit operand type traits (bf16 default, fp16 selectable; both run tcgen05 kind::f16)
+// --------------------------------------------------------------------------------------------
+template <typename T> struct Op16;
+template <> struct Op16<__nv_bfloat16> {
+    static constexpr uint32_t kUmmaFormat = 1;   // InstrDescriptor a/b_format: 1 = BF16
+    using vec2 = __nv_bfloat162;
+    __device__ __forceinline__ static uint32_t pack(float a, float b) {
+        __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+        return *reinterpret_cast<uint32_t*>(&v);
+    }
+    __device__ __forceinline__ static float2 unpack(uint32_t u) {
+        return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
+    }
+    __device__ __forceinline__ static __nv_bfloat16 from(float a) { return __float2bfloat16_rn(a); }
+};
+template <> struct Op16<__half> {
+    static constexpr uint32_t kUmmaFormat = 0;   // 0 = F16
+    using vec2 = __half2;
+    __device__ __forceinline__ static uint32_t pack(float a, float b) {
+        __half2 v = __floats2half2_rn(a, b);
+        return *reinterpret_cast<uint32_t*>(&v);
+    }
+    __device__ __forceinline__ static float2 unpack(uint32_t u) {
+        return __half22float2(*reinterpret_cast<__half2*>(&u));
+    }
+    __device__ __forceinline__ static __half from(float a) { return __float2half_rn(a); }
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.b32 %0, 1, 0, P;\n\t"
+        "}\n" : "=r"(pred));
+    return pred != 0;
+}
+
+// --------------------------------------------------------------------------------------------
+// mbarrier
+// --------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                 :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// Bounded wait: a protocol bug traps (reported as a launch failure) instead of hanging the GPU.
+#ifndef FITV2_MBAR_SPIN_LIMIT
+#define FITV2_MBAR_SPIN_LIMIT (1u << 24)
+#endif
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0;
+#pragma unroll 1
+    for (uint32_t spin = 0; spin < FITV2_MBAR_SPIN_LIMIT; ++spin) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred P;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, P;\n\t"
+            "}\n" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (done) return;
+    }
+    __trap();
+}
+
+// generic-proxy smem writes -> visible to the async proxy (TMA / tensor core reads)
+__device__ __forceinline__ void fence_proxy_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// --------------------------------------------------------------------------------------------
+// TMA
+// --------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
+    asm volatile("prefetch.tensormap [%0];" :: "l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+// 2-D tile load: c0 = innermost (contiguous) coordinate, c1 = row coordinate.
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        :: "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        :: "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
+// --------------------------------------------------------------------------------------------
+// tcgen05: TMEM allocation, UMMA issue/commit, TMEM loads
+// --------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {   // whole warp, .sync.aligned
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 :: "r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {     // whole warp
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after()  { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem], kind::f16 (bf16 or fp16 operands, fp32 accumulate). One thread issues.
+__device__ __forceinline__ void umma_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                        uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" :: "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// Arrive on an mbarrier once every previously issued UMMA of this thread has completed.
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                 :: "r"(smem_u32(bar)) : "memory");
+}
+
+// Instruction descriptor, kind::f16: fp32 accumulator, K-major A and B, M x N tile.
+//   [4,6) c_format=1(F32)  [7,10) a_format  [10,13) b_format  [15] a_major=K  [16] b_major=K
+//   [17,23) N>>3  [24,29) M>>4
+__host__ __device__ constexpr uint32_t umma_idesc(uint32_t fmt, uint32_t M, uint32_t N) {
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
+// Shared-memory matrix descriptor for a K-major operand stored as rows of `swizzle_bytes`
+// (128 / 64 / 32) with the matching hardware swizzle; 8-row groups are `8*swizzle_bytes` apart.
+//   [0,14) addr>>4  [16,30) LBO>>4 (unused for swizzled K-major)  [32,46) SBO>>4  [46,48) version=1
+//   [61,64) layout: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B, 6 = SWIZZLE_32B
+__device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t smem_addr, uint32_t swizzle_bytes) {
+    const uint64_t layout = swizzle_bytes == 128 ? 2ull : (swizzle_bytes == 64 ? 4ull : 6ull);
+    const uint64_t sbo = (8u * swizzle_bytes) >> 4;
+    return static_cast<uint64_t>((smem_addr >> 4) & 0x3FFFu) | (sbo << 32) | (1ull << 46) | (layout << 61);
+}
+
+// Byte offset of element-chunk (row r, 16-byte chunk c) inside a K-major panel whose rows are
+// `RowBytes` (128/64/32) wide and swizzled with the hardware pattern of that width:
+// address bits [4,4+B) ^= bits [7,7+B), B = log2(RowBytes/16).
+template <int RowBytes>
+__device__ __forceinline__ uint32_t swz_offset(uint32_t r, uint32_t c) {
+    static_assert(RowBytes == 128 || RowBytes == 64 || RowBytes == 32, "bad panel width");
+    constexpr uint32_t B = RowBytes == 128 ? 3 : (RowBytes == 64 ? 2 : 1);
+    const uint32_t x = (r >> (3 - B)) & ((1u << B) - 1);
+    return r * RowBytes + ((c ^ x) << 4);
+}
+
+// TMEM -> registers: this thread's lane (row), N consecutive 32-bit columns.
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+                 "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                   "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                   "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// --------------------------------------------------------------------------------------------
+// misc
+// --------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+
+// streaming 128-bit accesses (activations that are touched once per kernel)
+__device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+
+}  // namespace fitv2

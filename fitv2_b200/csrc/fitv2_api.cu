@@ -1,0 +1,575 @@
+// C-ABI of the B200-native FiTv2 hot path (see include/fitv2_b200.h).  Host orchestration only:
+// workspace carving, TMA descriptors, kernel selection and the per-NFE launch sequence that
+// replaces fit/model/fit_model.py:189-233 (FiT.forward) of the reference.
+#include "../../include/fitv2_b200.h"
+#include "common.cuh"
+#include "gemm_tc.cuh"
+#include "attention.cuh"
+#include "pointwise.cuh"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+using namespace fitv2;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t e__ = (expr);                                                                   \
+        if (e__ != cudaSuccess)                                                                     \
+            return fail(FITV2_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// 2-D K-major operand map: tensor (rows, cols) 16-bit with row pitch ld elements; box = 64 cols x box_rows,
+// 128B swizzle, out-of-bounds reads return zeros (M / K tails).
+int make_map(CUtensorMap* map, const void* ptr, int operand_dtype, uint64_t rows, uint64_t cols, uint64_t ld,
+             uint32_t box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return fail(FITV2_E_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {ld * 2};
+    cuuint32_t box[2] = {64, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, operand_dtype == FITV2_OPERAND_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                    2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return fail(FITV2_E_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu ld=%llu box_rows=%u ptr=%p", (int)r,
+                    (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows, ptr);
+    return FITV2_OK;
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Layout {
+    int rows = 0, tokens = 0, tokens_v = 0;
+    size_t x_res, h, ao, q, k, vt, hidden, te, t0, c, sc, lmid, gmod, mod, fmod, rope_cos, rope_sin, seg_uniform, total;
+};
+
+}  // namespace
+
+struct fitv2_handle {
+    fitv2_config cfg;
+    const void* w[FITV2_W_COUNT];
+    int64_t w_numel[FITV2_W_COUNT];
+    uint8_t* ws = nullptr;
+    int64_t ws_bytes = 0;
+    Layout lay;
+    bool maps_valid = false;
+    CUtensorMap map_h, map_ao, map_hidden;              // activations (A operands)
+    CUtensorMap map_wqkv, map_wproj, map_wgu, map_wfc2; // stacked weights (B operands)
+    int bn_resid = 0;
+    int num_sms = 148;
+    int64_t launches = 0;
+};
+
+namespace {
+
+int64_t expected_numel(const fitv2_config& c, int slot) {
+    const int64_t D = c.hidden_size, L = c.depth, Hm = c.mlp_hidden, lora = c.lora_dim, C = c.token_channels;
+    switch (slot) {
+        case FITV2_W_X_EMBED_W: return D * C;
+        case FITV2_W_X_EMBED_B: return D;
+        case FITV2_W_T_MLP0_W: return D * 256;
+        case FITV2_W_T_MLP0_B: return D;
+        case FITV2_W_T_MLP2_W: return D * D;
+        case FITV2_W_T_MLP2_B: return D;
+        case FITV2_W_Y_TABLE: return (int64_t)c.num_embeddings * D;
+        case FITV2_W_GLOBAL_ADALN_W: return 6 * D * D;
+        case FITV2_W_GLOBAL_ADALN_B: return 6 * D;
+        case FITV2_W_LORA_A_W: return L * lora * D;
+        case FITV2_W_LORA_A_B: return L * lora;
+        case FITV2_W_LORA_B_W: return L * 6 * D * lora;
+        case FITV2_W_LORA_B_B: return L * 6 * D;
+        case FITV2_W_FINAL_ADALN_W: return 2 * D * D;
+        case FITV2_W_FINAL_ADALN_B: return 2 * D;
+        case FITV2_W_FINAL_LINEAR_W: return C * D;
+        case FITV2_W_FINAL_LINEAR_B: return C;
+        case FITV2_W_QKV_W: return L * 3 * D * D;
+        case FITV2_W_QKV_B: return L * 3 * D;
+        case FITV2_W_PROJ_W: return L * D * D;
+        case FITV2_W_PROJ_B: return L * D;
+        case FITV2_W_GATEUP_W: return L * 2 * Hm * D;
+        case FITV2_W_GATEUP_B: return L * 2 * Hm;
+        case FITV2_W_FC2_W: return L * D * Hm;
+        case FITV2_W_FC2_B: return L * D;
+        case FITV2_W_ROPE_FREQS_H: return c.head_dim / 4;
+        case FITV2_W_ROPE_FREQS_W: return c.head_dim / 4;
+    }
+    return -1;
+}
+
+Layout make_layout(const fitv2_config& c, int rows, int tokens) {
+    Layout l;
+    l.rows = rows; l.tokens = tokens; l.tokens_v = (tokens + 7) / 8 * 8;
+    const size_t M = (size_t)rows * tokens, D = c.hidden_size, Hm = c.mlp_hidden, L = c.depth;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 1024); return o; };
+    l.x_res = take(M * D * 4);
+    l.h = take(M * D * 2);
+    l.ao = take(M * D * 2);
+    l.q = take(M * D * 2);
+    l.k = take(M * D * 2);
+    l.vt = take((size_t)rows * D * l.tokens_v * 2);
+    l.hidden = take(M * Hm * 2);
+    l.te = take((size_t)rows * 256 * 4);
+    l.t0 = take((size_t)rows * D * 4);
+    l.c = take((size_t)rows * D * 4);
+    l.sc = take((size_t)rows * D * 4);
+    l.lmid = take((size_t)rows * L * c.lora_dim * 4);
+    l.gmod = take((size_t)rows * 6 * D * 4);
+    l.mod = take(L * (size_t)rows * 6 * D * 4);
+    l.fmod = take((size_t)rows * 2 * D * 4);
+    l.rope_cos = take(M * (c.head_dim / 2) * 4);
+    l.rope_sin = take(M * (c.head_dim / 2) * 4);
+    l.seg_uniform = take((size_t)rows * 4);
+    l.total = off;
+    return l;
+}
+
+template <int BN, int EPI, typename OT, int DH>
+int launch_gemm_t(fitv2_handle* h, const CUtensorMap& ma, const CUtensorMap& mb, int M, int N, int K, int b_row_off,
+                  const GemmEpi& ep, cudaStream_t st) {
+    using Cfg = GemmCfg<BN>;
+    auto kern = gemm_tc_kernel<BN, EPI, OT, DH>;
+    static bool configured = false;
+    if (!configured) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+        configured = true;
+    }
+    if (N % BN != 0) return fail(FITV2_E_INVALID, "GEMM N=%d is not a multiple of the tile width %d", N, BN);
+    const int tiles = ((M + kGemmBM - 1) / kGemmBM) * (N / BN);
+    const int grid = tiles < h->num_sms ? tiles : h->num_sms;
+    kern<<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(ma, mb, M, N, K, b_row_off, ep);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+    return FITV2_OK;
+}
+
+template <int EPI, typename OT>
+int launch_gemm_bn(fitv2_handle* h, int bn, const CUtensorMap& ma, const CUtensorMap& mb, int M, int N, int K,
+                   int b_row_off, const GemmEpi& ep, cudaStream_t st) {
+    switch (bn) {
+        case 128: return launch_gemm_t<128, EPI, OT, 0>(h, ma, mb, M, N, K, b_row_off, ep, st);
+        case 144: return launch_gemm_t<144, EPI, OT, 0>(h, ma, mb, M, N, K, b_row_off, ep, st);
+        case 192: return launch_gemm_t<192, EPI, OT, 0>(h, ma, mb, M, N, K, b_row_off, ep, st);
+        case 256: return launch_gemm_t<256, EPI, OT, 0>(h, ma, mb, M, N, K, b_row_off, ep, st);
+    }
+    return fail(FITV2_E_INVALID, "unsupported GEMM tile width %d", bn);
+}
+
+// Tile width for the N = hidden_size projections: minimise (waves x per-tile cost) over the widths that divide N.
+int pick_bn(int M, int N, int num_sms) {
+    const int cands[4] = {256, 192, 144, 128};
+    int best = 0; long best_cost = 0;
+    for (int bn : cands) {
+        if (N % bn) continue;
+        const long tiles = (long)((M + kGemmBM - 1) / kGemmBM) * (N / bn);
+        const long waves = (tiles + num_sms - 1) / num_sms;
+        const long cost = waves * (bn + 16);
+        if (!best || cost < best_cost) { best = bn; best_cost = cost; }
+    }
+    return best;
+}
+
+template <typename OT>
+int launch_attention(fitv2_handle* h, const void* q, const void* k, const void* vt, const float* seg,
+                     const int* seg_uniform, void* out, int rows, int tokens, int tokens_v, cudaStream_t st,
+                     float* dbg_s = nullptr, float* dbg_o = nullptr) {
+    const fitv2_config& c = h->cfg;
+    const float scale_log2e = (1.0f / sqrtf((float)c.head_dim)) * 1.4426950408889634f;
+    dim3 grid((tokens + 127) / 128, c.num_heads, rows);
+    if (c.head_dim == 72) {
+        auto kern = attention_kernel<OT, 72>;
+        static bool configured = false;
+        if (!configured) { CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<72>::kSmemBytes)); configured = true; }
+        kern<<<grid, 128, AttnCfg<72>::kSmemBytes, st>>>((const OT*)q, (const OT*)k, (const OT*)vt, seg, seg_uniform, (OT*)out,
+                                                        c.num_heads, tokens, tokens_v, scale_log2e, dbg_s, dbg_o);
+    } else if (c.head_dim == 96) {
+        auto kern = attention_kernel<OT, 96>;
+        static bool configured = false;
+        if (!configured) { CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<96>::kSmemBytes)); configured = true; }
+        kern<<<grid, 128, AttnCfg<96>::kSmemBytes, st>>>((const OT*)q, (const OT*)k, (const OT*)vt, seg, seg_uniform, (OT*)out,
+                                                        c.num_heads, tokens, tokens_v, scale_log2e, dbg_s, dbg_o);
+    } else {
+        return fail(FITV2_E_INVALID, "head_dim %d not supported (72 or 96)", c.head_dim);
+    }
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+    return FITV2_OK;
+}
+
+template <typename OT>
+int launch_ln_modulate(fitv2_handle* h, const float* x, const float* shift, const float* scale, int mod_ld, void* out,
+                       int M, int D, int tokens, cudaStream_t st) {
+    const int nv = (D / 4 + 31) / 32;
+    const int blocks = (M * 32 + 255) / 256;
+    if (nv <= 1) ln_modulate_kernel<OT, 1><<<blocks, 256, 0, st>>>(x, shift, scale, mod_ld, (OT*)out, M, D, tokens);
+    else if (nv <= 3) ln_modulate_kernel<OT, 3><<<blocks, 256, 0, st>>>(x, shift, scale, mod_ld, (OT*)out, M, D, tokens);
+    else if (nv <= 9) ln_modulate_kernel<OT, 9><<<blocks, 256, 0, st>>>(x, shift, scale, mod_ld, (OT*)out, M, D, tokens);
+    else if (nv <= 18) ln_modulate_kernel<OT, 18><<<blocks, 256, 0, st>>>(x, shift, scale, mod_ld, (OT*)out, M, D, tokens);
+    else return fail(FITV2_E_INVALID, "hidden_size %d too large for the LayerNorm kernel", D);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+    return FITV2_OK;
+}
+
+int launch_small_linear(fitv2_handle* h, const SmallLinear& p, int batches, cudaStream_t st) {
+    dim3 grid((p.N + 63) / 64, (p.rows + 63) / 64, batches);
+    small_linear_kernel<<<grid, 256, 0, st>>>(p);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+    return FITV2_OK;
+}
+
+int ensure_maps(fitv2_handle* h) {
+    if (h->maps_valid) return FITV2_OK;
+    const fitv2_config& c = h->cfg;
+    const Layout& l = h->lay;
+    const uint64_t M = (uint64_t)l.rows * l.tokens, D = c.hidden_size, Hm = c.mlp_hidden, L = c.depth;
+    int rc;
+    if ((rc = make_map(&h->map_h, h->ws + l.h, c.operand_dtype, M, D, D, 128))) return rc;
+    if ((rc = make_map(&h->map_ao, h->ws + l.ao, c.operand_dtype, M, D, D, 128))) return rc;
+    if ((rc = make_map(&h->map_hidden, h->ws + l.hidden, c.operand_dtype, M, Hm, Hm, 128))) return rc;
+    h->bn_resid = pick_bn((int)M, (int)D, h->num_sms);
+    if (!h->bn_resid) return fail(FITV2_E_INVALID, "hidden_size %d has no supported tile width (multiple of 128/144/192/256)", (int)D);
+    if ((rc = make_map(&h->map_wqkv, h->w[FITV2_W_QKV_W], c.operand_dtype, L * 3 * D, D, D, 2 * c.head_dim))) return rc;
+    if ((rc = make_map(&h->map_wproj, h->w[FITV2_W_PROJ_W], c.operand_dtype, L * D, D, D, h->bn_resid))) return rc;
+    if ((rc = make_map(&h->map_wgu, h->w[FITV2_W_GATEUP_W], c.operand_dtype, L * 2 * Hm, D, D, 256))) return rc;
+    if ((rc = make_map(&h->map_wfc2, h->w[FITV2_W_FC2_W], c.operand_dtype, L * D, Hm, Hm, h->bn_resid))) return rc;
+    h->maps_valid = true;
+    return FITV2_OK;
+}
+
+template <typename OT>
+int forward_impl(fitv2_handle* h, const float* x, int x_rows, const float* t, const int64_t* y, const int64_t* grid,
+                 const float* mask, float* out, int rows, int tokens, cudaStream_t st) {
+    const fitv2_config& c = h->cfg;
+    const Layout& l = h->lay;
+    const int D = c.hidden_size, L = c.depth, Hm = c.mlp_hidden, lora = c.lora_dim, H = c.num_heads, DH = c.head_dim;
+    const int M = rows * tokens;
+    uint8_t* ws = h->ws;
+    float* x_res = (float*)(ws + l.x_res);
+    float* te = (float*)(ws + l.te);
+    float* t0 = (float*)(ws + l.t0);
+    float* cc = (float*)(ws + l.c);
+    float* sc = (float*)(ws + l.sc);
+    float* lmid = (float*)(ws + l.lmid);
+    float* gmod = (float*)(ws + l.gmod);
+    float* mod = (float*)(ws + l.mod);
+    float* fmod = (float*)(ws + l.fmod);
+    float* rcos = (float*)(ws + l.rope_cos);
+    float* rsin = (float*)(ws + l.rope_sin);
+    int* segu = (int*)(ws + l.seg_uniform);
+    int rc;
+
+    // ---- per-call tables: segment-uniformity flags, RoPE cos/sin (rope.py:308-333) ----
+    seg_uniform_kernel<<<rows, 128, 0, st>>>(mask, segu, tokens);
+    {
+        const size_t total = (size_t)M * (DH / 2);
+        const int blocks = (int)((total + 255) / 256);
+        rope_table_kernel<<<blocks, 256, 0, st>>>((const long long*)grid, (const float*)h->w[FITV2_W_ROPE_FREQS_H],
+                                                   (const float*)h->w[FITV2_W_ROPE_FREQS_W], c.rope_magnitude, rcos, rsin,
+                                                   rows, tokens, DH / 2);
+    }
+    // ---- conditioning (fit_model.py:202-209,218-219; modules.py:52-76,101-106,259-264,287-293) ----
+    timestep_features_kernel<<<(rows * 128 + 255) / 256, 256, 0, st>>>(t, c.time_shifting, te, rows);
+    CUDA_TRY(cudaGetLastError());
+    h->launches += 3;
+    SmallLinear p;
+    memset(&p, 0, sizeof(p));
+    p.rows = rows;
+    // t0 = W0 te + b0
+    p.A = te; p.lda = 256; p.W = (const float*)h->w[FITV2_W_T_MLP0_W]; p.bias = (const float*)h->w[FITV2_W_T_MLP0_B];
+    p.out = t0; p.ldo = D; p.N = D; p.K = 256;
+    if ((rc = launch_small_linear(h, p, 1, st))) return rc;
+    // c = W2 silu(t0) + b2 + E[y] ; sc = silu(c)
+    p.A = t0; p.lda = D; p.act_silu_in = 1; p.W = (const float*)h->w[FITV2_W_T_MLP2_W]; p.bias = (const float*)h->w[FITV2_W_T_MLP2_B];
+    p.emb = (const float*)h->w[FITV2_W_Y_TABLE]; p.labels = (const long long*)y; p.out = cc; p.out_silu = sc; p.N = D; p.K = D;
+    if ((rc = launch_small_linear(h, p, 1, st))) return rc;
+    p.act_silu_in = 0; p.emb = nullptr; p.labels = nullptr; p.out_silu = nullptr;
+    // global adaLN: gmod = Wg sc + bg
+    p.A = sc; p.lda = D; p.W = (const float*)h->w[FITV2_W_GLOBAL_ADALN_W]; p.bias = (const float*)h->w[FITV2_W_GLOBAL_ADALN_B];
+    p.out = gmod; p.ldo = 6 * D; p.N = 6 * D; p.K = D;
+    if ((rc = launch_small_linear(h, p, 1, st))) return rc;
+    // final adaLN: fmod = Wf sc + bf   (shift | scale)
+    p.W = (const float*)h->w[FITV2_W_FINAL_ADALN_W]; p.bias = (const float*)h->w[FITV2_W_FINAL_ADALN_B];
+    p.out = fmod; p.ldo = 2 * D; p.N = 2 * D;
+    if ((rc = launch_small_linear(h, p, 1, st))) return rc;
+    // LoRA down for all blocks at once: lmid = Wa_all sc + ba_all
+    p.W = (const float*)h->w[FITV2_W_LORA_A_W]; p.bias = (const float*)h->w[FITV2_W_LORA_A_B];
+    p.out = lmid; p.ldo = L * lora; p.N = L * lora;
+    if ((rc = launch_small_linear(h, p, 1, st))) return rc;
+    // LoRA up, batched over blocks: mod[l] = Wb[l] lmid[:, l] + bb[l] + gmod
+    p.A = lmid; p.a_batch_stride = lora; p.lda = L * lora;
+    p.W = (const float*)h->w[FITV2_W_LORA_B_W]; p.w_batch_stride = (size_t)6 * D * lora;
+    p.bias = (const float*)h->w[FITV2_W_LORA_B_B]; p.bias_batch_stride = 6 * D;
+    p.add = gmod; p.out = mod; p.out_batch_stride = (size_t)rows * 6 * D; p.ldo = 6 * D; p.N = 6 * D; p.K = lora;
+    if ((rc = launch_small_linear(h, p, L, st))) return rc;
+
+    // ---- patch embedding (modules.py:34-37); implicit cat([z, z]) when x_rows == rows / 2 ----
+    if (c.token_channels != 16) return fail(FITV2_E_INVALID, "token_channels %d not supported (16)", c.token_channels);
+    patch_embed_kernel<16><<<(M + 7) / 8, 256, 0, st>>>(x, (const float*)h->w[FITV2_W_X_EMBED_W], (const float*)h->w[FITV2_W_X_EMBED_B],
+                                                       x_res, M, D, x_rows * tokens);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+
+    GemmEpi ep;
+    for (int layer = 0; layer < L; ++layer) {
+        const float* modl = mod + (size_t)layer * rows * 6 * D;
+        // ---- attention branch (modules.py:272) ----
+        if ((rc = launch_ln_modulate<OT>(h, x_res, modl, modl + D, 6 * D, ws + l.h, M, D, tokens, st))) return rc;
+        memset(&ep, 0, sizeof(ep));
+        ep.bias = (const float*)h->w[FITV2_W_QKV_B] + (size_t)layer * 3 * D;
+        ep.tokens = tokens; ep.q = ws + l.q; ep.k = ws + l.k; ep.vt = ws + l.vt; ep.rope_cos = rcos; ep.rope_sin = rsin;
+        ep.heads = H; ep.tokens_v = l.tokens_v;
+        if (DH == 72) rc = launch_gemm_t<144, EPI_QKV, OT, 72>(h, h->map_h, h->map_wqkv, M, 3 * D, D, layer * 3 * D, ep, st);
+        else          rc = launch_gemm_t<192, EPI_QKV, OT, 96>(h, h->map_h, h->map_wqkv, M, 3 * D, D, layer * 3 * D, ep, st);
+        if (rc) return rc;
+        if ((rc = launch_attention<OT>(h, ws + l.q, ws + l.k, ws + l.vt, mask, segu, ws + l.ao, rows, tokens, l.tokens_v, st))) return rc;
+        memset(&ep, 0, sizeof(ep));
+        ep.bias = (const float*)h->w[FITV2_W_PROJ_B] + (size_t)layer * D;
+        ep.tokens = tokens; ep.x = x_res; ep.gate = modl + 2 * D; ep.gate_ld = 6 * D;
+        if ((rc = launch_gemm_bn<EPI_RESID, OT>(h, h->bn_resid, h->map_ao, h->map_wproj, M, D, D, layer * D, ep, st))) return rc;
+        // ---- SwiGLU branch (modules.py:273) ----
+        if ((rc = launch_ln_modulate<OT>(h, x_res, modl + 3 * D, modl + 4 * D, 6 * D, ws + l.h, M, D, tokens, st))) return rc;
+        memset(&ep, 0, sizeof(ep));
+        ep.bias = (const float*)h->w[FITV2_W_GATEUP_B] + (size_t)layer * 2 * Hm;
+        ep.tokens = tokens; ep.out16 = ws + l.hidden; ep.ld_out = Hm;
+        if ((rc = launch_gemm_t<256, EPI_SWIGLU, OT, 0>(h, h->map_h, h->map_wgu, M, 2 * Hm, D, layer * 2 * Hm, ep, st))) return rc;
+        memset(&ep, 0, sizeof(ep));
+        ep.bias = (const float*)h->w[FITV2_W_FC2_B] + (size_t)layer * D;
+        ep.tokens = tokens; ep.x = x_res; ep.gate = modl + 5 * D; ep.gate_ld = 6 * D;
+        if ((rc = launch_gemm_bn<EPI_RESID, OT>(h, h->bn_resid, h->map_hidden, h->map_wfc2, M, D, Hm, layer * D, ep, st))) return rc;
+    }
+
+    // ---- final layer + output mask (modules.py:292-296, fit_model.py:230) ----
+    {
+        const int nv = (D / 4 + 31) / 32;
+        const size_t smem = (size_t)16 * D * 4;
+        const int blocks = h->num_sms * 2;
+        if (nv <= 9) {
+            auto kern = final_layer_kernel<9, 16>;
+            static bool configured = false;
+            if (!configured) { CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 1152 * 4)); configured = true; }
+            kern<<<blocks, 256, smem, st>>>(x_res, fmod, (const float*)h->w[FITV2_W_FINAL_LINEAR_W], (const float*)h->w[FITV2_W_FINAL_LINEAR_B],
+                                            mask, out, M, D, tokens);
+        } else {
+            auto kern = final_layer_kernel<18, 16>;
+            static bool configured = false;
+            if (!configured) { CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 2304 * 4)); configured = true; }
+            kern<<<blocks, 256, smem, st>>>(x_res, fmod, (const float*)h->w[FITV2_W_FINAL_LINEAR_W], (const float*)h->w[FITV2_W_FINAL_LINEAR_B],
+                                            mask, out, M, D, tokens);
+        }
+        CUDA_TRY(cudaGetLastError());
+        h->launches++;
+    }
+    return FITV2_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+// exported C ABI
+// =================================================================================================
+extern "C" {
+
+const char* fitv2_last_error(void) { return g_last_error.c_str(); }
+const char* fitv2_version(void) { return "fitv2_b200 0.1 (sm_100a, tcgen05/TMEM/TMA)"; }
+
+int fitv2_create(const fitv2_config* cfg, fitv2_handle** out) {
+    if (!cfg || !out) return fail(FITV2_E_INVALID, "null argument");
+    const fitv2_config& c = *cfg;
+    if (c.hidden_size <= 0 || c.depth <= 0 || c.num_heads <= 0 || c.hidden_size != c.num_heads * c.head_dim)
+        return fail(FITV2_E_INVALID, "hidden_size %d != num_heads %d * head_dim %d", c.hidden_size, c.num_heads, c.head_dim);
+    if (c.head_dim != 72 && c.head_dim != 96)
+        return fail(FITV2_E_INVALID, "head_dim %d not supported (kernels are built for 72 and 96)", c.head_dim);
+    if (c.num_heads % 2) return fail(FITV2_E_INVALID, "num_heads %d must be even (two heads per QKV tile)", c.num_heads);
+    if (c.mlp_hidden % 128) return fail(FITV2_E_INVALID, "mlp_hidden %d must be a multiple of 128", c.mlp_hidden);
+    if (c.hidden_size > 2304 || c.hidden_size % 16) return fail(FITV2_E_INVALID, "hidden_size %d must be a multiple of 16 and <= 2304", c.hidden_size);
+    if (c.token_channels != 16) return fail(FITV2_E_INVALID, "token_channels %d not supported (p*p*C_in = 16)", c.token_channels);
+    if (c.lora_dim % 4) return fail(FITV2_E_INVALID, "lora_dim %d must be a multiple of 4", c.lora_dim);
+    if (c.operand_dtype != FITV2_OPERAND_BF16 && c.operand_dtype != FITV2_OPERAND_FP16)
+        return fail(FITV2_E_INVALID, "operand_dtype %d unknown", c.operand_dtype);
+    int dev = 0, major = 0, sms = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (major != 10) return fail(FITV2_E_INVALID, "device compute capability %d.x: this library contains sm_100a code only", major);
+    fitv2_handle* h = new fitv2_handle();
+    h->cfg = c;
+    memset(h->w, 0, sizeof(h->w));
+    memset(h->w_numel, 0, sizeof(h->w_numel));
+    h->num_sms = sms;
+    *out = h;
+    return FITV2_OK;
+}
+
+void fitv2_destroy(fitv2_handle* h) { delete h; }
+
+int fitv2_bind_weight(fitv2_handle* h, int slot, const void* dev_ptr, int64_t numel) {
+    if (!h || slot < 0 || slot >= FITV2_W_COUNT || !dev_ptr) return fail(FITV2_E_INVALID, "bad bind_weight argument (slot %d)", slot);
+    const int64_t want = expected_numel(h->cfg, slot);
+    if (numel != want) return fail(FITV2_E_INVALID, "weight slot %d: got %lld elements, expected %lld", slot, (long long)numel, (long long)want);
+    if (reinterpret_cast<uintptr_t>(dev_ptr) % 16) return fail(FITV2_E_INVALID, "weight slot %d pointer is not 16-byte aligned", slot);
+    h->w[slot] = dev_ptr;
+    h->w_numel[slot] = numel;
+    h->maps_valid = false;
+    return FITV2_OK;
+}
+
+int64_t fitv2_workspace_bytes(const fitv2_handle* h, int rows, int tokens) {
+    if (!h || rows <= 0 || tokens <= 0) return fail(FITV2_E_INVALID, "bad workspace query");
+    return (int64_t)make_layout(h->cfg, rows, tokens).total;
+}
+
+int fitv2_set_workspace(fitv2_handle* h, void* dev_ptr, int64_t bytes) {
+    if (!h || !dev_ptr || bytes <= 0) return fail(FITV2_E_INVALID, "bad workspace");
+    if (reinterpret_cast<uintptr_t>(dev_ptr) % 256) return fail(FITV2_E_INVALID, "workspace must be 256-byte aligned");
+    h->ws = static_cast<uint8_t*>(dev_ptr);
+    h->ws_bytes = bytes;
+    h->lay = Layout();
+    h->maps_valid = false;
+    return FITV2_OK;
+}
+
+int fitv2_forward(fitv2_handle* h, const float* x, int x_rows, const float* t, const int64_t* y, const int64_t* grid,
+                  const float* mask, float* out, int rows, int tokens, void* stream) {
+    if (!h || !x || !t || !y || !grid || !mask || !out) return fail(FITV2_E_INVALID, "null argument");
+    if (rows <= 0 || tokens <= 0) return fail(FITV2_E_INVALID, "rows %d / tokens %d must be positive", rows, tokens);
+    if (x_rows != rows && !(rows % 2 == 0 && x_rows == rows / 2))
+        return fail(FITV2_E_INVALID, "x_rows %d must equal rows %d or rows/2", x_rows, rows);
+    for (int s = 0; s < FITV2_W_COUNT; ++s)
+        if (!h->w[s]) return fail(FITV2_E_UNBOUND, "weight slot %d is not bound", s);
+    if (!h->ws) return fail(FITV2_E_UNBOUND, "workspace is not set");
+    if (h->lay.rows != rows || h->lay.tokens != tokens) {
+        Layout l = make_layout(h->cfg, rows, tokens);
+        if ((int64_t)l.total > h->ws_bytes)
+            return fail(FITV2_E_WORKSPACE, "workspace has %lld bytes, (rows=%d, tokens=%d) needs %lld", (long long)h->ws_bytes, rows, tokens, (long long)l.total);
+        h->lay = l;
+        h->maps_valid = false;
+    }
+    int rc = ensure_maps(h);
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (h->cfg.operand_dtype == FITV2_OPERAND_FP16)
+        return forward_impl<__half>(h, x, x_rows, t, y, grid, mask, out, rows, tokens, st);
+    return forward_impl<__nv_bfloat16>(h, x, x_rows, t, y, grid, mask, out, rows, tokens, st);
+}
+
+int fitv2_cfg_combine(float* out, const float* scale_per_sample, float scale, int half_rows, int tokens, int channels,
+                      int c_cfg, void* stream) {
+    if (!out || half_rows <= 0 || tokens <= 0 || channels <= 0 || c_cfg < 0 || c_cfg > channels)
+        return fail(FITV2_E_INVALID, "bad cfg_combine argument");
+    const size_t total = (size_t)half_rows * tokens * channels;
+    const int blocks = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
+    cfg_combine_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(out, scale_per_sample, scale, half_rows, tokens, channels, c_cfg);
+    CUDA_TRY(cudaGetLastError());
+    return FITV2_OK;
+}
+
+int fitv2_cfg_euler(float* z, const float* v2, float cfg_scale, float dsigma, const float* dsigma_dev, int half_rows,
+                    int tokens, int channels, void* stream) {
+    if (!z || !v2 || half_rows <= 0 || tokens <= 0 || channels <= 0) return fail(FITV2_E_INVALID, "bad cfg_euler argument");
+    const size_t half = (size_t)half_rows * tokens * channels;
+    if ((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(v2) | (half * 4)) % 16)
+        return fail(FITV2_E_INVALID, "cfg_euler needs 16-byte aligned z / v2 and a multiple of 4 elements per half");
+    const size_t nvec = half / 4;
+    const int blocks = (int)((nvec + 255) / 256 < 1184 ? (nvec + 255) / 256 : 1184);
+    cfg_euler_kernel<<<blocks > 0 ? blocks : 1, 256, 0, static_cast<cudaStream_t>(stream)>>>(z, v2, cfg_scale, dsigma, dsigma_dev, half);
+    CUDA_TRY(cudaGetLastError());
+    return FITV2_OK;
+}
+
+int fitv2_debug_gemm(fitv2_handle* h, int epilogue, const void* a, const void* w, const float* bias, float* out32, int M,
+                     int N, int K, int bn, void* stream) {
+    if (!h || !a || !w || !bias || !out32) return fail(FITV2_E_INVALID, "null argument");
+    if (epilogue != EPI_PLAIN) return fail(FITV2_E_INVALID, "debug_gemm supports the plain epilogue only");
+    CUtensorMap ma, mb;
+    int rc;
+    if ((rc = make_map(&ma, a, h->cfg.operand_dtype, M, K, K, 128))) return rc;
+    if ((rc = make_map(&mb, w, h->cfg.operand_dtype, N, K, K, bn))) return rc;
+    GemmEpi ep;
+    memset(&ep, 0, sizeof(ep));
+    ep.bias = bias; ep.out32 = out32; ep.ld_out = N; ep.tokens = 1;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (h->cfg.operand_dtype == FITV2_OPERAND_FP16) return launch_gemm_bn<EPI_PLAIN, __half>(h, bn, ma, mb, M, N, K, 0, ep, st);
+    return launch_gemm_bn<EPI_PLAIN, __nv_bfloat16>(h, bn, ma, mb, M, N, K, 0, ep, st);
+}
+
+int fitv2_debug_attention(fitv2_handle* h, const void* q, const void* k, const void* vt, const float* mask, void* out,
+                          int rows, int tokens, float* dbg_s, float* dbg_o, void* stream) {
+    if (!h || !q || !k || !vt || !mask || !out) return fail(FITV2_E_INVALID, "null argument");
+    if (!h->ws) return fail(FITV2_E_UNBOUND, "workspace is not set");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int* segu = reinterpret_cast<int*>(h->ws);            // first bytes of the workspace as scratch
+    seg_uniform_kernel<<<rows, 128, 0, st>>>(mask, segu, tokens);
+    CUDA_TRY(cudaGetLastError());
+    const int tokens_v = (tokens + 7) / 8 * 8;
+    if (h->cfg.operand_dtype == FITV2_OPERAND_FP16)
+        return launch_attention<__half>(h, q, k, vt, mask, segu, out, rows, tokens, tokens_v, st, dbg_s, dbg_o);
+    return launch_attention<__nv_bfloat16>(h, q, k, vt, mask, segu, out, rows, tokens, tokens_v, st, dbg_s, dbg_o);
+}
+
+int fitv2_debug_tap(fitv2_handle* h, int what, void* dst, int64_t bytes, void* stream) {
+    if (!h || !h->ws || !dst) return fail(FITV2_E_INVALID, "bad tap argument");
+    const Layout& l = h->lay;
+    if (!l.rows) return fail(FITV2_E_UNBOUND, "no forward has run yet");
+    const size_t M = (size_t)l.rows * l.tokens, D = h->cfg.hidden_size;
+    size_t off = 0, have = 0;
+    switch (what) {
+        case 0: off = l.c; have = (size_t)l.rows * D * 4; break;
+        case 1: off = l.gmod; have = (size_t)l.rows * 6 * D * 4; break;
+        case 2: off = l.mod; have = (size_t)h->cfg.depth * l.rows * 6 * D * 4; break;
+        case 3: off = l.fmod; have = (size_t)l.rows * 2 * D * 4; break;
+        case 4: off = l.x_res; have = M * D * 4; break;
+        case 5: off = l.q; have = M * D * 2; break;
+        case 6: off = l.k; have = M * D * 2; break;
+        case 7: off = l.vt; have = (size_t)l.rows * D * l.tokens_v * 2; break;
+        case 8: off = l.ao; have = M * D * 2; break;
+        case 9: off = l.h; have = M * D * 2; break;
+        case 10: off = l.hidden; have = M * h->cfg.mlp_hidden * 2; break;
+        case 11: off = l.rope_cos; have = M * (h->cfg.head_dim / 2) * 4; break;
+        case 12: off = l.rope_sin; have = M * (h->cfg.head_dim / 2) * 4; break;
+        case 13: off = l.seg_uniform; have = (size_t)l.rows * 4; break;
+        default: return fail(FITV2_E_INVALID, "unknown tap %d", what);
+    }
+    if ((size_t)bytes != have) return fail(FITV2_E_INVALID, "tap %d holds %lld bytes, caller asked for %lld", what, (long long)have, (long long)bytes);
+    CUDA_TRY(cudaMemcpyAsync(dst, h->ws + off, have, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+    return FITV2_OK;
+}
+
+int64_t fitv2_kernel_launches(const fitv2_handle* h) { return h ? h->launches : 0; }
+
+}  // extern "C"

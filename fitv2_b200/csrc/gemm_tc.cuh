@@ -1,0 +1,315 @@
+// Persistent, warp-specialised tcgen05 GEMM for the FiTv2 block projections.
+//
+//   C[M, N] = A[M, K] (16-bit, K-major) x W[N, K]^T (16-bit, K-major nn.Linear weight), fp32 accumulate in TMEM.
+//
+//   warp 0 : TMA producer  (cp.async.bulk.tensor, 128B swizzle, STAGES-deep mbarrier ring)
+//   warp 1 : TMEM allocator + single-thread tcgen05.mma issuer (128 x BN x 16 per instruction)
+//   warps 2-5 : epilogue (tcgen05.ld -> registers -> fused math -> global), double-buffered TMEM
+//               accumulators so the epilogue of tile i overlaps the main loop of tile i+1.
+//
+// Fused epilogues (reference lines they replace, paths relative to the reference repo):
+//   EPI_QKV    bias + per-head LayerNorm(q,k) + interleaved-pair 2-D RoPE, scatter to Q / K / V^T
+//              (fit/model/modules.py:166-174, fit/model/rope.py:107-111)
+//   EPI_RESID  x += gate[sample] * (acc + bias)                      (modules.py:205,272 and :273)
+//   EPI_SWIGLU hidden = silu(acc_gate + b_g) * (acc_up + b_x)        (timm SwiGLU; modules.py:251)
+//   EPI_PLAIN  out = acc + bias                                      (generic nn.Linear; tests)
+#pragma once
+#include "common.cuh"
+
+namespace fitv2 {
+
+enum { EPI_QKV = 0, EPI_RESID = 1, EPI_SWIGLU = 2, EPI_PLAIN = 3 };
+
+struct GemmEpi {
+    const float* bias;        // [N] fp32 (layer slice)
+    int tokens;               // tokens per sample row (m = sample * tokens + token)
+    // EPI_RESID
+    float* x;                 // [M, N] fp32 residual stream, updated in place
+    const float* gate;        // [samples, gate_ld] fp32, already offset to this layer's gate chunk
+    int gate_ld;
+    // EPI_SWIGLU / EPI_PLAIN
+    void* out16;              // [M, ld_out] 16-bit
+    float* out32;             // [M, ld_out] fp32 (EPI_PLAIN when out16 == nullptr)
+    int ld_out;
+    // EPI_QKV
+    void* q;                  // [samples, heads, tokens, DH]
+    void* k;                  // [samples, heads, tokens, DH]
+    void* vt;                 // [samples, heads, DH, tokens_v]   (V transposed: keys contiguous)
+    const float* rope_cos;    // [M, DH/2]
+    const float* rope_sin;    // [M, DH/2]
+    int heads;
+    int tokens_v;
+};
+
+constexpr int kGemmBM = 128;
+constexpr int kGemmBK = 64;
+constexpr int kGemmThreads = 192;
+constexpr int kSmemBudget = 227 * 1024;
+
+template <int BN> struct GemmCfg {
+    static constexpr int kABytes = kGemmBM * kGemmBK * 2;
+    static constexpr int kBBytes = BN * kGemmBK * 2;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kBarrierBytes = 1024;
+    static constexpr int kStagesRaw = (kSmemBudget - kBarrierBytes - 1024) / kStageBytes;
+    static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+    static constexpr int kSmemBytes = kStages * kStageBytes + kBarrierBytes + 1024;   // +1024 manual alignment slack
+    static constexpr int kAccStride = 256;                                           // TMEM columns between the 2 accumulators
+    static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N constraint for M=128");
+    static_assert(kBBytes % 1024 == 0, "B stage must keep 1024B alignment for SWIZZLE_128B");
+    static_assert(kStages >= 3, "pipeline too shallow");
+};
+
+template <int BN, int EPI, typename OT, int DH>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+               int M, int N, int K, int b_row_offset, GemmEpi ep)
+{
+    using Cfg = GemmCfg<BN>;
+    constexpr int STAGES = Cfg::kStages;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + STAGES * Cfg::kABytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + STAGES;
+    uint64_t* tfull_bar = bars + 2 * STAGES;
+    uint64_t* tempty_bar = bars + 2 * STAGES + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int m_tiles = (M + kGemmBM - 1) / kGemmBM;
+    const int n_tiles = N / BN;
+    const int num_tiles = m_tiles * n_tiles;
+    const int num_kb = (K + kGemmBK - 1) / kGemmBK;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tma_a);
+        tma_prefetch_desc(&tma_b);
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 128); }
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ------------------------------ TMA producer ------------------------------
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m_tile = tile / n_tiles, n_tile = tile % n_tiles;   // n fastest: a wave shares few A tiles
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+                    tma_load_2d(&tma_a, &full_bar[stage], smem_a + stage * Cfg::kABytes, kb * kGemmBK, m_tile * kGemmBM);
+                    tma_load_2d(&tma_b, &full_bar[stage], smem_b + stage * Cfg::kBBytes, kb * kGemmBK,
+                                b_row_offset + n_tile * BN);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ------------------------------ MMA issuer ------------------------------
+            constexpr uint32_t idesc = umma_idesc(Op16<OT>::kUmmaFormat, kGemmBM, BN);
+            int stage = 0; uint32_t phase = 0; int it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * Cfg::kAccStride;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint64_t da = umma_desc_kmajor(smem_u32(smem_a + stage * Cfg::kABytes), 128);
+                    const uint64_t db = umma_desc_kmajor(smem_u32(smem_b + stage * Cfg::kBBytes), 128);
+#pragma unroll
+                    for (int kk = 0; kk < kGemmBK / 16; ++kk)        // +32 bytes (>>4 = 2) per K=16 step inside the 128B atom
+                        umma_ss(d_tmem, da + 2 * kk, db + 2 * kk, idesc, (kb | kk) != 0);
+                    umma_commit(&empty_bar[stage]);                   // smem slot free once these MMAs retire
+                    if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else {
+        // ------------------------------ epilogue warps ------------------------------
+        const int quarter = warp & 3;                                 // TMEM lane quarter this warp may access
+        const int row_in_tile = quarter * 32 + lane;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int m_tile = tile / n_tiles, n_tile = tile % n_tiles;
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + acc * Cfg::kAccStride + (uint32_t(quarter * 32) << 16);
+            const int m = m_tile * kGemmBM + row_in_tile;
+            const bool row_ok = m < M;
+            const int n0 = n_tile * BN;
+
+            if constexpr (EPI == EPI_RESID) {
+                const int sample = row_ok ? m / ep.tokens : 0;
+                const float* gate = ep.gate + (size_t)sample * ep.gate_ld + n0;
+                const float* bias = ep.bias + n0;
+                float* xrow = ep.x + (size_t)(row_ok ? m : 0) * N + n0;
+#pragma unroll
+                for (int c = 0; c < BN / 16; ++c) {
+                    uint32_t v[16];
+                    tmem_ld16(t_row + c * 16, v);
+                    float4 xv[4];
+                    if (row_ok) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) xv[j] = *reinterpret_cast<const float4*>(xrow + c * 16 + j * 4);
+                    }
+                    tmem_ld_wait();
+                    if (c == BN / 16 - 1) { tc_fence_before(); mbar_arrive(&tempty_bar[acc]); }
+                    if (row_ok) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float4 g = __ldg(reinterpret_cast<const float4*>(gate + c * 16 + j * 4));
+                            const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c * 16 + j * 4));
+                            float4 o;
+                            o.x = xv[j].x + g.x * (__uint_as_float(v[j * 4 + 0]) + b.x);
+                            o.y = xv[j].y + g.y * (__uint_as_float(v[j * 4 + 1]) + b.y);
+                            o.z = xv[j].z + g.z * (__uint_as_float(v[j * 4 + 2]) + b.z);
+                            o.w = xv[j].w + g.w * (__uint_as_float(v[j * 4 + 3]) + b.w);
+                            *reinterpret_cast<float4*>(xrow + c * 16 + j * 4) = o;
+                        }
+                    }
+                }
+            } else if constexpr (EPI == EPI_SWIGLU) {
+                // tile columns: [0, BN/2) = gate rows of W, [BN/2, BN) = matching up rows (host packs W this way)
+                constexpr int HALF = BN / 2;
+                const float* bias = ep.bias + n0;
+                OT* orow = reinterpret_cast<OT*>(ep.out16) + (size_t)(row_ok ? m : 0) * ep.ld_out + n_tile * HALF;
+#pragma unroll
+                for (int c = 0; c < HALF / 16; ++c) {
+                    uint32_t g[16], u[16];
+                    tmem_ld16(t_row + c * 16, g);
+                    tmem_ld16(t_row + HALF + c * 16, u);
+                    tmem_ld_wait();
+                    if (c == HALF / 16 - 1) { tc_fence_before(); mbar_arrive(&tempty_bar[acc]); }
+                    uint32_t packed[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float g0 = __uint_as_float(g[2 * j]) + __ldg(bias + c * 16 + 2 * j);
+                        const float g1 = __uint_as_float(g[2 * j + 1]) + __ldg(bias + c * 16 + 2 * j + 1);
+                        const float u0 = __uint_as_float(u[2 * j]) + __ldg(bias + HALF + c * 16 + 2 * j);
+                        const float u1 = __uint_as_float(u[2 * j + 1]) + __ldg(bias + HALF + c * 16 + 2 * j + 1);
+                        packed[j] = Op16<OT>::pack(silu_f(g0) * u0, silu_f(g1) * u1);
+                    }
+                    if (row_ok) {
+                        uint4* dst = reinterpret_cast<uint4*>(orow + c * 16);
+                        dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                        dst[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+                    }
+                }
+            } else if constexpr (EPI == EPI_PLAIN) {
+                const float* bias = ep.bias + n0;
+#pragma unroll
+                for (int c = 0; c < BN / 16; ++c) {
+                    uint32_t v[16];
+                    tmem_ld16(t_row + c * 16, v);
+                    tmem_ld_wait();
+                    if (c == BN / 16 - 1) { tc_fence_before(); mbar_arrive(&tempty_bar[acc]); }
+                    if (row_ok) {
+                        if (ep.out16 != nullptr) {
+                            OT* orow = reinterpret_cast<OT*>(ep.out16) + (size_t)m * ep.ld_out + n0 + c * 16;
+                            uint32_t packed[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                packed[j] = Op16<OT>::pack(__uint_as_float(v[2 * j]) + __ldg(bias + c * 16 + 2 * j),
+                                                           __uint_as_float(v[2 * j + 1]) + __ldg(bias + c * 16 + 2 * j + 1));
+                            uint4* dst = reinterpret_cast<uint4*>(orow);
+                            dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                            dst[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+                        } else {
+                            float* orow = ep.out32 + (size_t)m * ep.ld_out + n0 + c * 16;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                float4 o;
+                                o.x = __uint_as_float(v[j * 4 + 0]) + __ldg(bias + c * 16 + j * 4 + 0);
+                                o.y = __uint_as_float(v[j * 4 + 1]) + __ldg(bias + c * 16 + j * 4 + 1);
+                                o.z = __uint_as_float(v[j * 4 + 2]) + __ldg(bias + c * 16 + j * 4 + 2);
+                                o.w = __uint_as_float(v[j * 4 + 3]) + __ldg(bias + c * 16 + j * 4 + 3);
+                                *reinterpret_cast<float4*>(orow + j * 4) = o;
+                            }
+                        }
+                    }
+                }
+            } else {   // EPI_QKV: BN == 2 * DH, every tile holds two whole heads of the same kind (heads is even)
+                static_assert(EPI != EPI_QKV || BN == 2 * DH, "QKV tile must be two heads wide");
+                static_assert(DH % 8 == 0, "head_dim must be a multiple of 8");
+                const int sample = row_ok ? m / ep.tokens : 0;
+                const int token = row_ok ? m - sample * ep.tokens : 0;
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    const int ghead = n_tile * 2 + hh;
+                    const int kind = ghead / ep.heads;              // 0 = q, 1 = k, 2 = v   (modules.py:166-167)
+                    const int head = ghead - kind * ep.heads;
+                    float v[DH];
+#pragma unroll
+                    for (int c = 0; c < DH / 8; ++c) tmem_ld8(t_row + hh * DH + c * 8, reinterpret_cast<uint32_t*>(v) + c * 8);
+                    tmem_ld_wait();
+                    if (hh == 1) { tc_fence_before(); mbar_arrive(&tempty_bar[acc]); }
+                    const float* bias = ep.bias + n0 + hh * DH;
+#pragma unroll
+                    for (int j = 0; j < DH; ++j) v[j] += __ldg(bias + j);
+                    if (kind < 2) {
+                        // LayerNorm over the head (no affine, eps 1e-6, biased variance): norms.py:41-42
+                        float mean = 0.f;
+#pragma unroll
+                        for (int j = 0; j < DH; ++j) mean += v[j];
+                        mean *= (1.0f / DH);
+                        float var = 0.f;
+#pragma unroll
+                        for (int j = 0; j < DH; ++j) { const float d = v[j] - mean; var += d * d; }
+                        const float rstd = rsqrtf(var * (1.0f / DH) + 1e-6f);
+                        const float* cs = ep.rope_cos + (size_t)(row_ok ? m : 0) * (DH / 2);
+                        const float* sn = ep.rope_sin + (size_t)(row_ok ? m : 0) * (DH / 2);
+                        OT* dst = reinterpret_cast<OT*>(kind == 0 ? ep.q : ep.k) +
+                                  (((size_t)sample * ep.heads + head) * ep.tokens + token) * DH;
+#pragma unroll
+                        for (int c = 0; c < DH / 8; ++c) {
+                            const float4 cv = __ldg(reinterpret_cast<const float4*>(cs + c * 4));
+                            const float4 sv = __ldg(reinterpret_cast<const float4*>(sn + c * 4));
+                            const float cc[4] = {cv.x, cv.y, cv.z, cv.w};
+                            const float ss[4] = {sv.x, sv.y, sv.z, sv.w};
+                            uint32_t packed[4];
+#pragma unroll
+                            for (int p = 0; p < 4; ++p) {
+                                const float x0 = (v[c * 8 + 2 * p] - mean) * rstd;
+                                const float x1 = (v[c * 8 + 2 * p + 1] - mean) * rstd;
+                                // q*cos + rotate_half(q)*sin with rotate_half: (x0,x1) -> (-x1,x0)
+                                packed[p] = Op16<OT>::pack(x0 * cc[p] - x1 * ss[p], x1 * cc[p] + x0 * ss[p]);
+                            }
+                            if (row_ok) *reinterpret_cast<uint4*>(dst + c * 8) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                        }
+                    } else if (row_ok) {
+                        // V^T[sample, head, d, token]: lanes hold consecutive tokens -> 64B runs per d
+                        OT* dst = reinterpret_cast<OT*>(ep.vt) + ((size_t)sample * ep.heads + head) * DH * ep.tokens_v + token;
+#pragma unroll
+                        for (int j = 0; j < DH; ++j) dst[(size_t)j * ep.tokens_v] = Op16<OT>::from(v[j]);
+                    }
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+}  // namespace fitv2

@@ -1,0 +1,376 @@
+// Memory-bound kernels of the FiTv2 hot path: 128-bit coalesced accesses, warp-shuffle reductions,
+// fp32 math.  Reference lines are cited per kernel (paths relative to the reference repo).
+#pragma once
+#include "common.cuh"
+
+namespace fitv2 {
+
+// ---------------------------------------------------------------------------------------------
+// CFG combine + Euler update  (sample_fitv2_ddp.py:310-314)
+//   v = uncond + s * (cond - uncond) ;  z = z + dsigma * v        -- evaluated in exactly that order,
+//   no FMA contraction, so the fp32 result is bit-identical to the PyTorch expression.
+// z: (B, n) fp32 updated in place, v2: (2B, n): rows [0,B) cond, [B,2B) uncond.  n = tokens * C.
+// ---------------------------------------------------------------------------------------------
+__global__ void cfg_euler_kernel(float* __restrict__ z, const float* __restrict__ v2, float cfg_scale, float dsigma,
+                                 const float* __restrict__ dsigma_dev, size_t half_elems)
+{
+    if (dsigma_dev) dsigma = *dsigma_dev;
+    const size_t nvec = half_elems >> 2;
+    const float4* cond = reinterpret_cast<const float4*>(v2);
+    const float4* uncond = reinterpret_cast<const float4*>(v2 + half_elems);
+    float4* zz = reinterpret_cast<float4*>(z);
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 c = cond[i], u = uncond[i];
+        float4 o = zz[i];
+        o.x = __fadd_rn(o.x, __fmul_rn(dsigma, __fadd_rn(u.x, __fmul_rn(cfg_scale, __fsub_rn(c.x, u.x)))));
+        o.y = __fadd_rn(o.y, __fmul_rn(dsigma, __fadd_rn(u.y, __fmul_rn(cfg_scale, __fsub_rn(c.y, u.y)))));
+        o.z = __fadd_rn(o.z, __fmul_rn(dsigma, __fadd_rn(u.z, __fmul_rn(cfg_scale, __fsub_rn(c.z, u.z)))));
+        o.w = __fadd_rn(o.w, __fmul_rn(dsigma, __fadd_rn(u.w, __fmul_rn(cfg_scale, __fsub_rn(c.w, u.w)))));
+        zz[i] = o;
+    }
+    // scalar tail (half_elems not a multiple of 4)
+    for (size_t i = (nvec << 2) + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < half_elems;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const float c = v2[i], u = v2[half_elems + i];
+        z[i] = __fadd_rn(z[i], __fmul_rn(dsigma, __fadd_rn(u, __fmul_rn(cfg_scale, __fsub_rn(c, u)))));
+    }
+}
+
+// forward_with_cfg channel-limited guidance (fit_model.py:253-275): channels [0, c_cfg) of BOTH halves become
+// uncond + s_b * (cond - uncond); channels >= c_cfg pass through.  out: (2B, tokens, C) in place.
+// scale_per_sample may be null (then `scale` is used for every sample).
+__global__ void cfg_combine_kernel(float* __restrict__ out, const float* __restrict__ scale_per_sample, float scale,
+                                   int B, int tokens, int C, int c_cfg)
+{
+    const size_t per_sample = (size_t)tokens * C;
+    const size_t total = (size_t)B * per_sample;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int ch = (int)(i % C);
+        if (ch >= c_cfg) continue;
+        const float s = scale_per_sample ? scale_per_sample[i / per_sample] : scale;
+        const float c = out[i], u = out[total + i];
+        const float g = __fadd_rn(u, __fmul_rn(s, __fsub_rn(c, u)));
+        out[i] = g;
+        out[total + i] = g;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Patch embedding  (fit/model/modules.py:34-37): x[m, :] = W (D x Cin) * xin[m % rows_in, :] + b
+// K = 16 -> bandwidth-bound (writes M*D fp32).  One block = 8 token rows; a thread owns 4 consecutive
+// output features and keeps their weight rows in registers.
+// ---------------------------------------------------------------------------------------------
+template <int CIN>
+__global__ void __launch_bounds__(256)
+patch_embed_kernel(const float* __restrict__ xin, const float* __restrict__ w, const float* __restrict__ b,
+                   float* __restrict__ x, int M, int D, int rows_in_tokens /* tokens * rows_in */)
+{
+    __shared__ float sx[8][CIN];
+    const int m0 = blockIdx.x * 8;
+    for (int i = threadIdx.x; i < 8 * CIN; i += blockDim.x) {
+        const int r = i / CIN, c = i % CIN;
+        const int m = m0 + r;
+        sx[r][c] = (m < M) ? xin[(size_t)(m % rows_in_tokens) * CIN + c] : 0.f;
+    }
+    __syncthreads();
+    for (int d0 = threadIdx.x * 4; d0 < D; d0 += blockDim.x * 4) {
+        float wr[4][CIN];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int c = 0; c < CIN; c += 4) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(w + (size_t)(d0 + j) * CIN + c));
+                wr[j][c] = t.x; wr[j][c + 1] = t.y; wr[j][c + 2] = t.z; wr[j][c + 3] = t.w;
+            }
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(b + d0));
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            if (m0 + r >= M) break;
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int c = 0; c < CIN; ++c) {
+                const float xv = sx[r][c];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[j] = fmaf(xv, wr[j][c], acc[j]);
+            }
+            *reinterpret_cast<float4*>(x + (size_t)(m0 + r) * D + d0) =
+                make_float4(acc[0] + bb.x, acc[1] + bb.y, acc[2] + bb.z, acc[3] + bb.w);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm (no affine, eps 1e-6) + adaLN modulate -> 16-bit GEMM operand
+//   h = LN(x) * (1 + scale[sample]) + shift[sample]      (norms.py:41-42, fit/model/utils.py:6-7, modules.py:272-273)
+// One warp per token row, the row lives in registers (NV float4 per lane), two-pass fp32 statistics.
+// ---------------------------------------------------------------------------------------------
+template <typename OT, int NV>
+__global__ void __launch_bounds__(256)
+ln_modulate_kernel(const float* __restrict__ x, const float* __restrict__ shift, const float* __restrict__ scale,
+                   int mod_ld, OT* __restrict__ h, int M, int D, int tokens)
+{
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= M) return;
+    const int m = warp;
+    const int nvec = D >> 2;
+    const float4* xr = reinterpret_cast<const float4*>(x + (size_t)m * D);
+    float4 v[NV];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int j = lane + 32 * i;
+        v[i] = (j < nvec) ? xr[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+        s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    const float mean = warp_sum(s) / (float)D;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int j = lane + 32 * i;
+        if (j < nvec) {
+            const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+            q += (a * a + b * b) + (c * c + d * d);
+        }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / (float)D + 1e-6f);
+    const int sample = m / tokens;
+    const float4* sh = reinterpret_cast<const float4*>(shift + (size_t)sample * mod_ld);
+    const float4* sc = reinterpret_cast<const float4*>(scale + (size_t)sample * mod_ld);
+    uint2* hr = reinterpret_cast<uint2*>(h + (size_t)m * D);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int j = lane + 32 * i;
+        if (j < nvec) {
+            const float4 a = __ldg(sh + j), g = __ldg(sc + j);
+            const float o0 = (v[i].x - mean) * rstd * (1.f + g.x) + a.x;
+            const float o1 = (v[i].y - mean) * rstd * (1.f + g.y) + a.y;
+            const float o2 = (v[i].z - mean) * rstd * (1.f + g.z) + a.z;
+            const float o3 = (v[i].w - mean) * rstd * (1.f + g.w) + a.w;
+            hr[j] = make_uint2(Op16<OT>::pack(o0, o1), Op16<OT>::pack(o2, o3));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Final layer  (modules.py:292-296, fit_model.py:230):
+//   out[m, :] = (W_o (Cout x D) * (LN(x[m]) * (1 + scale) + shift) + b_o) * mask[m]
+// N = 16 -> bandwidth-bound (reads M*D fp32).  One warp per row, W_o cached in shared memory.
+// ---------------------------------------------------------------------------------------------
+template <int NV, int COUT>
+__global__ void __launch_bounds__(256)
+final_layer_kernel(const float* __restrict__ x, const float* __restrict__ fmod /* (samples, 2D): shift | scale */,
+                   const float* __restrict__ w, const float* __restrict__ b, const float* __restrict__ mask,
+                   float* __restrict__ out, int M, int D, int tokens)
+{
+    extern __shared__ float sw[];                       // COUT * D
+    for (int i = threadIdx.x; i < COUT * D; i += blockDim.x) sw[i] = w[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    const int nvec = D >> 2;
+    for (int m = blockIdx.x * warps_per_block + (threadIdx.x >> 5); m < M; m += gridDim.x * warps_per_block) {
+        const float4* xr = reinterpret_cast<const float4*>(x + (size_t)m * D);
+        float4 v[NV];
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int j = lane + 32 * i;
+            v[i] = (j < nvec) ? xr[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+            s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        }
+        const float mean = warp_sum(s) / (float)D;
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int j = lane + 32 * i;
+            if (j < nvec) {
+                const float a = v[i].x - mean, bq = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+                q += (a * a + bq * bq) + (c * c + d * d);
+            }
+        }
+        const float rstd = rsqrtf(warp_sum(q) / (float)D + 1e-6f);
+        const int sample = m / tokens;
+        const float4* sh = reinterpret_cast<const float4*>(fmod + (size_t)sample * 2 * D);
+        const float4* sc = reinterpret_cast<const float4*>(fmod + (size_t)sample * 2 * D + D);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int j = lane + 32 * i;
+            if (j < nvec) {
+                const float4 a = __ldg(sh + j), g = __ldg(sc + j);
+                v[i].x = (v[i].x - mean) * rstd * (1.f + g.x) + a.x;
+                v[i].y = (v[i].y - mean) * rstd * (1.f + g.y) + a.y;
+                v[i].z = (v[i].z - mean) * rstd * (1.f + g.z) + a.z;
+                v[i].w = (v[i].w - mean) * rstd * (1.f + g.w) + a.w;
+            }
+        }
+        float acc[COUT];
+#pragma unroll
+        for (int o = 0; o < COUT; ++o) {
+            const float4* wr = reinterpret_cast<const float4*>(sw + (size_t)o * D);
+            float a = 0.f;
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                const int j = lane + 32 * i;
+                if (j < nvec) {
+                    const float4 ww = wr[j];
+                    a = fmaf(v[i].x, ww.x, a); a = fmaf(v[i].y, ww.y, a);
+                    a = fmaf(v[i].z, ww.z, a); a = fmaf(v[i].w, ww.w, a);
+                }
+            }
+            acc[o] = warp_sum(a);
+        }
+        if (lane < COUT) {
+            float r = 0.f;
+#pragma unroll
+            for (int o = 0; o < COUT; ++o) if (lane == o) r = acc[o];
+            out[(size_t)m * COUT + lane] = (r + __ldg(b + lane)) * mask[m];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// RoPE tables  (rope.py:165-170, 308-333): for token row m of sample s
+//   pair i <  dh/4 : angle = float(grid[s,1,n]) * freqs_h[i]            (h position)
+//   pair i >= dh/4 : angle = float(grid[s,0,n]) * freqs_w[i - dh/4]     (w position)
+//   cos/sin tables (M, dh/2) fp32, optionally scaled by the yarn / ntk-pro magnitude.
+// ---------------------------------------------------------------------------------------------
+__global__ void rope_table_kernel(const long long* __restrict__ grid, const float* __restrict__ freqs_h,
+                                  const float* __restrict__ freqs_w, float mag, float* __restrict__ cos_t,
+                                  float* __restrict__ sin_t, int samples, int tokens, int half /* dh/2 */)
+{
+    const int quarter = half >> 1;
+    const size_t total = (size_t)samples * tokens * half;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int p = (int)(i % half);
+        const size_t m = i / half;
+        const int n = (int)(m % tokens);
+        const int s = (int)(m / tokens);
+        const long long* g = grid + (size_t)s * 2 * tokens;
+        float ang;
+        if (p < quarter) ang = __fmul_rn((float)g[tokens + n], freqs_h[p]);
+        else             ang = __fmul_rn((float)g[n], freqs_w[p - quarter]);
+        float sv, cv;
+        sincosf(ang, &sv, &cv);
+        if (mag != 1.0f) { cv = __fmul_rn(cv, mag); sv = __fmul_rn(sv, mag); }
+        cos_t[i] = cv;
+        sin_t[i] = sv;
+    }
+}
+
+// Per-sample flag: 1 when every segment id of the sample is identical (attention skips the compares).
+__global__ void seg_uniform_kernel(const float* __restrict__ seg, int* __restrict__ flag, int tokens)
+{
+    const float* s = seg + (size_t)blockIdx.x * tokens;
+    const float first = s[0];
+    int same = 1;
+    for (int i = threadIdx.x; i < tokens; i += blockDim.x) same &= (s[i] == first);
+    same = __syncthreads_and(same);
+    if (threadIdx.x == 0) flag[blockIdx.x] = same;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Timestep features  (fit_model.py:202-203, modules.py:52-71):
+//   t' = min(ts*t / (1 + (ts-1)*t), 1);  te = [cos(t' f_i), sin(t' f_i)], f_i = exp(-ln(1e4) * i / 128)
+// ---------------------------------------------------------------------------------------------
+__global__ void timestep_features_kernel(const float* __restrict__ t, float time_shifting, float* __restrict__ te,
+                                         int samples)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= samples * 128) return;
+    const int s = i >> 7, j = i & 127;
+    float tt = t[s];
+    tt = __fdiv_rn(__fmul_rn(time_shifting, tt), __fadd_rn(1.0f, __fmul_rn(time_shifting - 1.0f, tt)));
+    tt = fminf(tt, 1.0f);
+    const float f = expf(__fdiv_rn(__fmul_rn(-9.210340371976184f, (float)j), 128.0f));
+    const float a = __fmul_rn(tt, f);
+    te[(size_t)s * 256 + j] = cosf(a);
+    te[(size_t)s * 256 + 128 + j] = sinf(a);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Small-M fp32 linear for the conditioning path (t-MLP, global adaLN, adaLN-LoRA, final adaLN):
+//   out[z][r, n] = sum_k act(A[z][r, k]) * W[z][n, k] + bias[z][n] (+ add[r, n]) (+ emb[label[r], n])
+// M = samples (64 with CFG) -> weight-bandwidth-bound; fp32 FMA keeps the modulation exact to
+// fp32 rounding because shift/scale/gate feed every token of every block.
+// 64x64 output tile per CTA, 16x16 threads with 4x4 register tiles, K chunks of 16 through smem.
+// ---------------------------------------------------------------------------------------------
+struct SmallLinear {
+    const float* A; size_t a_batch_stride; int lda;
+    const float* W; size_t w_batch_stride;
+    const float* bias; size_t bias_batch_stride;
+    const float* add;            // (rows, N) or null, shared by all batches
+    const float* emb; const long long* labels;   // optional embedding-row add (label gather), ld = N
+    float* out; size_t out_batch_stride; int ldo;
+    float* out_silu;             // optional second output: silu(out) (same layout)
+    int rows, N, K;
+    int act_silu_in;             // apply SiLU to A on load
+};
+
+__global__ void __launch_bounds__(256)
+small_linear_kernel(SmallLinear p)
+{
+    __shared__ float As[16][64 + 4];
+    __shared__ float Ws[16][64 + 4];
+    const int z = blockIdx.z;
+    const float* A = p.A + z * p.a_batch_stride;
+    const float* W = p.W + z * p.w_batch_stride;
+    const int n0 = blockIdx.x * 64, r0 = blockIdx.y * 64;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    const int lr = threadIdx.x >> 2;            // 0..63 : row (A) / col (W) loaded by this thread
+    const int lk = (threadIdx.x & 3) * 4;       // 0,4,8,12
+    for (int k0 = 0; k0 < p.K; k0 += 16) {
+        float4 av = make_float4(0.f, 0.f, 0.f, 0.f), wv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r0 + lr < p.rows && k0 + lk < p.K) {
+            av = *reinterpret_cast<const float4*>(A + (size_t)(r0 + lr) * p.lda + k0 + lk);
+            if (p.act_silu_in) {
+                av.x = av.x / (1.f + expf(-av.x)); av.y = av.y / (1.f + expf(-av.y));
+                av.z = av.z / (1.f + expf(-av.z)); av.w = av.w / (1.f + expf(-av.w));
+            }
+        }
+        if (n0 + lr < p.N && k0 + lk < p.K)
+            wv = __ldg(reinterpret_cast<const float4*>(W + (size_t)(n0 + lr) * p.K + k0 + lk));
+        __syncthreads();
+        As[lk + 0][lr] = av.x; As[lk + 1][lr] = av.y; As[lk + 2][lr] = av.z; As[lk + 3][lr] = av.w;
+        Ws[lk + 0][lr] = wv.x; Ws[lk + 1][lr] = wv.y; Ws[lk + 2][lr] = wv.z; Ws[lk + 3][lr] = wv.w;
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) {
+            const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+            const float4 w4 = *reinterpret_cast<const float4*>(&Ws[kk][tx * 4]);
+            const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+            const float w[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+        }
+    }
+    const float* bias = p.bias ? p.bias + z * p.bias_batch_stride : nullptr;
+    float* out = p.out + z * p.out_batch_stride;
+    float* out_silu = p.out_silu ? p.out_silu + z * p.out_batch_stride : nullptr;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = r0 + ty * 4 + i;
+        if (r >= p.rows) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
+            if (n >= p.N) continue;
+            float v = acc[i][j];
+            if (bias) v += bias[n];
+            if (p.add) v += p.add[(size_t)r * p.N + n];
+            if (p.emb) v += p.emb[(size_t)p.labels[r] * p.N + n];
+            out[(size_t)r * p.ldo + n] = v;
+            if (out_silu) out_silu[(size_t)r * p.ldo + n] = v / (1.f + expf(-v));
+        }
+    }
+}
+
+}  // namespace fitv2

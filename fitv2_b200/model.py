@@ -1,0 +1,345 @@
+"""``fitv2_b200.FiT`` — drop-in for ``fit.model.fit_model.FiT`` on the sampling hot path.
+
+Same constructor keywords (fit_model.py:25-65), same ``state_dict`` keys and shapes (so
+``init_from_ckpt`` / ``load_state_dict`` of a reference checkpoint work, eval_utils.py:12-71), same
+``forward`` / ``forward_with_cfg`` / ``unpatchify`` signatures (fit_model.py:171-275).  The math runs
+in hand-written sm_100a CUDA behind the C ABI of ``include/fitv2_b200.h``; PyTorch only owns the
+device memory and the stream.  There is no CPU path and no PyTorch fallback: unsupported
+configurations and non-CUDA tensors raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .rope import rope_frequencies
+
+
+class _Holder(nn.Module):
+    """Parameter container (never called)."""
+
+
+def _seq(*mods):
+    return nn.Sequential(*mods)
+
+
+class FiT(nn.Module):
+    """FiTv2 transformer (use_sit / SwiGLU / adaLN-LoRA / layernorm qk-norm / 2-D RoPE)."""
+
+    def __init__(self, context_size: int = 256, patch_size: int = 2, in_channels: int = 4, hidden_size: int = 1152,
+                 depth: int = 28, num_heads: int = 16, mlp_ratio: float = 4.0, class_dropout_prob: float = 0.1,
+                 num_classes: int = 1000, learn_sigma: bool = True, use_sit: bool = False, use_checkpoint: bool = False,
+                 use_swiglu: bool = False, use_swiglu_large: bool = False, rel_pos_embed: Optional[str] = "rope",
+                 norm_type: str = "layernorm", q_norm: Optional[str] = None, k_norm: Optional[str] = None,
+                 qk_norm_weight: bool = False, qkv_bias: bool = True, ffn_bias: bool = True, adaln_bias: bool = True,
+                 adaln_type: str = "normal", adaln_lora_dim: int = None, rope_theta: float = 10000.0,
+                 custom_freqs: str = "normal", max_pe_len_h: Optional[int] = None, max_pe_len_w: Optional[int] = None,
+                 decouple: bool = False, ori_max_pe_len: Optional[int] = None, online_rope: bool = False,
+                 add_rel_pe_to_v: bool = False, pretrain_ckpt: str = None, ignore_keys: list = None,
+                 finetune: str = None, time_shifting: int = 1, save_attention: bool = False,
+                 operand_dtype: str = "bf16", **kwargs):
+        super().__init__()
+        # ---- reject what the kernels do not implement (no silent fallback) ----
+        unsupported = []
+        if not use_sit: unsupported.append("use_sit=False (FiTv1 (B,C,N) layout)")
+        if learn_sigma: unsupported.append("learn_sigma=True")
+        if not use_swiglu or use_swiglu_large: unsupported.append("use_swiglu must be True and use_swiglu_large False")
+        if adaln_type != "lora" or not adaln_lora_dim: unsupported.append("adaln_type must be 'lora' with adaln_lora_dim")
+        if (rel_pos_embed or "").lower() != "rope": unsupported.append("rel_pos_embed must be 'rope'")
+        if norm_type != "layernorm": unsupported.append("norm_type must be 'layernorm'")
+        if q_norm != "layernorm" or k_norm != "layernorm" or qk_norm_weight: unsupported.append("q_norm/k_norm must be 'layernorm' without weight")
+        if not (qkv_bias and ffn_bias and adaln_bias): unsupported.append("qkv_bias/ffn_bias/adaln_bias must be True")
+        if online_rope: unsupported.append("online_rope=True")
+        if add_rel_pe_to_v: unsupported.append("add_rel_pe_to_v=True")
+        if use_checkpoint: unsupported.append("use_checkpoint=True (inference only)")
+        if finetune is not None or pretrain_ckpt is not None: unsupported.append("pretrain_ckpt/finetune (load weights with load_state_dict)")
+        if save_attention: unsupported.append("save_attention=True")
+        if patch_size ** 2 * in_channels != 16: unsupported.append("patch_size**2 * in_channels must be 16")
+        if hidden_size % num_heads or hidden_size // num_heads not in (72, 96): unsupported.append("head_dim must be 72 or 96")
+        if operand_dtype not in ("bf16", "fp16"): unsupported.append("operand_dtype must be 'bf16' or 'fp16'")
+        if unsupported:
+            raise NotImplementedError("fitv2_b200.FiT does not implement: " + "; ".join(unsupported))
+
+        self.context_size, self.hidden_size, self.depth = context_size, hidden_size, depth
+        self.learn_sigma, self.use_sit, self.use_checkpoint = learn_sigma, use_sit, use_checkpoint
+        self.mlp_ratio, self.class_dropout_prob, self.num_classes = mlp_ratio, class_dropout_prob, num_classes
+        self.in_channels = in_channels
+        self.out_channels = in_channels
+        self.patch_size, self.num_heads = patch_size, num_heads
+        self.adaln_type, self.adaln_lora_dim = adaln_type, adaln_lora_dim
+        self.online_rope, self.time_shifting, self.save_attention = online_rope, time_shifting, False
+        self.head_dim = hidden_size // num_heads
+        self.mlp_hidden = (int(hidden_size * mlp_ratio) * 2) // 3          # modules.py:246,250
+        self.operand_dtype = operand_dtype
+        self.rope_args = dict(head_dim=self.head_dim, custom_freqs=custom_freqs, theta=rope_theta,
+                              max_pe_len_h=max_pe_len_h, max_pe_len_w=max_pe_len_w, decouple=decouple,
+                              ori_max_pe_len=ori_max_pe_len)
+        rope_frequencies(**self.rope_args)                                  # validate early
+
+        # ---- parameters: same names / shapes / creation order as the reference (fit_model.py:84-112) ----
+        D, C = hidden_size, in_channels * patch_size ** 2
+        self.x_embedder = _Holder(); self.x_embedder.proj = nn.Linear(C, D)
+        self.t_embedder = _Holder(); self.t_embedder.mlp = _seq(nn.Linear(256, D), nn.SiLU(), nn.Linear(D, D))
+        self.y_embedder = _Holder()
+        self.y_embedder.embedding_table = nn.Embedding(num_classes + (class_dropout_prob > 0), D)
+        self.global_adaLN_modulation = _seq(nn.SiLU(), nn.Linear(D, 6 * D))
+        blocks = []
+        for _ in range(depth):
+            blk = _Holder()
+            blk.attn = _Holder(); blk.attn.qkv = nn.Linear(D, 3 * D); blk.attn.proj = nn.Linear(D, D)
+            blk.mlp = _Holder()
+            blk.mlp.fc1_g = nn.Linear(D, self.mlp_hidden); blk.mlp.fc1_x = nn.Linear(D, self.mlp_hidden)
+            blk.mlp.fc2 = nn.Linear(self.mlp_hidden, D)
+            blk.adaLN_modulation = _seq(nn.SiLU(), nn.Linear(D, adaln_lora_dim), nn.Linear(adaln_lora_dim, 6 * D))
+            blocks.append(blk)
+        self.blocks = nn.ModuleList(blocks)
+        self.final_layer = _Holder()
+        self.final_layer.linear = nn.Linear(D, C)
+        self.final_layer.adaLN_modulation = _seq(nn.SiLU(), nn.Linear(D, 2 * D))
+        self.initialize_weights()
+
+        self._handle = None
+        self._packed = None
+        self._workspace = None
+        self._ws_shape = None
+
+    # ------------------------------------------------------------------------------------------
+    # weights
+    # ------------------------------------------------------------------------------------------
+    def initialize_weights(self):
+        """Same scheme as fit_model.py:117-157 (xavier Linears, N(0,0.02) tables, zeroed adaLN/final)."""
+        def _basic_init(m):
+            if isinstance(m, nn.Linear):
+                nn.init.xavier_uniform_(m.weight)
+                if m.bias is not None:
+                    nn.init.constant_(m.bias, 0)
+        self.apply(_basic_init)
+        w = self.x_embedder.proj.weight.data
+        nn.init.xavier_uniform_(w.view([w.shape[0], -1]))
+        nn.init.constant_(self.x_embedder.proj.bias, 0)
+        nn.init.normal_(self.y_embedder.embedding_table.weight, std=0.02)
+        nn.init.normal_(self.t_embedder.mlp[0].weight, std=0.02)
+        nn.init.normal_(self.t_embedder.mlp[2].weight, std=0.02)
+        for blk in self.blocks:
+            nn.init.constant_(blk.adaLN_modulation[-1].weight, 0)
+            nn.init.constant_(blk.adaLN_modulation[-1].bias, 0)
+        for lin in (self.global_adaLN_modulation[-1], self.final_layer.adaLN_modulation[-1], self.final_layer.linear):
+            nn.init.constant_(lin.weight, 0)
+            nn.init.constant_(lin.bias, 0)
+
+    @torch.no_grad()
+    def randomize_zero_init_(self, seed: int = 1, std: float = 0.02):
+        """Benchmark / parity helper: the reference init makes the output identically zero (all adaLN
+        outputs and the final linear are zero-initialised), so every all-zero tensor is re-drawn
+        N(0, std^2) from a dedicated CPU generator in ``state_dict()`` order."""
+        g = torch.Generator().manual_seed(seed)
+        for _, p in self.state_dict().items():
+            if p.is_floating_point() and not bool(p.any()):
+                p.copy_((torch.randn(p.shape, generator=g, dtype=torch.float32) * std).to(p.dtype))
+        self._packed = None
+        return self
+
+    def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
+        out = super().load_state_dict(state_dict, strict=strict, assign=assign)
+        self._packed = None
+        return out
+
+    def _apply(self, fn, recurse=True):
+        out = super()._apply(fn, recurse)
+        self._packed = None
+        self._workspace = None
+        self._ws_shape = None
+        return out
+
+    @property
+    def dtype(self) -> torch.dtype:
+        return next(self.parameters()).dtype
+
+    @property
+    def device(self) -> torch.device:
+        return next(self.parameters()).device
+
+    # ------------------------------------------------------------------------------------------
+    # C-ABI plumbing
+    # ------------------------------------------------------------------------------------------
+    def _require_cuda(self):
+        dev = self.device
+        if dev.type != "cuda":
+            raise _lib.FitV2Error("fitv2_b200.FiT runs on CUDA (sm_100a) only; move the module with .to('cuda'). "
+                                  "There is no CPU fallback.")
+        return dev
+
+    @torch.no_grad()
+    def _ensure_packed(self):
+        if self._packed is not None:
+            return
+        dev = self._require_cuda()
+        lib = _lib.load()
+        fh, fw, mag = rope_frequencies(**self.rope_args)
+        with torch.cuda.device(dev):
+            if self._handle is None:
+                cfg = _lib.FitV2Config(self.hidden_size, self.depth, self.num_heads, self.head_dim, self.mlp_hidden,
+                                       self.adaln_lora_dim, self.in_channels * self.patch_size ** 2,
+                                       self.y_embedder.embedding_table.weight.shape[0],
+                                       _lib.OPERAND_FP16 if self.operand_dtype == "fp16" else _lib.OPERAND_BF16,
+                                       float(self.time_shifting), float(mag))
+                h = C.c_void_p()
+                _lib.check(lib.fitv2_create(C.byref(cfg), C.byref(h)), "fitv2_create")
+                self._handle = h
+            op = torch.float16 if self.operand_dtype == "fp16" else torch.bfloat16
+            f32 = lambda p: p.detach().to(device=dev, dtype=torch.float32).contiguous()
+            blocks = self.blocks
+            stack32 = lambda get: torch.stack([get(b).detach().to(device=dev, dtype=torch.float32) for b in blocks]).contiguous()
+            stack16 = lambda get: torch.stack([get(b).detach().to(device=dev, dtype=torch.float32).to(op) for b in blocks]).contiguous()
+            Hm = self.mlp_hidden
+
+            def gateup(b, attr):
+                g = getattr(b.mlp.fc1_g, attr).detach().to(device=dev, dtype=torch.float32)
+                u = getattr(b.mlp.fc1_x, attr).detach().to(device=dev, dtype=torch.float32)
+                g = g.reshape(Hm // 128, 128, *g.shape[1:])
+                u = u.reshape(Hm // 128, 128, *u.shape[1:])
+                return torch.cat([g, u], dim=1).reshape(2 * Hm, *g.shape[2:])
+
+            P = {
+                "X_EMBED_W": f32(self.x_embedder.proj.weight), "X_EMBED_B": f32(self.x_embedder.proj.bias),
+                "T_MLP0_W": f32(self.t_embedder.mlp[0].weight), "T_MLP0_B": f32(self.t_embedder.mlp[0].bias),
+                "T_MLP2_W": f32(self.t_embedder.mlp[2].weight), "T_MLP2_B": f32(self.t_embedder.mlp[2].bias),
+                "Y_TABLE": f32(self.y_embedder.embedding_table.weight),
+                "GLOBAL_ADALN_W": f32(self.global_adaLN_modulation[1].weight),
+                "GLOBAL_ADALN_B": f32(self.global_adaLN_modulation[1].bias),
+                "LORA_A_W": stack32(lambda b: b.adaLN_modulation[1].weight), "LORA_A_B": stack32(lambda b: b.adaLN_modulation[1].bias),
+                "LORA_B_W": stack32(lambda b: b.adaLN_modulation[2].weight), "LORA_B_B": stack32(lambda b: b.adaLN_modulation[2].bias),
+                "FINAL_ADALN_W": f32(self.final_layer.adaLN_modulation[1].weight),
+                "FINAL_ADALN_B": f32(self.final_layer.adaLN_modulation[1].bias),
+                "FINAL_LINEAR_W": f32(self.final_layer.linear.weight), "FINAL_LINEAR_B": f32(self.final_layer.linear.bias),
+                "QKV_W": stack16(lambda b: b.attn.qkv.weight), "QKV_B": stack32(lambda b: b.attn.qkv.bias),
+                "PROJ_W": stack16(lambda b: b.attn.proj.weight), "PROJ_B": stack32(lambda b: b.attn.proj.bias),
+                "GATEUP_W": torch.stack([gateup(b, "weight").to(op) for b in blocks]).contiguous(),
+                "GATEUP_B": torch.stack([gateup(b, "bias") for b in blocks]).contiguous(),
+                "FC2_W": stack16(lambda b: b.mlp.fc2.weight), "FC2_B": stack32(lambda b: b.mlp.fc2.bias),
+                "ROPE_FREQS_H": fh.to(dev).contiguous(), "ROPE_FREQS_W": fw.to(dev).contiguous(),
+            }
+            for name, tns in P.items():
+                want = op if name in _lib.OP16_SLOTS else torch.float32
+                assert tns.dtype == want and tns.is_contiguous(), name
+                _lib.check(lib.fitv2_bind_weight(self._handle, _lib.SLOT[name], C.c_void_p(tns.data_ptr()), tns.numel()),
+                           f"fitv2_bind_weight({name})")
+            self._packed = P
+
+    def _ensure_workspace(self, rows: int, tokens: int):
+        if self._ws_shape == (rows, tokens):
+            return
+        lib = _lib.load()
+        need = lib.fitv2_workspace_bytes(self._handle, rows, tokens)
+        if need <= 0:
+            _lib.check(int(need), "fitv2_workspace_bytes")
+        if self._workspace is None or self._workspace.numel() < need:
+            self._workspace = torch.zeros(int(need), dtype=torch.uint8, device=self.device)
+            _lib.check(lib.fitv2_set_workspace(self._handle, C.c_void_p(self._workspace.data_ptr()), self._workspace.numel()),
+                       "fitv2_set_workspace")
+        self._ws_shape = (rows, tokens)
+
+    def _run(self, x: torch.Tensor, t, y, grid, mask, rows: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """x (x_rows, N, C) fp32 contiguous with x_rows == rows or rows // 2 (implicit CFG duplication)."""
+        self._ensure_packed()
+        dev = self.device
+        for name, tns in (("x", x), ("t", t), ("y", y), ("grid", grid), ("mask", mask)):
+            if tns.device != dev:
+                raise _lib.FitV2Error(f"{name} is on {tns.device}, the model on {dev}")
+        x_rows, tokens, ch = x.shape
+        assert x.dtype == torch.float32 and x.is_contiguous()
+        t = t.to(torch.float32).contiguous()
+        y = y.to(torch.int64).contiguous()
+        grid = grid.to(torch.int64).contiguous()
+        mask = mask.to(torch.float32).contiguous()
+        if t.shape != (rows,) or y.shape != (rows,) or grid.shape != (rows, 2, tokens) or mask.shape != (rows, tokens):
+            raise ValueError(f"shape mismatch: rows={rows} tokens={tokens} t{tuple(t.shape)} y{tuple(y.shape)} "
+                             f"grid{tuple(grid.shape)} mask{tuple(mask.shape)}")
+        if out is None:
+            out = torch.empty((rows, tokens, ch), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            self._ensure_workspace(rows, tokens)
+            st = torch.cuda.current_stream(dev).cuda_stream
+            lib = _lib.load()
+            _lib.check(lib.fitv2_forward(self._handle, C.c_void_p(x.data_ptr()), x_rows, C.c_void_p(t.data_ptr()),
+                                         C.c_void_p(y.data_ptr()), C.c_void_p(grid.data_ptr()), C.c_void_p(mask.data_ptr()),
+                                         C.c_void_p(out.data_ptr()), rows, tokens, C.c_void_p(st)), "fitv2_forward")
+        return out
+
+    # ------------------------------------------------------------------------------------------
+    # reference-facing API
+    # ------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, x, t, y, grid, mask, size=None):
+        """fit_model.py:189-233.  x (B,N,p*p*C), t (B,), y (B,), grid (B,2,N), mask (B,N); ``size`` is unused
+        (online_rope=False).  Returns the velocity (B,N,p*p*C) in x.dtype."""
+        xf = x.to(torch.float32).contiguous()
+        out = self._run(xf, t, y, grid, mask, rows=x.shape[0])
+        return out if x.dtype == torch.float32 else out.to(x.dtype)
+
+    @torch.no_grad()
+    def forward_with_cfg(self, x, t, y, grid, mask, size, cfg_scale, scale_pow=0.0):
+        """fit_model.py:235-275: forward on cat([x[:B], x[:B]]), CFG on the first 3*p*p channels only."""
+        rows = x.shape[0]
+        half = rows // 2
+        xf = x[:half].to(torch.float32).contiguous()
+        out = self._run(xf, t, y, grid, mask, rows=rows)               # implicit cat([half, half])
+        c_cfg = 3 * self.patch_size * self.patch_size
+        scale_ptr, scale = None, float(cfg_scale)
+        if scale_pow != 0.0:
+            tt = t.to(torch.float32)
+            step = (1 - torch.cos(((1 - torch.clamp_max(tt, 1.0)) ** scale_pow) * torch.pi)) * 1 / 2
+            per = ((cfg_scale - 1) * step + 1)[:half].contiguous()
+            scale_ptr = C.c_void_p(per.data_ptr())
+        lib = _lib.load()
+        with torch.cuda.device(self.device):
+            st = torch.cuda.current_stream(self.device).cuda_stream
+            _lib.check(lib.fitv2_cfg_combine(C.c_void_p(out.data_ptr()), scale_ptr, scale, half, out.shape[1], out.shape[2],
+                                             c_cfg, C.c_void_p(st)), "fitv2_cfg_combine")
+        return out if x.dtype == torch.float32 else out.to(x.dtype)
+
+    def unpatchify(self, x, hw):
+        """fit_model.py:171-187 (use_sit): (B,(h w),(c p1 p2)) -> (B,c,h*p1,w*p2).  Pure permutation, outside
+        the timed path."""
+        h, w = hw
+        p = self.patch_size
+        B = x.shape[0]
+        x = x.reshape(B, h // p, w // p, -1, p, p)
+        return x.permute(0, 3, 1, 4, 2, 5).reshape(B, -1, h, w)
+
+    # ------------------------------------------------------------------------------------------
+    # introspection used by tests / bench
+    # ------------------------------------------------------------------------------------------
+    def kernel_launches(self) -> int:
+        return int(_lib.load().fitv2_kernel_launches(self._handle)) if self._handle is not None else 0
+
+    def debug_tap(self, name: str) -> torch.Tensor:
+        """Copy an internal buffer of the LAST forward (see _lib.TAPS)."""
+        rows, tokens = self._ws_shape
+        D, H, dh, Hm, L = self.hidden_size, self.num_heads, self.head_dim, self.mlp_hidden, self.depth
+        op = torch.float16 if self.operand_dtype == "fp16" else torch.bfloat16
+        tv = (tokens + 7) // 8 * 8
+        shapes = dict(c=((rows, D), torch.float32), gmod=((rows, 6 * D), torch.float32), mod=((L, rows, 6 * D), torch.float32),
+                      fmod=((rows, 2 * D), torch.float32), x_res=((rows, tokens, D), torch.float32),
+                      q=((rows, H, tokens, dh), op), k=((rows, H, tokens, dh), op), vt=((rows, H, dh, tv), op),
+                      attn_out=((rows, tokens, D), op), h=((rows, tokens, D), op), hidden=((rows, tokens, Hm), op),
+                      rope_cos=((rows, tokens, dh // 2), torch.float32), rope_sin=((rows, tokens, dh // 2), torch.float32),
+                      seg_uniform=((rows,), torch.int32))
+        shape, dt = shapes[name]
+        dst = torch.empty(shape, dtype=dt, device=self.device)
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(_lib.load().fitv2_debug_tap(self._handle, _lib.TAPS[name], C.c_void_p(dst.data_ptr()),
+                                               dst.numel() * dst.element_size(), C.c_void_p(st)), f"tap {name}")
+        return dst
+
+    def __del__(self):
+        try:
+            if getattr(self, "_handle", None) is not None:
+                _lib.load().fitv2_destroy(self._handle)
+                self._handle = None
+        except Exception:
+            pass

@@ -1,0 +1,96 @@
+"""CFG Euler/ODE sampler loop of ``sample_fitv2_ddp.py:273-314`` driven through the C ABI.
+
+One step = one ``fitv2_forward`` over 2n rows (the ``cat([z, z])`` of the script is done implicitly by
+the patch-embed kernel) + one fused ``fitv2_cfg_euler`` kernel (CFG combine over all 16 channels and
+the Euler update, fp32, bit-exact with the script's expression).  With ``use_cuda_graph`` the whole step
+is captured once and replayed; the per-step timestep and step size live in device buffers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+from .model import FiT
+
+
+def make_grid(n: int, n_patch_h: int, n_patch_w: int, device=None) -> torch.Tensor:
+    """sample_fitv2_ddp.py:263-268 — (n, 2, N) int64, [:,0] = w index, [:,1] = h index."""
+    gh = torch.arange(n_patch_h, dtype=torch.long)
+    gw = torch.arange(n_patch_w, dtype=torch.long)
+    g = torch.meshgrid(gw, gh, indexing="xy")
+    grid = torch.cat([g[0].reshape(1, -1), g[1].reshape(1, -1)], dim=0).repeat(n, 1, 1)
+    return grid.to(device) if device is not None else grid
+
+
+class EulerCFGSampler:
+    """Holds the static per-batch tensors (labels, grid, mask, sigma schedule) of one sampling job."""
+
+    def __init__(self, model: FiT, y: torch.Tensor, grid: torch.Tensor, mask: torch.Tensor, num_steps: int,
+                 cfg_scale: float, use_cuda_graph: bool = False):
+        if cfg_scale <= 1.0:
+            raise NotImplementedError("the fused sampler implements the CFG branch (cfg_scale > 1) of the script")
+        self.model, self.num_steps, self.cfg_scale = model, num_steps, float(cfg_scale)
+        dev = model.device
+        n = y.shape[0]
+        self.n = n
+        self.y2 = torch.cat([y.to(dev, torch.int64), torch.full((n,), model.num_classes, dtype=torch.int64, device=dev)], 0)
+        self.grid2 = torch.cat([grid, grid], 0).to(dev, torch.int64).contiguous()
+        self.mask2 = torch.cat([mask, mask], 0).to(dev, torch.float32).contiguous()
+        sig = torch.linspace(0, 1, num_steps + 1)                       # CPU fp32, as the script (:287)
+        self.sigmas = sig
+        self.dsig = (sig[1:] - sig[:-1]).to(dev).contiguous()           # fp32 differences, per step
+        self.t_table = sig[:-1, None].expand(num_steps, 2 * n).to(dev).contiguous()
+        self.use_cuda_graph = use_cuda_graph
+        self._graph = None
+        self._t_cur = torch.zeros(2 * n, dtype=torch.float32, device=dev)
+        self._ds_cur = torch.zeros(1, dtype=torch.float32, device=dev)
+        self._v2 = None
+        self._z = None
+
+    def _step(self, z: torch.Tensor, t_rows: torch.Tensor, dsig_dev: torch.Tensor):
+        m = self.model
+        self._v2 = m._run(z, t_rows, self.y2, self.grid2, self.mask2, rows=2 * self.n, out=self._v2)
+        st = torch.cuda.current_stream(m.device).cuda_stream
+        _lib.check(_lib.load().fitv2_cfg_euler(C.c_void_p(z.data_ptr()), C.c_void_p(self._v2.data_ptr()), self.cfg_scale, 0.0,
+                                               C.c_void_p(dsig_dev.data_ptr()), self.n, z.shape[1], z.shape[2], C.c_void_p(st)),
+                   "fitv2_cfg_euler")
+
+    @torch.no_grad()
+    def sample(self, z: torch.Tensor, first_steps: Optional[int] = None) -> torch.Tensor:
+        """z (n, N, C) fp32 on the model device; returns the latents after the trajectory (a new tensor)."""
+        m = self.model
+        z = z.to(m.device, torch.float32).contiguous().clone()
+        steps = self.num_steps if first_steps is None else first_steps
+        with torch.cuda.device(m.device):
+            if not self.use_cuda_graph:
+                for i in range(steps):
+                    self._step(z, self.t_table[i], self.dsig[i:i + 1])
+                return z
+            if self._graph is None:
+                self._z = torch.empty_like(z)
+                self._z.copy_(z)
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):                           # warm-up outside capture (workspace, maps)
+                    self._t_cur.copy_(self.t_table[0]); self._ds_cur.zero_()
+                    self._step(self._z, self._t_cur, self._ds_cur)
+                torch.cuda.current_stream().wait_stream(side)
+                self._graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self._graph):
+                    self._step(self._z, self._t_cur, self._ds_cur)
+            self._z.copy_(z)
+            for i in range(steps):
+                self._t_cur.copy_(self.t_table[i])
+                self._ds_cur.copy_(self.dsig[i:i + 1])
+                self._graph.replay()
+            return self._z.clone()
+
+
+@torch.no_grad()
+def euler_cfg_sample(model: FiT, z, y, grid, mask, size=None, num_steps: int = 250, cfg_scale: float = 1.5,
+                     use_cuda_graph: bool = False, first_steps: Optional[int] = None) -> torch.Tensor:
+    """Functional form of the script's loop: z (n,N,C), y (n,), grid (n,2,N), mask (n,N)."""
+    return EulerCFGSampler(model, y, grid, mask, num_steps, cfg_scale, use_cuda_graph).sample(z, first_steps)

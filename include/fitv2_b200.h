@@ -1,0 +1,140 @@
+/* fitv2_b200 — C ABI of the B200-native FiTv2 denoising hot path.
+ *
+ * This is the drop-in boundary: a reference-side binding (Python ctypes) calls
+ * these entry points in place of fit.model.fit_model.FiT.forward / forward_with_cfg and the
+ * CFG + Euler update of sample_fitv2_ddp.py.  Plain pointers and sizes only; no torch types.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative FITV2_E_* code on failure; the message of the
+ *     last failure on the calling thread is available from fitv2_last_error();
+ *   - all device pointers are CUDA device memory owned by the CALLER (the library never allocates
+ *     or frees device memory; the workspace is caller-provided via fitv2_set_workspace);
+ *   - all work is enqueued on the `stream` argument (a cudaStream_t passed as void*), nothing
+ *     synchronises; the calls are CUDA-graph capturable;
+ *   - a handle is not thread-safe; use one handle per stream/thread.
+ */
+#ifndef FITV2_B200_H_
+#define FITV2_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FITV2_OK              0
+#define FITV2_E_INVALID      -1   /* bad argument / unsupported configuration            */
+#define FITV2_E_UNBOUND      -2   /* a weight or the workspace has not been bound        */
+#define FITV2_E_CUDA         -3   /* CUDA runtime / driver error (see fitv2_last_error)  */
+#define FITV2_E_WORKSPACE    -4   /* workspace too small for the requested (rows, tokens) */
+
+#define FITV2_OPERAND_BF16    0   /* 16-bit GEMM / attention operand type: bfloat16 (default) */
+#define FITV2_OPERAND_FP16    1   /* float16 (same tensor-core rate, 3 more mantissa bits)   */
+
+/* Model geometry: the constructor contract of fit.model.fit_model.FiT (fit_model.py:25-65) for the
+ * FiTv2 family (use_sit, SwiGLU, adaLN-LoRA, layernorm q/k norm, rope). */
+typedef struct fitv2_config {
+    int32_t hidden_size;      /* D      : 1152 (XL/2), 2304 (3B/2)                  */
+    int32_t depth;            /* L      : 36, 40                                    */
+    int32_t num_heads;        /* H      : 16, 24 (must be even)                     */
+    int32_t head_dim;         /* D / H  : 72 or 96                                  */
+    int32_t mlp_hidden;       /* (int(D*mlp_ratio)*2)//3 : 3072, 6144               */
+    int32_t lora_dim;         /* adaln_lora_dim : 288, 576                          */
+    int32_t token_channels;   /* p*p*C_in : 16                                      */
+    int32_t num_embeddings;   /* rows of y_embedder.embedding_table : 1001          */
+    int32_t operand_dtype;    /* FITV2_OPERAND_*                                    */
+    float   time_shifting;    /* fit_model.py:202 ; 1.0 for the released configs    */
+    float   rope_magnitude;   /* cos/sin magnitude (yarn mscale / ntk-pro proportion), 1.0 otherwise */
+} fitv2_config;
+
+typedef struct fitv2_handle fitv2_handle;
+
+/* Weight slots.  fp32 slots hold the reference parameter unchanged; OP16 slots hold the parameter
+ * converted to the handle's operand dtype.  Stacked slots are the per-block parameters concatenated
+ * over blocks (leading dimension = depth).                                     reference parameter */
+enum fitv2_weight {
+    FITV2_W_X_EMBED_W = 0,     /* fp32 (D, 16)          x_embedder.proj.weight                        */
+    FITV2_W_X_EMBED_B,         /* fp32 (D)              x_embedder.proj.bias                          */
+    FITV2_W_T_MLP0_W,          /* fp32 (D, 256)         t_embedder.mlp.0.weight                       */
+    FITV2_W_T_MLP0_B,          /* fp32 (D)                                                           */
+    FITV2_W_T_MLP2_W,          /* fp32 (D, D)           t_embedder.mlp.2.weight                       */
+    FITV2_W_T_MLP2_B,          /* fp32 (D)                                                           */
+    FITV2_W_Y_TABLE,           /* fp32 (num_embeddings, D)  y_embedder.embedding_table.weight         */
+    FITV2_W_GLOBAL_ADALN_W,    /* fp32 (6D, D)          global_adaLN_modulation.1.weight              */
+    FITV2_W_GLOBAL_ADALN_B,    /* fp32 (6D)                                                          */
+    FITV2_W_LORA_A_W,          /* fp32 (L*lora, D)      blocks.i.adaLN_modulation.1.weight, stacked   */
+    FITV2_W_LORA_A_B,          /* fp32 (L*lora)                                                      */
+    FITV2_W_LORA_B_W,          /* fp32 (L, 6D, lora)    blocks.i.adaLN_modulation.2.weight, stacked   */
+    FITV2_W_LORA_B_B,          /* fp32 (L, 6D)                                                       */
+    FITV2_W_FINAL_ADALN_W,     /* fp32 (2D, D)          final_layer.adaLN_modulation.1.weight         */
+    FITV2_W_FINAL_ADALN_B,     /* fp32 (2D)                                                          */
+    FITV2_W_FINAL_LINEAR_W,    /* fp32 (16, D)          final_layer.linear.weight                     */
+    FITV2_W_FINAL_LINEAR_B,    /* fp32 (16)                                                          */
+    FITV2_W_QKV_W,             /* OP16 (L, 3D, D)       blocks.i.attn.qkv.weight                      */
+    FITV2_W_QKV_B,             /* fp32 (L, 3D)                                                       */
+    FITV2_W_PROJ_W,            /* OP16 (L, D, D)        blocks.i.attn.proj.weight                     */
+    FITV2_W_PROJ_B,            /* fp32 (L, D)                                                        */
+    FITV2_W_GATEUP_W,          /* OP16 (L, 2*Hm, D)     blocks.i.mlp.fc1_g / fc1_x interleaved in 128-row groups:
+                                  rows [256t, 256t+128) = fc1_g rows [128t, 128t+128), next 128 = fc1_x rows */
+    FITV2_W_GATEUP_B,          /* fp32 (L, 2*Hm)        same interleave                               */
+    FITV2_W_FC2_W,             /* OP16 (L, D, Hm)       blocks.i.mlp.fc2.weight                       */
+    FITV2_W_FC2_B,             /* fp32 (L, D)                                                        */
+    FITV2_W_ROPE_FREQS_H,      /* fp32 (head_dim/4)     VisionRotaryEmbedding.freqs_h (rope.py:162)   */
+    FITV2_W_ROPE_FREQS_W,      /* fp32 (head_dim/4)     VisionRotaryEmbedding.freqs_w                 */
+    FITV2_W_COUNT
+};
+
+const char* fitv2_last_error(void);
+const char* fitv2_version(void);
+
+/* Replaces FiT.__init__ (fit/model/fit_model.py:25-115) for the geometry part. */
+int fitv2_create(const fitv2_config* cfg, fitv2_handle** out);
+void fitv2_destroy(fitv2_handle* h);
+
+/* Replaces load_state_dict / init_from_ckpt binding (fit/utils/eval_utils.py:12-71): records the device
+ * pointer of one packed weight.  `numel` is checked against the slot's expected element count. */
+int fitv2_bind_weight(fitv2_handle* h, int slot, const void* dev_ptr, int64_t numel);
+
+/* Bytes of scratch the forward needs for (rows = batch incl. CFG duplication, tokens per row). */
+int64_t fitv2_workspace_bytes(const fitv2_handle* h, int rows, int tokens);
+int fitv2_set_workspace(fitv2_handle* h, void* dev_ptr, int64_t bytes);
+
+/* Replaces FiT.forward (fit/model/fit_model.py:189-233), use_sit layout.
+ *   x      fp32 (x_rows, tokens, C)  latent tokens; x_rows == rows, or rows/2 when the caller wants the
+ *                                    CFG duplication cat([z, z]) of sample_fitv2_ddp.py:299 done implicitly
+ *   t      fp32 (rows)               timesteps in [0, 1]
+ *   y      int64 (rows)              class labels (num_classes = null class)
+ *   grid   int64 (rows, 2, tokens)   [:,0] = w index, [:,1] = h index
+ *   mask   fp32 (rows, tokens)       segment ids (0 = padding)
+ *   out    fp32 (rows, tokens, C)    velocity; rows with mask 0 are exactly 0
+ */
+int fitv2_forward(fitv2_handle* h, const float* x, int x_rows, const float* t, const int64_t* y,
+                  const int64_t* grid, const float* mask, float* out, int rows, int tokens, void* stream);
+
+/* Replaces the CFG lines of FiT.forward_with_cfg (fit_model.py:253-275): in place on out (2B, tokens, C),
+ * channels [0, c_cfg) of both halves <- uncond + s*(cond - uncond).  scale_per_sample (B) may be NULL. */
+int fitv2_cfg_combine(float* out, const float* scale_per_sample, float scale, int half_rows, int tokens,
+                      int channels, int c_cfg, void* stream);
+
+/* Replaces sample_fitv2_ddp.py:310-314: z (B, tokens, C) += dsigma * (uncond + cfg*(cond - uncond)),
+ * v2 = (2B, tokens, C) with rows [0,B) conditional.  fp32, bit-exact with the PyTorch expression.
+ * dsigma_dev (nullable): when non-NULL the step size sigma_next - sigma_cur is read from this device
+ * scalar instead of `dsigma`, so one captured CUDA graph can be replayed for every step. */
+int fitv2_cfg_euler(float* z, const float* v2, float cfg_scale, float dsigma, const float* dsigma_dev,
+                    int half_rows, int tokens, int channels, void* stream);
+
+/* Component entry points (same kernels the forward uses) — exercised by the parity tests. */
+int fitv2_debug_gemm(fitv2_handle* h, int epilogue /*3 = plain*/, const void* a, const void* w, const float* bias,
+                     float* out32, int M, int N, int K, int bn, void* stream);
+/* dbg_s (128x128 fp32) / dbg_o (128 x head_dim_padded fp32), both nullable: raw S = Q K^T and P V tiles of
+ * CTA (0,0,0), first key tile. */
+int fitv2_debug_attention(fitv2_handle* h, const void* q, const void* k, const void* vt, const float* mask,
+                          void* out, int rows, int tokens, float* dbg_s, float* dbg_o, void* stream);
+int fitv2_debug_tap(fitv2_handle* h, int what, void* dst, int64_t bytes, void* stream);
+int64_t fitv2_kernel_launches(const fitv2_handle* h);   /* launches enqueued by this handle so far */
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* FITV2_B200_H_ */
