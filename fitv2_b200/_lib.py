@@ -24,6 +24,8 @@ WEIGHT_SLOTS = [
 SLOT = {n: i for i, n in enumerate(WEIGHT_SLOTS)}
 OP16_SLOTS = {"QKV_W", "PROJ_W", "GATEUP_W", "FC2_W"}
 
+PROFILE_CLASSES = ["conditioning", "ln_modulate", "qkv_gemm", "attention", "proj_gemm", "gateup_gemm", "fc2_gemm", "embed_final"]
+
 TAPS = dict(c=0, gmod=1, mod=2, fmod=3, x_res=4, q=5, k=6, vt=7, attn_out=8, h=9, hidden=10,
             rope_cos=11, rope_sin=12, seg_uniform=13)
 
@@ -72,6 +74,8 @@ def load():
     lib.fitv2_debug_tap.argtypes = [vp, i32, vp, i64, vp]
     lib.fitv2_kernel_launches.argtypes = [vp]
     lib.fitv2_kernel_launches.restype = i64
+    lib.fitv2_profile_set.argtypes = [vp, C.c_uint32]
+    lib.fitv2_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     _lib = lib
     return lib
 
@@ -86,4 +90,5 @@ EXPORTED_SYMBOLS = [
     "fitv2_last_error", "fitv2_version", "fitv2_create", "fitv2_destroy", "fitv2_bind_weight",
     "fitv2_workspace_bytes", "fitv2_set_workspace", "fitv2_forward", "fitv2_cfg_combine", "fitv2_cfg_euler",
     "fitv2_debug_gemm", "fitv2_debug_attention", "fitv2_debug_tap", "fitv2_kernel_launches",
+    "fitv2_profile_set", "fitv2_profile_read",
 ]

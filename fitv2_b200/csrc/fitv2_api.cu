@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <vector>
 
 using namespace fitv2;
 
@@ -79,6 +80,9 @@ struct Layout {
 
 }  // namespace
 
+enum { PC_COND = 0, PC_LNMOD, PC_QKV, PC_ATTN, PC_PROJ, PC_GATEUP, PC_FC2, PC_MISC, PC_COUNT };
+struct ProfEvt { cudaEvent_t a, b; int cls; };
+
 struct fitv2_handle {
     fitv2_config cfg;
     const void* w[FITV2_W_COUNT];
@@ -92,6 +96,11 @@ struct fitv2_handle {
     int bn_resid = 0;
     int num_sms = 148;
     int64_t launches = 0;
+    // optional per-kernel-class CUDA-event timing (fitv2_profile_*)
+    uint32_t prof_mask = 0;
+    std::vector<ProfEvt> prof_pool;
+    size_t prof_used = 0;
+    int prof_open = -1;
 };
 
 namespace {
@@ -156,6 +165,21 @@ Layout make_layout(const fitv2_config& c, int rows, int tokens) {
     l.seg_uniform = take((size_t)rows * 4);
     l.total = off;
     return l;
+}
+
+// Event-bracket the launches of one kernel class on the launching stream (only when enabled).
+inline void prof_begin(fitv2_handle* h, int cls, cudaStream_t st) {
+    if (!(h->prof_mask & (1u << cls)) || h->prof_used >= h->prof_pool.size()) return;
+    ProfEvt& e = h->prof_pool[h->prof_used];
+    e.cls = cls;
+    cudaEventRecord(e.a, st);
+    h->prof_open = (int)h->prof_used;
+}
+inline void prof_end(fitv2_handle* h, cudaStream_t st) {
+    if (h->prof_open < 0) return;
+    cudaEventRecord(h->prof_pool[h->prof_open].b, st);
+    h->prof_used++;
+    h->prof_open = -1;
 }
 
 template <int BN, int EPI, typename OT, int DH>
@@ -295,6 +319,7 @@ int forward_impl(fitv2_handle* h, const float* x, int x_rows, const float* t, co
     int rc;
 
     // ---- per-call tables: segment-uniformity flags, RoPE cos/sin (rope.py:308-333) ----
+    prof_begin(h, PC_COND, st);
     seg_uniform_kernel<<<rows, 128, 0, st>>>(mask, segu, tokens);
     {
         const size_t total = (size_t)M * (DH / 2);
@@ -337,44 +362,62 @@ int forward_impl(fitv2_handle* h, const float* x, int x_rows, const float* t, co
     p.bias = (const float*)h->w[FITV2_W_LORA_B_B]; p.bias_batch_stride = 6 * D;
     p.add = gmod; p.out = mod; p.out_batch_stride = (size_t)rows * 6 * D; p.ldo = 6 * D; p.N = 6 * D; p.K = lora;
     if ((rc = launch_small_linear(h, p, L, st))) return rc;
+    prof_end(h, st);
 
     // ---- patch embedding (modules.py:34-37); implicit cat([z, z]) when x_rows == rows / 2 ----
     if (c.token_channels != 16) return fail(FITV2_E_INVALID, "token_channels %d not supported (16)", c.token_channels);
+    prof_begin(h, PC_MISC, st);
     patch_embed_kernel<16><<<(M + 7) / 8, 256, 0, st>>>(x, (const float*)h->w[FITV2_W_X_EMBED_W], (const float*)h->w[FITV2_W_X_EMBED_B],
                                                        x_res, M, D, x_rows * tokens);
     CUDA_TRY(cudaGetLastError());
     h->launches++;
+    prof_end(h, st);
 
     GemmEpi ep;
     for (int layer = 0; layer < L; ++layer) {
         const float* modl = mod + (size_t)layer * rows * 6 * D;
         // ---- attention branch (modules.py:272) ----
+        prof_begin(h, PC_LNMOD, st);
         if ((rc = launch_ln_modulate<OT>(h, x_res, modl, modl + D, 6 * D, ws + l.h, M, D, tokens, st))) return rc;
+        prof_end(h, st);
         memset(&ep, 0, sizeof(ep));
         ep.bias = (const float*)h->w[FITV2_W_QKV_B] + (size_t)layer * 3 * D;
         ep.tokens = tokens; ep.q = ws + l.q; ep.k = ws + l.k; ep.vt = ws + l.vt; ep.rope_cos = rcos; ep.rope_sin = rsin;
         ep.heads = H; ep.tokens_v = l.tokens_v;
+        prof_begin(h, PC_QKV, st);
         if (DH == 72) rc = launch_gemm_t<144, EPI_QKV, OT, 72>(h, h->map_h, h->map_wqkv, M, 3 * D, D, layer * 3 * D, ep, st);
         else          rc = launch_gemm_t<192, EPI_QKV, OT, 96>(h, h->map_h, h->map_wqkv, M, 3 * D, D, layer * 3 * D, ep, st);
         if (rc) return rc;
+        prof_end(h, st);
+        prof_begin(h, PC_ATTN, st);
         if ((rc = launch_attention<OT>(h, ws + l.q, ws + l.k, ws + l.vt, mask, segu, ws + l.ao, rows, tokens, l.tokens_v, st))) return rc;
+        prof_end(h, st);
         memset(&ep, 0, sizeof(ep));
         ep.bias = (const float*)h->w[FITV2_W_PROJ_B] + (size_t)layer * D;
         ep.tokens = tokens; ep.x = x_res; ep.gate = modl + 2 * D; ep.gate_ld = 6 * D;
+        prof_begin(h, PC_PROJ, st);
         if ((rc = launch_gemm_bn<EPI_RESID, OT>(h, h->bn_resid, h->map_ao, h->map_wproj, M, D, D, layer * D, ep, st))) return rc;
+        prof_end(h, st);
         // ---- SwiGLU branch (modules.py:273) ----
+        prof_begin(h, PC_LNMOD, st);
         if ((rc = launch_ln_modulate<OT>(h, x_res, modl + 3 * D, modl + 4 * D, 6 * D, ws + l.h, M, D, tokens, st))) return rc;
+        prof_end(h, st);
         memset(&ep, 0, sizeof(ep));
         ep.bias = (const float*)h->w[FITV2_W_GATEUP_B] + (size_t)layer * 2 * Hm;
         ep.tokens = tokens; ep.out16 = ws + l.hidden; ep.ld_out = Hm;
+        prof_begin(h, PC_GATEUP, st);
         if ((rc = launch_gemm_t<256, EPI_SWIGLU, OT, 0>(h, h->map_h, h->map_wgu, M, 2 * Hm, D, layer * 2 * Hm, ep, st))) return rc;
+        prof_end(h, st);
         memset(&ep, 0, sizeof(ep));
         ep.bias = (const float*)h->w[FITV2_W_FC2_B] + (size_t)layer * D;
         ep.tokens = tokens; ep.x = x_res; ep.gate = modl + 5 * D; ep.gate_ld = 6 * D;
+        prof_begin(h, PC_FC2, st);
         if ((rc = launch_gemm_bn<EPI_RESID, OT>(h, h->bn_resid, h->map_hidden, h->map_wfc2, M, D, Hm, layer * D, ep, st))) return rc;
+        prof_end(h, st);
     }
 
     // ---- final layer + output mask (modules.py:292-296, fit_model.py:230) ----
+    prof_begin(h, PC_MISC, st);
     {
         const int nv = (D / 4 + 31) / 32;
         const size_t smem = (size_t)16 * D * 4;
@@ -395,6 +438,7 @@ int forward_impl(fitv2_handle* h, const float* x, int x_rows, const float* t, co
         CUDA_TRY(cudaGetLastError());
         h->launches++;
     }
+    prof_end(h, st);
     return FITV2_OK;
 }
 
@@ -436,7 +480,11 @@ int fitv2_create(const fitv2_config* cfg, fitv2_handle** out) {
     return FITV2_OK;
 }
 
-void fitv2_destroy(fitv2_handle* h) { delete h; }
+void fitv2_destroy(fitv2_handle* h) {
+    if (!h) return;
+    for (auto& e : h->prof_pool) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    delete h;
+}
 
 int fitv2_bind_weight(fitv2_handle* h, int slot, const void* dev_ptr, int64_t numel) {
     if (!h || slot < 0 || slot >= FITV2_W_COUNT || !dev_ptr) return fail(FITV2_E_INVALID, "bad bind_weight argument (slot %d)", slot);
@@ -571,5 +619,35 @@ int fitv2_debug_tap(fitv2_handle* h, int what, void* dst, int64_t bytes, void* s
 }
 
 int64_t fitv2_kernel_launches(const fitv2_handle* h) { return h ? h->launches : 0; }
+
+int fitv2_profile_set(fitv2_handle* h, uint32_t class_mask) {
+    if (!h) return fail(FITV2_E_INVALID, "null handle");
+    if (class_mask && h->prof_pool.empty()) {
+        h->prof_pool.resize(8192);
+        for (auto& e : h->prof_pool) {
+            CUDA_TRY(cudaEventCreate(&e.a));
+            CUDA_TRY(cudaEventCreate(&e.b));
+        }
+    }
+    h->prof_mask = class_mask;
+    h->prof_used = 0;
+    h->prof_open = -1;
+    return FITV2_OK;
+}
+
+int fitv2_profile_read(fitv2_handle* h, double* ms_sum, int64_t* count) {
+    if (!h || !ms_sum || !count) return fail(FITV2_E_INVALID, "null argument");
+    for (int i = 0; i < PC_COUNT; ++i) { ms_sum[i] = 0.0; count[i] = 0; }
+    for (size_t i = 0; i < h->prof_used; ++i) {
+        ProfEvt& e = h->prof_pool[i];
+        CUDA_TRY(cudaEventSynchronize(e.b));
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, e.a, e.b));
+        ms_sum[e.cls] += ms;
+        count[e.cls]++;
+    }
+    h->prof_used = 0;
+    return FITV2_OK;
+}
 
 }  // extern "C"

@@ -191,44 +191,54 @@ class FiT(nn.Module):
                 _lib.check(lib.fitv2_create(C.byref(cfg), C.byref(h)), "fitv2_create")
                 self._handle = h
             op = torch.float16 if self.operand_dtype == "fp16" else torch.bfloat16
-            f32 = lambda p: p.detach().to(device=dev, dtype=torch.float32).contiguous()
-            blocks = self.blocks
-            stack32 = lambda get: torch.stack([get(b).detach().to(device=dev, dtype=torch.float32) for b in blocks]).contiguous()
-            stack16 = lambda get: torch.stack([get(b).detach().to(device=dev, dtype=torch.float32).to(op) for b in blocks]).contiguous()
-            Hm = self.mlp_hidden
-
-            def gateup(b, attr):
-                g = getattr(b.mlp.fc1_g, attr).detach().to(device=dev, dtype=torch.float32)
-                u = getattr(b.mlp.fc1_x, attr).detach().to(device=dev, dtype=torch.float32)
-                g = g.reshape(Hm // 128, 128, *g.shape[1:])
-                u = u.reshape(Hm // 128, 128, *u.shape[1:])
-                return torch.cat([g, u], dim=1).reshape(2 * Hm, *g.shape[2:])
-
-            P = {
-                "X_EMBED_W": f32(self.x_embedder.proj.weight), "X_EMBED_B": f32(self.x_embedder.proj.bias),
-                "T_MLP0_W": f32(self.t_embedder.mlp[0].weight), "T_MLP0_B": f32(self.t_embedder.mlp[0].bias),
-                "T_MLP2_W": f32(self.t_embedder.mlp[2].weight), "T_MLP2_B": f32(self.t_embedder.mlp[2].bias),
-                "Y_TABLE": f32(self.y_embedder.embedding_table.weight),
-                "GLOBAL_ADALN_W": f32(self.global_adaLN_modulation[1].weight),
-                "GLOBAL_ADALN_B": f32(self.global_adaLN_modulation[1].bias),
-                "LORA_A_W": stack32(lambda b: b.adaLN_modulation[1].weight), "LORA_A_B": stack32(lambda b: b.adaLN_modulation[1].bias),
-                "LORA_B_W": stack32(lambda b: b.adaLN_modulation[2].weight), "LORA_B_B": stack32(lambda b: b.adaLN_modulation[2].bias),
-                "FINAL_ADALN_W": f32(self.final_layer.adaLN_modulation[1].weight),
-                "FINAL_ADALN_B": f32(self.final_layer.adaLN_modulation[1].bias),
-                "FINAL_LINEAR_W": f32(self.final_layer.linear.weight), "FINAL_LINEAR_B": f32(self.final_layer.linear.bias),
-                "QKV_W": stack16(lambda b: b.attn.qkv.weight), "QKV_B": stack32(lambda b: b.attn.qkv.bias),
-                "PROJ_W": stack16(lambda b: b.attn.proj.weight), "PROJ_B": stack32(lambda b: b.attn.proj.bias),
-                "GATEUP_W": torch.stack([gateup(b, "weight").to(op) for b in blocks]).contiguous(),
-                "GATEUP_B": torch.stack([gateup(b, "bias") for b in blocks]).contiguous(),
-                "FC2_W": stack16(lambda b: b.mlp.fc2.weight), "FC2_B": stack32(lambda b: b.mlp.fc2.bias),
-                "ROPE_FREQS_H": fh.to(dev).contiguous(), "ROPE_FREQS_W": fw.to(dev).contiguous(),
-            }
+            P = self.pack_weights(dev)
             for name, tns in P.items():
                 want = op if name in _lib.OP16_SLOTS else torch.float32
                 assert tns.dtype == want and tns.is_contiguous(), name
                 _lib.check(lib.fitv2_bind_weight(self._handle, _lib.SLOT[name], C.c_void_p(tns.data_ptr()), tns.numel()),
                            f"fitv2_bind_weight({name})")
             self._packed = P
+
+    @torch.no_grad()
+    def pack_weights(self, dev) -> dict:
+        """Kernel-side weight layouts (include/fitv2_b200.h, enum fitv2_weight): fp32 conditioning weights,
+        per-block weights stacked over depth, 16-bit GEMM operands, fc1_g/fc1_x interleaved in 128-row groups
+        so that one 256-wide GEMM tile holds matching gate and up columns."""
+        fh, fw, _ = rope_frequencies(**self.rope_args)
+        op = torch.float16 if self.operand_dtype == "fp16" else torch.bfloat16
+        f32 = lambda p: p.detach().to(device=dev, dtype=torch.float32).contiguous()
+        blocks = self.blocks
+        stack32 = lambda get: torch.stack([get(b).detach().to(device=dev, dtype=torch.float32) for b in blocks]).contiguous()
+        stack16 = lambda get: torch.stack([get(b).detach().to(device=dev, dtype=torch.float32).to(op) for b in blocks]).contiguous()
+        Hm = self.mlp_hidden
+
+        def gateup(b, attr):
+            g = getattr(b.mlp.fc1_g, attr).detach().to(device=dev, dtype=torch.float32)
+            u = getattr(b.mlp.fc1_x, attr).detach().to(device=dev, dtype=torch.float32)
+            g = g.reshape(Hm // 128, 128, *g.shape[1:])
+            u = u.reshape(Hm // 128, 128, *u.shape[1:])
+            return torch.cat([g, u], dim=1).reshape(2 * Hm, *g.shape[2:])
+
+        P = {
+            "X_EMBED_W": f32(self.x_embedder.proj.weight), "X_EMBED_B": f32(self.x_embedder.proj.bias),
+            "T_MLP0_W": f32(self.t_embedder.mlp[0].weight), "T_MLP0_B": f32(self.t_embedder.mlp[0].bias),
+            "T_MLP2_W": f32(self.t_embedder.mlp[2].weight), "T_MLP2_B": f32(self.t_embedder.mlp[2].bias),
+            "Y_TABLE": f32(self.y_embedder.embedding_table.weight),
+            "GLOBAL_ADALN_W": f32(self.global_adaLN_modulation[1].weight),
+            "GLOBAL_ADALN_B": f32(self.global_adaLN_modulation[1].bias),
+            "LORA_A_W": stack32(lambda b: b.adaLN_modulation[1].weight), "LORA_A_B": stack32(lambda b: b.adaLN_modulation[1].bias),
+            "LORA_B_W": stack32(lambda b: b.adaLN_modulation[2].weight), "LORA_B_B": stack32(lambda b: b.adaLN_modulation[2].bias),
+            "FINAL_ADALN_W": f32(self.final_layer.adaLN_modulation[1].weight),
+            "FINAL_ADALN_B": f32(self.final_layer.adaLN_modulation[1].bias),
+            "FINAL_LINEAR_W": f32(self.final_layer.linear.weight), "FINAL_LINEAR_B": f32(self.final_layer.linear.bias),
+            "QKV_W": stack16(lambda b: b.attn.qkv.weight), "QKV_B": stack32(lambda b: b.attn.qkv.bias),
+            "PROJ_W": stack16(lambda b: b.attn.proj.weight), "PROJ_B": stack32(lambda b: b.attn.proj.bias),
+            "GATEUP_W": torch.stack([gateup(b, "weight").to(op) for b in blocks]).contiguous(),
+            "GATEUP_B": torch.stack([gateup(b, "bias") for b in blocks]).contiguous(),
+            "FC2_W": stack16(lambda b: b.mlp.fc2.weight), "FC2_B": stack32(lambda b: b.mlp.fc2.bias),
+            "ROPE_FREQS_H": fh.to(dev).contiguous(), "ROPE_FREQS_W": fw.to(dev).contiguous(),
+        }
+        return P
 
     def _ensure_workspace(self, rows: int, tokens: int):
         if self._ws_shape == (rows, tokens):
@@ -316,6 +326,25 @@ class FiT(nn.Module):
     # ------------------------------------------------------------------------------------------
     def kernel_launches(self) -> int:
         return int(_lib.load().fitv2_kernel_launches(self._handle)) if self._handle is not None else 0
+
+    def profile(self, classes=None):
+        """Enable (list of names from _lib.PROFILE_CLASSES, or 'all') / disable (None) CUDA-event timing per
+        kernel class inside fitv2_forward."""
+        self._ensure_packed()
+        if classes is None:
+            mask = 0
+        elif classes == "all":
+            mask = (1 << len(_lib.PROFILE_CLASSES)) - 1
+        else:
+            mask = sum(1 << _lib.PROFILE_CLASSES.index(c) for c in classes)
+        _lib.check(_lib.load().fitv2_profile_set(self._handle, mask), "fitv2_profile_set")
+
+    def profile_read(self) -> dict:
+        """{class: (total_ms, launches)} accumulated since the last read (synchronises on the events)."""
+        n = len(_lib.PROFILE_CLASSES)
+        ms, cnt = (C.c_double * n)(), (C.c_int64 * n)()
+        _lib.check(_lib.load().fitv2_profile_read(self._handle, ms, cnt), "fitv2_profile_read")
+        return {name: (float(ms[i]), int(cnt[i])) for i, name in enumerate(_lib.PROFILE_CLASSES)}
 
     def debug_tap(self, name: str) -> torch.Tensor:
         """Copy an internal buffer of the LAST forward (see _lib.TAPS)."""

@@ -134,6 +134,13 @@ int fitv2_debug_attention(fitv2_handle* h, const void* q, const void* k, const v
 int fitv2_debug_tap(fitv2_handle* h, int what, void* dst, int64_t bytes, void* stream);
 int64_t fitv2_kernel_launches(const fitv2_handle* h);   /* launches enqueued by this handle so far */
 
+/* Per-kernel-class device timing with CUDA events on the launching stream (measurement support for bench.py).
+ * Classes: 0 conditioning, 1 LayerNorm+modulate, 2 QKV GEMM, 3 attention, 4 proj GEMM, 5 gate/up GEMM,
+ * 6 fc2 GEMM, 7 patch-embed + final layer.  class_mask bit i enables class i; 0 disables.  Not capturable. */
+#define FITV2_PROFILE_CLASSES 8
+int fitv2_profile_set(fitv2_handle* h, uint32_t class_mask);
+int fitv2_profile_read(fitv2_handle* h, double* ms_sum /*[8]*/, int64_t* count /*[8]*/);
+
 #ifdef __cplusplus
 }
 #endif

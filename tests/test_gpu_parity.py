@@ -1,0 +1,281 @@
+"""GPU parity tests (run on a B200 with `-m gpu`): the CUDA path, called through the C ABI, against the CPU
+oracle and the committed golden fixtures of the REAL reference.
+
+Tolerances (stated, per north_star / SURVEY.md §8d):
+  * per-NFE velocity: max_abs(ours - ref) / max_abs(ref) <= 1e-2 with 16-bit GEMM operands and fp32 accumulate;
+  * fused CFG + Euler update, token masks, RoPE position tables: bit-exact / 1e-6;
+  * latents after a trajectory prefix: <= 1e-2 (error of z is dsigma-weighted, far below the velocity error).
+"""
+import ctypes as C
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import fitv2_oracle as O          # checker only
+from fitv2_b200 import FiT, EulerCFGSampler, euler_cfg_sample, make_grid, _lib
+
+V_TOL = 1e-2
+KW = dict(learn_sigma=False, use_sit=True, use_swiglu=True, q_norm="layernorm", k_norm="layernorm", adaln_type="lora")
+XL = dict(hidden_size=1152, num_heads=16, adaln_lora_dim=288)
+B3 = dict(hidden_size=2304, num_heads=24, adaln_lora_dim=576)
+
+
+def rel(a, b):
+    return float((a.float().cpu() - b.float().cpu()).abs().max() / b.float().abs().max().clamp_min(1e-30))
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr())
+
+
+def build_model(depth, width=XL, operand="bf16", **extra):
+    torch.manual_seed(0)
+    m = FiT(**KW, depth=depth, operand_dtype=operand, **width, **extra).randomize_zero_init_(1)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    return m.cuda().eval(), sd, O.FiTConfig(depth=depth, **width, **extra)
+
+
+def inputs(R, hp, wp, seed=3):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(R, hp * wp, 16, generator=g)
+    t = torch.rand(R, generator=g)
+    y = torch.randint(0, 1001, (R,), generator=g)
+    return x, t, y, make_grid(R, hp, wp), torch.ones(R, hp * wp)
+
+
+def run(m, *a):
+    return m(*[v.cuda() for v in a]).cpu()
+
+
+@pytest.fixture(scope="module")
+def lib(built_lib):
+    assert torch.cuda.is_available() and torch.cuda.get_device_capability(0)[0] == 10
+    return _lib.load()
+
+
+@pytest.fixture(scope="module")
+def xl2_padded(lib):
+    return build_model(2, custom_freqs="ntk-aware", max_pe_len_h=10, max_pe_len_w=20, decouple=True, ori_max_pe_len=16)
+
+
+# ------------------------------------------------------------------------------------------------
+# elementwise: CFG + Euler (bit-exact) and channel-limited CFG combine
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,N", [(2, 256), (32, 256), (3, 200), (1, 7), (32, 1024)])
+def test_cfg_euler_bit_exact(lib, B, N):
+    g = torch.Generator().manual_seed(B * 1000 + N)
+    z, v2 = torch.randn(B, N, 16, generator=g), torch.randn(2 * B, N, 16, generator=g)
+    sig = torch.linspace(0, 1, 251)
+    for idx in (0, 17, 249):
+        ref = O.cfg_euler_update(z, v2, 1.5, sig[idx], sig[idx + 1])
+        zc = z.cuda().clone()
+        _lib.check(lib.fitv2_cfg_euler(_p(zc), _p(v2.cuda()), 1.5, float(sig[idx + 1] - sig[idx]), None, B, N, 16, None))
+        assert torch.equal(zc.cpu(), ref)
+        zc = z.cuda().clone()                      # step size from a device scalar (graph-replay form)
+        ds = (sig[idx + 1] - sig[idx]).reshape(1).cuda()
+        _lib.check(lib.fitv2_cfg_euler(_p(zc), _p(v2.cuda()), 1.5, 0.0, _p(ds), B, N, 16, None))
+        assert torch.equal(zc.cpu(), ref)
+
+
+def test_cfg_combine_matches_forward_with_cfg_rule(lib):
+    g = torch.Generator().manual_seed(0)
+    out = torch.randn(6, 50, 16, generator=g)
+    per = torch.tensor([1.5, 2.0, 4.0])
+    ref = out.clone()
+    c, u = out[:3, :, :12], out[3:, :, :12]
+    gd = u + per.view(-1, 1, 1) * (c - u)
+    ref[:3, :, :12], ref[3:, :, :12] = gd, gd
+    oc = out.cuda()
+    _lib.check(lib.fitv2_cfg_combine(_p(oc), _p(per.cuda()), 0.0, 3, 50, 16, 12, None))
+    assert torch.equal(oc.cpu(), ref) and torch.equal(oc.cpu()[:, :, 12:], out[:, :, 12:])
+
+
+# ------------------------------------------------------------------------------------------------
+# components through the C ABI: tcgen05 GEMM and masked flash attention
+# ------------------------------------------------------------------------------------------------
+def _handle(lib, operand=0, D=1152, H=16, dh=72, Hm=3072, lora=288):
+    cfg = _lib.FitV2Config(D, 1, H, dh, Hm, lora, 16, 1001, operand, 1.0, 1.0)
+    h = C.c_void_p()
+    _lib.check(lib.fitv2_create(C.byref(cfg), C.byref(h)))
+    ws = torch.zeros(1 << 20, dtype=torch.uint8, device="cuda")
+    _lib.check(lib.fitv2_set_workspace(h, _p(ws), ws.numel()))
+    return h, ws
+
+
+@pytest.mark.parametrize("M,N,K,bn", [(128, 128, 64, 128), (256, 288, 128, 144), (200, 288, 1152, 144), (128, 256, 96, 128),
+                                      (4096, 1152, 3072, 192), (16384, 6144, 1152, 256), (1000, 3456, 1152, 144)])
+@pytest.mark.parametrize("operand", [0, 1])
+def test_gemm_matches_fp32_reference(lib, M, N, K, bn, operand):
+    """C = A W^T + b with 16-bit operands and fp32 accumulation == fp32 matmul of the same (rounded) operands."""
+    h, ws = _handle(lib, operand)
+    dt = torch.float16 if operand else torch.bfloat16
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g, device="cuda").to(dt)
+    w = (torch.randn(N, K, generator=g, device="cuda") * 0.05).to(dt)
+    bias = torch.randn(N, generator=g, device="cuda")
+    out = torch.full((M, N), float("nan"), device="cuda")
+    _lib.check(lib.fitv2_debug_gemm(h, 3, _p(a), _p(w), _p(bias), _p(out), M, N, K, bn, None))
+    ref = a.double() @ w.double().t() + bias.double()
+    assert rel(out, ref) < 2e-5
+    lib.fitv2_destroy(h)
+
+
+def _attention_oracle(q, k, v, mask):
+    """fit/model/modules.py:176-204 (checker, fp32 CPU)."""
+    am = mask[:, None, None, :]
+    am = (am == am.transpose(-2, -1))
+    o = torch.nn.functional.scaled_dot_product_attention(q, k, v, attn_mask=am)
+    R, H, T, dh = q.shape
+    return o.transpose(1, 2).reshape(R, T, H * dh) * (mask != 0).float()[..., None]
+
+
+@pytest.mark.parametrize("R,T,dh,H,masked", [(1, 128, 72, 16, False), (2, 256, 72, 16, False), (2, 200, 72, 16, False), (2, 256, 72, 16, True),
+                                             (1, 1024, 72, 16, False), (3, 100, 72, 16, True), (2, 256, 96, 24, True), (1, 1, 72, 16, False),
+                                             (2, 77, 96, 24, True)])
+def test_attention_matches_oracle(lib, R, T, dh, H, masked):
+    h, ws = _handle(lib, 0, D=H * dh, H=H, dh=dh, Hm=3072 if dh == 72 else 6144, lora=288 if dh == 72 else 576)
+    g = torch.Generator().manual_seed(R * 7 + T)
+    q, k, v = [torch.randn(R, H, T, dh, generator=g).bfloat16() for _ in range(3)]
+    mask = torch.ones(R, T)
+    if masked:                                   # segment ids: 0 = padding, other ids = packed images
+        mask[0, T - T // 4:] = 0
+        if R > 1:
+            mask[1, : T // 3] = 2
+    tv = (T + 7) // 8 * 8
+    vt = torch.zeros(R, H, dh, tv, dtype=torch.bfloat16)
+    vt[..., :T] = v.transpose(-1, -2)
+    out = torch.full((R, T, H * dh), float("nan"), dtype=torch.bfloat16, device="cuda")
+    _lib.check(lib.fitv2_debug_attention(h, _p(q.cuda()), _p(k.cuda()), _p(vt.cuda()), _p(mask.cuda()), _p(out), R, T, None, None, None))
+    ref = _attention_oracle(q.float(), k.float(), v.float(), mask)
+    assert rel(out, ref) < 6e-3                  # P and the output are rounded to bf16 (2^-9)
+    assert bool((out.float().cpu()[mask == 0] == 0).all())
+    lib.fitv2_destroy(h)
+
+
+# ------------------------------------------------------------------------------------------------
+# FiT.forward / forward_with_cfg against the reference goldens and the oracle
+# ------------------------------------------------------------------------------------------------
+def test_forward_golden_padded_mixed_aspect(xl2_padded, golden_dir):
+    """BASELINE.json configs[2] flavour: dynntk + decouple, mixed 10x20 / 16x16 / 8x24 / 20x10 padded to 256."""
+    m, sd, cfg = xl2_padded
+    fx = torch.load(os.path.join(golden_dir, "xl_depth2_padded.pt"))
+    a = (fx["x"], fx["t"], fx["y"], fx["grid"], fx["mask"])
+    out = run(m, *a)
+    assert rel(out, fx["out"]) < V_TOL
+    assert bool((out[fx["mask"] == 0] == 0).all())                          # pad rows exactly zero
+    ag = [v.cuda() for v in a]
+    assert rel(m.forward_with_cfg(*ag, None, 1.5), fx["out_cfg"]) < V_TOL
+    oc = m.forward_with_cfg(*ag, None, 4.0, scale_pow=2.0).cpu()
+    assert rel(oc, fx["out_cfg_pow"]) < V_TOL
+    assert torch.equal(oc[:2, :, :12], oc[2:, :, :12])                      # guided channels duplicated in both halves
+    # token mask / RoPE position tables: bit-exact indices, 1e-6 tables
+    cos, sin = O.rope_cos_sin(cfg, fx["grid"])
+    assert float((m.debug_tap("rope_cos").cpu() - cos[..., 0::2]).abs().max()) < 1e-6
+    assert float((m.debug_tap("rope_sin").cpu() - sin[..., 0::2]).abs().max()) < 1e-6
+    assert m.debug_tap("seg_uniform").cpu().tolist() == [int(bool((r == r[0]).all())) for r in fx["mask"]]
+
+
+def test_forward_invariants(xl2_padded, golden_dir):
+    m, sd, cfg = xl2_padded
+    fx = torch.load(os.path.join(golden_dir, "xl_depth2_padded.pt"))
+    a = (fx["x"], fx["t"], fx["y"], fx["grid"], fx["mask"])
+    out = run(m, *a)
+    assert torch.equal(run(m, *a), out)                                     # deterministic / idempotent
+    out2 = run(m, fx["x"], fx["t"], fx["y"], fx["grid"], fx["mask"] * 2)
+    assert torch.equal(out2, out * 2)                                       # raw-mask multiply (fit_model.py:230)
+    assert torch.equal(run(m, fx["x"], fx["t"], fx["y"], fx["grid"], fx["mask"].bool()), out)
+    solo = run(m, fx["x"][:1, :200], fx["t"][:1], fx["y"][:1], fx["grid"][:1, :, :200], fx["mask"][:1, :200])
+    assert rel(solo, out[:1, :200]) < 2e-3                                  # padding invariance (different tiling, same math)
+    ob = m(fx["x"].cuda().bfloat16(), *[v.cuda() for v in a[1:]])           # --mixed bf16 callers get bf16 back
+    assert ob.dtype == torch.bfloat16 and rel(ob, out) < 3e-2
+    # garbage in the padded positions of x must not leak into valid tokens
+    xg = fx["x"].clone()
+    xg[fx["mask"] == 0] = 1e3
+    og = run(m, xg, *a[1:])
+    valid = fx["mask"] != 0
+    assert rel(og[valid], out[valid]) < 1e-6 and bool((og[~valid] == 0).all())
+
+
+def test_forward_stage_taps_depth1(lib):
+    """Per-stage parity on a depth-1 XL-width model: conditioning (fp32), QKV epilogue, attention, residual."""
+    m, sd, cfg = build_model(1)
+    x, t, y, grid, mask = inputs(4, 16, 16)
+    taps = {}
+    ref = O.forward(cfg, sd, x, t, y, grid, mask, taps=taps)
+    out = run(m, x, t, y, grid, mask)
+    assert rel(out, ref) < V_TOL
+    assert rel(m.debug_tap("c"), taps["c"]) < 1e-5 and rel(m.debug_tap("gmod"), taps["global_adaln"]) < 1e-5
+    for name, want in (("q", taps["q"]), ("k", taps["k"]), ("attn_out", taps["attn_out"])):
+        assert rel(m.debug_tap(name), want) < 8e-3, name
+    assert rel(m.debug_tap("vt")[..., :256], taps["v"].transpose(-1, -2)) < 8e-3
+    assert rel(m.debug_tap("x_res"), taps["x1"]) < 5e-3
+    assert m.kernel_launches() == 18
+
+
+@pytest.mark.parametrize("width,operand", [(B3, "bf16"), (XL, "fp16")])
+def test_forward_other_widths_and_operands(lib, width, operand):
+    m, sd, cfg = build_model(2 if width is XL else 1, width, operand)
+    a = inputs(3, 10, 20, seed=5)                                            # 200 tokens: M tail + key tail
+    assert rel(run(m, *a), O.forward(cfg, sd, *a)) < (2e-3 if operand == "fp16" else V_TOL)
+
+
+def test_xl_config1_full_depth_and_sampler(lib, golden_dir):
+    """BASELINE.json configs[0]: XL/2 depth 36, CFG Euler steps at batch 2 against the REAL reference's outputs."""
+    fx = torch.load(os.path.join(golden_dir, "xl_config1.pt"))
+    m, sd, cfg = build_model(36)
+    n, N = 2, 256
+    grid, mask = make_grid(n, 16, 16), torch.ones(n, N)
+    smp = EulerCFGSampler(m, fx["y"].cuda(), grid.cuda(), mask.cuda(), 250, 1.5)
+    z1 = smp.sample(fx["z"].cuda(), first_steps=1).cpu()
+    v2 = smp._v2.cpu()
+    assert rel(v2, fx["v_step0"]) < V_TOL                                    # per-NFE velocity
+    sig = torch.linspace(0, 1, 251)
+    assert torch.equal(z1, O.cfg_euler_update(fx["z"], v2, 1.5, sig[0], sig[1]))   # fused update bit-exact on our velocity
+    assert rel(z1, fx["z_step0"]) < 1e-4
+    z2 = smp.sample(fx["z"].cuda(), first_steps=2).cpu()
+    assert rel(z2, fx["z_step1"]) < 1e-4
+    y2 = torch.cat([fx["y"], torch.full((n,), 1000)])
+    vmid = run(m, torch.cat([fx["z"], fx["z"]]), torch.full((2 * n,), 0.5), y2, torch.cat([grid, grid]), torch.cat([mask, mask]))
+    assert rel(vmid, fx["v_t05"]) < V_TOL
+    # CUDA-graph replay of the step == eager launches, bit for bit
+    zg = EulerCFGSampler(m, fx["y"].cuda(), grid.cuda(), mask.cuda(), 250, 1.5, use_cuda_graph=True).sample(fx["z"].cuda(), first_steps=2).cpu()
+    assert torch.equal(zg, z2)
+    # full-size batch (32 samples -> 64 rows, M = 16384): rows are independent, so the first two samples must
+    # reproduce the batch-2 result (size-independent property at BASELINE.json's full size)
+    g = torch.Generator().manual_seed(1)
+    zb = torch.cat([fx["z"], torch.randn(30, N, 16, generator=g)])
+    yb = torch.cat([fx["y"], torch.randint(0, 1000, (30,), generator=g)])
+    zfull = euler_cfg_sample(m, zb.cuda(), yb.cuda(), make_grid(32, 16, 16).cuda(), torch.ones(32, N).cuda(), None, 250, 1.5, first_steps=2).cpu()
+    assert rel(zfull[:2], z2) < 1e-5 and bool(torch.isfinite(zfull).all())
+
+
+def test_trajectory_prefix_matches_oracle(lib):
+    """Latents after the first 6 Euler steps of a depth-4 XL-width model vs the oracle loop (error accumulates
+    through the ODE; stated tolerance 1e-2 on max_abs(dz)/max_abs(z))."""
+    m, sd, cfg = build_model(4)
+    n, hp, wp = 2, 16, 16
+    g = torch.Generator().manual_seed(21)
+    z, y = torch.randn(n, hp * wp, 16, generator=g), torch.tensor([5, 321])
+    grid, mask = make_grid(n, hp, wp), torch.ones(n, hp * wp)
+    ref = O.euler_cfg_sample(cfg, sd, z, y, grid, mask, None, steps=250, cfg_scale=1.5, first_steps=6)
+    got = euler_cfg_sample(m, z.cuda(), y.cuda(), grid.cuda(), mask.cuda(), None, 250, 1.5, first_steps=6).cpu()
+    assert rel(got, ref) < 1e-2 and rel(got - z, ref - z) < 2e-2
+
+
+def test_errors_are_loud(lib):
+    m, sd, cfg = build_model(1)
+    x, t, y, grid, mask = [v.cuda() for v in inputs(2, 4, 4)]
+    with pytest.raises(ValueError):
+        m(x, t[:1], y, grid, mask)
+    with pytest.raises(_lib.FitV2Error):
+        m(x.cpu(), t, y, grid, mask)
+    h = C.c_void_p()
+    cfgc = _lib.FitV2Config(1152, 1, 16, 72, 3072, 288, 16, 1001, 0, 1.0, 1.0)
+    _lib.check(lib.fitv2_create(C.byref(cfgc), C.byref(h)))
+    out = torch.empty(2, 16, 16, device="cuda")
+    rc = lib.fitv2_forward(h, _p(x), 2, _p(t), _p(y), _p(grid), _p(mask.float()), _p(out), 2, 16, None)
+    assert rc == -2 and b"not bound" in lib.fitv2_last_error()             # unbound weights: error, no fallback
+    lib.fitv2_destroy(h)

@@ -1,0 +1,125 @@
+"""Host-side logic of the drop-in (CPU only): constructor contract, state_dict keys, init parity with the
+reference scheme, RoPE frequency rules, weight packing, C-ABI library exports and error behaviour."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from oracle import fitv2_oracle as O
+from fitv2_b200 import FiT, FitV2Error, _lib
+from fitv2_b200.rope import rope_frequencies
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+KW = dict(learn_sigma=False, use_sit=True, use_swiglu=True, q_norm="layernorm", k_norm="layernorm", adaln_type="lora")
+XL1 = dict(hidden_size=1152, depth=1, num_heads=16, adaln_lora_dim=288)
+
+
+def test_rope_rules_match_oracle():
+    cases = [(72, "normal", None, None, False, None), (96, "normal", None, None, False, None),
+             (72, "ntk-aware", 10, 20, True, 16), (72, "ntk-aware", 32, 32, True, 16), (72, "ntk-aware", 10, 20, False, 16),
+             (72, "linear", 10, 20, True, 16), (72, "ntk-aware-pro1", 20, 20, False, 16), (72, "ntk-aware-pro2", 20, 20, False, 16),
+             (72, "ntk-by-parts", 24, 40, True, 16), (72, "yarn", 24, 40, True, 16), (96, "yarn", 32, 32, False, 16)]
+    for dh, cf, h, w, dec, ori in cases:
+        fh, fw, mag = rope_frequencies(dh, cf, 10000.0, h, w, dec, ori)
+        cfg = O.FiTConfig(hidden_size=dh * 2, num_heads=2, custom_freqs=cf, max_pe_len_h=h, max_pe_len_w=w, decouple=dec, ori_max_pe_len=ori)
+        ofh, ofw, omag = O.rope_setup(cfg)
+        assert torch.equal(fh, ofh) and torch.equal(fw, ofw) and mag == omag, (dh, cf)
+    with pytest.raises(ValueError):
+        rope_frequencies(72, "bogus")
+    with pytest.raises(ValueError):
+        rope_frequencies(72, "yarn")            # missing max_pe_len / ori_max_pe_len
+
+
+def test_constructor_contract_and_rejections():
+    m = FiT(**KW, **XL1, context_size=256, patch_size=2, in_channels=4, mlp_ratio=4.0, class_dropout_prob=0.1, num_classes=1000,
+            use_swiglu_large=False, use_checkpoint=False, qk_norm_weight=False, rel_pos_embed="rope", abs_pos_embed=None,
+            custom_freqs="normal", online_rope=False)     # every key of configs/fitv2/config_fitv2_xl.yaml:26-47 + injected keys
+    assert m.in_channels == 4 and m.dtype == torch.float32 and m.mlp_hidden == 3072 and m.head_dim == 72
+    for bad in (dict(use_sit=False), dict(adaln_type="normal"), dict(online_rope=True), dict(q_norm=None), dict(learn_sigma=True),
+                dict(use_swiglu=False), dict(num_heads=18), dict(operand_dtype="fp8"), dict(add_rel_pe_to_v=True)):
+        with pytest.raises(NotImplementedError):
+            FiT(**{**KW, **XL1, **bad})
+    with pytest.raises(FitV2Error):                        # no CPU fallback
+        m(torch.zeros(1, 16, 16), torch.zeros(1), torch.zeros(1, dtype=torch.long), torch.zeros(1, 2, 16, dtype=torch.long), torch.ones(1, 16))
+
+
+def test_state_dict_keys_and_init_parity():
+    torch.manual_seed(0)
+    m = FiT(**KW, **XL1)
+    cfg = O.FiTConfig(**XL1)
+    ref = O.reference_init_state_dict(cfg, 0)
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(ref.keys())
+    assert all(sd[k].shape == ref[k].shape and torch.equal(sd[k], ref[k]) for k in ref)
+    # SURVEY.md A.3 names
+    for k in ("x_embedder.proj.weight", "t_embedder.mlp.0.weight", "t_embedder.mlp.2.bias", "y_embedder.embedding_table.weight",
+              "global_adaLN_modulation.1.weight", "blocks.0.attn.qkv.weight", "blocks.0.attn.proj.bias", "blocks.0.mlp.fc1_g.weight",
+              "blocks.0.mlp.fc1_x.bias", "blocks.0.mlp.fc2.weight", "blocks.0.adaLN_modulation.1.weight", "blocks.0.adaLN_modulation.2.bias",
+              "final_layer.linear.weight", "final_layer.adaLN_modulation.1.bias"):
+        assert k in sd
+    m.randomize_zero_init_(1)
+    syn = O.synthetic_state_dict(cfg)
+    assert all(torch.equal(m.state_dict()[k], syn[k]) for k in syn)
+    # checkpoint round trip with the reference's strict=False loader semantics
+    m2 = FiT(**KW, **XL1)
+    missing, unexpected = m2.load_state_dict(syn, strict=False)
+    assert not missing and not unexpected and m2._packed is None
+    assert torch.equal(m2.unpatchify(torch.arange(2 * 4 * 16.).reshape(2, 4, 16), (4, 4)),
+                       O.unpatchify(cfg, torch.arange(2 * 4 * 16.).reshape(2, 4, 16), (4, 4)))
+
+
+def test_weight_packing_layout():
+    torch.manual_seed(0)
+    m = FiT(**KW, **XL1).randomize_zero_init_(1)
+    P = m.pack_weights(torch.device("cpu"))
+    assert set(P) == set(_lib.WEIGHT_SLOTS)
+    D, Hm = 1152, 3072
+    assert P["QKV_W"].shape == (1, 3 * D, D) and P["QKV_W"].dtype == torch.bfloat16
+    assert P["GATEUP_W"].shape == (1, 2 * Hm, D) and P["GATEUP_B"].shape == (1, 2 * Hm)
+    g, u = m.blocks[0].mlp.fc1_g, m.blocks[0].mlp.fc1_x
+    W, B = P["GATEUP_W"][0].float(), P["GATEUP_B"][0]
+    for t in (0, 5, 23):                                   # tile t: [128 gate rows | 128 up rows]
+        assert torch.equal(W[256 * t:256 * t + 128], g.weight[128 * t:128 * t + 128].bfloat16().float())
+        assert torch.equal(W[256 * t + 128:256 * t + 256], u.weight[128 * t:128 * t + 128].bfloat16().float())
+        assert torch.equal(B[256 * t:256 * t + 128], g.bias[128 * t:128 * t + 128])
+        assert torch.equal(B[256 * t + 128:256 * t + 256], u.bias[128 * t:128 * t + 128])
+    # emulate the fused epilogue from the packed layout and compare with timm SwiGLU semantics
+    x = torch.randn(5, D)
+    acc = x @ W.t() + B
+    hid = torch.cat([torch.nn.functional.silu(acc[:, 256 * t:256 * t + 128]) * acc[:, 256 * t + 128:256 * t + 256] for t in range(Hm // 128)], 1)
+    ref = torch.nn.functional.silu(x @ g.weight.bfloat16().float().t() + g.bias) * (x @ u.weight.bfloat16().float().t() + u.bias)
+    assert torch.allclose(hid, ref, atol=1e-5)
+    assert P["LORA_A_W"].shape == (1, 288, D) and P["LORA_B_W"].shape == (1, 6 * D, 288) and P["ROPE_FREQS_H"].shape == (18,)
+    m16 = FiT(**KW, **XL1, operand_dtype="fp16")
+    assert m16.pack_weights(torch.device("cpu"))["FC2_W"].dtype == torch.float16
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    with open(os.path.join(ROOT, "include", "fitv2_b200.h")) as f:
+        hdr = f.read()
+    declared = sorted(set(re.findall(r"\b(fitv2_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(declared) >= 14
+    lib = ctypes.CDLL(built_lib)
+    for sym in declared:
+        assert hasattr(lib, sym), f"{sym} declared in include/fitv2_b200.h but not exported"
+    assert sorted(_lib.EXPORTED_SYMBOLS) == declared
+    # enum order in the header == python slot table
+    enum = re.findall(r"FITV2_W_([A-Z0-9_]+)\s*(?:=\s*0)?,", hdr.split("enum fitv2_weight")[1].split("FITV2_W_COUNT")[0])
+    assert enum == _lib.WEIGHT_SLOTS
+
+
+def test_c_abi_argument_errors(built_lib):
+    lib = _lib.load()
+    assert b"sm_100a" in lib.fitv2_version()
+    h = ctypes.c_void_p()
+    bad = _lib.FitV2Config(1000, 1, 16, 72, 3072, 288, 16, 1001, 0, 1.0, 1.0)       # hidden != heads*head_dim
+    assert lib.fitv2_create(ctypes.byref(bad), ctypes.byref(h)) == -1 and b"hidden_size" in lib.fitv2_last_error()
+    bad = _lib.FitV2Config(1024, 1, 16, 64, 3072, 288, 16, 1001, 0, 1.0, 1.0)       # head_dim 64 not built
+    assert lib.fitv2_create(ctypes.byref(bad), ctypes.byref(h)) == -1 and b"head_dim" in lib.fitv2_last_error()
+    assert lib.fitv2_cfg_euler(None, None, 1.5, 0.004, None, 1, 1, 16, None) == -1
+    assert lib.fitv2_cfg_combine(None, None, 1.5, 1, 1, 16, 12, None) == -1
+    if not torch.cuda.is_available():
+        ok = _lib.FitV2Config(1152, 1, 16, 72, 3072, 288, 16, 1001, 0, 1.0, 1.0)
+        assert lib.fitv2_create(ctypes.byref(ok), ctypes.byref(h)) == -3              # no device: CUDA error, not a fallback
