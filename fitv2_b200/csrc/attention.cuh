@@ -66,14 +66,16 @@ attention_kernel(const OT* __restrict__ q, const OT* __restrict__ k, const OT* _
     if (warp == 0) { __syncwarp(); tmem_alloc(tmem_slot, 256); }
 
     // ---- stage the Q tile (zero rows past the sequence end, zero pad columns) ----
-    for (int id = tid; id < 128 * C::kChunks; id += 128) {
+    // All copies are 16-byte cp.async (zero-fill for out-of-range chunks), issued back to back so that the
+    // whole tile is in flight at once; Q joins the first K/V group.
+#pragma unroll
+    for (int i = 0; i < C::kChunks; ++i) {
+        const int id = tid + i * 128;
         const int r = id / C::kChunks, c = id % C::kChunks;
-        uint4 val = make_uint4(0, 0, 0, 0);
-        if (q0 + r < tokens && c < C::kRealChunks)
-            val = *reinterpret_cast<const uint4*>(qg + (size_t)(q0 + r) * DH + c * 8);
+        const bool ok = q0 + r < tokens && c < C::kRealChunks;
         uint8_t* dst = c < 8 ? smem + C::kOffQ + swz_offset<128>(r, c)
                              : smem + C::kOffQT + swz_offset<C::kTailBytes>(r, c - 8);
-        *reinterpret_cast<uint4*>(dst) = val;
+        cp_async16(dst, ok ? qg + (size_t)(q0 + r) * DH + c * 8 : qg, ok ? 16 : 0);
     }
     tc_fence_before();
     __syncthreads();
@@ -99,30 +101,27 @@ attention_kernel(const OT* __restrict__ q, const OT* __restrict__ k, const OT* _
     for (int t = 0; t < kv_tiles; ++t, ph ^= 1) {
         const int kv0 = t * 128;
         // ---- stage K tile, V^T tile, key segment ids (previous tile's MMAs have retired: bar_o was awaited) ----
-        for (int id = tid; id < 128 * C::kChunks; id += 128) {
+#pragma unroll
+        for (int i = 0; i < C::kChunks; ++i) {
+            const int id = tid + i * 128;
             const int r = id / C::kChunks, c = id % C::kChunks;
-            uint4 val = make_uint4(0, 0, 0, 0);
-            if (kv0 + r < tokens && c < C::kRealChunks)
-                val = *reinterpret_cast<const uint4*>(kg + (size_t)(kv0 + r) * DH + c * 8);
+            const bool ok = kv0 + r < tokens && c < C::kRealChunks;
             uint8_t* dst = c < 8 ? smem + C::kOffK + swz_offset<128>(r, c)
                                  : smem + C::kOffKT + swz_offset<C::kTailBytes>(r, c - 8);
-            *reinterpret_cast<uint4*>(dst) = val;
+            cp_async16(dst, ok ? kg + (size_t)(kv0 + r) * DH + c * 8 : kg, ok ? 16 : 0);
         }
-        for (int id = tid; id < C::kDHP * 16; id += 128) {
+#pragma unroll
+        for (int i = 0; i < C::kDHP * 16 / 128; ++i) {
+            const int id = tid + i * 128;
             const int d = id >> 4, c = id & 15;                        // row d of V^T, 8 keys per chunk
             const int kv = kv0 + c * 8;
-            uint4 val = make_uint4(0, 0, 0, 0);
-            if (d < DH && kv < tokens) {
-                val = *reinterpret_cast<const uint4*>(vg + (size_t)d * tokens_v + kv);
-                if (kv + 8 > tokens) {                                 // boundary chunk: clear keys past the end
-                    uint16_t* h = reinterpret_cast<uint16_t*>(&val);
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) if (kv + e >= tokens) h[e] = 0;
-                }
-            }
-            *reinterpret_cast<uint4*>(smem + C::kOffV + (c >> 3) * C::kVPanel + swz_offset<128>(d, c & 7)) = val;
+            const bool ok = d < DH && kv < tokens;
+            const int bytes = ok ? min(8, tokens - kv) * 2 : 0;        // boundary chunk: keys past the end are zero-filled
+            cp_async16(smem + C::kOffV + (c >> 3) * C::kVPanel + swz_offset<128>(d, c & 7),
+                       ok ? vg + (size_t)d * tokens_v + kv : vg, bytes);
         }
         seg_kv[tid] = (kv0 + tid < tokens) ? segb[kv0 + tid] : 0.f;
+        cp_async_wait_all();
         fence_proxy_async_smem();
         __syncthreads();
 
@@ -144,6 +143,7 @@ attention_kernel(const OT* __restrict__ q, const OT* __restrict__ k, const OT* _
 
         // ---- online softmax, pass 1: masked row maximum ----
         const int kv_valid = min(128, tokens - kv0);
+        const bool dense = uniform && kv_valid == 128;                 // CTA-uniform: no per-element masking needed
         float tmax = -INFINITY;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -154,16 +154,21 @@ attention_kernel(const OT* __restrict__ q, const OT* __restrict__ k, const OT* _
 #pragma unroll
                 for (int j = 0; j < 32; ++j) dbg_s[tid * 128 + c * 32 + j] = __uint_as_float(v[j]);   // raw S tile (debug)
             }
+            if (dense) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const int col = c * 32 + j;
-                const bool ok = col < kv_valid && (uniform || seg_kv[col] == my_seg);
-                tmax = fmaxf(tmax, ok ? __uint_as_float(v[j]) : -INFINITY);
+                for (int j = 0; j < 32; ++j) tmax = fmaxf(tmax, __uint_as_float(v[j]));
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int col = c * 32 + j;
+                    const bool ok = col < kv_valid && (uniform || seg_kv[col] == my_seg);
+                    tmax = fmaxf(tmax, ok ? __uint_as_float(v[j]) : -INFINITY);
+                }
             }
         }
         const float m_new = fmaxf(m_run, tmax);
         const float m_scaled = (m_new == -INFINITY) ? 0.f : m_new * scale_log2e;
-        const float alpha = (m_run == -INFINITY) ? 0.f : exp2f(m_run * scale_log2e - m_scaled);
+        const float alpha = (m_run == -INFINITY) ? 0.f : fast_exp2(m_run * scale_log2e - m_scaled);
         m_run = m_new;
 
         // ---- pass 2: p = exp2(s*c - m*c), row sum of the ROUNDED p, P -> smem (A operand of P V) ----
@@ -174,16 +179,27 @@ attention_kernel(const OT* __restrict__ q, const OT* __restrict__ k, const OT* _
             tmem_ld32(t_s + c * 32, v);
             tmem_ld_wait();
             uint32_t packed[16];
+            if (dense) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const int col = c * 32 + 2 * j;
-                const bool ok0 = col < kv_valid && (uniform || seg_kv[col] == my_seg);
-                const bool ok1 = col + 1 < kv_valid && (uniform || seg_kv[col + 1] == my_seg);
-                const float p0 = ok0 ? exp2f(fmaf(__uint_as_float(v[2 * j]), scale_log2e, -m_scaled)) : 0.f;
-                const float p1 = ok1 ? exp2f(fmaf(__uint_as_float(v[2 * j + 1]), scale_log2e, -m_scaled)) : 0.f;
-                packed[j] = Op16<OT>::pack(p0, p1);
-                const float2 r = Op16<OT>::unpack(packed[j]);
-                lsum += r.x + r.y;
+                for (int j = 0; j < 16; ++j) {
+                    const float p0 = fast_exp2(fmaf(__uint_as_float(v[2 * j]), scale_log2e, -m_scaled));
+                    const float p1 = fast_exp2(fmaf(__uint_as_float(v[2 * j + 1]), scale_log2e, -m_scaled));
+                    packed[j] = Op16<OT>::pack(p0, p1);
+                    const float2 r = Op16<OT>::unpack(packed[j]);
+                    lsum += r.x + r.y;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int col = c * 32 + 2 * j;
+                    const bool ok0 = col < kv_valid && (uniform || seg_kv[col] == my_seg);
+                    const bool ok1 = col + 1 < kv_valid && (uniform || seg_kv[col + 1] == my_seg);
+                    const float p0 = ok0 ? fast_exp2(fmaf(__uint_as_float(v[2 * j]), scale_log2e, -m_scaled)) : 0.f;
+                    const float p1 = ok1 ? fast_exp2(fmaf(__uint_as_float(v[2 * j + 1]), scale_log2e, -m_scaled)) : 0.f;
+                    packed[j] = Op16<OT>::pack(p0, p1);
+                    const float2 r = Op16<OT>::unpack(packed[j]);
+                    lsum += r.x + r.y;
+                }
             }
 #pragma unroll
             for (int g = 0; g < 4; ++g) {                              // 4 chunks of 8 keys per 32 columns

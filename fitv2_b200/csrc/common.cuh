@@ -208,6 +208,27 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float fast_exp2(float x) {          // MUFU.EX2, 2 ulp; exp2(-inf) = 0
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// silu(g) * u with MUFU exp2 / rcp (the result is rounded to 16 bits right after)
+__device__ __forceinline__ float silu_mul(float g, float u) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + fast_exp2(-1.4426950408889634f * g)));
+    return g * u * r;
+}
+
+// 16-byte asynchronous global->shared copy; bytes beyond `src_bytes` (0..16) are zero-filled.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;"
+                 :: "r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
 
 // streaming 128-bit accesses (activations that are touched once per kernel)
 __device__ __forceinline__ float4 ld_stream_f4(const float4* p) {

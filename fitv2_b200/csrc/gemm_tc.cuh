@@ -4,7 +4,7 @@
 //
 //   warp 0 : TMA producer  (cp.async.bulk.tensor, 128B swizzle, STAGES-deep mbarrier ring)
 //   warp 1 : TMEM allocator + single-thread tcgen05.mma issuer (128 x BN x 16 per instruction)
-//   warps 2-5 : epilogue (tcgen05.ld -> registers -> fused math -> global), double-buffered TMEM
+//   warps 2-9 : epilogue (tcgen05.ld -> registers -> fused math -> global), double-buffered TMEM
 //               accumulators so the epilogue of tile i overlaps the main loop of tile i+1.
 //
 // Fused epilogues (reference lines they replace, paths relative to the reference repo):
@@ -43,7 +43,7 @@ struct GemmEpi {
 
 constexpr int kGemmBM = 128;
 constexpr int kGemmBK = 64;
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;     // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
 constexpr int kSmemBudget = 227 * 1024;
 
 template <int BN> struct GemmCfg {
@@ -89,7 +89,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         tma_prefetch_desc(&tma_a);
         tma_prefetch_desc(&tma_b);
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 128); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 256); }
         mbar_fence_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -141,70 +141,85 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         }
     } else {
         // ------------------------------ epilogue warps ------------------------------
+        // 8 warps: warp pairs (w, w+4) share a TMEM lane quarter and split the tile's columns in two halves,
+        // so every SM sub-partition runs two epilogue warps.
         const int quarter = warp & 3;                                 // TMEM lane quarter this warp may access
+        const int half = (warp - 2) >> 2;                             // 0: left half of the tile columns, 1: right half
         const int row_in_tile = quarter * 32 + lane;
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int m_tile = tile / n_tiles, n_tile = tile % n_tiles;
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
-            mbar_wait(&tfull_bar[acc], acc_phase);
-            tc_fence_after();
             const uint32_t t_row = tmem_base + acc * Cfg::kAccStride + (uint32_t(quarter * 32) << 16);
             const int m = m_tile * kGemmBM + row_in_tile;
             const bool row_ok = m < M;
             const int n0 = n_tile * BN;
 
             if constexpr (EPI == EPI_RESID) {
+                constexpr int HALF = BN / 2;                          // columns per warp
+                constexpr int NG = HALF / 8;                          // groups of 8 columns
+                static_assert(HALF % 8 == 0, "tile half must be a multiple of 8 columns");
                 const int sample = row_ok ? m / ep.tokens : 0;
-                const float* gate = ep.gate + (size_t)sample * ep.gate_ld + n0;
-                const float* bias = ep.bias + n0;
-                float* xrow = ep.x + (size_t)(row_ok ? m : 0) * N + n0;
+                const float* gate = ep.gate + (size_t)sample * ep.gate_ld + n0 + half * HALF;
+                const float* bias = ep.bias + n0 + half * HALF;
+                float* xrow = ep.x + (size_t)(row_ok ? m : 0) * N + n0 + half * HALF;
+                // residual values do not depend on the accumulator: fetch the first group before waiting for the MMAs
+                float4 xv[2], xn[2];
+                if (row_ok) { xv[0] = *reinterpret_cast<const float4*>(xrow); xv[1] = *reinterpret_cast<const float4*>(xrow + 4); }
+                mbar_wait(&tfull_bar[acc], acc_phase);
+                tc_fence_after();
 #pragma unroll
-                for (int c = 0; c < BN / 16; ++c) {
-                    uint32_t v[16];
-                    tmem_ld16(t_row + c * 16, v);
-                    float4 xv[4];
-                    if (row_ok) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) xv[j] = *reinterpret_cast<const float4*>(xrow + c * 16 + j * 4);
+                for (int c = 0; c < NG; ++c) {
+                    if (row_ok && c + 1 < NG) {
+                        xn[0] = *reinterpret_cast<const float4*>(xrow + (c + 1) * 8);
+                        xn[1] = *reinterpret_cast<const float4*>(xrow + (c + 1) * 8 + 4);
                     }
+                    uint32_t v[8];
+                    tmem_ld8(t_row + half * HALF + c * 8, v);
                     tmem_ld_wait();
-                    if (c == BN / 16 - 1) { tc_fence_before(); mbar_arrive(&tempty_bar[acc]); }
+                    if (c == NG - 1) { tc_fence_before(); mbar_arrive(&tempty_bar[acc]); }
                     if (row_ok) {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const float4 g = __ldg(reinterpret_cast<const float4*>(gate + c * 16 + j * 4));
-                            const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c * 16 + j * 4));
+                        for (int j = 0; j < 2; ++j) {
+                            const float4 g = __ldg(reinterpret_cast<const float4*>(gate + c * 8 + j * 4));
+                            const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c * 8 + j * 4));
                             float4 o;
                             o.x = xv[j].x + g.x * (__uint_as_float(v[j * 4 + 0]) + b.x);
                             o.y = xv[j].y + g.y * (__uint_as_float(v[j * 4 + 1]) + b.y);
                             o.z = xv[j].z + g.z * (__uint_as_float(v[j * 4 + 2]) + b.z);
                             o.w = xv[j].w + g.w * (__uint_as_float(v[j * 4 + 3]) + b.w);
-                            *reinterpret_cast<float4*>(xrow + c * 16 + j * 4) = o;
+                            *reinterpret_cast<float4*>(xrow + c * 8 + j * 4) = o;
                         }
                     }
+                    xv[0] = xn[0]; xv[1] = xn[1];
                 }
             } else if constexpr (EPI == EPI_SWIGLU) {
                 // tile columns: [0, BN/2) = gate rows of W, [BN/2, BN) = matching up rows (host packs W this way)
-                constexpr int HALF = BN / 2;
-                const float* bias = ep.bias + n0;
-                OT* orow = reinterpret_cast<OT*>(ep.out16) + (size_t)(row_ok ? m : 0) * ep.ld_out + n_tile * HALF;
+                constexpr int HALF = BN / 2;                          // outputs per tile
+                constexpr int Q = HALF / 2;                           // outputs per warp
+                static_assert(Q % 16 == 0, "SwiGLU tile must hold a multiple of 32 outputs per half");
+                const float* bias_g = ep.bias + n0 + half * Q;
+                const float* bias_u = ep.bias + n0 + HALF + half * Q;
+                OT* orow = reinterpret_cast<OT*>(ep.out16) + (size_t)(row_ok ? m : 0) * ep.ld_out + n_tile * HALF + half * Q;
+                mbar_wait(&tfull_bar[acc], acc_phase);
+                tc_fence_after();
 #pragma unroll
-                for (int c = 0; c < HALF / 16; ++c) {
+                for (int c = 0; c < Q / 16; ++c) {
                     uint32_t g[16], u[16];
-                    tmem_ld16(t_row + c * 16, g);
-                    tmem_ld16(t_row + HALF + c * 16, u);
+                    tmem_ld16(t_row + half * Q + c * 16, g);
+                    tmem_ld16(t_row + HALF + half * Q + c * 16, u);
                     tmem_ld_wait();
-                    if (c == HALF / 16 - 1) { tc_fence_before(); mbar_arrive(&tempty_bar[acc]); }
+                    if (c == Q / 16 - 1) { tc_fence_before(); mbar_arrive(&tempty_bar[acc]); }
                     uint32_t packed[8];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float g0 = __uint_as_float(g[2 * j]) + __ldg(bias + c * 16 + 2 * j);
-                        const float g1 = __uint_as_float(g[2 * j + 1]) + __ldg(bias + c * 16 + 2 * j + 1);
-                        const float u0 = __uint_as_float(u[2 * j]) + __ldg(bias + HALF + c * 16 + 2 * j);
-                        const float u1 = __uint_as_float(u[2 * j + 1]) + __ldg(bias + HALF + c * 16 + 2 * j + 1);
-                        packed[j] = Op16<OT>::pack(silu_f(g0) * u0, silu_f(g1) * u1);
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 bg = __ldg(reinterpret_cast<const float4*>(bias_g + c * 16 + j * 4));
+                        const float4 bu = __ldg(reinterpret_cast<const float4*>(bias_u + c * 16 + j * 4));
+                        packed[2 * j] = Op16<OT>::pack(silu_mul(__uint_as_float(g[4 * j]) + bg.x, __uint_as_float(u[4 * j]) + bu.x),
+                                                       silu_mul(__uint_as_float(g[4 * j + 1]) + bg.y, __uint_as_float(u[4 * j + 1]) + bu.y));
+                        packed[2 * j + 1] = Op16<OT>::pack(silu_mul(__uint_as_float(g[4 * j + 2]) + bg.z, __uint_as_float(u[4 * j + 2]) + bu.z),
+                                                           silu_mul(__uint_as_float(g[4 * j + 3]) + bg.w, __uint_as_float(u[4 * j + 3]) + bu.w));
                     }
                     if (row_ok) {
                         uint4* dst = reinterpret_cast<uint4*>(orow + c * 16);
@@ -213,92 +228,90 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     }
                 }
             } else if constexpr (EPI == EPI_PLAIN) {
-                const float* bias = ep.bias + n0;
+                constexpr int HALF = BN / 2;
+                constexpr int NG = HALF / 8;
+                const float* bias = ep.bias + n0 + half * HALF;
+                mbar_wait(&tfull_bar[acc], acc_phase);
+                tc_fence_after();
 #pragma unroll
-                for (int c = 0; c < BN / 16; ++c) {
-                    uint32_t v[16];
-                    tmem_ld16(t_row + c * 16, v);
+                for (int c = 0; c < NG; ++c) {
+                    uint32_t v[8];
+                    tmem_ld8(t_row + half * HALF + c * 8, v);
                     tmem_ld_wait();
-                    if (c == BN / 16 - 1) { tc_fence_before(); mbar_arrive(&tempty_bar[acc]); }
+                    if (c == NG - 1) { tc_fence_before(); mbar_arrive(&tempty_bar[acc]); }
                     if (row_ok) {
+                        float o[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) o[j] = __uint_as_float(v[j]) + __ldg(bias + c * 8 + j);
                         if (ep.out16 != nullptr) {
-                            OT* orow = reinterpret_cast<OT*>(ep.out16) + (size_t)m * ep.ld_out + n0 + c * 16;
-                            uint32_t packed[8];
-#pragma unroll
-                            for (int j = 0; j < 8; ++j)
-                                packed[j] = Op16<OT>::pack(__uint_as_float(v[2 * j]) + __ldg(bias + c * 16 + 2 * j),
-                                                           __uint_as_float(v[2 * j + 1]) + __ldg(bias + c * 16 + 2 * j + 1));
-                            uint4* dst = reinterpret_cast<uint4*>(orow);
-                            dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-                            dst[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+                            OT* orow = reinterpret_cast<OT*>(ep.out16) + (size_t)m * ep.ld_out + n0 + half * HALF + c * 8;
+                            *reinterpret_cast<uint4*>(orow) = make_uint4(Op16<OT>::pack(o[0], o[1]), Op16<OT>::pack(o[2], o[3]),
+                                                                         Op16<OT>::pack(o[4], o[5]), Op16<OT>::pack(o[6], o[7]));
                         } else {
-                            float* orow = ep.out32 + (size_t)m * ep.ld_out + n0 + c * 16;
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                float4 o;
-                                o.x = __uint_as_float(v[j * 4 + 0]) + __ldg(bias + c * 16 + j * 4 + 0);
-                                o.y = __uint_as_float(v[j * 4 + 1]) + __ldg(bias + c * 16 + j * 4 + 1);
-                                o.z = __uint_as_float(v[j * 4 + 2]) + __ldg(bias + c * 16 + j * 4 + 2);
-                                o.w = __uint_as_float(v[j * 4 + 3]) + __ldg(bias + c * 16 + j * 4 + 3);
-                                *reinterpret_cast<float4*>(orow + j * 4) = o;
-                            }
+                            float* orow = ep.out32 + (size_t)m * ep.ld_out + n0 + half * HALF + c * 8;
+                            *reinterpret_cast<float4*>(orow) = make_float4(o[0], o[1], o[2], o[3]);
+                            *reinterpret_cast<float4*>(orow + 4) = make_float4(o[4], o[5], o[6], o[7]);
                         }
                     }
                 }
-            } else {   // EPI_QKV: BN == 2 * DH, every tile holds two whole heads of the same kind (heads is even)
+            } else {   // EPI_QKV: BN == 2 * DH, every tile holds two whole heads of the same kind (heads is even);
+                       // the two column halves are exactly the two heads.
                 static_assert(EPI != EPI_QKV || BN == 2 * DH, "QKV tile must be two heads wide");
                 static_assert(DH % 8 == 0, "head_dim must be a multiple of 8");
                 const int sample = row_ok ? m / ep.tokens : 0;
                 const int token = row_ok ? m - sample * ep.tokens : 0;
+                const int ghead = n_tile * 2 + half;
+                const int kind = ghead / ep.heads;                  // 0 = q, 1 = k, 2 = v   (modules.py:166-167)
+                const int head = ghead - kind * ep.heads;
+                const float* bias = ep.bias + n0 + half * DH;
+                mbar_wait(&tfull_bar[acc], acc_phase);
+                tc_fence_after();
+                float v[DH];
 #pragma unroll
-                for (int hh = 0; hh < 2; ++hh) {
-                    const int ghead = n_tile * 2 + hh;
-                    const int kind = ghead / ep.heads;              // 0 = q, 1 = k, 2 = v   (modules.py:166-167)
-                    const int head = ghead - kind * ep.heads;
-                    float v[DH];
+                for (int c = 0; c < DH / 8; ++c) tmem_ld8(t_row + half * DH + c * 8, reinterpret_cast<uint32_t*>(v) + c * 8);
+                tmem_ld_wait();
+                tc_fence_before();
+                mbar_arrive(&tempty_bar[acc]);
 #pragma unroll
-                    for (int c = 0; c < DH / 8; ++c) tmem_ld8(t_row + hh * DH + c * 8, reinterpret_cast<uint32_t*>(v) + c * 8);
-                    tmem_ld_wait();
-                    if (hh == 1) { tc_fence_before(); mbar_arrive(&tempty_bar[acc]); }
-                    const float* bias = ep.bias + n0 + hh * DH;
+                for (int c = 0; c < DH / 4; ++c) {
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c * 4));
+                    v[c * 4] += b.x; v[c * 4 + 1] += b.y; v[c * 4 + 2] += b.z; v[c * 4 + 3] += b.w;
+                }
+                if (kind < 2) {
+                    // LayerNorm over the head (no affine, eps 1e-6, biased variance): norms.py:41-42
+                    float mean = 0.f;
 #pragma unroll
-                    for (int j = 0; j < DH; ++j) v[j] += __ldg(bias + j);
-                    if (kind < 2) {
-                        // LayerNorm over the head (no affine, eps 1e-6, biased variance): norms.py:41-42
-                        float mean = 0.f;
+                    for (int j = 0; j < DH; ++j) mean += v[j];
+                    mean *= (1.0f / DH);
+                    float var = 0.f;
 #pragma unroll
-                        for (int j = 0; j < DH; ++j) mean += v[j];
-                        mean *= (1.0f / DH);
-                        float var = 0.f;
+                    for (int j = 0; j < DH; ++j) { const float d = v[j] - mean; var += d * d; }
+                    const float rstd = rsqrtf(var * (1.0f / DH) + 1e-6f);
+                    const float* cs = ep.rope_cos + (size_t)(row_ok ? m : 0) * (DH / 2);
+                    const float* sn = ep.rope_sin + (size_t)(row_ok ? m : 0) * (DH / 2);
+                    OT* dst = reinterpret_cast<OT*>(kind == 0 ? ep.q : ep.k) +
+                              (((size_t)sample * ep.heads + head) * ep.tokens + token) * DH;
 #pragma unroll
-                        for (int j = 0; j < DH; ++j) { const float d = v[j] - mean; var += d * d; }
-                        const float rstd = rsqrtf(var * (1.0f / DH) + 1e-6f);
-                        const float* cs = ep.rope_cos + (size_t)(row_ok ? m : 0) * (DH / 2);
-                        const float* sn = ep.rope_sin + (size_t)(row_ok ? m : 0) * (DH / 2);
-                        OT* dst = reinterpret_cast<OT*>(kind == 0 ? ep.q : ep.k) +
-                                  (((size_t)sample * ep.heads + head) * ep.tokens + token) * DH;
+                    for (int c = 0; c < DH / 8; ++c) {
+                        const float4 cv = __ldg(reinterpret_cast<const float4*>(cs + c * 4));
+                        const float4 sv = __ldg(reinterpret_cast<const float4*>(sn + c * 4));
+                        const float cc[4] = {cv.x, cv.y, cv.z, cv.w};
+                        const float ss[4] = {sv.x, sv.y, sv.z, sv.w};
+                        uint32_t packed[4];
 #pragma unroll
-                        for (int c = 0; c < DH / 8; ++c) {
-                            const float4 cv = __ldg(reinterpret_cast<const float4*>(cs + c * 4));
-                            const float4 sv = __ldg(reinterpret_cast<const float4*>(sn + c * 4));
-                            const float cc[4] = {cv.x, cv.y, cv.z, cv.w};
-                            const float ss[4] = {sv.x, sv.y, sv.z, sv.w};
-                            uint32_t packed[4];
-#pragma unroll
-                            for (int p = 0; p < 4; ++p) {
-                                const float x0 = (v[c * 8 + 2 * p] - mean) * rstd;
-                                const float x1 = (v[c * 8 + 2 * p + 1] - mean) * rstd;
-                                // q*cos + rotate_half(q)*sin with rotate_half: (x0,x1) -> (-x1,x0)
-                                packed[p] = Op16<OT>::pack(x0 * cc[p] - x1 * ss[p], x1 * cc[p] + x0 * ss[p]);
-                            }
-                            if (row_ok) *reinterpret_cast<uint4*>(dst + c * 8) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                        for (int p = 0; p < 4; ++p) {
+                            const float x0 = (v[c * 8 + 2 * p] - mean) * rstd;
+                            const float x1 = (v[c * 8 + 2 * p + 1] - mean) * rstd;
+                            // q*cos + rotate_half(q)*sin with rotate_half: (x0,x1) -> (-x1,x0)
+                            packed[p] = Op16<OT>::pack(x0 * cc[p] - x1 * ss[p], x1 * cc[p] + x0 * ss[p]);
                         }
-                    } else if (row_ok) {
-                        // V^T[sample, head, d, token]: lanes hold consecutive tokens -> 64B runs per d
-                        OT* dst = reinterpret_cast<OT*>(ep.vt) + ((size_t)sample * ep.heads + head) * DH * ep.tokens_v + token;
-#pragma unroll
-                        for (int j = 0; j < DH; ++j) dst[(size_t)j * ep.tokens_v] = Op16<OT>::from(v[j]);
+                        if (row_ok) *reinterpret_cast<uint4*>(dst + c * 8) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
                     }
+                } else if (row_ok) {
+                    // V^T[sample, head, d, token]: lanes hold consecutive tokens -> 64B runs per d
+                    OT* dst = reinterpret_cast<OT*>(ep.vt) + ((size_t)sample * ep.heads + head) * DH * ep.tokens_v + token;
+#pragma unroll
+                    for (int j = 0; j < DH; ++j) dst[(size_t)j * ep.tokens_v] = Op16<OT>::from(v[j]);
                 }
             }
         }

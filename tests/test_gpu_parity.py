@@ -69,14 +69,15 @@ def test_cfg_euler_bit_exact(lib, B, N):
     g = torch.Generator().manual_seed(B * 1000 + N)
     z, v2 = torch.randn(B, N, 16, generator=g), torch.randn(2 * B, N, 16, generator=g)
     sig = torch.linspace(0, 1, 251)
+    vd = v2.cuda()
     for idx in (0, 17, 249):
         ref = O.cfg_euler_update(z, v2, 1.5, sig[idx], sig[idx + 1])
         zc = z.cuda().clone()
-        _lib.check(lib.fitv2_cfg_euler(_p(zc), _p(v2.cuda()), 1.5, float(sig[idx + 1] - sig[idx]), None, B, N, 16, None))
+        _lib.check(lib.fitv2_cfg_euler(_p(zc), _p(vd), 1.5, float(sig[idx + 1] - sig[idx]), None, B, N, 16, None))
         assert torch.equal(zc.cpu(), ref)
         zc = z.cuda().clone()                      # step size from a device scalar (graph-replay form)
         ds = (sig[idx + 1] - sig[idx]).reshape(1).cuda()
-        _lib.check(lib.fitv2_cfg_euler(_p(zc), _p(v2.cuda()), 1.5, 0.0, _p(ds), B, N, 16, None))
+        _lib.check(lib.fitv2_cfg_euler(_p(zc), _p(vd), 1.5, 0.0, _p(ds), B, N, 16, None))
         assert torch.equal(zc.cpu(), ref)
 
 
@@ -148,7 +149,9 @@ def test_attention_matches_oracle(lib, R, T, dh, H, masked):
     vt = torch.zeros(R, H, dh, tv, dtype=torch.bfloat16)
     vt[..., :T] = v.transpose(-1, -2)
     out = torch.full((R, T, H * dh), float("nan"), dtype=torch.bfloat16, device="cuda")
-    _lib.check(lib.fitv2_debug_attention(h, _p(q.cuda()), _p(k.cuda()), _p(vt.cuda()), _p(mask.cuda()), _p(out), R, T, None, None, None))
+    qd, kd, vd, md = q.cuda(), k.cuda(), vt.cuda(), mask.cuda()          # keep the device tensors alive across the call
+    _lib.check(lib.fitv2_debug_attention(h, _p(qd), _p(kd), _p(vd), _p(md), _p(out), R, T, None, None, None))
+    torch.cuda.synchronize()
     ref = _attention_oracle(q.float(), k.float(), v.float(), mask)
     assert rel(out, ref) < 6e-3                  # P and the output are rounded to bf16 (2^-9)
     assert bool((out.float().cpu()[mask == 0] == 0).all())

@@ -1,0 +1,27 @@
+"""Small deterministic workload for ncu: XL/2-width, depth-2 FiTv2, 64 rows x 256 tokens, 2 forwards."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+from bench import WORKLOADS
+from fitv2_b200 import FiT, make_grid
+
+wl = sys.argv[1] if len(sys.argv) > 1 else "xl256"
+depth = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+kw, (hp, wp), rope_kw = WORKLOADS[wl]
+kw = dict(kw, depth=depth)
+torch.manual_seed(0)
+m = FiT(learn_sigma=False, use_sit=True, use_swiglu=True, q_norm="layernorm", k_norm="layernorm", adaln_type="lora",
+        **kw, **rope_kw).randomize_zero_init_(1).cuda().eval()
+R, N = 64, hp * wp
+g = torch.Generator().manual_seed(0)
+x = torch.randn(R, N, 16, generator=g).cuda()
+t = torch.full((R,), 0.3).cuda()
+y = torch.randint(0, 1001, (R,), generator=g).cuda()
+grid, mask = make_grid(R, hp, wp).cuda(), torch.ones(R, N).cuda()
+for _ in range(2):
+    out = m(x, t, y, grid, mask)
+torch.cuda.synchronize()
+print("ok", float(out.abs().max()))
