@@ -185,7 +185,7 @@ inline void prof_end(fitv2_handle* h, cudaStream_t st) {
 template <int BN, int EPI, typename OT, int DH>
 int launch_gemm_t(fitv2_handle* h, const CUtensorMap& ma, const CUtensorMap& mb, int M, int N, int K, int b_row_off,
                   const GemmEpi& ep, cudaStream_t st) {
-    using Cfg = GemmCfg<BN>;
+    using Cfg = GemmCfg<BN, EPI, DH>;
     auto kern = gemm_tc_kernel<BN, EPI, OT, DH>;
     static bool configured = false;
     if (!configured) {

@@ -4,8 +4,11 @@
 //
 //   warp 0 : TMA producer  (cp.async.bulk.tensor, 128B swizzle, STAGES-deep mbarrier ring)
 //   warp 1 : TMEM allocator + single-thread tcgen05.mma issuer (128 x BN x 16 per instruction)
-//   warps 2-9 : epilogue (tcgen05.ld -> registers -> fused math -> global), double-buffered TMEM
-//               accumulators so the epilogue of tile i overlaps the main loop of tile i+1.
+//   warps 2-9 : epilogue.  Warp pairs (w, w+4) share a TMEM lane quarter and split the tile columns in two
+//               halves.  tcgen05.ld gives every lane one accumulator ROW; a warp-private shared-memory slab
+//               (XOR-swizzled, conflict-free) transposes it so that the global accesses are coalesced
+//               (a warp instruction touches 4 full 128-byte lines instead of 32 partial ones).
+//               TMEM accumulators are double-buffered: the epilogue of tile i overlaps the main loop of i+1.
 //
 // Fused epilogues (reference lines they replace, paths relative to the reference repo):
 //   EPI_QKV    bias + per-head LayerNorm(q,k) + interleaved-pair 2-D RoPE, scatter to Q / K / V^T
@@ -35,8 +38,8 @@ struct GemmEpi {
     void* q;                  // [samples, heads, tokens, DH]
     void* k;                  // [samples, heads, tokens, DH]
     void* vt;                 // [samples, heads, DH, tokens_v]   (V transposed: keys contiguous)
-    const float* rope_cos;    // [M, DH/2]
-    const float* rope_sin;    // [M, DH/2]
+    const float* rope_cos;    // [DH/2, M]   (pair-major: lanes of a warp read consecutive token rows)
+    const float* rope_sin;    // [DH/2, M]
     int heads;
     int tokens_v;
 };
@@ -46,32 +49,49 @@ constexpr int kGemmBK = 64;
 constexpr int kGemmThreads = 320;     // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
 constexpr int kSmemBudget = 227 * 1024;
 
-template <int BN> struct GemmCfg {
+template <int BN, int EPI, int DH> struct GemmCfg {
     static constexpr int kABytes = kGemmBM * kGemmBK * 2;
     static constexpr int kBBytes = BN * kGemmBK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kBarrierBytes = 1024;
-    static constexpr int kStagesRaw = (kSmemBudget - kBarrierBytes - 1024) / kStageBytes;
+    // epilogue staging: per warp 32 rows; QKV rows hold one head (16-bit) with a bank-conflict-free pitch,
+    // the other epilogues use 128-byte XOR-swizzled rows.
+    static constexpr int kEpiPitch = EPI == EPI_QKV ? ((DH * 2 / 4) % 8 == 4 ? DH * 2 : DH * 2 + 16) : 128;
+    static constexpr int kEpiWarpBytes = 32 * kEpiPitch;
+    static constexpr int kEpiBytes = (EPI == EPI_PLAIN ? 0 : 8 * kEpiWarpBytes);
+    static constexpr int kStagesRaw = (kSmemBudget - kBarrierBytes - 1024 - kEpiBytes) / kStageBytes;
     static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
-    static constexpr int kSmemBytes = kStages * kStageBytes + kBarrierBytes + 1024;   // +1024 manual alignment slack
+    static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + kBarrierBytes + 1024;   // +1024 alignment slack
     static constexpr int kAccStride = 256;                                           // TMEM columns between the 2 accumulators
     static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N constraint for M=128");
     static_assert(kBBytes % 1024 == 0, "B stage must keep 1024B alignment for SWIZZLE_128B");
     static_assert(kStages >= 3, "pipeline too shallow");
+    static_assert(EPI != EPI_QKV || DH * 64 <= kEpiWarpBytes, "V^T staging does not fit");
 };
+
+// ---- warp-private staging slab: 32 rows x 128 bytes, 16-byte chunk c of row r lives at chunk (c ^ (r & 7)) ----
+__device__ __forceinline__ uint32_t slab_off(int r, int c) { return r * 128 + ((c ^ (r & 7)) << 4); }
+
+// Coalesced (row, chunk) owned by `lane` in iteration i when a slab row holds CPR 16-byte chunks.
+template <int CPR> __device__ __forceinline__ void slab_task(int i, int lane, int& r, int& c) {
+    const int task = i * 32 + lane;
+    r = task / CPR;
+    c = task % CPR;
+}
 
 template <int BN, int EPI, typename OT, int DH>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                int M, int N, int K, int b_row_offset, GemmEpi ep)
 {
-    using Cfg = GemmCfg<BN>;
+    using Cfg = GemmCfg<BN, EPI, DH>;
     constexpr int STAGES = Cfg::kStages;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + STAGES * Cfg::kABytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes);
+    uint8_t* smem_epi = smem + STAGES * Cfg::kStageBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + Cfg::kEpiBytes);
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + STAGES;
     uint64_t* tfull_bar = bars + 2 * STAGES;
@@ -141,67 +161,99 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         }
     } else {
         // ------------------------------ epilogue warps ------------------------------
-        // 8 warps: warp pairs (w, w+4) share a TMEM lane quarter and split the tile's columns in two halves,
-        // so every SM sub-partition runs two epilogue warps.
         const int quarter = warp & 3;                                 // TMEM lane quarter this warp may access
         const int half = (warp - 2) >> 2;                             // 0: left half of the tile columns, 1: right half
-        const int row_in_tile = quarter * 32 + lane;
+        uint8_t* stg = smem_epi + (warp - 2) * Cfg::kEpiWarpBytes;    // warp-private staging slab
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int m_tile = tile / n_tiles, n_tile = tile % n_tiles;
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
             const uint32_t t_row = tmem_base + acc * Cfg::kAccStride + (uint32_t(quarter * 32) << 16);
-            const int m = m_tile * kGemmBM + row_in_tile;
-            const bool row_ok = m < M;
+            const int m_warp = m_tile * kGemmBM + quarter * 32;       // first row owned by this warp
+            const int rows_valid = min(32, M - m_warp);               // <= 0 when the whole warp is past the M tail
+            const int m = m_warp + lane;
+            const bool row_ok = lane < rows_valid;
             const int n0 = n_tile * BN;
+            const int s_first = m_warp / ep.tokens;
+            const bool one_sample = rows_valid > 0 && (m_warp + rows_valid - 1) / ep.tokens == s_first;
 
             if constexpr (EPI == EPI_RESID) {
                 constexpr int HALF = BN / 2;                          // columns per warp
-                constexpr int NG = HALF / 8;                          // groups of 8 columns
-                static_assert(HALF % 8 == 0, "tile half must be a multiple of 8 columns");
-                const int sample = row_ok ? m / ep.tokens : 0;
-                const float* gate = ep.gate + (size_t)sample * ep.gate_ld + n0 + half * HALF;
-                const float* bias = ep.bias + n0 + half * HALF;
-                float* xrow = ep.x + (size_t)(row_ok ? m : 0) * N + n0 + half * HALF;
-                // residual values do not depend on the accumulator: fetch the first group before waiting for the MMAs
-                float4 xv[2], xn[2];
-                if (row_ok) { xv[0] = *reinterpret_cast<const float4*>(xrow); xv[1] = *reinterpret_cast<const float4*>(xrow + 4); }
+                constexpr int NFULL = HALF / 32, REM = HALF % 32;     // 32-column slabs + one remainder slab
+                static_assert(REM == 0 || REM == 8 || REM == 16, "unsupported tile half width");
+                const int col0 = n0 + half * HALF;
+                float* xbase = ep.x + (size_t)m_warp * N + col0;
+                // The residual does not depend on the accumulator: the first slab of x is fetched (coalesced
+                // mapping) before waiting for the MMAs of this tile.
+                float4 xa[8], xb[8];
+                auto load_x = [&](float4* dst, int s0, auto cpr_tag) {
+                    constexpr int CPR = decltype(cpr_tag)::value;
+#pragma unroll
+                    for (int i = 0; i < CPR; ++i) {                   // CPR chunks/row * 32 rows / 32 lanes = CPR iterations
+                        int r, c; slab_task<CPR>(i, lane, r, c);
+                        if (r < rows_valid) dst[i] = *reinterpret_cast<const float4*>(xbase + (size_t)r * N + s0 + c * 4);
+                    }
+                };
+                auto do_slab = [&](int s0, bool last, auto cpr_tag, auto next_tag, int next_s0) {
+                    constexpr int CPR = decltype(cpr_tag)::value;     // 16-byte chunks per slab row (W = 4 * CPR columns)
+                    constexpr int NCPR = decltype(next_tag)::value;
+                    uint32_t v[CPR * 4];
+                    if constexpr (CPR == 8) tmem_ld32(t_row + half * HALF + s0, v);
+                    else if constexpr (CPR == 4) tmem_ld16(t_row + half * HALF + s0, v);
+                    else tmem_ld8(t_row + half * HALF + s0, v);
+                    tmem_ld_wait();
+                    if (last) { tc_fence_before(); mbar_arrive(&tempty_bar[acc]); }
+#pragma unroll
+                    for (int c = 0; c < CPR; ++c)
+                        *reinterpret_cast<uint4*>(stg + slab_off(lane, c)) = make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+                    __syncwarp();
+                    if constexpr (NCPR > 0) load_x(xb, next_s0, next_tag);      // prefetch the next slab of x
+                    int r0, c0; slab_task<CPR>(0, lane, r0, c0);                 // this lane's chunk column is the same in every iteration
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + s0 + c0 * 4));
+                    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (one_sample) g = __ldg(reinterpret_cast<const float4*>(ep.gate + (size_t)s_first * ep.gate_ld + col0 + s0 + c0 * 4));
+#pragma unroll
+                    for (int i = 0; i < CPR; ++i) {
+                        int r, c; slab_task<CPR>(i, lane, r, c);
+                        if (r < rows_valid) {
+                            if (!one_sample)
+                                g = __ldg(reinterpret_cast<const float4*>(ep.gate + (size_t)((m_warp + r) / ep.tokens) * ep.gate_ld + col0 + s0 + c * 4));
+                            const float4 a = *reinterpret_cast<const float4*>(stg + slab_off(r, c));
+                            float4 o;
+                            o.x = xa[i].x + g.x * (a.x + b.x);
+                            o.y = xa[i].y + g.y * (a.y + b.y);
+                            o.z = xa[i].z + g.z * (a.z + b.z);
+                            o.w = xa[i].w + g.w * (a.w + b.w);
+                            *reinterpret_cast<float4*>(xbase + (size_t)r * N + s0 + c * 4) = o;
+                        }
+                    }
+                    __syncwarp();
+                    if constexpr (NCPR > 0) {
+#pragma unroll
+                        for (int i = 0; i < NCPR; ++i) xa[i] = xb[i];
+                    }
+                };
+                using C8 = std::integral_constant<int, 8>;
+                using CR = std::integral_constant<int, REM / 4>;
+                using C0 = std::integral_constant<int, 0>;
+                if constexpr (NFULL > 0) load_x(xa, 0, C8{}); else load_x(xa, 0, CR{});
                 mbar_wait(&tfull_bar[acc], acc_phase);
                 tc_fence_after();
 #pragma unroll
-                for (int c = 0; c < NG; ++c) {
-                    if (row_ok && c + 1 < NG) {
-                        xn[0] = *reinterpret_cast<const float4*>(xrow + (c + 1) * 8);
-                        xn[1] = *reinterpret_cast<const float4*>(xrow + (c + 1) * 8 + 4);
-                    }
-                    uint32_t v[8];
-                    tmem_ld8(t_row + half * HALF + c * 8, v);
-                    tmem_ld_wait();
-                    if (c == NG - 1) { tc_fence_before(); mbar_arrive(&tempty_bar[acc]); }
-                    if (row_ok) {
-#pragma unroll
-                        for (int j = 0; j < 2; ++j) {
-                            const float4 g = __ldg(reinterpret_cast<const float4*>(gate + c * 8 + j * 4));
-                            const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c * 8 + j * 4));
-                            float4 o;
-                            o.x = xv[j].x + g.x * (__uint_as_float(v[j * 4 + 0]) + b.x);
-                            o.y = xv[j].y + g.y * (__uint_as_float(v[j * 4 + 1]) + b.y);
-                            o.z = xv[j].z + g.z * (__uint_as_float(v[j * 4 + 2]) + b.z);
-                            o.w = xv[j].w + g.w * (__uint_as_float(v[j * 4 + 3]) + b.w);
-                            *reinterpret_cast<float4*>(xrow + c * 8 + j * 4) = o;
-                        }
-                    }
-                    xv[0] = xn[0]; xv[1] = xn[1];
+                for (int s = 0; s < NFULL; ++s) {
+                    if (s + 1 < NFULL) do_slab(s * 32, false, C8{}, C8{}, (s + 1) * 32);
+                    else if constexpr (REM > 0) do_slab(s * 32, false, C8{}, CR{}, (s + 1) * 32);
+                    else do_slab(s * 32, true, C8{}, C0{}, 0);
                 }
+                if constexpr (REM > 0) do_slab(NFULL * 32, true, CR{}, C0{}, 0);
             } else if constexpr (EPI == EPI_SWIGLU) {
                 // tile columns: [0, BN/2) = gate rows of W, [BN/2, BN) = matching up rows (host packs W this way)
                 constexpr int HALF = BN / 2;                          // outputs per tile
-                constexpr int Q = HALF / 2;                           // outputs per warp
-                static_assert(Q % 16 == 0, "SwiGLU tile must hold a multiple of 32 outputs per half");
+                constexpr int Q = HALF / 2;                           // outputs per warp: 64 -> one 128-byte slab row
+                static_assert(Q == 64, "SwiGLU epilogue is written for 256-wide tiles");
                 const float* bias_g = ep.bias + n0 + half * Q;
                 const float* bias_u = ep.bias + n0 + HALF + half * Q;
-                OT* orow = reinterpret_cast<OT*>(ep.out16) + (size_t)(row_ok ? m : 0) * ep.ld_out + n_tile * HALF + half * Q;
                 mbar_wait(&tfull_bar[acc], acc_phase);
                 tc_fence_after();
 #pragma unroll
@@ -221,12 +273,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                         packed[2 * j + 1] = Op16<OT>::pack(silu_mul(__uint_as_float(g[4 * j + 2]) + bg.z, __uint_as_float(u[4 * j + 2]) + bu.z),
                                                            silu_mul(__uint_as_float(g[4 * j + 3]) + bg.w, __uint_as_float(u[4 * j + 3]) + bu.w));
                     }
-                    if (row_ok) {
-                        uint4* dst = reinterpret_cast<uint4*>(orow + c * 16);
-                        dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-                        dst[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
-                    }
+                    *reinterpret_cast<uint4*>(stg + slab_off(lane, 2 * c)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                    *reinterpret_cast<uint4*>(stg + slab_off(lane, 2 * c + 1)) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
                 }
+                __syncwarp();
+                OT* obase = reinterpret_cast<OT*>(ep.out16) + (size_t)m_warp * ep.ld_out + n_tile * HALF + half * Q;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {                         // 4 rows x 128 contiguous bytes per warp instruction
+                    int r, c; slab_task<8>(i, lane, r, c);
+                    if (r < rows_valid)
+                        *reinterpret_cast<uint4*>(obase + (size_t)r * ep.ld_out + c * 8) = *reinterpret_cast<const uint4*>(stg + slab_off(r, c));
+                }
+                __syncwarp();
             } else if constexpr (EPI == EPI_PLAIN) {
                 constexpr int HALF = BN / 2;
                 constexpr int NG = HALF / 8;
@@ -258,12 +316,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                        // the two column halves are exactly the two heads.
                 static_assert(EPI != EPI_QKV || BN == 2 * DH, "QKV tile must be two heads wide");
                 static_assert(DH % 8 == 0, "head_dim must be a multiple of 8");
-                const int sample = row_ok ? m / ep.tokens : 0;
-                const int token = row_ok ? m - sample * ep.tokens : 0;
+                constexpr int CH = DH / 8;                            // 16-byte chunks per head row
+                constexpr int PITCH = Cfg::kEpiPitch;
                 const int ghead = n_tile * 2 + half;
-                const int kind = ghead / ep.heads;                  // 0 = q, 1 = k, 2 = v   (modules.py:166-167)
+                const int kind = ghead / ep.heads;                    // 0 = q, 1 = k, 2 = v   (modules.py:166-167)
                 const int head = ghead - kind * ep.heads;
                 const float* bias = ep.bias + n0 + half * DH;
+                const int token0 = m_warp - s_first * ep.tokens;      // token index of the warp's first row
                 mbar_wait(&tfull_bar[acc], acc_phase);
                 tc_fence_after();
                 float v[DH];
@@ -287,31 +346,66 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 #pragma unroll
                     for (int j = 0; j < DH; ++j) { const float d = v[j] - mean; var += d * d; }
                     const float rstd = rsqrtf(var * (1.0f / DH) + 1e-6f);
-                    const float* cs = ep.rope_cos + (size_t)(row_ok ? m : 0) * (DH / 2);
-                    const float* sn = ep.rope_sin + (size_t)(row_ok ? m : 0) * (DH / 2);
-                    OT* dst = reinterpret_cast<OT*>(kind == 0 ? ep.q : ep.k) +
-                              (((size_t)sample * ep.heads + head) * ep.tokens + token) * DH;
+                    const float* cs = ep.rope_cos + (row_ok ? m : 0);        // pair-major tables: coalesced across lanes
+                    const float* sn = ep.rope_sin + (row_ok ? m : 0);
 #pragma unroll
-                    for (int c = 0; c < DH / 8; ++c) {
-                        const float4 cv = __ldg(reinterpret_cast<const float4*>(cs + c * 4));
-                        const float4 sv = __ldg(reinterpret_cast<const float4*>(sn + c * 4));
-                        const float cc[4] = {cv.x, cv.y, cv.z, cv.w};
-                        const float ss[4] = {sv.x, sv.y, sv.z, sv.w};
+                    for (int c = 0; c < CH; ++c) {
                         uint32_t packed[4];
 #pragma unroll
                         for (int p = 0; p < 4; ++p) {
+                            const float cc = __ldg(cs + (size_t)(c * 4 + p) * M);
+                            const float ss = __ldg(sn + (size_t)(c * 4 + p) * M);
                             const float x0 = (v[c * 8 + 2 * p] - mean) * rstd;
                             const float x1 = (v[c * 8 + 2 * p + 1] - mean) * rstd;
                             // q*cos + rotate_half(q)*sin with rotate_half: (x0,x1) -> (-x1,x0)
-                            packed[p] = Op16<OT>::pack(x0 * cc[p] - x1 * ss[p], x1 * cc[p] + x0 * ss[p]);
+                            packed[p] = Op16<OT>::pack(x0 * cc - x1 * ss, x1 * cc + x0 * ss);
                         }
-                        if (row_ok) *reinterpret_cast<uint4*>(dst + c * 8) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                        *reinterpret_cast<uint4*>(stg + lane * PITCH + c * 16) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
                     }
-                } else if (row_ok) {
-                    // V^T[sample, head, d, token]: lanes hold consecutive tokens -> 64B runs per d
-                    OT* dst = reinterpret_cast<OT*>(ep.vt) + ((size_t)sample * ep.heads + head) * DH * ep.tokens_v + token;
+                    __syncwarp();
+                    OT* dbase = reinterpret_cast<OT*>(kind == 0 ? ep.q : ep.k);
+                    if (one_sample) {
+                        // 32 token rows of one (sample, head) are contiguous in Q / K: flat 512-byte runs per instruction
+                        OT* dst = dbase + (((size_t)s_first * ep.heads + head) * ep.tokens + token0) * DH;
 #pragma unroll
-                    for (int j = 0; j < DH; ++j) dst[(size_t)j * ep.tokens_v] = Op16<OT>::from(v[j]);
+                        for (int i = 0; i < CH; ++i) {
+                            const int idx = i * 32 + lane, r = idx / CH, c = idx - r * CH;
+                            if (r < rows_valid)
+                                *reinterpret_cast<uint4*>(dst + (size_t)idx * 8) = *reinterpret_cast<const uint4*>(stg + r * PITCH + c * 16);
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < CH; ++i) {
+                            const int idx = i * 32 + lane, r = idx / CH, c = idx - r * CH;
+                            if (r < rows_valid) {
+                                const int sm = (m_warp + r) / ep.tokens, tk = (m_warp + r) - sm * ep.tokens;
+                                OT* dst = dbase + (((size_t)sm * ep.heads + head) * ep.tokens + tk) * DH;
+                                *reinterpret_cast<uint4*>(dst + c * 8) = *reinterpret_cast<const uint4*>(stg + r * PITCH + c * 16);
+                            }
+                        }
+                    }
+                    __syncwarp();
+                } else {
+                    // V^T[sample, head, d, token]
+                    if (one_sample && rows_valid == 32 && (token0 & 7) == 0) {
+                        // transpose through the slab: [d][32 tokens] 16-bit, then 16-byte (8-token) stores
+                        OT* s16 = reinterpret_cast<OT*>(stg);
+#pragma unroll
+                        for (int j = 0; j < DH; ++j) s16[j * 32 + lane] = Op16<OT>::from(v[j]);
+                        __syncwarp();
+                        OT* dst = reinterpret_cast<OT*>(ep.vt) + ((size_t)s_first * ep.heads + head) * DH * ep.tokens_v + token0;
+#pragma unroll
+                        for (int i = 0; i < DH * 4 / 32; ++i) {
+                            const int idx = i * 32 + lane, d = idx >> 2, part = idx & 3;
+                            *reinterpret_cast<uint4*>(dst + (size_t)d * ep.tokens_v + part * 8) = *reinterpret_cast<const uint4*>(stg + d * 64 + part * 16);
+                        }
+                        __syncwarp();
+                    } else if (row_ok) {
+                        const int sm = m / ep.tokens, tk = m - sm * ep.tokens;
+                        OT* dst = reinterpret_cast<OT*>(ep.vt) + ((size_t)sm * ep.heads + head) * DH * ep.tokens_v + tk;
+#pragma unroll
+                        for (int j = 0; j < DH; ++j) dst[(size_t)j * ep.tokens_v] = Op16<OT>::from(v[j]);
+                    }
                 }
             }
         }

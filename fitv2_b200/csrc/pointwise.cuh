@@ -233,7 +233,7 @@ final_layer_kernel(const float* __restrict__ x, const float* __restrict__ fmod /
 // RoPE tables  (rope.py:165-170, 308-333): for token row m of sample s
 //   pair i <  dh/4 : angle = float(grid[s,1,n]) * freqs_h[i]            (h position)
 //   pair i >= dh/4 : angle = float(grid[s,0,n]) * freqs_w[i - dh/4]     (w position)
-//   cos/sin tables (M, dh/2) fp32, optionally scaled by the yarn / ntk-pro magnitude.
+//   cos/sin tables (dh/2, M) fp32 (pair-major), optionally scaled by the yarn / ntk-pro magnitude.
 // ---------------------------------------------------------------------------------------------
 __global__ void rope_table_kernel(const long long* __restrict__ grid, const float* __restrict__ freqs_h,
                                   const float* __restrict__ freqs_w, float mag, float* __restrict__ cos_t,
@@ -242,8 +242,9 @@ __global__ void rope_table_kernel(const long long* __restrict__ grid, const floa
     const int quarter = half >> 1;
     const size_t total = (size_t)samples * tokens * half;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int p = (int)(i % half);
-        const size_t m = i / half;
+        const size_t M = (size_t)samples * tokens;           // pair-major layout [dh/2][M]: lanes -> consecutive token rows
+        const int p = (int)(i / M);
+        const size_t m = i % M;
         const int n = (int)(m % tokens);
         const int s = (int)(m / tokens);
         const long long* g = grid + (size_t)s * 2 * tokens;

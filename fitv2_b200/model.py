@@ -356,7 +356,7 @@ class FiT(nn.Module):
                       fmod=((rows, 2 * D), torch.float32), x_res=((rows, tokens, D), torch.float32),
                       q=((rows, H, tokens, dh), op), k=((rows, H, tokens, dh), op), vt=((rows, H, dh, tv), op),
                       attn_out=((rows, tokens, D), op), h=((rows, tokens, D), op), hidden=((rows, tokens, Hm), op),
-                      rope_cos=((rows, tokens, dh // 2), torch.float32), rope_sin=((rows, tokens, dh // 2), torch.float32),
+                      rope_cos=((dh // 2, rows, tokens), torch.float32), rope_sin=((dh // 2, rows, tokens), torch.float32),
                       seg_uniform=((rows,), torch.int32))
         shape, dt = shapes[name]
         dst = torch.empty(shape, dtype=dt, device=self.device)

@@ -176,8 +176,8 @@ def test_forward_golden_padded_mixed_aspect(xl2_padded, golden_dir):
     assert torch.equal(oc[:2, :, :12], oc[2:, :, :12])                      # guided channels duplicated in both halves
     # token mask / RoPE position tables: bit-exact indices, 1e-6 tables
     cos, sin = O.rope_cos_sin(cfg, fx["grid"])
-    assert float((m.debug_tap("rope_cos").cpu() - cos[..., 0::2]).abs().max()) < 1e-6
-    assert float((m.debug_tap("rope_sin").cpu() - sin[..., 0::2]).abs().max()) < 1e-6
+    assert float((m.debug_tap("rope_cos").cpu() - cos[..., 0::2].permute(2, 0, 1)).abs().max()) < 1e-6   # pair-major table
+    assert float((m.debug_tap("rope_sin").cpu() - sin[..., 0::2].permute(2, 0, 1)).abs().max()) < 1e-6
     assert m.debug_tap("seg_uniform").cpu().tolist() == [int(bool((r == r[0]).all())) for r in fx["mask"]]
 
 

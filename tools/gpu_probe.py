@@ -245,7 +245,7 @@ def _forward_compare(m, sd, kw, x, t, y, grid, mask, taps=True, quant=None):
         print(f"  tap vt        max-rel-err {rel(vt, tp['v'].transpose(-1, -2)):.3e}")
         rc = m.debug_tap("rope_cos").cpu()
         cos, sin = O.rope_cos_sin(cfg, grid)
-        print(f"  tap rope_cos  max-abs-err {float((rc - cos[..., 0::2]).abs().max()):.3e}")
+        print(f"  tap rope_cos  max-abs-err {float((rc - cos[..., 0::2].permute(2, 0, 1)).abs().max()):.3e}")
     return out, ref
 
 
