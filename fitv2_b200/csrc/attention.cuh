@@ -4,13 +4,22 @@
 //     attn_mask[b,i,j] = (mask[b,i] == mask[b,j])                (segment-id equality, NOT a pad mask)
 //     o = softmax(q k^T / sqrt(dh) + attn_mask) v ;  o *= (mask != 0)
 //
-// One CTA = one (sample, head, 128-query tile).  Keys are consumed in tiles of 128 with an online
-// softmax.  Both contractions run on tcgen05:
+// One CTA = one (sample, head, 128-query tile); keys are consumed in tiles of 128.  Both contractions run
+// on tcgen05:
 //     S = Q K^T   : M=128 queries, N=128 keys, K=DHP (head_dim padded to a multiple of 16)
-//     O = P V     : M=128 queries, N=DHP,      K=128 keys   (V arrives transposed, keys contiguous)
+//     O += P V    : M=128 queries, N=DHP,      K=128 keys   (V arrives transposed, keys contiguous),
+//                   accumulated in TMEM across key tiles and read back once.
 // Q/K/V^T/P are staged in shared memory in the canonical K-major swizzled layouts (a 64-element
-// SWIZZLE_128B panel plus a 16/32-element SWIZZLE_32B/64B tail panel for head_dim 72/96),
-// accumulators live in TMEM, the softmax runs in registers in fp32 (exp2 with folded scale).
+// SWIZZLE_128B panel plus a 16/32-element SWIZZLE_32B/64B tail panel for head_dim 72/96) with cp.async;
+// the next key tile's K (V) is prefetched while the softmax (P V product) of the current one runs.
+//
+// Softmax without a running maximum: q and k are LayerNorm'ed without affine (modules.py:168) and RoPE is a
+// rotation scaled by `mag`, so |q| = |k| = mag*sqrt(dh) and every logit obeys
+//     q.k / sqrt(dh) <= mag^2 * sqrt(dh)            (8.5 for dh=72, 9.8 for dh=96, mag = 1).
+// softmax is shift invariant, so that constant bound replaces the row maximum: p = exp(s - bound) can never
+// overflow, stays far above fp32/bf16 underflow (>= e^-2*bound), and no online rescaling pass is needed.
+// (For fp16 operands the host lowers the bound by 8*ln2 so that p stays clear of the fp16 subnormal range;
+// the scale cancels in the final division by the row sum.)
 // Two CTAs are resident per SM so one CTA's softmax overlaps the other's MMAs / loads.
 #pragma once
 #include "common.cuh"
@@ -38,11 +47,14 @@ template <int DH> struct AttnCfg {
     static_assert(kTail == 16 || kTail == 32, "head_dim must be 72..80 or 88..96 (64 + 16/32 tail)");
 };
 
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
 template <typename OT, int DH>
 __global__ void __launch_bounds__(128, 2)
 attention_kernel(const OT* __restrict__ q, const OT* __restrict__ k, const OT* __restrict__ vt,
                  const float* __restrict__ seg, const int* __restrict__ seg_uniform,
-                 OT* __restrict__ out, int heads, int tokens, int tokens_v, float scale_log2e,
+                 OT* __restrict__ out, int heads, int tokens, int tokens_v, float scale_log2e, float bound_log2e,
                  float* __restrict__ dbg_s, float* __restrict__ dbg_o)
 {
     using C = AttnCfg<DH>;
@@ -61,46 +73,10 @@ attention_kernel(const OT* __restrict__ q, const OT* __restrict__ k, const OT* _
     const OT* vg = vt + bh * DH * tokens_v;
     const float* segb = seg + (size_t)sample * tokens;
     const bool uniform = seg_uniform[sample] != 0;
-
-    if (tid == 0) { mbar_init(bar_s, 1); mbar_init(bar_o, 1); mbar_fence_init(); }
-    if (warp == 0) { __syncwarp(); tmem_alloc(tmem_slot, 256); }
-
-    // ---- stage the Q tile (zero rows past the sequence end, zero pad columns) ----
-    // All copies are 16-byte cp.async (zero-fill for out-of-range chunks), issued back to back so that the
-    // whole tile is in flight at once; Q joins the first K/V group.
-#pragma unroll
-    for (int i = 0; i < C::kChunks; ++i) {
-        const int id = tid + i * 128;
-        const int r = id / C::kChunks, c = id % C::kChunks;
-        const bool ok = q0 + r < tokens && c < C::kRealChunks;
-        uint8_t* dst = c < 8 ? smem + C::kOffQ + swz_offset<128>(r, c)
-                             : smem + C::kOffQT + swz_offset<C::kTailBytes>(r, c - 8);
-        cp_async16(dst, ok ? qg + (size_t)(q0 + r) * DH + c * 8 : qg, ok ? 16 : 0);
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-    const uint32_t t_s = tmem_base + (uint32_t(warp * 32) << 16);        // S accumulator, columns [0,128)
-    const uint32_t t_o = t_s + 128;                                      // O accumulator, columns [128,128+DHP)
-
-    const int qi = q0 + tid;
-    const bool q_ok = qi < tokens;
-    const float my_seg = q_ok ? segb[qi] : 0.f;
-
-    float o_acc[C::kDHP];
-#pragma unroll
-    for (int j = 0; j < C::kDHP; ++j) o_acc[j] = 0.f;
-    float m_run = -INFINITY, l_run = 0.f;
-
-    constexpr uint32_t idesc_s = umma_idesc(Op16<OT>::kUmmaFormat, 128, 128);
-    constexpr uint32_t idesc_o = umma_idesc(Op16<OT>::kUmmaFormat, 128, C::kDHP);
     const int kv_tiles = (tokens + 127) / 128;
-    uint32_t ph = 0;
 
-    for (int t = 0; t < kv_tiles; ++t, ph ^= 1) {
-        const int kv0 = t * 128;
-        // ---- stage K tile, V^T tile, key segment ids (previous tile's MMAs have retired: bar_o was awaited) ----
+    // 16-byte cp.async copies (zero-fill for out-of-range chunks), issued back to back so a whole tile is in flight
+    auto load_k = [&](int kv0) {
 #pragma unroll
         for (int i = 0; i < C::kChunks; ++i) {
             const int id = tid + i * 128;
@@ -110,6 +86,8 @@ attention_kernel(const OT* __restrict__ q, const OT* __restrict__ k, const OT* _
                                  : smem + C::kOffKT + swz_offset<C::kTailBytes>(r, c - 8);
             cp_async16(dst, ok ? kg + (size_t)(kv0 + r) * DH + c * 8 : kg, ok ? 16 : 0);
         }
+    };
+    auto load_v = [&](int kv0) {
 #pragma unroll
         for (int i = 0; i < C::kDHP * 16 / 128; ++i) {
             const int id = tid + i * 128;
@@ -120,8 +98,46 @@ attention_kernel(const OT* __restrict__ q, const OT* __restrict__ k, const OT* _
             cp_async16(smem + C::kOffV + (c >> 3) * C::kVPanel + swz_offset<128>(d, c & 7),
                        ok ? vg + (size_t)d * tokens_v + kv : vg, bytes);
         }
+    };
+
+    if (tid == 0) { mbar_init(bar_s, 1); mbar_init(bar_o, 1); mbar_fence_init(); }
+    if (warp == 0) { __syncwarp(); tmem_alloc(tmem_slot, 256); }
+
+    // ---- group 0: Q tile + K tile 0;  group 1: V tile 0 ----
+#pragma unroll
+    for (int i = 0; i < C::kChunks; ++i) {
+        const int id = tid + i * 128;
+        const int r = id / C::kChunks, c = id % C::kChunks;
+        const bool ok = q0 + r < tokens && c < C::kRealChunks;
+        uint8_t* dst = c < 8 ? smem + C::kOffQ + swz_offset<128>(r, c)
+                             : smem + C::kOffQT + swz_offset<C::kTailBytes>(r, c - 8);
+        cp_async16(dst, ok ? qg + (size_t)(q0 + r) * DH + c * 8 : qg, ok ? 16 : 0);
+    }
+    load_k(0);
+    cp_async_commit();
+    load_v(0);
+    cp_async_commit();
+
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t t_s = tmem_base + (uint32_t(warp * 32) << 16);        // S accumulator, columns [0,128)
+    const uint32_t t_o = t_s + 128;                                      // O accumulator, columns [128,128+DHP)
+
+    const int qi = q0 + tid;
+    const bool q_ok = qi < tokens;
+    const float my_seg = q_ok ? segb[qi] : 0.f;
+    float l_run = 0.f;
+
+    constexpr uint32_t idesc_s = umma_idesc(Op16<OT>::kUmmaFormat, 128, 128);
+    constexpr uint32_t idesc_o = umma_idesc(Op16<OT>::kUmmaFormat, 128, C::kDHP);
+    uint32_t ph = 0;
+
+    for (int t = 0; t < kv_tiles; ++t, ph ^= 1) {
+        const int kv0 = t * 128;
         seg_kv[tid] = (kv0 + tid < tokens) ? segb[kv0 + tid] : 0.f;
-        cp_async_wait_all();
+        cp_async_wait<1>();                                            // K(t) (and Q) have landed; V(t) may still be in flight
         fence_proxy_async_smem();
         __syncthreads();
 
@@ -140,11 +156,14 @@ attention_kernel(const OT* __restrict__ q, const OT* __restrict__ k, const OT* _
         }
         mbar_wait(bar_s, ph);
         tc_fence_after();
+        // the K buffer is free again: prefetch the next key tile behind the softmax
+        if (t + 1 < kv_tiles) load_k(kv0 + 128);
+        cp_async_commit();
 
-        // ---- online softmax, pass 1: masked row maximum ----
+        // ---- p = exp2(s*c - bound*c)  (single pass, see header), row sum, P -> smem (A operand of P V) ----
         const int kv_valid = min(128, tokens - kv0);
         const bool dense = uniform && kv_valid == 128;                 // CTA-uniform: no per-element masking needed
-        float tmax = -INFINITY;
+        float lsum = 0.f;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             uint32_t v[32];
@@ -154,39 +173,14 @@ attention_kernel(const OT* __restrict__ q, const OT* __restrict__ k, const OT* _
 #pragma unroll
                 for (int j = 0; j < 32; ++j) dbg_s[tid * 128 + c * 32 + j] = __uint_as_float(v[j]);   // raw S tile (debug)
             }
-            if (dense) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) tmax = fmaxf(tmax, __uint_as_float(v[j]));
-            } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int col = c * 32 + j;
-                    const bool ok = col < kv_valid && (uniform || seg_kv[col] == my_seg);
-                    tmax = fmaxf(tmax, ok ? __uint_as_float(v[j]) : -INFINITY);
-                }
-            }
-        }
-        const float m_new = fmaxf(m_run, tmax);
-        const float m_scaled = (m_new == -INFINITY) ? 0.f : m_new * scale_log2e;
-        const float alpha = (m_run == -INFINITY) ? 0.f : fast_exp2(m_run * scale_log2e - m_scaled);
-        m_run = m_new;
-
-        // ---- pass 2: p = exp2(s*c - m*c), row sum of the ROUNDED p, P -> smem (A operand of P V) ----
-        float lsum = 0.f;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            uint32_t v[32];
-            tmem_ld32(t_s + c * 32, v);
-            tmem_ld_wait();
             uint32_t packed[16];
             if (dense) {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    const float p0 = fast_exp2(fmaf(__uint_as_float(v[2 * j]), scale_log2e, -m_scaled));
-                    const float p1 = fast_exp2(fmaf(__uint_as_float(v[2 * j + 1]), scale_log2e, -m_scaled));
+                    const float p0 = fast_exp2(fmaf(__uint_as_float(v[2 * j]), scale_log2e, -bound_log2e));
+                    const float p1 = fast_exp2(fmaf(__uint_as_float(v[2 * j + 1]), scale_log2e, -bound_log2e));
                     packed[j] = Op16<OT>::pack(p0, p1);
-                    const float2 r = Op16<OT>::unpack(packed[j]);
-                    lsum += r.x + r.y;
+                    lsum += p0 + p1;
                 }
             } else {
 #pragma unroll
@@ -194,11 +188,10 @@ attention_kernel(const OT* __restrict__ q, const OT* __restrict__ k, const OT* _
                     const int col = c * 32 + 2 * j;
                     const bool ok0 = col < kv_valid && (uniform || seg_kv[col] == my_seg);
                     const bool ok1 = col + 1 < kv_valid && (uniform || seg_kv[col + 1] == my_seg);
-                    const float p0 = ok0 ? fast_exp2(fmaf(__uint_as_float(v[2 * j]), scale_log2e, -m_scaled)) : 0.f;
-                    const float p1 = ok1 ? fast_exp2(fmaf(__uint_as_float(v[2 * j + 1]), scale_log2e, -m_scaled)) : 0.f;
+                    const float p0 = ok0 ? fast_exp2(fmaf(__uint_as_float(v[2 * j]), scale_log2e, -bound_log2e)) : 0.f;
+                    const float p1 = ok1 ? fast_exp2(fmaf(__uint_as_float(v[2 * j + 1]), scale_log2e, -bound_log2e)) : 0.f;
                     packed[j] = Op16<OT>::pack(p0, p1);
-                    const float2 r = Op16<OT>::unpack(packed[j]);
-                    lsum += r.x + r.y;
+                    lsum += p0 + p1;
                 }
             }
 #pragma unroll
@@ -208,41 +201,39 @@ attention_kernel(const OT* __restrict__ q, const OT* __restrict__ k, const OT* _
                     make_uint4(packed[g * 4], packed[g * 4 + 1], packed[g * 4 + 2], packed[g * 4 + 3]);
             }
         }
-        l_run = l_run * alpha + lsum;
+        l_run += lsum;
+        cp_async_wait<1>();                                            // V(t) has landed (K(t+1) may still be in flight)
         tc_fence_before();
         fence_proxy_async_smem();
         __syncthreads();
 
-        // ---- O_tile = P V ----
+        // ---- O += P V ----
         if (tid == 0) {
             tc_fence_after();
 #pragma unroll
             for (int kk = 0; kk < 8; ++kk) {
                 const uint64_t dp = umma_desc_kmajor(smem_u32(smem + C::kOffP + (kk >> 2) * C::kPPanel), 128) + 2 * (kk & 3);
                 const uint64_t dv = umma_desc_kmajor(smem_u32(smem + C::kOffV + (kk >> 2) * C::kVPanel), 128) + 2 * (kk & 3);
-                umma_ss(tmem_base + 128, dp, dv, idesc_o, kk != 0);
+                umma_ss(tmem_base + 128, dp, dv, idesc_o, (t | kk) != 0);
             }
             umma_commit(bar_o);
         }
-        mbar_wait(bar_o, ph);
+        mbar_wait(bar_o, ph);                                          // P and V buffers are free, O(t) accumulated
         tc_fence_after();
-#pragma unroll
-        for (int c = 0; c < C::kDHP / 16; ++c) {
-            uint32_t v[16];
-            tmem_ld16(t_o + c * 16, v);
-            tmem_ld_wait();
-            if (dbg_o != nullptr && t == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) dbg_o[tid * C::kDHP + c * 16 + j] = __uint_as_float(v[j]);  // raw P V tile (debug)
-            }
-#pragma unroll
-            for (int j = 0; j < 16; ++j) o_acc[c * 16 + j] = o_acc[c * 16 + j] * alpha + __uint_as_float(v[j]);
-        }
-        tc_fence_before();
-        __syncthreads();          // all TMEM reads + smem operand reads of this tile are done before restaging
+        if (t + 1 < kv_tiles) load_v(kv0 + 128);
+        cp_async_commit();
     }
+    cp_async_wait<0>();
 
-    // ---- normalise, zero padded queries (mask != 0), write (M, heads*DH) rows for the proj GEMM ----
+    // ---- O / l, zero padded queries (mask != 0), write (M, heads*DH) rows for the proj GEMM ----
+    float o[C::kDHP];
+#pragma unroll
+    for (int c = 0; c < C::kDHP / 16; ++c) tmem_ld16(t_o + c * 16, reinterpret_cast<uint32_t*>(o) + c * 16);
+    tmem_ld_wait();
+    if (dbg_o != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+#pragma unroll
+        for (int j = 0; j < C::kDHP; ++j) dbg_o[tid * C::kDHP + j] = o[j];                         // raw P V accumulator (debug)
+    }
     if (q_ok) {
         const float inv = (my_seg != 0.f && l_run > 0.f) ? 1.0f / l_run : 0.f;
         OT* dst = out + ((size_t)sample * tokens + qi) * (heads * DH) + head * DH;
@@ -250,10 +241,11 @@ attention_kernel(const OT* __restrict__ q, const OT* __restrict__ k, const OT* _
         for (int c = 0; c < DH / 8; ++c) {
             uint32_t pk[4];
 #pragma unroll
-            for (int p = 0; p < 4; ++p) pk[p] = Op16<OT>::pack(o_acc[c * 8 + 2 * p] * inv, o_acc[c * 8 + 2 * p + 1] * inv);
+            for (int p = 0; p < 4; ++p) pk[p] = Op16<OT>::pack(o[c * 8 + 2 * p] * inv, o[c * 8 + 2 * p + 1] * inv);
             *reinterpret_cast<uint4*>(dst + c * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         }
     }
+    tc_fence_before();
     __syncthreads();
     if (warp == 0) { __syncwarp(); tmem_dealloc(tmem_base, 256); }
 }

@@ -233,19 +233,23 @@ int launch_attention(fitv2_handle* h, const void* q, const void* k, const void* 
                      float* dbg_s = nullptr, float* dbg_o = nullptr) {
     const fitv2_config& c = h->cfg;
     const float scale_log2e = (1.0f / sqrtf((float)c.head_dim)) * 1.4426950408889634f;
+    // logit bound from the affine-free QK-LayerNorm (see attention.cuh): |q.k|/sqrt(dh) <= mag^2 * sqrt(dh); 2% margin.
+    // fp16 operands: shift by 8 binades so that P stays in the normal fp16 range (cancels in O / l).
+    const float bound_log2e = c.rope_magnitude * c.rope_magnitude * sqrtf((float)c.head_dim) * 1.02f * 1.4426950408889634f -
+                              (c.operand_dtype == FITV2_OPERAND_FP16 ? 8.0f : 0.0f);
     dim3 grid((tokens + 127) / 128, c.num_heads, rows);
     if (c.head_dim == 72) {
         auto kern = attention_kernel<OT, 72>;
         static bool configured = false;
         if (!configured) { CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<72>::kSmemBytes)); configured = true; }
         kern<<<grid, 128, AttnCfg<72>::kSmemBytes, st>>>((const OT*)q, (const OT*)k, (const OT*)vt, seg, seg_uniform, (OT*)out,
-                                                        c.num_heads, tokens, tokens_v, scale_log2e, dbg_s, dbg_o);
+                                                        c.num_heads, tokens, tokens_v, scale_log2e, bound_log2e, dbg_s, dbg_o);
     } else if (c.head_dim == 96) {
         auto kern = attention_kernel<OT, 96>;
         static bool configured = false;
         if (!configured) { CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<96>::kSmemBytes)); configured = true; }
         kern<<<grid, 128, AttnCfg<96>::kSmemBytes, st>>>((const OT*)q, (const OT*)k, (const OT*)vt, seg, seg_uniform, (OT*)out,
-                                                        c.num_heads, tokens, tokens_v, scale_log2e, dbg_s, dbg_o);
+                                                        c.num_heads, tokens, tokens_v, scale_log2e, bound_log2e, dbg_s, dbg_o);
     } else {
         return fail(FITV2_E_INVALID, "head_dim %d not supported (72 or 96)", c.head_dim);
     }

@@ -115,38 +115,49 @@ ln_modulate_kernel(const float* __restrict__ x, const float* __restrict__ shift,
     const int m = warp;
     const int nvec = D >> 2;
     const float4* xr = reinterpret_cast<const float4*>(x + (size_t)m * D);
-    float4 v[NV];
-    float s = 0.f;
+    const int sample = m / tokens;
+    const float4* sh = reinterpret_cast<const float4*>(shift + (size_t)sample * mod_ld);
+    const float4* sc = reinterpret_cast<const float4*>(scale + (size_t)sample * mod_ld);
+    // every load of the row (x, shift, scale) is issued before the first use: 3*NV 128-bit requests in flight per lane
+    float4 v[NV], a[NV], g[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
         const int j = lane + 32 * i;
-        v[i] = (j < nvec) ? xr[j] : make_float4(0.f, 0.f, 0.f, 0.f);
-        s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        v[i] = (j < nvec) ? ld_stream_f4(xr + j) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
+    constexpr bool kEarlyMod = NV <= 9;                 // wider rows (3B) would not fit the register file
+    if constexpr (kEarlyMod) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int j = lane + 32 * i;
+            a[i] = (j < nvec) ? __ldg(sh + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            g[i] = (j < nvec) ? __ldg(sc + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
     const float mean = warp_sum(s) / (float)D;
     float q = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
         const int j = lane + 32 * i;
         if (j < nvec) {
-            const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
-            q += (a * a + b * b) + (c * c + d * d);
+            const float d0 = v[i].x - mean, d1 = v[i].y - mean, d2 = v[i].z - mean, d3 = v[i].w - mean;
+            q += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
         }
     }
     const float rstd = rsqrtf(warp_sum(q) / (float)D + 1e-6f);
-    const int sample = m / tokens;
-    const float4* sh = reinterpret_cast<const float4*>(shift + (size_t)sample * mod_ld);
-    const float4* sc = reinterpret_cast<const float4*>(scale + (size_t)sample * mod_ld);
     uint2* hr = reinterpret_cast<uint2*>(h + (size_t)m * D);
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
         const int j = lane + 32 * i;
         if (j < nvec) {
-            const float4 a = __ldg(sh + j), g = __ldg(sc + j);
-            const float o0 = (v[i].x - mean) * rstd * (1.f + g.x) + a.x;
-            const float o1 = (v[i].y - mean) * rstd * (1.f + g.y) + a.y;
-            const float o2 = (v[i].z - mean) * rstd * (1.f + g.z) + a.z;
-            const float o3 = (v[i].w - mean) * rstd * (1.f + g.w) + a.w;
+            if constexpr (!kEarlyMod) { a[i] = __ldg(sh + j); g[i] = __ldg(sc + j); }
+            const float o0 = (v[i].x - mean) * rstd * (1.f + g[i].x) + a[i].x;
+            const float o1 = (v[i].y - mean) * rstd * (1.f + g[i].y) + a[i].y;
+            const float o2 = (v[i].z - mean) * rstd * (1.f + g[i].z) + a[i].z;
+            const float o3 = (v[i].w - mean) * rstd * (1.f + g[i].w) + a[i].w;
             hr[j] = make_uint2(Op16<OT>::pack(o0, o1), Op16<OT>::pack(o2, o3));
         }
     }
