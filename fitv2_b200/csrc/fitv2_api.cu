@@ -17,6 +17,9 @@ using namespace fitv2;
 
 namespace {
 
+// Thread-block cluster size of the production GEMMs (weight-tile TMA multicast across the cluster).
+constexpr int kGemmCluster = 2;
+
 thread_local std::string g_last_error;
 
 int fail(int code, const char* fmt, ...) {
@@ -182,33 +185,46 @@ inline void prof_end(fitv2_handle* h, cudaStream_t st) {
     h->prof_open = -1;
 }
 
-template <int BN, int EPI, typename OT, int DH>
+template <int BN, int EPI, typename OT, int DH, int CL = kGemmCluster>
 int launch_gemm_t(fitv2_handle* h, const CUtensorMap& ma, const CUtensorMap& mb, int M, int N, int K, int b_row_off,
                   const GemmEpi& ep, cudaStream_t st) {
-    using Cfg = GemmCfg<BN, EPI, DH>;
-    auto kern = gemm_tc_kernel<BN, EPI, OT, DH>;
+    using Cfg = GemmCfg<BN, EPI, DH, CL>;
+    auto kern = gemm_tc_kernel<BN, EPI, OT, DH, CL>;
     static bool configured = false;
     if (!configured) {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
         configured = true;
     }
     if (N % BN != 0) return fail(FITV2_E_INVALID, "GEMM N=%d is not a multiple of the tile width %d", N, BN);
-    const int tiles = ((M + kGemmBM - 1) / kGemmBM) * (N / BN);
-    const int grid = tiles < h->num_sms ? tiles : h->num_sms;
-    kern<<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(ma, mb, M, N, K, b_row_off, ep);
+    const int m_tiles = (M + kGemmBM - 1) / kGemmBM;
+    const int groups = ((m_tiles + CL - 1) / CL) * (N / BN);
+    const int max_clusters = h->num_sms / CL;
+    const int grid = (groups < max_clusters ? groups : max_clusters) * CL;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ma, mb, M, N, K, b_row_off, ep));
     CUDA_TRY(cudaGetLastError());
     h->launches++;
     return FITV2_OK;
 }
 
-template <int EPI, typename OT>
+template <int EPI, typename OT, int CL = kGemmCluster>
 int launch_gemm_bn(fitv2_handle* h, int bn, const CUtensorMap& ma, const CUtensorMap& mb, int M, int N, int K,
                    int b_row_off, const GemmEpi& ep, cudaStream_t st) {
     switch (bn) {
-        case 128: return launch_gemm_t<128, EPI, OT, 0>(h, ma, mb, M, N, K, b_row_off, ep, st);
-        case 144: return launch_gemm_t<144, EPI, OT, 0>(h, ma, mb, M, N, K, b_row_off, ep, st);
-        case 192: return launch_gemm_t<192, EPI, OT, 0>(h, ma, mb, M, N, K, b_row_off, ep, st);
-        case 256: return launch_gemm_t<256, EPI, OT, 0>(h, ma, mb, M, N, K, b_row_off, ep, st);
+        case 128: return launch_gemm_t<128, EPI, OT, 0, CL>(h, ma, mb, M, N, K, b_row_off, ep, st);
+        case 144: return launch_gemm_t<144, EPI, OT, 0, CL>(h, ma, mb, M, N, K, b_row_off, ep, st);
+        case 192: return launch_gemm_t<192, EPI, OT, 0, CL>(h, ma, mb, M, N, K, b_row_off, ep, st);
+        case 256: return launch_gemm_t<256, EPI, OT, 0, CL>(h, ma, mb, M, N, K, b_row_off, ep, st);
     }
     return fail(FITV2_E_INVALID, "unsupported GEMM tile width %d", bn);
 }
@@ -219,7 +235,8 @@ int pick_bn(int M, int N, int num_sms) {
     int best = 0; long best_cost = 0;
     for (int bn : cands) {
         if (N % bn) continue;
-        const long tiles = (long)((M + kGemmBM - 1) / kGemmBM) * (N / bn);
+        const long m_tiles = (M + kGemmBM - 1) / kGemmBM;
+        const long tiles = ((m_tiles + kGemmCluster - 1) / kGemmCluster) * kGemmCluster * (N / bn);
         const long waves = (tiles + num_sms - 1) / num_sms;
         const long cost = waves * (bn + 16);
         if (!best || cost < best_cost) { best = bn; best_cost = cost; }
@@ -292,10 +309,10 @@ int ensure_maps(fitv2_handle* h) {
     if ((rc = make_map(&h->map_hidden, h->ws + l.hidden, c.operand_dtype, M, Hm, Hm, 128))) return rc;
     h->bn_resid = pick_bn((int)M, (int)D, h->num_sms);
     if (!h->bn_resid) return fail(FITV2_E_INVALID, "hidden_size %d has no supported tile width (multiple of 128/144/192/256)", (int)D);
-    if ((rc = make_map(&h->map_wqkv, h->w[FITV2_W_QKV_W], c.operand_dtype, L * 3 * D, D, D, 2 * c.head_dim))) return rc;
-    if ((rc = make_map(&h->map_wproj, h->w[FITV2_W_PROJ_W], c.operand_dtype, L * D, D, D, h->bn_resid))) return rc;
-    if ((rc = make_map(&h->map_wgu, h->w[FITV2_W_GATEUP_W], c.operand_dtype, L * 2 * Hm, D, D, 256))) return rc;
-    if ((rc = make_map(&h->map_wfc2, h->w[FITV2_W_FC2_W], c.operand_dtype, L * D, Hm, Hm, h->bn_resid))) return rc;
+    if ((rc = make_map(&h->map_wqkv, h->w[FITV2_W_QKV_W], c.operand_dtype, L * 3 * D, D, D, 2 * c.head_dim / kGemmCluster))) return rc;
+    if ((rc = make_map(&h->map_wproj, h->w[FITV2_W_PROJ_W], c.operand_dtype, L * D, D, D, h->bn_resid / kGemmCluster))) return rc;
+    if ((rc = make_map(&h->map_wgu, h->w[FITV2_W_GATEUP_W], c.operand_dtype, L * 2 * Hm, D, D, 256 / kGemmCluster))) return rc;
+    if ((rc = make_map(&h->map_wfc2, h->w[FITV2_W_FC2_W], c.operand_dtype, L * D, Hm, Hm, h->bn_resid / kGemmCluster))) return rc;
     h->maps_valid = true;
     return FITV2_OK;
 }
@@ -567,17 +584,23 @@ int fitv2_cfg_euler(float* z, const float* v2, float cfg_scale, float dsigma, co
 int fitv2_debug_gemm(fitv2_handle* h, int epilogue, const void* a, const void* w, const float* bias, float* out32, int M,
                      int N, int K, int bn, void* stream) {
     if (!h || !a || !w || !bias || !out32) return fail(FITV2_E_INVALID, "null argument");
-    if (epilogue != EPI_PLAIN) return fail(FITV2_E_INVALID, "debug_gemm supports the plain epilogue only");
+    if (epilogue != EPI_PLAIN && epilogue != EPI_PLAIN + 1)
+        return fail(FITV2_E_INVALID, "debug_gemm supports the plain epilogue only (3 = single CTA, 4 = 2-CTA multicast cluster)");
+    const bool clustered = epilogue == EPI_PLAIN + 1;
     CUtensorMap ma, mb;
     int rc;
     if ((rc = make_map(&ma, a, h->cfg.operand_dtype, M, K, K, 128))) return rc;
-    if ((rc = make_map(&mb, w, h->cfg.operand_dtype, N, K, K, bn))) return rc;
+    if ((rc = make_map(&mb, w, h->cfg.operand_dtype, N, K, K, clustered ? bn / 2 : bn))) return rc;
     GemmEpi ep;
     memset(&ep, 0, sizeof(ep));
     ep.bias = bias; ep.out32 = out32; ep.ld_out = N; ep.tokens = 1;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (h->cfg.operand_dtype == FITV2_OPERAND_FP16) return launch_gemm_bn<EPI_PLAIN, __half>(h, bn, ma, mb, M, N, K, 0, ep, st);
-    return launch_gemm_bn<EPI_PLAIN, __nv_bfloat16>(h, bn, ma, mb, M, N, K, 0, ep, st);
+    if (clustered) {
+        if (h->cfg.operand_dtype == FITV2_OPERAND_FP16) return launch_gemm_bn<EPI_PLAIN, __half, 2>(h, bn, ma, mb, M, N, K, 0, ep, st);
+        return launch_gemm_bn<EPI_PLAIN, __nv_bfloat16, 2>(h, bn, ma, mb, M, N, K, 0, ep, st);
+    }
+    if (h->cfg.operand_dtype == FITV2_OPERAND_FP16) return launch_gemm_bn<EPI_PLAIN, __half, 1>(h, bn, ma, mb, M, N, K, 0, ep, st);
+    return launch_gemm_bn<EPI_PLAIN, __nv_bfloat16, 1>(h, bn, ma, mb, M, N, K, 0, ep, st);
 }
 
 int fitv2_debug_attention(fitv2_handle* h, const void* q, const void* k, const void* vt, const float* mask, void* out,

@@ -49,7 +49,7 @@ constexpr int kGemmBK = 64;
 constexpr int kGemmThreads = 320;     // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
 constexpr int kSmemBudget = 227 * 1024;
 
-template <int BN, int EPI, int DH> struct GemmCfg {
+template <int BN, int EPI, int DH, int CL = 1> struct GemmCfg {
     static constexpr int kABytes = kGemmBM * kGemmBK * 2;
     static constexpr int kBBytes = BN * kGemmBK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
@@ -67,6 +67,11 @@ template <int BN, int EPI, int DH> struct GemmCfg {
     static_assert(kBBytes % 1024 == 0, "B stage must keep 1024B alignment for SWIZZLE_128B");
     static_assert(kStages >= 3, "pipeline too shallow");
     static_assert(EPI != EPI_QKV || DH * 64 <= kEpiWarpBytes, "V^T staging does not fit");
+    // CL = 2: the two CTAs of a cluster work on vertically adjacent tiles (same columns); each loads one half of
+    // the weight tile and TMA-multicasts it into both CTAs' shared memory, halving the L2 -> SM traffic of B.
+    static constexpr int kBRowsPerCta = BN / CL;
+    static_assert(CL == 1 || CL == 2, "cluster size 1 or 2");
+    static_assert((kBRowsPerCta * kGemmBK * 2) % 1024 == 0, "multicast slice must keep 1024B alignment");
 };
 
 // ---- warp-private staging slab: 32 rows x 128 bytes, 16-byte chunk c of row r lives at chunk (c ^ (r & 7)) ----
@@ -79,12 +84,12 @@ template <int CPR> __device__ __forceinline__ void slab_task(int i, int lane, in
     c = task % CPR;
 }
 
-template <int BN, int EPI, typename OT, int DH>
+template <int BN, int EPI, typename OT, int DH, int CL>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                int M, int N, int K, int b_row_offset, GemmEpi ep)
 {
-    using Cfg = GemmCfg<BN, EPI, DH>;
+    using Cfg = GemmCfg<BN, EPI, DH, CL>;
     constexpr int STAGES = Cfg::kStages;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -102,19 +107,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     const int lane = threadIdx.x & 31;
     const int m_tiles = (M + kGemmBM - 1) / kGemmBM;
     const int n_tiles = N / BN;
-    const int num_tiles = m_tiles * n_tiles;
+    // work items are tile groups of CL vertically adjacent tiles; CTA `cta_rank` of the cluster takes row tile
+    // group * CL + cta_rank (a phantom tile past the M tail computes on zero-filled rows and stores nothing)
+    const int num_groups = ((m_tiles + CL - 1) / CL) * n_tiles;
     const int num_kb = (K + kGemmBK - 1) / kGemmBK;
+    const uint32_t cta_rank = CL > 1 ? cluster_ctarank() : 0u;
+    const int group0 = blockIdx.x / CL, group_stride = gridDim.x / CL;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tma_a);
         tma_prefetch_desc(&tma_b);
-        for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], CL); }
         for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 256); }
         mbar_fence_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, 512);
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CL > 1) cluster_sync(); else __syncthreads();   // peer barriers must be initialised before any multicast
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -122,14 +131,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         if (lane == 0) {
             // ------------------------------ TMA producer ------------------------------
             int stage = 0; uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m_tile = tile / n_tiles, n_tile = tile % n_tiles;   // n fastest: a wave shares few A tiles
+            for (int grp = group0; grp < num_groups; grp += group_stride) {
+                const int m_tile = (grp / n_tiles) * CL + (int)cta_rank, n_tile = grp % n_tiles;   // n fastest: a wave shares few A tiles
                 for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_wait(&empty_bar[stage], phase ^ 1);      // CL > 1: every CTA of the cluster has drained this slot
                     mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
                     tma_load_2d(&tma_a, &full_bar[stage], smem_a + stage * Cfg::kABytes, kb * kGemmBK, m_tile * kGemmBM);
-                    tma_load_2d(&tma_b, &full_bar[stage], smem_b + stage * Cfg::kBBytes, kb * kGemmBK,
-                                b_row_offset + n_tile * BN);
+                    if constexpr (CL == 1) {
+                        tma_load_2d(&tma_b, &full_bar[stage], smem_b + stage * Cfg::kBBytes, kb * kGemmBK,
+                                    b_row_offset + n_tile * BN);
+                    } else {
+                        tma_load_2d_multicast(&tma_b, &full_bar[stage],
+                                              smem_b + stage * Cfg::kBBytes + cta_rank * (Cfg::kBRowsPerCta * kGemmBK * 2),
+                                              kb * kGemmBK, b_row_offset + n_tile * BN + (int)cta_rank * Cfg::kBRowsPerCta,
+                                              (uint16_t)((1u << CL) - 1));
+                    }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -139,7 +155,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             // ------------------------------ MMA issuer ------------------------------
             constexpr uint32_t idesc = umma_idesc(Op16<OT>::kUmmaFormat, kGemmBM, BN);
             int stage = 0; uint32_t phase = 0; int it = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            for (int grp = group0; grp < num_groups; grp += group_stride, ++it) {
                 const int acc = it & 1;
                 const uint32_t acc_phase = (it >> 1) & 1;
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
@@ -153,7 +169,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 #pragma unroll
                     for (int kk = 0; kk < kGemmBK / 16; ++kk)        // +32 bytes (>>4 = 2) per K=16 step inside the 128B atom
                         umma_ss(d_tmem, da + 2 * kk, db + 2 * kk, idesc, (kb | kk) != 0);
-                    umma_commit(&empty_bar[stage]);                   // smem slot free once these MMAs retire
+                    if constexpr (CL == 1) umma_commit(&empty_bar[stage]);   // smem slot free once these MMAs retire
+                    else umma_commit_multicast(&empty_bar[stage], (uint16_t)((1u << CL) - 1));   // ... in every CTA of the cluster
                     if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -165,8 +182,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         const int half = (warp - 2) >> 2;                             // 0: left half of the tile columns, 1: right half
         uint8_t* stg = smem_epi + (warp - 2) * Cfg::kEpiWarpBytes;    // warp-private staging slab
         int it = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-            const int m_tile = tile / n_tiles, n_tile = tile % n_tiles;
+        for (int grp = group0; grp < num_groups; grp += group_stride, ++it) {
+            const int m_tile = (grp / n_tiles) * CL + (int)cta_rank, n_tile = grp % n_tiles;
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
             const uint32_t t_row = tmem_base + acc * Cfg::kAccStride + (uint32_t(quarter * 32) << 16);
@@ -412,7 +429,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     }
 
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CL > 1) cluster_sync(); else __syncthreads();   // the peer may still multicast into / signal this CTA
     if (warp == 1) {
         __syncwarp();
         tmem_dealloc(tmem_base, 512);
