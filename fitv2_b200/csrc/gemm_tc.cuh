@@ -3,12 +3,19 @@
 //   C[M, N] = A[M, K] (16-bit, K-major) x W[N, K]^T (16-bit, K-major nn.Linear weight), fp32 accumulate in TMEM.
 //
 //   warp 0 : TMA producer  (cp.async.bulk.tensor, 128B swizzle, STAGES-deep mbarrier ring)
-//   warp 1 : TMEM allocator + single-thread tcgen05.mma issuer (128 x BN x 16 per instruction)
+//   warp 1 : TMEM allocator + single-thread tcgen05.mma issuer
 //   warps 2-9 : epilogue.  Warp pairs (w, w+4) share a TMEM lane quarter and split the tile columns in two
 //               halves.  tcgen05.ld gives every lane one accumulator ROW; a warp-private shared-memory slab
 //               (XOR-swizzled, conflict-free) transposes it so that the global accesses are coalesced
 //               (a warp instruction touches 4 full 128-byte lines instead of 32 partial ones).
 //               TMEM accumulators are double-buffered: the epilogue of tile i overlaps the main loop of i+1.
+//
+// CL = 1: one CTA per 128 x BN tile, tcgen05.mma.cta_group::1.
+// CL = 2: a cluster of two CTAs (one TPC) computes a 256 x BN tile with tcgen05.mma.cta_group::2: each CTA
+//         stages its own 128 rows of A and only HALF of the weight tile, the leader CTA issues the UMMAs, each
+//         SM accumulates and post-processes its own 128 rows.  1-SM UMMA is bounded by shared-memory bandwidth
+//         on Blackwell (operand reads + TMA writes share 128 B/clk/SM: measured 44% / 76% tensor-pipe
+//         utilisation at BN = 144 / 256); the pair halves the B traffic per SM.
 //
 // Fused epilogues (reference lines they replace, paths relative to the reference repo):
 //   EPI_QKV    bias + per-head LayerNorm(q,k) + interleaved-pair 2-D RoPE, scatter to Q / K / V^T
@@ -18,6 +25,7 @@
 //   EPI_PLAIN  out = acc + bias                                      (generic nn.Linear; tests)
 #pragma once
 #include "common.cuh"
+#include "tc2sm.cuh"
 
 namespace fitv2 {
 
@@ -44,15 +52,18 @@ struct GemmEpi {
     int tokens_v;
 };
 
-constexpr int kGemmBM = 128;
+constexpr int kGemmBM = 128;          // rows per CTA
 constexpr int kGemmBK = 64;
 constexpr int kGemmThreads = 320;     // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
 constexpr int kSmemBudget = 227 * 1024;
 
 template <int BN, int EPI, int DH, int CL = 1> struct GemmCfg {
+    static_assert(CL == 1 || CL == 2, "cluster size 1 or 2");
     static constexpr int kABytes = kGemmBM * kGemmBK * 2;
-    static constexpr int kBBytes = BN * kGemmBK * 2;
-    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kBRowsPerCta = BN / CL;                       // CL = 2: each CTA stages half of the weight tile
+    static constexpr int kBBytes = kBRowsPerCta * kGemmBK * 2;
+    static constexpr int kStageBytes = kABytes + kBBytes;              // per CTA
+    static constexpr int kTxBytes = kStageBytes * CL;                  // credited to the (leader's) full barrier per stage
     static constexpr int kBarrierBytes = 1024;
     // epilogue staging: per warp 32 rows; QKV rows hold one head (16-bit) with a bank-conflict-free pitch,
     // the other epilogues use 128-byte XOR-swizzled rows.
@@ -63,15 +74,10 @@ template <int BN, int EPI, int DH, int CL = 1> struct GemmCfg {
     static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
     static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + kBarrierBytes + 1024;   // +1024 alignment slack
     static constexpr int kAccStride = 256;                                           // TMEM columns between the 2 accumulators
-    static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N constraint for M=128");
+    static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N constraint for M=128/256");
     static_assert(kBBytes % 1024 == 0, "B stage must keep 1024B alignment for SWIZZLE_128B");
     static_assert(kStages >= 3, "pipeline too shallow");
     static_assert(EPI != EPI_QKV || DH * 64 <= kEpiWarpBytes, "V^T staging does not fit");
-    // CL = 2: the two CTAs of a cluster work on vertically adjacent tiles (same columns); each loads one half of
-    // the weight tile and TMA-multicasts it into both CTAs' shared memory, halving the L2 -> SM traffic of B.
-    static constexpr int kBRowsPerCta = BN / CL;
-    static_assert(CL == 1 || CL == 2, "cluster size 1 or 2");
-    static_assert((kBRowsPerCta * kGemmBK * 2) % 1024 == 0, "multicast slice must keep 1024B alignment");
 };
 
 // ---- warp-private staging slab: 32 rows x 128 bytes, 16-byte chunk c of row r lives at chunk (c ^ (r & 7)) ----
@@ -107,58 +113,63 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     const int lane = threadIdx.x & 31;
     const int m_tiles = (M + kGemmBM - 1) / kGemmBM;
     const int n_tiles = N / BN;
-    // work items are tile groups of CL vertically adjacent tiles; CTA `cta_rank` of the cluster takes row tile
+    // work items are groups of CL vertically adjacent 128-row tiles; CTA `cta_rank` of the cluster owns row tile
     // group * CL + cta_rank (a phantom tile past the M tail computes on zero-filled rows and stores nothing)
     const int num_groups = ((m_tiles + CL - 1) / CL) * n_tiles;
     const int num_kb = (K + kGemmBK - 1) / kGemmBK;
     const uint32_t cta_rank = CL > 1 ? cluster_ctarank() : 0u;
+    const bool leader = cta_rank == 0;
     const int group0 = blockIdx.x / CL, group_stride = gridDim.x / CL;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tma_a);
         tma_prefetch_desc(&tma_b);
-        for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], CL); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 256); }
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 256 * CL); }
         mbar_fence_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    if (warp == 1) {
+        if constexpr (CL == 2) tmem_alloc_2sm(tmem_slot, 512); else tmem_alloc(tmem_slot, 512);
+    }
     tc_fence_before();
-    if constexpr (CL > 1) cluster_sync(); else __syncthreads();   // peer barriers must be initialised before any multicast
+    if constexpr (CL > 1) cluster_sync(); else __syncthreads();   // the peer's barriers must exist before anything signals them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
         if (lane == 0) {
-            // ------------------------------ TMA producer ------------------------------
+            // ------------------------------ TMA producer (every CTA) ------------------------------
             int stage = 0; uint32_t phase = 0;
             for (int grp = group0; grp < num_groups; grp += group_stride) {
                 const int m_tile = (grp / n_tiles) * CL + (int)cta_rank, n_tile = grp % n_tiles;   // n fastest: a wave shares few A tiles
                 for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);      // CL > 1: every CTA of the cluster has drained this slot
-                    mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-                    tma_load_2d(&tma_a, &full_bar[stage], smem_a + stage * Cfg::kABytes, kb * kGemmBK, m_tile * kGemmBM);
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem_a + stage * Cfg::kABytes;
+                    uint8_t* sb = smem_b + stage * Cfg::kBBytes;
                     if constexpr (CL == 1) {
-                        tma_load_2d(&tma_b, &full_bar[stage], smem_b + stage * Cfg::kBBytes, kb * kGemmBK,
-                                    b_row_offset + n_tile * BN);
+                        mbar_arrive_expect_tx(&full_bar[stage], Cfg::kTxBytes);
+                        tma_load_2d(&tma_a, &full_bar[stage], sa, kb * kGemmBK, m_tile * kGemmBM);
+                        tma_load_2d(&tma_b, &full_bar[stage], sb, kb * kGemmBK, b_row_offset + n_tile * BN);
                     } else {
-                        tma_load_2d_multicast(&tma_b, &full_bar[stage],
-                                              smem_b + stage * Cfg::kBBytes + cta_rank * (Cfg::kBRowsPerCta * kGemmBK * 2),
-                                              kb * kGemmBK, b_row_offset + n_tile * BN + (int)cta_rank * Cfg::kBRowsPerCta,
-                                              (uint16_t)((1u << CL) - 1));
+                        // both CTAs' loads are credited to the leader's barrier, which expects the pair's bytes
+                        if (leader) mbar_arrive_expect_tx(&full_bar[stage], Cfg::kTxBytes);
+                        tma_load_2d_2sm(&tma_a, &full_bar[stage], sa, kb * kGemmBK, m_tile * kGemmBM);
+                        tma_load_2d_2sm(&tma_b, &full_bar[stage], sb, kb * kGemmBK,
+                                        b_row_offset + n_tile * BN + (int)cta_rank * Cfg::kBRowsPerCta);
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ------------------------------ MMA issuer ------------------------------
-            constexpr uint32_t idesc = umma_idesc(Op16<OT>::kUmmaFormat, kGemmBM, BN);
+        if (lane == 0 && (CL == 1 || leader)) {
+            // ------------------------------ MMA issuer (leader CTA) ------------------------------
+            constexpr uint32_t idesc = umma_idesc(Op16<OT>::kUmmaFormat, kGemmBM * CL, BN);
             int stage = 0; uint32_t phase = 0; int it = 0;
             for (int grp = group0; grp < num_groups; grp += group_stride, ++it) {
                 const int acc = it & 1;
                 const uint32_t acc_phase = (it >> 1) & 1;
-                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);          // CL = 2: both CTAs' epilogues have drained it
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * Cfg::kAccStride;
                 for (int kb = 0; kb < num_kb; ++kb) {
@@ -167,20 +178,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     const uint64_t da = umma_desc_kmajor(smem_u32(smem_a + stage * Cfg::kABytes), 128);
                     const uint64_t db = umma_desc_kmajor(smem_u32(smem_b + stage * Cfg::kBBytes), 128);
 #pragma unroll
-                    for (int kk = 0; kk < kGemmBK / 16; ++kk)        // +32 bytes (>>4 = 2) per K=16 step inside the 128B atom
-                        umma_ss(d_tmem, da + 2 * kk, db + 2 * kk, idesc, (kb | kk) != 0);
-                    if constexpr (CL == 1) umma_commit(&empty_bar[stage]);   // smem slot free once these MMAs retire
-                    else umma_commit_multicast(&empty_bar[stage], (uint16_t)((1u << CL) - 1));   // ... in every CTA of the cluster
-                    if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);
+                    for (int kk = 0; kk < kGemmBK / 16; ++kk) {      // +32 bytes (>>4 = 2) per K=16 step inside the 128B atom
+                        if constexpr (CL == 1) umma_ss(d_tmem, da + 2 * kk, db + 2 * kk, idesc, (kb | kk) != 0);
+                        else umma_ss_2sm(d_tmem, da + 2 * kk, db + 2 * kk, idesc, (kb | kk) != 0);
+                    }
+                    // smem slot free (in both CTAs) once these MMAs retire; accumulator ready after the last k-block
+                    if constexpr (CL == 1) {
+                        umma_commit(&empty_bar[stage]);
+                        if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);
+                    } else {
+                        umma_commit_2sm(&empty_bar[stage]);
+                        if (kb == num_kb - 1) umma_commit_2sm(&tfull_bar[acc]);
+                    }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else {
-        // ------------------------------ epilogue warps ------------------------------
+        // ------------------------------ epilogue warps (every CTA: its own 128 rows) ------------------------------
         const int quarter = warp & 3;                                 // TMEM lane quarter this warp may access
         const int half = (warp - 2) >> 2;                             // 0: left half of the tile columns, 1: right half
         uint8_t* stg = smem_epi + (warp - 2) * Cfg::kEpiWarpBytes;    // warp-private staging slab
+        // hand the accumulator back to the MMA issuer (which lives in the leader CTA)
+        auto release_acc = [&](int acc) {
+            tc_fence_before();
+            if (CL == 1 || leader) mbar_arrive(&tempty_bar[acc]);
+            else mbar_arrive_remote(&tempty_bar[acc], 0);
+        };
         int it = 0;
         for (int grp = group0; grp < num_groups; grp += group_stride, ++it) {
             const int m_tile = (grp / n_tiles) * CL + (int)cta_rank, n_tile = grp % n_tiles;
@@ -220,7 +244,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     else if constexpr (CPR == 4) tmem_ld16(t_row + half * HALF + s0, v);
                     else tmem_ld8(t_row + half * HALF + s0, v);
                     tmem_ld_wait();
-                    if (last) { tc_fence_before(); mbar_arrive(&tempty_bar[acc]); }
+                    if (last) release_acc(acc);
 #pragma unroll
                     for (int c = 0; c < CPR; ++c)
                         *reinterpret_cast<uint4*>(stg + slab_off(lane, c)) = make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
@@ -279,7 +303,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     tmem_ld16(t_row + half * Q + c * 16, g);
                     tmem_ld16(t_row + HALF + half * Q + c * 16, u);
                     tmem_ld_wait();
-                    if (c == Q / 16 - 1) { tc_fence_before(); mbar_arrive(&tempty_bar[acc]); }
+                    if (c == Q / 16 - 1) release_acc(acc);
                     uint32_t packed[8];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
@@ -313,7 +337,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     uint32_t v[8];
                     tmem_ld8(t_row + half * HALF + c * 8, v);
                     tmem_ld_wait();
-                    if (c == NG - 1) { tc_fence_before(); mbar_arrive(&tempty_bar[acc]); }
+                    if (c == NG - 1) release_acc(acc);
                     if (row_ok) {
                         float o[8];
 #pragma unroll
@@ -346,8 +370,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 #pragma unroll
                 for (int c = 0; c < DH / 8; ++c) tmem_ld8(t_row + half * DH + c * 8, reinterpret_cast<uint32_t*>(v) + c * 8);
                 tmem_ld_wait();
-                tc_fence_before();
-                mbar_arrive(&tempty_bar[acc]);
+                release_acc(acc);
 #pragma unroll
                 for (int c = 0; c < DH / 4; ++c) {
                     const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c * 4));
@@ -429,10 +452,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     }
 
     tc_fence_before();
-    if constexpr (CL > 1) cluster_sync(); else __syncthreads();   // the peer may still multicast into / signal this CTA
+    if constexpr (CL > 1) cluster_sync(); else __syncthreads();   // the pair must be done with this CTA's smem / TMEM / barriers
     if (warp == 1) {
         __syncwarp();
-        tmem_dealloc(tmem_base, 512);
+        if constexpr (CL == 2) tmem_dealloc_2sm(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
     }
 }
 

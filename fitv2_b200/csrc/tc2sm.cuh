@@ -1,0 +1,56 @@
+// 2-SM (CTA pair, cta_group::2) variants of the tcgen05 / TMA primitives.  A cluster of two CTAs on one TPC
+// executes a single 256-row UMMA: each CTA stages its own 128 rows of A and HALF of the B tile; the leader
+// CTA (cluster rank 0) issues the instruction, each SM accumulates its own 128 rows in its own TMEM.
+// Compared with cta_group::1 this halves the shared-memory traffic of B per SM, which is what bounds
+// 1-SM UMMA on Blackwell (smem reads of A+B plus the TMA writes share 128 B/clk/SM).
+#pragma once
+#include "common.cuh"
+
+namespace fitv2 {
+
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address -> leader CTA
+
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* dst_smem, uint32_t ncols) {   // same warp id in both CTAs
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                 :: "r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(taddr), "r"(ncols) : "memory");
+}
+
+// TMA tile load executed by either CTA of the pair; the transaction bytes are credited to the LEADER's mbarrier
+// (same shared-memory offset), the data lands in the executing CTA's shared memory.
+__device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        :: "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
+        : "memory");
+}
+
+// D[tmem of both CTAs] (+)= A (128 rows per CTA) * B (N/2 rows per CTA), M = 256.  Leader CTA, one thread.
+__device__ __forceinline__ void umma_ss_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" :: "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// Arrive on the same-offset mbarrier of both CTAs once the pair's previously issued UMMAs have completed.
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 :: "r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+// Arrive on the mbarrier at the same offset in CTA `cta` of the cluster.
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+    asm volatile(
+        "{\n\t"
+        ".reg .b32 remAddr32;\n\t"
+        "mapa.shared::cluster.u32 remAddr32, %0, %1;\n\t"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [remAddr32];\n\t"
+        "}\n" :: "r"(smem_u32(bar)), "r"(cta) : "memory");
+}
+
+}  // namespace fitv2
