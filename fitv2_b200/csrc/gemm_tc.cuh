@@ -136,14 +136,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // Producer and MMA loops are executed by the WHOLE warp (warp-uniform control flow lets the compiler keep the
+    // descriptors / addresses in uniform registers, which the UTMALDG / UTCHMMA instructions consume directly);
+    // one elected lane issues the asynchronous operations.
     if (warp == 0) {
-        if (lane == 0) {
-            // ------------------------------ TMA producer (every CTA) ------------------------------
-            int stage = 0; uint32_t phase = 0;
-            for (int grp = group0; grp < num_groups; grp += group_stride) {
-                const int m_tile = (grp / n_tiles) * CL + (int)cta_rank, n_tile = grp % n_tiles;   // n fastest: a wave shares few A tiles
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
+        // ------------------------------ TMA producer (every CTA) ------------------------------
+        int stage = 0; uint32_t phase = 0;
+        for (int grp = group0; grp < num_groups; grp += group_stride) {
+            const int m_tile = (grp / n_tiles) * CL + (int)cta_rank, n_tile = grp % n_tiles;   // n fastest: a wave shares few A tiles
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                if (elect_one()) {
                     uint8_t* sa = smem_a + stage * Cfg::kABytes;
                     uint8_t* sb = smem_b + stage * Cfg::kBBytes;
                     if constexpr (CL == 1) {
@@ -157,14 +160,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                         tma_load_2d_2sm(&tma_b, &full_bar[stage], sb, kb * kGemmBK,
                                         b_row_offset + n_tile * BN + (int)cta_rank * Cfg::kBRowsPerCta);
                     }
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0 && (CL == 1 || leader)) {
+        if (CL == 1 || leader) {
             // ------------------------------ MMA issuer (leader CTA) ------------------------------
             constexpr uint32_t idesc = umma_idesc(Op16<OT>::kUmmaFormat, kGemmBM * CL, BN);
+            const uint64_t da0 = umma_desc_kmajor(smem_u32(smem_a), 128);
+            const uint64_t db0 = umma_desc_kmajor(smem_u32(smem_b), 128);
             int stage = 0; uint32_t phase = 0; int it = 0;
             for (int grp = group0; grp < num_groups; grp += group_stride, ++it) {
                 const int acc = it & 1;
@@ -175,21 +181,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
-                    const uint64_t da = umma_desc_kmajor(smem_u32(smem_a + stage * Cfg::kABytes), 128);
-                    const uint64_t db = umma_desc_kmajor(smem_u32(smem_b + stage * Cfg::kBBytes), 128);
+                    if (elect_one()) {
+                        const uint64_t da = da0 + (uint64_t)(stage * (Cfg::kABytes >> 4));   // start-address field is addr >> 4
+                        const uint64_t db = db0 + (uint64_t)(stage * (Cfg::kBBytes >> 4));
 #pragma unroll
-                    for (int kk = 0; kk < kGemmBK / 16; ++kk) {      // +32 bytes (>>4 = 2) per K=16 step inside the 128B atom
-                        if constexpr (CL == 1) umma_ss(d_tmem, da + 2 * kk, db + 2 * kk, idesc, (kb | kk) != 0);
-                        else umma_ss_2sm(d_tmem, da + 2 * kk, db + 2 * kk, idesc, (kb | kk) != 0);
+                        for (int kk = 0; kk < kGemmBK / 16; ++kk) {  // +32 bytes (>>4 = 2) per K=16 step inside the 128B atom
+                            if constexpr (CL == 1) umma_ss(d_tmem, da + 2 * kk, db + 2 * kk, idesc, (kb | kk) != 0);
+                            else umma_ss_2sm(d_tmem, da + 2 * kk, db + 2 * kk, idesc, (kb | kk) != 0);
+                        }
+                        // smem slot free (in both CTAs) once these MMAs retire; accumulator ready after the last k-block
+                        if constexpr (CL == 1) {
+                            umma_commit(&empty_bar[stage]);
+                            if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);
+                        } else {
+                            umma_commit_2sm(&empty_bar[stage]);
+                            if (kb == num_kb - 1) umma_commit_2sm(&tfull_bar[acc]);
+                        }
                     }
-                    // smem slot free (in both CTAs) once these MMAs retire; accumulator ready after the last k-block
-                    if constexpr (CL == 1) {
-                        umma_commit(&empty_bar[stage]);
-                        if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);
-                    } else {
-                        umma_commit_2sm(&empty_bar[stage]);
-                        if (kb == num_kb - 1) umma_commit_2sm(&tfull_bar[acc]);
-                    }
+                    __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
