@@ -23,6 +23,7 @@
 // Two CTAs are resident per SM so one CTA's softmax overlaps the other's MMAs / loads.
 #pragma once
 #include "common.cuh"
+#include "tc2sm.cuh"
 
 namespace fitv2 {
 
@@ -125,6 +126,7 @@ attention_kernel(const OT* __restrict__ q, const OT* __restrict__ k, const OT* _
     const uint32_t t_s = tmem_base + (uint32_t(warp * 32) << 16);        // S accumulator, columns [0,128)
     const uint32_t t_o = t_s + 128;                                      // O accumulator, columns [128,128+DHP)
 
+    const uint32_t smem_p = smem_u32(smem + C::kOffP);                   // shared-space address of the P panels
     const int qi = q0 + tid;
     const bool q_ok = qi < tokens;
     const float my_seg = q_ok ? segb[qi] : 0.f;
@@ -197,8 +199,8 @@ attention_kernel(const OT* __restrict__ q, const OT* __restrict__ k, const OT* _
 #pragma unroll
             for (int g = 0; g < 4; ++g) {                              // 4 chunks of 8 keys per 32 columns
                 const int chunk = c * 4 + g;                            // 0..15 across the 128-key tile
-                *reinterpret_cast<uint4*>(smem + C::kOffP + (chunk >> 3) * C::kPPanel + swz_offset<128>(tid, chunk & 7)) =
-                    make_uint4(packed[g * 4], packed[g * 4 + 1], packed[g * 4 + 2], packed[g * 4 + 3]);
+                sts128(smem_p + (chunk >> 3) * C::kPPanel + swz_offset<128>(tid, chunk & 7),
+                       make_uint4(packed[g * 4], packed[g * 4 + 1], packed[g * 4 + 2], packed[g * 4 + 3]));
             }
         }
         l_run += lsum;

@@ -27,6 +27,7 @@ template <> struct Op16<__nv_bfloat16> {
         return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
     }
     __device__ __forceinline__ static __nv_bfloat16 from(float a) { return __float2bfloat16_rn(a); }
+    __device__ __forceinline__ static uint16_t bits(float a) { return __bfloat16_as_ushort(__float2bfloat16_rn(a)); }
 };
 template <> struct Op16<__half> {
     static constexpr uint32_t kUmmaFormat = 0;   // 0 = F16
@@ -39,6 +40,7 @@ template <> struct Op16<__half> {
         return __half22float2(*reinterpret_cast<__half2*>(&u));
     }
     __device__ __forceinline__ static __half from(float a) { return __float2half_rn(a); }
+    __device__ __forceinline__ static uint16_t bits(float a) { return __half_as_ushort(__float2half_rn(a)); }
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

@@ -207,7 +207,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         // ------------------------------ epilogue warps (every CTA: its own 128 rows) ------------------------------
         const int quarter = warp & 3;                                 // TMEM lane quarter this warp may access
         const int half = (warp - 2) >> 2;                             // 0: left half of the tile columns, 1: right half
-        uint8_t* stg = smem_epi + (warp - 2) * Cfg::kEpiWarpBytes;    // warp-private staging slab
+        const uint32_t stg = smem_u32(smem_epi) + (warp - 2) * Cfg::kEpiWarpBytes;   // warp-private staging slab (shared-space address)
         // hand the accumulator back to the MMA issuer (which lives in the leader CTA)
         auto release_acc = [&](int acc) {
             tc_fence_before();
@@ -256,7 +256,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     if (last) release_acc(acc);
 #pragma unroll
                     for (int c = 0; c < CPR; ++c)
-                        *reinterpret_cast<uint4*>(stg + slab_off(lane, c)) = make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+                        sts128(stg + slab_off(lane, c), make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]));
                     __syncwarp();
                     if constexpr (NCPR > 0) load_x(xb, next_s0, next_tag);      // prefetch the next slab of x
                     int r0, c0; slab_task<CPR>(0, lane, r0, c0);                 // this lane's chunk column is the same in every iteration
@@ -269,7 +269,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                         if (r < rows_valid) {
                             if (!one_sample)
                                 g = __ldg(reinterpret_cast<const float4*>(ep.gate + (size_t)((m_warp + r) / ep.tokens) * ep.gate_ld + col0 + s0 + c * 4));
-                            const float4 a = *reinterpret_cast<const float4*>(stg + slab_off(r, c));
+                            const uint4 au = lds128(stg + slab_off(r, c));
+                            const float4 a = make_float4(__uint_as_float(au.x), __uint_as_float(au.y), __uint_as_float(au.z), __uint_as_float(au.w));
                             float4 o;
                             o.x = xa[i].x + g.x * (a.x + b.x);
                             o.y = xa[i].y + g.y * (a.y + b.y);
@@ -323,8 +324,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                         packed[2 * j + 1] = Op16<OT>::pack(silu_mul(__uint_as_float(g[4 * j + 2]) + bg.z, __uint_as_float(u[4 * j + 2]) + bu.z),
                                                            silu_mul(__uint_as_float(g[4 * j + 3]) + bg.w, __uint_as_float(u[4 * j + 3]) + bu.w));
                     }
-                    *reinterpret_cast<uint4*>(stg + slab_off(lane, 2 * c)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-                    *reinterpret_cast<uint4*>(stg + slab_off(lane, 2 * c + 1)) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+                    sts128(stg + slab_off(lane, 2 * c), make_uint4(packed[0], packed[1], packed[2], packed[3]));
+                    sts128(stg + slab_off(lane, 2 * c + 1), make_uint4(packed[4], packed[5], packed[6], packed[7]));
                 }
                 __syncwarp();
                 OT* obase = reinterpret_cast<OT*>(ep.out16) + (size_t)m_warp * ep.ld_out + n_tile * HALF + half * Q;
@@ -332,7 +333,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 for (int i = 0; i < 8; ++i) {                         // 4 rows x 128 contiguous bytes per warp instruction
                     int r, c; slab_task<8>(i, lane, r, c);
                     if (r < rows_valid)
-                        *reinterpret_cast<uint4*>(obase + (size_t)r * ep.ld_out + c * 8) = *reinterpret_cast<const uint4*>(stg + slab_off(r, c));
+                        *reinterpret_cast<uint4*>(obase + (size_t)r * ep.ld_out + c * 8) = lds128(stg + slab_off(r, c));
                 }
                 __syncwarp();
             } else if constexpr (EPI == EPI_PLAIN) {
@@ -409,7 +410,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                             // q*cos + rotate_half(q)*sin with rotate_half: (x0,x1) -> (-x1,x0)
                             packed[p] = Op16<OT>::pack(x0 * cc - x1 * ss, x1 * cc + x0 * ss);
                         }
-                        *reinterpret_cast<uint4*>(stg + lane * PITCH + c * 16) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                        sts128(stg + lane * PITCH + c * 16, make_uint4(packed[0], packed[1], packed[2], packed[3]));
                     }
                     __syncwarp();
                     OT* dbase = reinterpret_cast<OT*>(kind == 0 ? ep.q : ep.k);
@@ -420,7 +421,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                         for (int i = 0; i < CH; ++i) {
                             const int idx = i * 32 + lane, r = idx / CH, c = idx - r * CH;
                             if (r < rows_valid)
-                                *reinterpret_cast<uint4*>(dst + (size_t)idx * 8) = *reinterpret_cast<const uint4*>(stg + r * PITCH + c * 16);
+                                *reinterpret_cast<uint4*>(dst + (size_t)idx * 8) = lds128(stg + r * PITCH + c * 16);
                         }
                     } else {
 #pragma unroll
@@ -429,7 +430,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                             if (r < rows_valid) {
                                 const int sm = (m_warp + r) / ep.tokens, tk = (m_warp + r) - sm * ep.tokens;
                                 OT* dst = dbase + (((size_t)sm * ep.heads + head) * ep.tokens + tk) * DH;
-                                *reinterpret_cast<uint4*>(dst + c * 8) = *reinterpret_cast<const uint4*>(stg + r * PITCH + c * 16);
+                                *reinterpret_cast<uint4*>(dst + c * 8) = lds128(stg + r * PITCH + c * 16);
                             }
                         }
                     }
@@ -438,15 +439,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     // V^T[sample, head, d, token]
                     if (one_sample && rows_valid == 32 && (token0 & 7) == 0) {
                         // transpose through the slab: [d][32 tokens] 16-bit, then 16-byte (8-token) stores
-                        OT* s16 = reinterpret_cast<OT*>(stg);
 #pragma unroll
-                        for (int j = 0; j < DH; ++j) s16[j * 32 + lane] = Op16<OT>::from(v[j]);
+                        for (int j = 0; j < DH; ++j) sts16(stg + (j * 32 + lane) * 2, Op16<OT>::bits(v[j]));
                         __syncwarp();
                         OT* dst = reinterpret_cast<OT*>(ep.vt) + ((size_t)s_first * ep.heads + head) * DH * ep.tokens_v + token0;
 #pragma unroll
                         for (int i = 0; i < DH * 4 / 32; ++i) {
                             const int idx = i * 32 + lane, d = idx >> 2, part = idx & 3;
-                            *reinterpret_cast<uint4*>(dst + (size_t)d * ep.tokens_v + part * 8) = *reinterpret_cast<const uint4*>(stg + d * 64 + part * 16);
+                            *reinterpret_cast<uint4*>(dst + (size_t)d * ep.tokens_v + part * 8) = lds128(stg + d * 64 + part * 16);
                         }
                         __syncwarp();
                     } else if (row_ok) {

@@ -49,8 +49,21 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) 
         "{\n\t"
         ".reg .b32 remAddr32;\n\t"
         "mapa.shared::cluster.u32 remAddr32, %0, %1;\n\t"
-        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [remAddr32];\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [remAddr32];\n\t"
         "}\n" :: "r"(smem_u32(bar)), "r"(cta) : "memory");
+}
+
+// explicit shared-space accesses (a pointer derived from the dynamic smem base is otherwise treated as generic)
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" :: "r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts16(uint32_t addr, uint16_t v) {
+    asm volatile("st.shared.b16 [%0], %1;" :: "r"(addr), "h"(v) : "memory");
 }
 
 }  // namespace fitv2
