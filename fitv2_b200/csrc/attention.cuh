@@ -9,9 +9,12 @@
 //     S = Q K^T   : M=128 queries, N=128 keys, K=DHP (head_dim padded to a multiple of 16)
 //     O += P V    : M=128 queries, N=DHP,      K=128 keys   (V arrives transposed, keys contiguous),
 //                   accumulated in TMEM across key tiles and read back once.
-// Q/K/V^T/P are staged in shared memory in the canonical K-major swizzled layouts (a 64-element
-// SWIZZLE_128B panel plus a 16/32-element SWIZZLE_32B/64B tail panel for head_dim 72/96) with cp.async;
-// the next key tile's K (V) is prefetched while the softmax (P V product) of the current one runs.
+// Q/K/V^T tiles are loaded by TMA (3-D tensor maps over (dim, token, sample*head); out-of-bounds rows/columns
+// are zero-filled, which pads head_dim 72 -> 80 and the sequence tail for free) straight into the canonical
+// K-major swizzled panels: a 64-element SWIZZLE_128B panel plus a 16/32-element SWIZZLE_32B/64B tail panel for
+// head_dim 72/96.  K(t+1) is prefetched behind the softmax of tile t, V(t+1) behind its P V product.
+// 256 threads: two threads per query row (warps w and w+4 share a TMEM lane quarter), each owning 64 of the 128
+// key columns of a tile, which doubles the number of warps hiding the TMEM / MUFU latencies of the softmax.
 //
 // Softmax without a running maximum: q and k are LayerNorm'ed without affine (modules.py:168) and RoPE is a
 // rotation scaled by `mag`, so |q| = |k| = mag*sqrt(dh) and every logit obeys
@@ -31,8 +34,6 @@ template <int DH> struct AttnCfg {
     static constexpr int kDHP = (DH + 15) / 16 * 16;          // 72 -> 80, 96 -> 96
     static constexpr int kTail = kDHP - 64;                    // elements in the tail panel (16 or 32)
     static constexpr int kTailBytes = kTail * 2;               // 32 or 64
-    static constexpr int kChunks = kDHP / 8;                   // 16-byte chunks per staged Q/K row
-    static constexpr int kRealChunks = DH / 8;
     static constexpr int kQMain = 128 * 128, kQTail = 128 * kTailBytes;
     static constexpr int kOffQ = 0;
     static constexpr int kOffQT = kOffQ + kQMain;
@@ -42,92 +43,69 @@ template <int DH> struct AttnCfg {
     static constexpr int kVPanel = ((kDHP * 128 + 1023) / 1024) * 1024;   // one 64-key panel of V^T
     static constexpr int kOffP = kOffV + 2 * kVPanel;
     static constexpr int kPPanel = 128 * 128;
-    static constexpr int kOffSeg = kOffP + 2 * kPPanel;
-    static constexpr int kOffBar = kOffSeg + 128 * 4;
+    static constexpr int kOffSeg = kOffP + 2 * kPPanel;        // 128 key segment ids
+    static constexpr int kOffSum = kOffSeg + 128 * 4;          // 256 partial row sums
+    static constexpr int kOffBar = kOffSum + 256 * 4;
     static constexpr int kSmemBytes = kOffBar + 64 + 1024;     // + alignment slack
+    static constexpr uint32_t kQKBytes = kQMain + kQTail;      // bytes of one Q or K tile (TMA writes full boxes)
+    static constexpr uint32_t kVBytes = 2 * kDHP * 128;
+    static constexpr int kThreads = 256;
     static_assert(kTail == 16 || kTail == 32, "head_dim must be 72..80 or 88..96 (64 + 16/32 tail)");
 };
 
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
-
 template <typename OT, int DH>
-__global__ void __launch_bounds__(128, 2)
-attention_kernel(const OT* __restrict__ q, const OT* __restrict__ k, const OT* __restrict__ vt,
+__global__ void __launch_bounds__(256, 2)
+attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_qt,
+                 const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_kt,
+                 const __grid_constant__ CUtensorMap map_v,
                  const float* __restrict__ seg, const int* __restrict__ seg_uniform,
-                 OT* __restrict__ out, int heads, int tokens, int tokens_v, float scale_log2e, float bound_log2e,
+                 OT* __restrict__ out, int heads, int tokens, float scale_log2e, float bound_log2e,
                  float* __restrict__ dbg_s, float* __restrict__ dbg_o)
 {
     using C = AttnCfg<DH>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     float* seg_kv = reinterpret_cast<float*>(smem + C::kOffSeg);
-    uint64_t* bar_s = reinterpret_cast<uint64_t*>(smem + C::kOffBar);
-    uint64_t* bar_o = bar_s + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_s + 2);
+    float* l_part = reinterpret_cast<float*>(smem + C::kOffSum);
+    uint64_t* bar_s = reinterpret_cast<uint64_t*>(smem + C::kOffBar);   // S = Q K^T done
+    uint64_t* bar_o = bar_s + 1;                                        // O += P V done
+    uint64_t* bar_k = bar_s + 2;                                        // (Q and) K tile landed
+    uint64_t* bar_v = bar_s + 3;                                        // V^T tile landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_s + 4);
 
     const int tid = threadIdx.x, warp = tid >> 5;
+    const int row = tid & 127;                                          // query row inside the tile == TMEM lane
+    const int half = tid >> 7;                                          // which 64 key columns / output half this thread owns
     const int q0 = blockIdx.x * 128, head = blockIdx.y, sample = blockIdx.z;
-    const size_t bh = (size_t)sample * heads + head;
-    const OT* qg = q + bh * tokens * DH;
-    const OT* kg = k + bh * tokens * DH;
-    const OT* vg = vt + bh * DH * tokens_v;
+    const int bh = sample * heads + head;
     const float* segb = seg + (size_t)sample * tokens;
     const bool uniform = seg_uniform[sample] != 0;
     const int kv_tiles = (tokens + 127) / 128;
 
-    // 16-byte cp.async copies (zero-fill for out-of-range chunks), issued back to back so a whole tile is in flight
-    auto load_k = [&](int kv0) {
-#pragma unroll
-        for (int i = 0; i < C::kChunks; ++i) {
-            const int id = tid + i * 128;
-            const int r = id / C::kChunks, c = id % C::kChunks;
-            const bool ok = kv0 + r < tokens && c < C::kRealChunks;
-            uint8_t* dst = c < 8 ? smem + C::kOffK + swz_offset<128>(r, c)
-                                 : smem + C::kOffKT + swz_offset<C::kTailBytes>(r, c - 8);
-            cp_async16(dst, ok ? kg + (size_t)(kv0 + r) * DH + c * 8 : kg, ok ? 16 : 0);
-        }
-    };
-    auto load_v = [&](int kv0) {
-#pragma unroll
-        for (int i = 0; i < C::kDHP * 16 / 128; ++i) {
-            const int id = tid + i * 128;
-            const int d = id >> 4, c = id & 15;                        // row d of V^T, 8 keys per chunk
-            const int kv = kv0 + c * 8;
-            const bool ok = d < DH && kv < tokens;
-            const int bytes = ok ? min(8, tokens - kv) * 2 : 0;        // boundary chunk: keys past the end are zero-filled
-            cp_async16(smem + C::kOffV + (c >> 3) * C::kVPanel + swz_offset<128>(d, c & 7),
-                       ok ? vg + (size_t)d * tokens_v + kv : vg, bytes);
-        }
-    };
-
-    if (tid == 0) { mbar_init(bar_s, 1); mbar_init(bar_o, 1); mbar_fence_init(); }
-    if (warp == 0) { __syncwarp(); tmem_alloc(tmem_slot, 256); }
-
-    // ---- group 0: Q tile + K tile 0;  group 1: V tile 0 ----
-#pragma unroll
-    for (int i = 0; i < C::kChunks; ++i) {
-        const int id = tid + i * 128;
-        const int r = id / C::kChunks, c = id % C::kChunks;
-        const bool ok = q0 + r < tokens && c < C::kRealChunks;
-        uint8_t* dst = c < 8 ? smem + C::kOffQ + swz_offset<128>(r, c)
-                             : smem + C::kOffQT + swz_offset<C::kTailBytes>(r, c - 8);
-        cp_async16(dst, ok ? qg + (size_t)(q0 + r) * DH + c * 8 : qg, ok ? 16 : 0);
+    if (tid == 0) {
+        tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v);
+        mbar_init(bar_s, 1); mbar_init(bar_o, 1); mbar_init(bar_k, 1); mbar_init(bar_v, 1);
+        mbar_fence_init();
+        // Q tile + K tile 0 on bar_k, V tile 0 on bar_v
+        mbar_arrive_expect_tx(bar_k, 2 * C::kQKBytes);
+        tma_load_3d(&map_q, bar_k, smem + C::kOffQ, 0, q0, bh);
+        tma_load_3d(&map_qt, bar_k, smem + C::kOffQT, 64, q0, bh);
+        tma_load_3d(&map_k, bar_k, smem + C::kOffK, 0, 0, bh);
+        tma_load_3d(&map_kt, bar_k, smem + C::kOffKT, 64, 0, bh);
+        mbar_arrive_expect_tx(bar_v, C::kVBytes);
+        tma_load_3d(&map_v, bar_v, smem + C::kOffV, 0, 0, bh);
+        tma_load_3d(&map_v, bar_v, smem + C::kOffV + C::kVPanel, 64, 0, bh);
     }
-    load_k(0);
-    cp_async_commit();
-    load_v(0);
-    cp_async_commit();
-
+    if (warp == 1) tmem_alloc(tmem_slot, 256);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t t_s = tmem_base + (uint32_t(warp * 32) << 16);        // S accumulator, columns [0,128)
-    const uint32_t t_o = t_s + 128;                                      // O accumulator, columns [128,128+DHP)
+    const uint32_t t_s = tmem_base + (uint32_t((warp & 3) * 32) << 16) + half * 64;   // S columns [0,128): this thread's 64
+    const uint32_t t_o = tmem_base + (uint32_t((warp & 3) * 32) << 16) + 128;         // O columns [128,128+DHP)
+    const uint32_t smem_p = smem_u32(smem + C::kOffP);
 
-    const uint32_t smem_p = smem_u32(smem + C::kOffP);                   // shared-space address of the P panels
-    const int qi = q0 + tid;
+    const int qi = q0 + row;
     const bool q_ok = qi < tokens;
     const float my_seg = q_ok ? segb[qi] : 0.f;
     float l_run = 0.f;
@@ -138,13 +116,11 @@ attention_kernel(const OT* __restrict__ q, const OT* __restrict__ k, const OT* _
 
     for (int t = 0; t < kv_tiles; ++t, ph ^= 1) {
         const int kv0 = t * 128;
-        seg_kv[tid] = (kv0 + tid < tokens) ? segb[kv0 + tid] : 0.f;
-        cp_async_wait<1>();                                            // K(t) (and Q) have landed; V(t) may still be in flight
-        fence_proxy_async_smem();
-        __syncthreads();
+        if (tid < 128) seg_kv[tid] = (kv0 + tid < tokens) ? segb[kv0 + tid] : 0.f;
 
         // ---- S = Q K^T ----
         if (tid == 0) {
+            mbar_wait(bar_k, ph);                                      // K(t) (and Q) landed
             tc_fence_after();
             const uint64_t dq = umma_desc_kmajor(smem_u32(smem + C::kOffQ), 128);
             const uint64_t dk = umma_desc_kmajor(smem_u32(smem + C::kOffK), 128);
@@ -156,24 +132,28 @@ attention_kernel(const OT* __restrict__ q, const OT* __restrict__ k, const OT* _
             for (int kk = 0; kk < C::kTail / 16; ++kk) umma_ss(tmem_base, dqt + 2 * kk, dkt + 2 * kk, idesc_s, 1);
             umma_commit(bar_s);
         }
+        __syncthreads();                                               // seg_kv visible
         mbar_wait(bar_s, ph);
         tc_fence_after();
-        // the K buffer is free again: prefetch the next key tile behind the softmax
-        if (t + 1 < kv_tiles) load_k(kv0 + 128);
-        cp_async_commit();
+        if (tid == 0 && t + 1 < kv_tiles) {                            // the K buffer is free: prefetch K(t+1) behind the softmax
+            mbar_arrive_expect_tx(bar_k, C::kQKBytes);
+            tma_load_3d(&map_k, bar_k, smem + C::kOffK, 0, kv0 + 128, bh);
+            tma_load_3d(&map_kt, bar_k, smem + C::kOffKT, 64, kv0 + 128, bh);
+        }
 
         // ---- p = exp2(s*c - bound*c)  (single pass, see header), row sum, P -> smem (A operand of P V) ----
         const int kv_valid = min(128, tokens - kv0);
         const bool dense = uniform && kv_valid == 128;                 // CTA-uniform: no per-element masking needed
         float lsum = 0.f;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < 2; ++c) {
             uint32_t v[32];
             tmem_ld32(t_s + c * 32, v);
             tmem_ld_wait();
+            const int colbase = half * 64 + c * 32;
             if (dbg_s != nullptr && t == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) dbg_s[tid * 128 + c * 32 + j] = __uint_as_float(v[j]);   // raw S tile (debug)
+                for (int j = 0; j < 32; ++j) dbg_s[row * 128 + colbase + j] = __uint_as_float(v[j]);   // raw S tile (debug)
             }
             uint32_t packed[16];
             if (dense) {
@@ -187,7 +167,7 @@ attention_kernel(const OT* __restrict__ q, const OT* __restrict__ k, const OT* _
             } else {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    const int col = c * 32 + 2 * j;
+                    const int col = colbase + 2 * j;
                     const bool ok0 = col < kv_valid && (uniform || seg_kv[col] == my_seg);
                     const bool ok1 = col + 1 < kv_valid && (uniform || seg_kv[col + 1] == my_seg);
                     const float p0 = ok0 ? fast_exp2(fmaf(__uint_as_float(v[2 * j]), scale_log2e, -bound_log2e)) : 0.f;
@@ -197,20 +177,20 @@ attention_kernel(const OT* __restrict__ q, const OT* __restrict__ k, const OT* _
                 }
             }
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {                              // 4 chunks of 8 keys per 32 columns
-                const int chunk = c * 4 + g;                            // 0..15 across the 128-key tile
-                sts128(smem_p + (chunk >> 3) * C::kPPanel + swz_offset<128>(tid, chunk & 7),
+            for (int g = 0; g < 4; ++g) {                              // 4 chunks of 8 keys per 32 columns; panel = this thread's half
+                const int chunk = c * 4 + g;                            // 0..7 inside the 64-key panel
+                sts128(smem_p + half * C::kPPanel + swz_offset<128>(row, chunk),
                        make_uint4(packed[g * 4], packed[g * 4 + 1], packed[g * 4 + 2], packed[g * 4 + 3]));
             }
         }
         l_run += lsum;
-        cp_async_wait<1>();                                            // V(t) has landed (K(t+1) may still be in flight)
         tc_fence_before();
         fence_proxy_async_smem();
         __syncthreads();
 
         // ---- O += P V ----
         if (tid == 0) {
+            mbar_wait(bar_v, ph);                                      // V(t) landed
             tc_fence_after();
 #pragma unroll
             for (int kk = 0; kk < 8; ++kk) {
@@ -222,34 +202,43 @@ attention_kernel(const OT* __restrict__ q, const OT* __restrict__ k, const OT* _
         }
         mbar_wait(bar_o, ph);                                          // P and V buffers are free, O(t) accumulated
         tc_fence_after();
-        if (t + 1 < kv_tiles) load_v(kv0 + 128);
-        cp_async_commit();
+        if (tid == 0 && t + 1 < kv_tiles) {
+            mbar_arrive_expect_tx(bar_v, C::kVBytes);
+            tma_load_3d(&map_v, bar_v, smem + C::kOffV, kv0 + 128, 0, bh);
+            tma_load_3d(&map_v, bar_v, smem + C::kOffV + C::kVPanel, kv0 + 192, 0, bh);
+        }
     }
-    cp_async_wait<0>();
 
     // ---- O / l, zero padded queries (mask != 0), write (M, heads*DH) rows for the proj GEMM ----
-    float o[C::kDHP];
-#pragma unroll
-    for (int c = 0; c < C::kDHP / 16; ++c) tmem_ld16(t_o + c * 16, reinterpret_cast<uint32_t*>(o) + c * 16);
+    l_part[tid] = l_run;
+    constexpr int OH = C::kDHP / 2;                                    // output columns per thread: 40 or 48
+    float o[OH];
+    tmem_ld32(t_o + half * OH, reinterpret_cast<uint32_t*>(o));
+    if constexpr (OH == 40) tmem_ld8(t_o + half * OH + 32, reinterpret_cast<uint32_t*>(o) + 32);
+    else tmem_ld16(t_o + half * OH + 32, reinterpret_cast<uint32_t*>(o) + 32);
     tmem_ld_wait();
+    __syncthreads();
+    const float l_tot = l_part[row] + l_part[row + 128];
     if (dbg_o != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
 #pragma unroll
-        for (int j = 0; j < C::kDHP; ++j) dbg_o[tid * C::kDHP + j] = o[j];                         // raw P V accumulator (debug)
+        for (int j = 0; j < OH; ++j) dbg_o[row * C::kDHP + half * OH + j] = o[j];                    // raw P V accumulator (debug)
     }
     if (q_ok) {
-        const float inv = (my_seg != 0.f && l_run > 0.f) ? 1.0f / l_run : 0.f;
-        OT* dst = out + ((size_t)sample * tokens + qi) * (heads * DH) + head * DH;
+        const float inv = (my_seg != 0.f && l_tot > 0.f) ? 1.0f / l_tot : 0.f;
+        OT* dst = out + ((size_t)sample * tokens + qi) * (heads * DH) + head * DH + half * OH;
 #pragma unroll
-        for (int c = 0; c < DH / 8; ++c) {
-            uint32_t pk[4];
+        for (int c = 0; c < OH / 8; ++c) {
+            if (half * OH + c * 8 < DH) {                              // skip the zero-pad columns 72..79
+                uint32_t pk[4];
 #pragma unroll
-            for (int p = 0; p < 4; ++p) pk[p] = Op16<OT>::pack(o[c * 8 + 2 * p] * inv, o[c * 8 + 2 * p + 1] * inv);
-            *reinterpret_cast<uint4*>(dst + c * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                for (int p = 0; p < 4; ++p) pk[p] = Op16<OT>::pack(o[c * 8 + 2 * p] * inv, o[c * 8 + 2 * p + 1] * inv);
+                *reinterpret_cast<uint4*>(dst + c * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) { __syncwarp(); tmem_dealloc(tmem_base, 256); }
+    if (warp == 1) { __syncwarp(); tmem_dealloc(tmem_base, 256); }
 }
 
 }  // namespace fitv2

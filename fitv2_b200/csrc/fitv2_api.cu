@@ -74,6 +74,26 @@ int make_map(CUtensorMap* map, const void* ptr, int operand_dtype, uint64_t rows
     return FITV2_OK;
 }
 
+// 3-D map (d0 contiguous, d1, d2) with a (box0, box1, 1) box; swizzle_bytes = 128 / 64 / 32 must equal box0 * 2.
+int make_map3(CUtensorMap* map, const void* ptr, int operand_dtype, uint64_t d0, uint64_t d1, uint64_t d2,
+              uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box0, uint32_t box1, int swizzle_bytes) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return fail(FITV2_E_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+    cuuint64_t dims[3] = {d0, d1, d2};
+    cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
+    cuuint32_t box[3] = {box0, box1, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+    CUresult r = fn(map, operand_dtype == FITV2_OPERAND_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                    3, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return fail(FITV2_E_CUDA, "cuTensorMapEncodeTiled(3d) failed (%d) dims=%llu,%llu,%llu box=%u,%u ptr=%p", (int)r,
+                    (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2, box0, box1, ptr);
+    return FITV2_OK;
+}
+
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct Layout {
@@ -255,18 +275,28 @@ int launch_attention(fitv2_handle* h, const void* q, const void* k, const void* 
     const float bound_log2e = c.rope_magnitude * c.rope_magnitude * sqrtf((float)c.head_dim) * 1.02f * 1.4426950408889634f -
                               (c.operand_dtype == FITV2_OPERAND_FP16 ? 8.0f : 0.0f);
     dim3 grid((tokens + 127) / 128, c.num_heads, rows);
+    // TMA maps over Q / K (dh, tokens, rows*heads) and V^T (tokens_v, dh, rows*heads); out-of-bounds = zero fill
+    const uint64_t DHu = c.head_dim, BH = (uint64_t)rows * c.num_heads;
+    const int dhp = (c.head_dim + 15) / 16 * 16, tail = dhp - 64;
+    CUtensorMap mq, mqt, mk, mkt, mv;
+    int rc;
+    if ((rc = make_map3(&mq, q, c.operand_dtype, DHu, tokens, BH, DHu * 2, (uint64_t)tokens * DHu * 2, 64, 128, 128))) return rc;
+    if ((rc = make_map3(&mqt, q, c.operand_dtype, DHu, tokens, BH, DHu * 2, (uint64_t)tokens * DHu * 2, tail, 128, tail * 2))) return rc;
+    if ((rc = make_map3(&mk, k, c.operand_dtype, DHu, tokens, BH, DHu * 2, (uint64_t)tokens * DHu * 2, 64, 128, 128))) return rc;
+    if ((rc = make_map3(&mkt, k, c.operand_dtype, DHu, tokens, BH, DHu * 2, (uint64_t)tokens * DHu * 2, tail, 128, tail * 2))) return rc;
+    if ((rc = make_map3(&mv, vt, c.operand_dtype, tokens_v, DHu, BH, (uint64_t)tokens_v * 2, DHu * tokens_v * 2, 64, dhp, 128))) return rc;
     if (c.head_dim == 72) {
         auto kern = attention_kernel<OT, 72>;
         static bool configured = false;
         if (!configured) { CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<72>::kSmemBytes)); configured = true; }
-        kern<<<grid, 128, AttnCfg<72>::kSmemBytes, st>>>((const OT*)q, (const OT*)k, (const OT*)vt, seg, seg_uniform, (OT*)out,
-                                                        c.num_heads, tokens, tokens_v, scale_log2e, bound_log2e, dbg_s, dbg_o);
+        kern<<<grid, AttnCfg<72>::kThreads, AttnCfg<72>::kSmemBytes, st>>>(mq, mqt, mk, mkt, mv, seg, seg_uniform, (OT*)out,
+                                                        c.num_heads, tokens, scale_log2e, bound_log2e, dbg_s, dbg_o);
     } else if (c.head_dim == 96) {
         auto kern = attention_kernel<OT, 96>;
         static bool configured = false;
         if (!configured) { CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<96>::kSmemBytes)); configured = true; }
-        kern<<<grid, 128, AttnCfg<96>::kSmemBytes, st>>>((const OT*)q, (const OT*)k, (const OT*)vt, seg, seg_uniform, (OT*)out,
-                                                        c.num_heads, tokens, tokens_v, scale_log2e, bound_log2e, dbg_s, dbg_o);
+        kern<<<grid, AttnCfg<96>::kThreads, AttnCfg<96>::kSmemBytes, st>>>(mq, mqt, mk, mkt, mv, seg, seg_uniform, (OT*)out,
+                                                        c.num_heads, tokens, scale_log2e, bound_log2e, dbg_s, dbg_o);
     } else {
         return fail(FITV2_E_INVALID, "head_dim %d not supported (72 or 96)", c.head_dim);
     }
