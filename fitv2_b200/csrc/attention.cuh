@@ -4,15 +4,17 @@
 //     attn_mask[b,i,j] = (mask[b,i] == mask[b,j])                (segment-id equality, NOT a pad mask)
 //     o = softmax(q k^T / sqrt(dh) + attn_mask) v ;  o *= (mask != 0)
 //
-// One CTA = one (sample, head, 128-query tile); keys are consumed in tiles of 128.  Both contractions run
-// on tcgen05:
+// Persistent kernel: 2 CTAs per SM loop over work items (sample, head, 128-query tile); keys are consumed in
+// tiles of 128.  Both contractions run on tcgen05:
 //     S = Q K^T   : M=128 queries, N=128 keys, K=DHP (head_dim padded to a multiple of 16)
 //     O += P V    : M=128 queries, N=DHP,      K=128 keys   (V arrives transposed, keys contiguous),
-//                   accumulated in TMEM across key tiles and read back once.
+//                   accumulated in TMEM across key tiles and read back once per item.
 // Q/K/V^T tiles are loaded by TMA (3-D tensor maps over (dim, token, sample*head); out-of-bounds rows/columns
 // are zero-filled, which pads head_dim 72 -> 80 and the sequence tail for free) straight into the canonical
 // K-major swizzled panels: a 64-element SWIZZLE_128B panel plus a 16/32-element SWIZZLE_32B/64B tail panel for
-// head_dim 72/96.  K(t+1) is prefetched behind the softmax of tile t, V(t+1) behind its P V product.
+// head_dim 72/96.  Every buffer is refilled as soon as its last reader has retired: K(t+1) — or Q and K(0) of
+// the NEXT work item — behind the softmax of tile t, V(t+1) / V(0) of the next item behind the P V product, so
+// the loads of an item are hidden behind the previous item's tail.
 // 256 threads: two threads per query row (warps w and w+4 share a TMEM lane quarter), each owning 64 of the 128
 // key columns of a tile, which doubles the number of warps hiding the TMEM / MUFU latencies of the softmax.
 //
@@ -23,7 +25,6 @@
 // overflow, stays far above fp32/bf16 underflow (>= e^-2*bound), and no online rescaling pass is needed.
 // (For fp16 operands the host lowers the bound by 8*ln2 so that p stays clear of the fp16 subnormal range;
 // the scale cancels in the final division by the row sum.)
-// Two CTAs are resident per SM so one CTA's softmax overlaps the other's MMAs / loads.
 #pragma once
 #include "common.cuh"
 #include "tc2sm.cuh"
@@ -59,7 +60,7 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                  const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_kt,
                  const __grid_constant__ CUtensorMap map_v,
                  const float* __restrict__ seg, const int* __restrict__ seg_uniform,
-                 OT* __restrict__ out, int heads, int tokens, float scale_log2e, float bound_log2e,
+                 OT* __restrict__ out, int heads, int tokens, int num_items, float scale_log2e, float bound_log2e,
                  float* __restrict__ dbg_s, float* __restrict__ dbg_o)
 {
     using C = AttnCfg<DH>;
@@ -67,34 +68,42 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     float* seg_kv = reinterpret_cast<float*>(smem + C::kOffSeg);
     float* l_part = reinterpret_cast<float*>(smem + C::kOffSum);
-    uint64_t* bar_s = reinterpret_cast<uint64_t*>(smem + C::kOffBar);   // S = Q K^T done
+    uint64_t* bar_s = reinterpret_cast<uint64_t*>(smem + C::kOffBar);   // S = Q K^T done          (one phase per key tile)
     uint64_t* bar_o = bar_s + 1;                                        // O += P V done
-    uint64_t* bar_k = bar_s + 2;                                        // (Q and) K tile landed
+    uint64_t* bar_k = bar_s + 2;                                        // K tile (and Q for tile 0) landed
     uint64_t* bar_v = bar_s + 3;                                        // V^T tile landed
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_s + 4);
 
     const int tid = threadIdx.x, warp = tid >> 5;
     const int row = tid & 127;                                          // query row inside the tile == TMEM lane
     const int half = tid >> 7;                                          // which 64 key columns / output half this thread owns
-    const int q0 = blockIdx.x * 128, head = blockIdx.y, sample = blockIdx.z;
-    const int bh = sample * heads + head;
-    const float* segb = seg + (size_t)sample * tokens;
-    const bool uniform = seg_uniform[sample] != 0;
-    const int kv_tiles = (tokens + 127) / 128;
+    const int q_tiles = (tokens + 127) / 128, kv_tiles = q_tiles;
 
-    if (tid == 0) {
-        tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v);
-        mbar_init(bar_s, 1); mbar_init(bar_o, 1); mbar_init(bar_k, 1); mbar_init(bar_v, 1);
-        mbar_fence_init();
-        // Q tile + K tile 0 on bar_k, V tile 0 on bar_v
+    // work item -> (query tile, sample*head); query tiles of one (sample, head) are adjacent so K / V stay in L2
+    auto issue_qk0 = [&](int item) {                                    // tid 0 only
+        const int bh = item / q_tiles, q0 = (item - bh * q_tiles) * 128;
         mbar_arrive_expect_tx(bar_k, 2 * C::kQKBytes);
         tma_load_3d(&map_q, bar_k, smem + C::kOffQ, 0, q0, bh);
         tma_load_3d(&map_qt, bar_k, smem + C::kOffQT, 64, q0, bh);
         tma_load_3d(&map_k, bar_k, smem + C::kOffK, 0, 0, bh);
         tma_load_3d(&map_kt, bar_k, smem + C::kOffKT, 64, 0, bh);
+    };
+    auto issue_k = [&](int bh, int kv0) {
+        mbar_arrive_expect_tx(bar_k, C::kQKBytes);
+        tma_load_3d(&map_k, bar_k, smem + C::kOffK, 0, kv0, bh);
+        tma_load_3d(&map_kt, bar_k, smem + C::kOffKT, 64, kv0, bh);
+    };
+    auto issue_v = [&](int bh, int kv0) {
         mbar_arrive_expect_tx(bar_v, C::kVBytes);
-        tma_load_3d(&map_v, bar_v, smem + C::kOffV, 0, 0, bh);
-        tma_load_3d(&map_v, bar_v, smem + C::kOffV + C::kVPanel, 64, 0, bh);
+        tma_load_3d(&map_v, bar_v, smem + C::kOffV, kv0, 0, bh);
+        tma_load_3d(&map_v, bar_v, smem + C::kOffV + C::kVPanel, kv0 + 64, 0, bh);
+    };
+
+    if (tid == 0) {
+        tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v);
+        mbar_init(bar_s, 1); mbar_init(bar_o, 1); mbar_init(bar_k, 1); mbar_init(bar_v, 1);
+        mbar_fence_init();
+        if ((int)blockIdx.x < num_items) { issue_qk0(blockIdx.x); issue_v(blockIdx.x / q_tiles, 0); }
     }
     if (warp == 1) tmem_alloc(tmem_slot, 256);
     tc_fence_before();
@@ -104,137 +113,143 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     const uint32_t t_s = tmem_base + (uint32_t((warp & 3) * 32) << 16) + half * 64;   // S columns [0,128): this thread's 64
     const uint32_t t_o = tmem_base + (uint32_t((warp & 3) * 32) << 16) + 128;         // O columns [128,128+DHP)
     const uint32_t smem_p = smem_u32(smem + C::kOffP);
-
-    const int qi = q0 + row;
-    const bool q_ok = qi < tokens;
-    const float my_seg = q_ok ? segb[qi] : 0.f;
-    float l_run = 0.f;
-
     constexpr uint32_t idesc_s = umma_idesc(Op16<OT>::kUmmaFormat, 128, 128);
     constexpr uint32_t idesc_o = umma_idesc(Op16<OT>::kUmmaFormat, 128, C::kDHP);
-    uint32_t ph = 0;
+    uint32_t ph = 0;                                                    // parity of the running key-tile counter
 
-    for (int t = 0; t < kv_tiles; ++t, ph ^= 1) {
-        const int kv0 = t * 128;
-        if (tid < 128) seg_kv[tid] = (kv0 + tid < tokens) ? segb[kv0 + tid] : 0.f;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        const int bh = item / q_tiles, q0 = (item - bh * q_tiles) * 128;
+        const int sample = bh / heads, head = bh - sample * heads;
+        const int next_item = item + gridDim.x;
+        const float* segb = seg + (size_t)sample * tokens;
+        const bool uniform = seg_uniform[sample] != 0;
+        const int qi = q0 + row;
+        const bool q_ok = qi < tokens;
+        const float my_seg = q_ok ? segb[qi] : 0.f;
+        float l_run = 0.f;
 
-        // ---- S = Q K^T ----
-        if (tid == 0) {
-            mbar_wait(bar_k, ph);                                      // K(t) (and Q) landed
+        for (int t = 0; t < kv_tiles; ++t, ph ^= 1) {
+            const int kv0 = t * 128;
+            if (tid < 128) seg_kv[tid] = (kv0 + tid < tokens) ? segb[kv0 + tid] : 0.f;
+
+            // ---- S = Q K^T ----
+            if (tid == 0) {
+                mbar_wait(bar_k, ph);                                  // K(t) (and Q) landed
+                tc_fence_after();
+                const uint64_t dq = umma_desc_kmajor(smem_u32(smem + C::kOffQ), 128);
+                const uint64_t dk = umma_desc_kmajor(smem_u32(smem + C::kOffK), 128);
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) umma_ss(tmem_base, dq + 2 * kk, dk + 2 * kk, idesc_s, kk != 0);
+                const uint64_t dqt = umma_desc_kmajor(smem_u32(smem + C::kOffQT), C::kTailBytes);
+                const uint64_t dkt = umma_desc_kmajor(smem_u32(smem + C::kOffKT), C::kTailBytes);
+#pragma unroll
+                for (int kk = 0; kk < C::kTail / 16; ++kk) umma_ss(tmem_base, dqt + 2 * kk, dkt + 2 * kk, idesc_s, 1);
+                umma_commit(bar_s);
+            }
+            __syncthreads();                                           // seg_kv visible; previous item's epilogue finished
+            mbar_wait(bar_s, ph);
             tc_fence_after();
-            const uint64_t dq = umma_desc_kmajor(smem_u32(smem + C::kOffQ), 128);
-            const uint64_t dk = umma_desc_kmajor(smem_u32(smem + C::kOffK), 128);
+            if (tid == 0) {                                            // K (and, after the last tile, Q) buffers are free
+                if (t + 1 < kv_tiles) issue_k(bh, kv0 + 128);
+                else if (next_item < num_items) issue_qk0(next_item);
+            }
+
+            // ---- p = exp2(s*c - bound*c)  (single pass, see header), row sum, P -> smem (A operand of P V) ----
+            const int kv_valid = min(128, tokens - kv0);
+            const bool dense = uniform && kv_valid == 128;             // CTA-uniform: no per-element masking needed
+            float lsum = 0.f;
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) umma_ss(tmem_base, dq + 2 * kk, dk + 2 * kk, idesc_s, kk != 0);
-            const uint64_t dqt = umma_desc_kmajor(smem_u32(smem + C::kOffQT), C::kTailBytes);
-            const uint64_t dkt = umma_desc_kmajor(smem_u32(smem + C::kOffKT), C::kTailBytes);
+            for (int c = 0; c < 2; ++c) {
+                uint32_t v[32];
+                tmem_ld32(t_s + c * 32, v);
+                tmem_ld_wait();
+                const int colbase = half * 64 + c * 32;
+                if (dbg_s != nullptr && t == 0 && item == 0) {
 #pragma unroll
-            for (int kk = 0; kk < C::kTail / 16; ++kk) umma_ss(tmem_base, dqt + 2 * kk, dkt + 2 * kk, idesc_s, 1);
-            umma_commit(bar_s);
-        }
-        __syncthreads();                                               // seg_kv visible
-        mbar_wait(bar_s, ph);
-        tc_fence_after();
-        if (tid == 0 && t + 1 < kv_tiles) {                            // the K buffer is free: prefetch K(t+1) behind the softmax
-            mbar_arrive_expect_tx(bar_k, C::kQKBytes);
-            tma_load_3d(&map_k, bar_k, smem + C::kOffK, 0, kv0 + 128, bh);
-            tma_load_3d(&map_kt, bar_k, smem + C::kOffKT, 64, kv0 + 128, bh);
+                    for (int j = 0; j < 32; ++j) dbg_s[row * 128 + colbase + j] = __uint_as_float(v[j]);   // raw S tile (debug)
+                }
+                uint32_t packed[16];
+                if (dense) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float p0 = fast_exp2(fmaf(__uint_as_float(v[2 * j]), scale_log2e, -bound_log2e));
+                        const float p1 = fast_exp2(fmaf(__uint_as_float(v[2 * j + 1]), scale_log2e, -bound_log2e));
+                        packed[j] = Op16<OT>::pack(p0, p1);
+                        lsum += p0 + p1;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int col = colbase + 2 * j;
+                        const bool ok0 = col < kv_valid && (uniform || seg_kv[col] == my_seg);
+                        const bool ok1 = col + 1 < kv_valid && (uniform || seg_kv[col + 1] == my_seg);
+                        const float p0 = ok0 ? fast_exp2(fmaf(__uint_as_float(v[2 * j]), scale_log2e, -bound_log2e)) : 0.f;
+                        const float p1 = ok1 ? fast_exp2(fmaf(__uint_as_float(v[2 * j + 1]), scale_log2e, -bound_log2e)) : 0.f;
+                        packed[j] = Op16<OT>::pack(p0, p1);
+                        lsum += p0 + p1;
+                    }
+                }
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {                          // 4 chunks of 8 keys per 32 columns; panel = this thread's half
+                    const int chunk = c * 4 + g;                        // 0..7 inside the 64-key panel
+                    sts128(smem_p + half * C::kPPanel + swz_offset<128>(row, chunk),
+                           make_uint4(packed[g * 4], packed[g * 4 + 1], packed[g * 4 + 2], packed[g * 4 + 3]));
+                }
+            }
+            l_run += lsum;
+            tc_fence_before();
+            fence_proxy_async_smem();
+            __syncthreads();
+
+            // ---- O += P V ----
+            if (tid == 0) {
+                mbar_wait(bar_v, ph);                                  // V(t) landed
+                tc_fence_after();
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) {
+                    const uint64_t dp = umma_desc_kmajor(smem_u32(smem + C::kOffP + (kk >> 2) * C::kPPanel), 128) + 2 * (kk & 3);
+                    const uint64_t dv = umma_desc_kmajor(smem_u32(smem + C::kOffV + (kk >> 2) * C::kVPanel), 128) + 2 * (kk & 3);
+                    umma_ss(tmem_base + 128, dp, dv, idesc_o, (t | kk) != 0);
+                }
+                umma_commit(bar_o);
+            }
+            mbar_wait(bar_o, ph);                                      // P and V buffers are free, O(t) accumulated
+            tc_fence_after();
+            if (tid == 0) {
+                if (t + 1 < kv_tiles) issue_v(bh, kv0 + 128);
+                else if (next_item < num_items) issue_v(next_item / q_tiles, 0);
+            }
         }
 
-        // ---- p = exp2(s*c - bound*c)  (single pass, see header), row sum, P -> smem (A operand of P V) ----
-        const int kv_valid = min(128, tokens - kv0);
-        const bool dense = uniform && kv_valid == 128;                 // CTA-uniform: no per-element masking needed
-        float lsum = 0.f;
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-            uint32_t v[32];
-            tmem_ld32(t_s + c * 32, v);
-            tmem_ld_wait();
-            const int colbase = half * 64 + c * 32;
-            if (dbg_s != nullptr && t == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) dbg_s[row * 128 + colbase + j] = __uint_as_float(v[j]);   // raw S tile (debug)
-            }
-            uint32_t packed[16];
-            if (dense) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const float p0 = fast_exp2(fmaf(__uint_as_float(v[2 * j]), scale_log2e, -bound_log2e));
-                    const float p1 = fast_exp2(fmaf(__uint_as_float(v[2 * j + 1]), scale_log2e, -bound_log2e));
-                    packed[j] = Op16<OT>::pack(p0, p1);
-                    lsum += p0 + p1;
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int col = colbase + 2 * j;
-                    const bool ok0 = col < kv_valid && (uniform || seg_kv[col] == my_seg);
-                    const bool ok1 = col + 1 < kv_valid && (uniform || seg_kv[col + 1] == my_seg);
-                    const float p0 = ok0 ? fast_exp2(fmaf(__uint_as_float(v[2 * j]), scale_log2e, -bound_log2e)) : 0.f;
-                    const float p1 = ok1 ? fast_exp2(fmaf(__uint_as_float(v[2 * j + 1]), scale_log2e, -bound_log2e)) : 0.f;
-                    packed[j] = Op16<OT>::pack(p0, p1);
-                    lsum += p0 + p1;
-                }
-            }
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {                              // 4 chunks of 8 keys per 32 columns; panel = this thread's half
-                const int chunk = c * 4 + g;                            // 0..7 inside the 64-key panel
-                sts128(smem_p + half * C::kPPanel + swz_offset<128>(row, chunk),
-                       make_uint4(packed[g * 4], packed[g * 4 + 1], packed[g * 4 + 2], packed[g * 4 + 3]));
-            }
-        }
-        l_run += lsum;
+        // ---- O / l, zero padded queries (mask != 0), write (M, heads*DH) rows for the proj GEMM ----
+        l_part[tid] = l_run;
+        constexpr int OH = C::kDHP / 2;                                // output columns per thread: 40 or 48
+        float o[OH];
+        tmem_ld32(t_o + half * OH, reinterpret_cast<uint32_t*>(o));
+        if constexpr (OH == 40) tmem_ld8(t_o + half * OH + 32, reinterpret_cast<uint32_t*>(o) + 32);
+        else tmem_ld16(t_o + half * OH + 32, reinterpret_cast<uint32_t*>(o) + 32);
+        tmem_ld_wait();
         tc_fence_before();
-        fence_proxy_async_smem();
         __syncthreads();
-
-        // ---- O += P V ----
-        if (tid == 0) {
-            mbar_wait(bar_v, ph);                                      // V(t) landed
-            tc_fence_after();
+        const float l_tot = l_part[row] + l_part[row + 128];
+        if (dbg_o != nullptr && item == 0) {
 #pragma unroll
-            for (int kk = 0; kk < 8; ++kk) {
-                const uint64_t dp = umma_desc_kmajor(smem_u32(smem + C::kOffP + (kk >> 2) * C::kPPanel), 128) + 2 * (kk & 3);
-                const uint64_t dv = umma_desc_kmajor(smem_u32(smem + C::kOffV + (kk >> 2) * C::kVPanel), 128) + 2 * (kk & 3);
-                umma_ss(tmem_base + 128, dp, dv, idesc_o, (t | kk) != 0);
-            }
-            umma_commit(bar_o);
+            for (int j = 0; j < OH; ++j) dbg_o[row * C::kDHP + half * OH + j] = o[j];                // raw P V accumulator (debug)
         }
-        mbar_wait(bar_o, ph);                                          // P and V buffers are free, O(t) accumulated
-        tc_fence_after();
-        if (tid == 0 && t + 1 < kv_tiles) {
-            mbar_arrive_expect_tx(bar_v, C::kVBytes);
-            tma_load_3d(&map_v, bar_v, smem + C::kOffV, kv0 + 128, 0, bh);
-            tma_load_3d(&map_v, bar_v, smem + C::kOffV + C::kVPanel, kv0 + 192, 0, bh);
-        }
-    }
-
-    // ---- O / l, zero padded queries (mask != 0), write (M, heads*DH) rows for the proj GEMM ----
-    l_part[tid] = l_run;
-    constexpr int OH = C::kDHP / 2;                                    // output columns per thread: 40 or 48
-    float o[OH];
-    tmem_ld32(t_o + half * OH, reinterpret_cast<uint32_t*>(o));
-    if constexpr (OH == 40) tmem_ld8(t_o + half * OH + 32, reinterpret_cast<uint32_t*>(o) + 32);
-    else tmem_ld16(t_o + half * OH + 32, reinterpret_cast<uint32_t*>(o) + 32);
-    tmem_ld_wait();
-    __syncthreads();
-    const float l_tot = l_part[row] + l_part[row + 128];
-    if (dbg_o != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+        if (q_ok) {
+            const float inv = (my_seg != 0.f && l_tot > 0.f) ? 1.0f / l_tot : 0.f;
+            OT* dst = out + ((size_t)sample * tokens + qi) * (heads * DH) + head * DH + half * OH;
 #pragma unroll
-        for (int j = 0; j < OH; ++j) dbg_o[row * C::kDHP + half * OH + j] = o[j];                    // raw P V accumulator (debug)
-    }
-    if (q_ok) {
-        const float inv = (my_seg != 0.f && l_tot > 0.f) ? 1.0f / l_tot : 0.f;
-        OT* dst = out + ((size_t)sample * tokens + qi) * (heads * DH) + head * DH + half * OH;
+            for (int c = 0; c < OH / 8; ++c) {
+                if (half * OH + c * 8 < DH) {                          // skip the zero-pad columns 72..79
+                    uint32_t pk[4];
 #pragma unroll
-        for (int c = 0; c < OH / 8; ++c) {
-            if (half * OH + c * 8 < DH) {                              // skip the zero-pad columns 72..79
-                uint32_t pk[4];
-#pragma unroll
-                for (int p = 0; p < 4; ++p) pk[p] = Op16<OT>::pack(o[c * 8 + 2 * p] * inv, o[c * 8 + 2 * p + 1] * inv);
-                *reinterpret_cast<uint4*>(dst + c * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    for (int p = 0; p < 4; ++p) pk[p] = Op16<OT>::pack(o[c * 8 + 2 * p] * inv, o[c * 8 + 2 * p + 1] * inv);
+                    *reinterpret_cast<uint4*>(dst + c * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                }
             }
         }
+        // l_part / seg_kv are rewritten only after the next item's first __syncthreads
     }
     tc_fence_before();
     __syncthreads();

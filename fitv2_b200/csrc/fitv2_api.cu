@@ -274,7 +274,8 @@ int launch_attention(fitv2_handle* h, const void* q, const void* k, const void* 
     // fp16 operands: shift by 8 binades so that P stays in the normal fp16 range (cancels in O / l).
     const float bound_log2e = c.rope_magnitude * c.rope_magnitude * sqrtf((float)c.head_dim) * 1.02f * 1.4426950408889634f -
                               (c.operand_dtype == FITV2_OPERAND_FP16 ? 8.0f : 0.0f);
-    dim3 grid((tokens + 127) / 128, c.num_heads, rows);
+    const int num_items = ((tokens + 127) / 128) * c.num_heads * rows;          // (query tile, head, sample) work items
+    const int grid = num_items < 2 * h->num_sms ? num_items : 2 * h->num_sms;     // persistent: two CTAs per SM
     // TMA maps over Q / K (dh, tokens, rows*heads) and V^T (tokens_v, dh, rows*heads); out-of-bounds = zero fill
     const uint64_t DHu = c.head_dim, BH = (uint64_t)rows * c.num_heads;
     const int dhp = (c.head_dim + 15) / 16 * 16, tail = dhp - 64;
@@ -290,13 +291,13 @@ int launch_attention(fitv2_handle* h, const void* q, const void* k, const void* 
         static bool configured = false;
         if (!configured) { CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<72>::kSmemBytes)); configured = true; }
         kern<<<grid, AttnCfg<72>::kThreads, AttnCfg<72>::kSmemBytes, st>>>(mq, mqt, mk, mkt, mv, seg, seg_uniform, (OT*)out,
-                                                        c.num_heads, tokens, scale_log2e, bound_log2e, dbg_s, dbg_o);
+                                                        c.num_heads, tokens, num_items, scale_log2e, bound_log2e, dbg_s, dbg_o);
     } else if (c.head_dim == 96) {
         auto kern = attention_kernel<OT, 96>;
         static bool configured = false;
         if (!configured) { CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<96>::kSmemBytes)); configured = true; }
         kern<<<grid, AttnCfg<96>::kThreads, AttnCfg<96>::kSmemBytes, st>>>(mq, mqt, mk, mkt, mv, seg, seg_uniform, (OT*)out,
-                                                        c.num_heads, tokens, scale_log2e, bound_log2e, dbg_s, dbg_o);
+                                                        c.num_heads, tokens, num_items, scale_log2e, bound_log2e, dbg_s, dbg_o);
     } else {
         return fail(FITV2_E_INVALID, "head_dim %d not supported (72 or 96)", c.head_dim);
     }
