@@ -231,73 +231,68 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             if constexpr (EPI == EPI_RESID) {
                 constexpr int HALF = BN / 2;                          // columns per warp
                 constexpr int NFULL = HALF / 32, REM = HALF % 32;     // 32-column slabs + one remainder slab
+                constexpr int NS = NFULL + (REM ? 1 : 0);
+                constexpr int NPF = NS < 3 ? NS : 3;                  // slabs of x kept in flight (register ring)
                 static_assert(REM == 0 || REM == 8 || REM == 16, "unsupported tile half width");
                 const int col0 = n0 + half * HALF;
                 float* xbase = ep.x + (size_t)m_warp * N + col0;
-                // The residual does not depend on the accumulator: the first slab of x is fetched (coalesced
-                // mapping) before waiting for the MMAs of this tile.
-                float4 xa[8], xb[8];
-                auto load_x = [&](float4* dst, int s0, auto cpr_tag) {
-                    constexpr int CPR = decltype(cpr_tag)::value;
+                // The residual does not depend on the accumulator: the x values of (up to) the whole tile half are
+                // requested, in the coalesced mapping, BEFORE waiting for the MMAs of this tile, so the HBM latency
+                // of the fp32 residual stream hides behind the main loop (it was the bound of the proj/fc2 GEMMs).
+                float4 xr[NPF][8];
+                auto load_x = [&](int slot, int sl) {                 // slot / sl are compile-time constants after unrolling
+                    const int cpr = sl < NFULL ? 8 : REM / 4;         // 16-byte chunks per slab row
 #pragma unroll
-                    for (int i = 0; i < CPR; ++i) {                   // CPR chunks/row * 32 rows / 32 lanes = CPR iterations
-                        int r, c; slab_task<CPR>(i, lane, r, c);
-                        if (r < rows_valid) dst[i] = *reinterpret_cast<const float4*>(xbase + (size_t)r * N + s0 + c * 4);
+                    for (int i = 0; i < 8; ++i) {
+                        if (i < cpr) {
+                            const int task = i * 32 + lane, r = task / cpr, c = task - r * cpr;
+                            if (r < rows_valid) xr[slot][i] = *reinterpret_cast<const float4*>(xbase + (size_t)r * N + sl * 32 + c * 4);
+                        }
                     }
                 };
-                auto do_slab = [&](int s0, bool last, auto cpr_tag, auto next_tag, int next_s0) {
-                    constexpr int CPR = decltype(cpr_tag)::value;     // 16-byte chunks per slab row (W = 4 * CPR columns)
-                    constexpr int NCPR = decltype(next_tag)::value;
-                    uint32_t v[CPR * 4];
-                    if constexpr (CPR == 8) tmem_ld32(t_row + half * HALF + s0, v);
-                    else if constexpr (CPR == 4) tmem_ld16(t_row + half * HALF + s0, v);
+#pragma unroll
+                for (int sl = 0; sl < NPF; ++sl) load_x(sl, sl);
+                mbar_wait(&tfull_bar[acc], acc_phase);
+                tc_fence_after();
+#pragma unroll
+                for (int sl = 0; sl < NS; ++sl) {
+                    const int cpr = sl < NFULL ? 8 : REM / 4;
+                    const int s0 = sl * 32;
+                    uint32_t v[32];
+                    if (cpr == 8) tmem_ld32(t_row + half * HALF + s0, v);
+                    else if (cpr == 4) tmem_ld16(t_row + half * HALF + s0, v);
                     else tmem_ld8(t_row + half * HALF + s0, v);
                     tmem_ld_wait();
-                    if (last) release_acc(acc);
+                    if (sl == NS - 1) release_acc(acc);
 #pragma unroll
-                    for (int c = 0; c < CPR; ++c)
-                        sts128(stg + slab_off(lane, c), make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]));
+                    for (int c = 0; c < 8; ++c)
+                        if (c < cpr) sts128(stg + slab_off(lane, c), make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]));
                     __syncwarp();
-                    if constexpr (NCPR > 0) load_x(xb, next_s0, next_tag);      // prefetch the next slab of x
-                    int r0, c0; slab_task<CPR>(0, lane, r0, c0);                 // this lane's chunk column is the same in every iteration
+                    const int c0 = lane % cpr;                        // this lane's chunk column is the same in every iteration
                     const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + s0 + c0 * 4));
                     float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (one_sample) g = __ldg(reinterpret_cast<const float4*>(ep.gate + (size_t)s_first * ep.gate_ld + col0 + s0 + c0 * 4));
 #pragma unroll
-                    for (int i = 0; i < CPR; ++i) {
-                        int r, c; slab_task<CPR>(i, lane, r, c);
-                        if (r < rows_valid) {
-                            if (!one_sample)
-                                g = __ldg(reinterpret_cast<const float4*>(ep.gate + (size_t)((m_warp + r) / ep.tokens) * ep.gate_ld + col0 + s0 + c * 4));
-                            const uint4 au = lds128(stg + slab_off(r, c));
-                            const float4 a = make_float4(__uint_as_float(au.x), __uint_as_float(au.y), __uint_as_float(au.z), __uint_as_float(au.w));
-                            float4 o;
-                            o.x = xa[i].x + g.x * (a.x + b.x);
-                            o.y = xa[i].y + g.y * (a.y + b.y);
-                            o.z = xa[i].z + g.z * (a.z + b.z);
-                            o.w = xa[i].w + g.w * (a.w + b.w);
-                            *reinterpret_cast<float4*>(xbase + (size_t)r * N + s0 + c * 4) = o;
+                    for (int i = 0; i < 8; ++i) {
+                        if (i < cpr) {
+                            const int task = i * 32 + lane, r = task / cpr, c = task - r * cpr;
+                            if (r < rows_valid) {
+                                if (!one_sample)
+                                    g = __ldg(reinterpret_cast<const float4*>(ep.gate + (size_t)((m_warp + r) / ep.tokens) * ep.gate_ld + col0 + s0 + c * 4));
+                                const uint4 au = lds128(stg + slab_off(r, c));
+                                const float4 xv = xr[sl % NPF][i];
+                                float4 o;
+                                o.x = xv.x + g.x * (__uint_as_float(au.x) + b.x);
+                                o.y = xv.y + g.y * (__uint_as_float(au.y) + b.y);
+                                o.z = xv.z + g.z * (__uint_as_float(au.z) + b.z);
+                                o.w = xv.w + g.w * (__uint_as_float(au.w) + b.w);
+                                *reinterpret_cast<float4*>(xbase + (size_t)r * N + s0 + c * 4) = o;
+                            }
                         }
                     }
                     __syncwarp();
-                    if constexpr (NCPR > 0) {
-#pragma unroll
-                        for (int i = 0; i < NCPR; ++i) xa[i] = xb[i];
-                    }
-                };
-                using C8 = std::integral_constant<int, 8>;
-                using CR = std::integral_constant<int, REM / 4>;
-                using C0 = std::integral_constant<int, 0>;
-                if constexpr (NFULL > 0) load_x(xa, 0, C8{}); else load_x(xa, 0, CR{});
-                mbar_wait(&tfull_bar[acc], acc_phase);
-                tc_fence_after();
-#pragma unroll
-                for (int s = 0; s < NFULL; ++s) {
-                    if (s + 1 < NFULL) do_slab(s * 32, false, C8{}, C8{}, (s + 1) * 32);
-                    else if constexpr (REM > 0) do_slab(s * 32, false, C8{}, CR{}, (s + 1) * 32);
-                    else do_slab(s * 32, true, C8{}, C0{}, 0);
+                    if (sl + NPF < NS) load_x(sl % NPF, sl + NPF);    // refill the ring slot (only tiles wider than 3 slabs)
                 }
-                if constexpr (REM > 0) do_slab(NFULL * 32, true, CR{}, C0{}, 0);
             } else if constexpr (EPI == EPI_SWIGLU) {
                 // tile columns: [0, BN/2) = gate rows of W, [BN/2, BN) = matching up rows (host packs W this way)
                 constexpr int HALF = BN / 2;                          // outputs per tile
@@ -388,14 +383,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 }
                 if (kind < 2) {
                     // LayerNorm over the head (no affine, eps 1e-6, biased variance): norms.py:41-42
-                    float mean = 0.f;
+                    float s4[4] = {0.f, 0.f, 0.f, 0.f};               // 4 independent chains instead of one 72-long one
 #pragma unroll
-                    for (int j = 0; j < DH; ++j) mean += v[j];
-                    mean *= (1.0f / DH);
-                    float var = 0.f;
+                    for (int j = 0; j < DH; j += 4) { s4[0] += v[j]; s4[1] += v[j + 1]; s4[2] += v[j + 2]; s4[3] += v[j + 3]; }
+                    const float mean = ((s4[0] + s4[1]) + (s4[2] + s4[3])) * (1.0f / DH);
+                    float q4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                    for (int j = 0; j < DH; ++j) { const float d = v[j] - mean; var += d * d; }
-                    const float rstd = rsqrtf(var * (1.0f / DH) + 1e-6f);
+                    for (int j = 0; j < DH; j += 4) {
+                        const float d0 = v[j] - mean, d1 = v[j + 1] - mean, d2 = v[j + 2] - mean, d3 = v[j + 3] - mean;
+                        q4[0] = fmaf(d0, d0, q4[0]); q4[1] = fmaf(d1, d1, q4[1]); q4[2] = fmaf(d2, d2, q4[2]); q4[3] = fmaf(d3, d3, q4[3]);
+                    }
+                    const float rstd = rsqrtf(((q4[0] + q4[1]) + (q4[2] + q4[3])) * (1.0f / DH) + 1e-6f);
                     const float* cs = ep.rope_cos + (row_ok ? m : 0);        // pair-major tables: coalesced across lanes
                     const float* sn = ep.rope_sin + (row_ok ? m : 0);
 #pragma unroll
