@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfitv2_b200.so")
+LIB_PATH = os.environ.get("FITV2_B200_LIB", os.path.join(_HERE, "libfitv2_b200.so"))   # override: A/B kernel experiments
 
 OPERAND_BF16, OPERAND_FP16 = 0, 1
 

@@ -252,16 +252,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 };
 #pragma unroll
                 for (int sl = 0; sl < NPF; ++sl) load_x(sl, sl);
-                // bias / gate of this lane's chunk column for every slab, also ahead of the accumulator wait
-                float4 bs[NS], gs[NS];
-#pragma unroll
-                for (int sl = 0; sl < NS; ++sl) {
-                    const int cpr = sl < NFULL ? 8 : REM / 4;
-                    const int cc = col0 + sl * 32 + (lane % cpr) * 4;
-                    bs[sl] = __ldg(reinterpret_cast<const float4*>(ep.bias + cc));
-                    gs[sl] = one_sample ? __ldg(reinterpret_cast<const float4*>(ep.gate + (size_t)s_first * ep.gate_ld + cc))
-                                        : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
                 mbar_wait(&tfull_bar[acc], acc_phase);
                 tc_fence_after();
 #pragma unroll
@@ -278,8 +268,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     for (int c = 0; c < 8; ++c)
                         if (c < cpr) sts128(stg + slab_off(lane, c), make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]));
                     __syncwarp();
-                    const float4 b = bs[sl];                          // this lane's chunk column is the same in every iteration
-                    float4 g = gs[sl];
+                    const int c0 = lane % cpr;                        // this lane's chunk column is the same in every iteration
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + s0 + c0 * 4));
+                    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (one_sample) g = __ldg(reinterpret_cast<const float4*>(ep.gate + (size_t)s_first * ep.gate_ld + col0 + s0 + c0 * 4));
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         if (i < cpr) {
