@@ -311,12 +311,6 @@ int launch_ln_modulate(fitv2_handle* h, const float* x, const float* shift, cons
                        int M, int D, int tokens, cudaStream_t st) {
     const int nv = (D / 4 + 31) / 32;
     const int blocks = (M * 32 + 255) / 256;
-    if (tokens % 16 == 0 && nv > 3 && nv <= 9) {          // XL widths: two rows per warp, shift/scale staged in smem
-        ln_modulate2_kernel<OT, 9><<<(M + 15) / 16, 256, (size_t)2 * D * 4, st>>>(x, shift, scale, mod_ld, (OT*)out, M, D, tokens);
-        CUDA_TRY(cudaGetLastError());
-        h->launches++;
-        return FITV2_OK;
-    }
     if (nv <= 1) ln_modulate_kernel<OT, 1><<<blocks, 256, 0, st>>>(x, shift, scale, mod_ld, (OT*)out, M, D, tokens);
     else if (nv <= 3) ln_modulate_kernel<OT, 3><<<blocks, 256, 0, st>>>(x, shift, scale, mod_ld, (OT*)out, M, D, tokens);
     else if (nv <= 9) ln_modulate_kernel<OT, 9><<<blocks, 256, 0, st>>>(x, shift, scale, mod_ld, (OT*)out, M, D, tokens);
@@ -328,7 +322,7 @@ int launch_ln_modulate(fitv2_handle* h, const float* x, const float* shift, cons
 }
 
 int launch_small_linear(fitv2_handle* h, const SmallLinear& p, int batches, cudaStream_t st) {
-    dim3 grid((p.N + 127) / 128, (p.rows + 63) / 64, batches);
+    dim3 grid((p.N + 63) / 64, (p.rows + 63) / 64, batches);
     small_linear_kernel<<<grid, 256, 0, st>>>(p);
     CUDA_TRY(cudaGetLastError());
     h->launches++;

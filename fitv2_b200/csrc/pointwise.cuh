@@ -163,68 +163,6 @@ ln_modulate_kernel(const float* __restrict__ x, const float* __restrict__ shift,
     }
 }
 
-// Variant used when every block's 16 rows belong to one sample (tokens % 16 == 0): the sample's shift / scale rows
-// are staged once per block in shared memory and every warp normalises TWO rows, so each lane keeps 2*NV
-// independent 128-bit DRAM requests in flight (the kernel is HBM-latency bound).
-template <typename OT, int NV>
-__global__ void __launch_bounds__(256)
-ln_modulate2_kernel(const float* __restrict__ x, const float* __restrict__ shift, const float* __restrict__ scale,
-                    int mod_ld, OT* __restrict__ h, int M, int D, int tokens)
-{
-    extern __shared__ float4 smod[];                     // [2][D/4] : shift | scale of this block's sample
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int nvec = D >> 2;
-    const int m0 = blockIdx.x * 16 + warp * 2;
-    const float4* xr0 = reinterpret_cast<const float4*>(x + (size_t)m0 * D);
-    const float4* xr1 = xr0 + nvec;
-    const bool ok0 = m0 < M, ok1 = m0 + 1 < M;
-    float4 v0[NV], v1[NV];
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-        const int j = lane + 32 * i;
-        v0[i] = (ok0 && j < nvec) ? ld_stream_f4(xr0 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-        v1[i] = (ok1 && j < nvec) ? ld_stream_f4(xr1 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    {
-        const int sample = (blockIdx.x * 16) / tokens;
-        const float4* sh = reinterpret_cast<const float4*>(shift + (size_t)sample * mod_ld);
-        const float4* sc = reinterpret_cast<const float4*>(scale + (size_t)sample * mod_ld);
-        for (int j = threadIdx.x; j < nvec; j += blockDim.x) { smod[j] = __ldg(sh + j); smod[nvec + j] = __ldg(sc + j); }
-    }
-    float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-        s0 += (v0[i].x + v0[i].y) + (v0[i].z + v0[i].w);
-        s1 += (v1[i].x + v1[i].y) + (v1[i].z + v1[i].w);
-    }
-    const float mean0 = warp_sum(s0) / (float)D, mean1 = warp_sum(s1) / (float)D;
-    float q0 = 0.f, q1 = 0.f;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-        if (lane + 32 * i < nvec) {
-            float a = v0[i].x - mean0, b = v0[i].y - mean0, c = v0[i].z - mean0, d = v0[i].w - mean0;
-            q0 += (a * a + b * b) + (c * c + d * d);
-            a = v1[i].x - mean1; b = v1[i].y - mean1; c = v1[i].z - mean1; d = v1[i].w - mean1;
-            q1 += (a * a + b * b) + (c * c + d * d);
-        }
-    }
-    const float rstd0 = rsqrtf(warp_sum(q0) / (float)D + 1e-6f), rstd1 = rsqrtf(warp_sum(q1) / (float)D + 1e-6f);
-    __syncthreads();                                     // smod filled
-    uint2* hr0 = reinterpret_cast<uint2*>(h + (size_t)m0 * D);
-    uint2* hr1 = hr0 + nvec;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-        const int j = lane + 32 * i;
-        if (j < nvec) {
-            const float4 a = smod[j], g = smod[nvec + j];
-            if (ok0) hr0[j] = make_uint2(Op16<OT>::pack((v0[i].x - mean0) * rstd0 * (1.f + g.x) + a.x, (v0[i].y - mean0) * rstd0 * (1.f + g.y) + a.y),
-                                         Op16<OT>::pack((v0[i].z - mean0) * rstd0 * (1.f + g.z) + a.z, (v0[i].w - mean0) * rstd0 * (1.f + g.w) + a.w));
-            if (ok1) hr1[j] = make_uint2(Op16<OT>::pack((v1[i].x - mean1) * rstd1 * (1.f + g.x) + a.x, (v1[i].y - mean1) * rstd1 * (1.f + g.y) + a.y),
-                                         Op16<OT>::pack((v1[i].z - mean1) * rstd1 * (1.f + g.z) + a.z, (v1[i].w - mean1) * rstd1 * (1.f + g.w) + a.w));
-        }
-    }
-}
-
 // ---------------------------------------------------------------------------------------------
 // Final layer  (modules.py:292-296, fit_model.py:230):
 //   out[m, :] = (W_o (Cout x D) * (LN(x[m]) * (1 + scale) + shift) + b_o) * mask[m]
@@ -367,7 +305,7 @@ __global__ void timestep_features_kernel(const float* __restrict__ t, float time
 //   out[z][r, n] = sum_k act(A[z][r, k]) * W[z][n, k] + bias[z][n] (+ add[r, n]) (+ emb[label[r], n])
 // M = samples (64 with CFG) -> weight-bandwidth-bound; fp32 FMA keeps the modulation exact to
 // fp32 rounding because shift/scale/gate feed every token of every block.
-// 64x128 output tile per CTA, 16x16 threads with 4x8 register tiles, K chunks of 16 through double-buffered smem.
+// 64x64 output tile per CTA, 16x16 threads with 4x4 register tiles, K chunks of 16 through smem.
 // ---------------------------------------------------------------------------------------------
 struct SmallLinear {
     const float* A; size_t a_batch_stride; int lda;
@@ -384,65 +322,47 @@ struct SmallLinear {
 __global__ void __launch_bounds__(256)
 small_linear_kernel(SmallLinear p)
 {
-    // 64 (rows) x 128 (outputs) tile per CTA, 16 x 16 threads with 4 x 8 register tiles, K chunks of 16 staged
-    // through double-buffered shared memory; the next chunk's global loads are in flight while the current one is
-    // multiplied (one __syncthreads per chunk).
-    __shared__ float As[2][16][64 + 4];
-    __shared__ float Ws[2][16][128 + 4];
+    __shared__ float As[16][64 + 4];
+    __shared__ float Ws[16][64 + 4];
     const int z = blockIdx.z;
     const float* A = p.A + z * p.a_batch_stride;
     const float* W = p.W + z * p.w_batch_stride;
-    const int n0 = blockIdx.x * 128, r0 = blockIdx.y * 64;
+    const int n0 = blockIdx.x * 64, r0 = blockIdx.y * 64;
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-    float acc[4][8];
+    float acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
-    const int lr = threadIdx.x >> 2;            // 0..63 : row of A / rows lr and lr+64 of W loaded by this thread
+    const int lr = threadIdx.x >> 2;            // 0..63 : row (A) / col (W) loaded by this thread
     const int lk = (threadIdx.x & 3) * 4;       // 0,4,8,12
-    float4 av, wv0, wv1;
-    auto fetch = [&](int k0) {
-        av = wv0 = wv1 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (k0 + lk < p.K) {
-            if (r0 + lr < p.rows) {
-                av = *reinterpret_cast<const float4*>(A + (size_t)(r0 + lr) * p.lda + k0 + lk);
-                if (p.act_silu_in) {
-                    av.x = av.x / (1.f + expf(-av.x)); av.y = av.y / (1.f + expf(-av.y));
-                    av.z = av.z / (1.f + expf(-av.z)); av.w = av.w / (1.f + expf(-av.w));
-                }
+    for (int k0 = 0; k0 < p.K; k0 += 16) {
+        float4 av = make_float4(0.f, 0.f, 0.f, 0.f), wv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r0 + lr < p.rows && k0 + lk < p.K) {
+            av = *reinterpret_cast<const float4*>(A + (size_t)(r0 + lr) * p.lda + k0 + lk);
+            if (p.act_silu_in) {
+                av.x = av.x / (1.f + expf(-av.x)); av.y = av.y / (1.f + expf(-av.y));
+                av.z = av.z / (1.f + expf(-av.z)); av.w = av.w / (1.f + expf(-av.w));
             }
-            if (n0 + lr < p.N) wv0 = __ldg(reinterpret_cast<const float4*>(W + (size_t)(n0 + lr) * p.K + k0 + lk));
-            if (n0 + lr + 64 < p.N) wv1 = __ldg(reinterpret_cast<const float4*>(W + (size_t)(n0 + lr + 64) * p.K + k0 + lk));
         }
-    };
-    auto stash = [&](int buf) {
-        As[buf][lk + 0][lr] = av.x; As[buf][lk + 1][lr] = av.y; As[buf][lk + 2][lr] = av.z; As[buf][lk + 3][lr] = av.w;
-        Ws[buf][lk + 0][lr] = wv0.x; Ws[buf][lk + 1][lr] = wv0.y; Ws[buf][lk + 2][lr] = wv0.z; Ws[buf][lk + 3][lr] = wv0.w;
-        Ws[buf][lk + 0][lr + 64] = wv1.x; Ws[buf][lk + 1][lr + 64] = wv1.y; Ws[buf][lk + 2][lr + 64] = wv1.z; Ws[buf][lk + 3][lr + 64] = wv1.w;
-    };
-    fetch(0);
-    stash(0);
-    __syncthreads();
-    int buf = 0;
-    for (int k0 = 0; k0 < p.K; k0 += 16, buf ^= 1) {
-        const bool more = k0 + 16 < p.K;
-        if (more) fetch(k0 + 16);
+        if (n0 + lr < p.N && k0 + lk < p.K)
+            wv = __ldg(reinterpret_cast<const float4*>(W + (size_t)(n0 + lr) * p.K + k0 + lk));
+        __syncthreads();
+        As[lk + 0][lr] = av.x; As[lk + 1][lr] = av.y; As[lk + 2][lr] = av.z; As[lk + 3][lr] = av.w;
+        Ws[lk + 0][lr] = wv.x; Ws[lk + 1][lr] = wv.y; Ws[lk + 2][lr] = wv.z; Ws[lk + 3][lr] = wv.w;
+        __syncthreads();
 #pragma unroll
         for (int kk = 0; kk < 16; ++kk) {
-            const float4 a4 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
-            const float4 w0 = *reinterpret_cast<const float4*>(&Ws[buf][kk][tx * 4]);        // columns tx*4 .. +3
-            const float4 w1 = *reinterpret_cast<const float4*>(&Ws[buf][kk][64 + tx * 4]);   // columns 64 + tx*4 .. +3
+            const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+            const float4 w4 = *reinterpret_cast<const float4*>(&Ws[kk][tx * 4]);
             const float a[4] = {a4.x, a4.y, a4.z, a4.w};
-            const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+            const float w[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
         }
-        if (more) stash(buf ^ 1);
-        __syncthreads();
     }
     const float* bias = p.bias ? p.bias + z * p.bias_batch_stride : nullptr;
     float* out = p.out + z * p.out_batch_stride;
@@ -452,8 +372,8 @@ small_linear_kernel(SmallLinear p)
         const int r = r0 + ty * 4 + i;
         if (r >= p.rows) continue;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int n = n0 + (j >> 2) * 64 + tx * 4 + (j & 3);
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
             if (n >= p.N) continue;
             float v = acc[i][j];
             if (bias) v += bias[n];
