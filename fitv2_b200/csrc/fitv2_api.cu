@@ -17,6 +17,9 @@ using namespace fitv2;
 
 namespace {
 
+// scratch for the split-K partial sums of the conditioning linears
+constexpr size_t kCondPartialBytes = 24u << 20;
+
 // Thread-block cluster size of the production GEMMs (weight-tile TMA multicast across the cluster).
 constexpr int kGemmCluster = 2;
 
@@ -98,7 +101,7 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct Layout {
     int rows = 0, tokens = 0, tokens_v = 0;
-    size_t x_res, h, ao, q, k, vt, hidden, te, t0, c, sc, lmid, gmod, mod, fmod, rope_cos, rope_sin, seg_uniform, total;
+    size_t x_res, h, ao, q, k, vt, hidden, te, t0, c, sc, lmid, gmod, mod, fmod, rope_cos, rope_sin, seg_uniform, cpart, total;
 };
 
 }  // namespace
@@ -186,6 +189,7 @@ Layout make_layout(const fitv2_config& c, int rows, int tokens) {
     l.rope_cos = take(M * (c.head_dim / 2) * 4);
     l.rope_sin = take(M * (c.head_dim / 2) * 4);
     l.seg_uniform = take((size_t)rows * 4);
+    l.cpart = take(kCondPartialBytes);
     l.total = off;
     return l;
 }
@@ -321,11 +325,28 @@ int launch_ln_modulate(fitv2_handle* h, const float* x, const float* shift, cons
     return FITV2_OK;
 }
 
-int launch_small_linear(fitv2_handle* h, const SmallLinear& p, int batches, cudaStream_t st) {
-    dim3 grid((p.N + 63) / 64, (p.rows + 63) / 64, batches);
+int launch_small_linear(fitv2_handle* h, SmallLinear p, int batches, cudaStream_t st) {
+    const int col_tiles = (p.N + 63) / 64, row_blocks = (p.rows + 63) / 64;
+    const long ctas = (long)col_tiles * row_blocks * batches;
+    // fill the GPU: split K when the output alone gives fewer than ~2 CTAs per SM (each split keeps >= 64 of K)
+    long ksplit = (2L * h->num_sms + ctas - 1) / ctas;
+    const long max_by_k = p.K / 64 > 0 ? p.K / 64 : 1;
+    const long max_by_mem = (long)(kCondPartialBytes / ((size_t)batches * p.rows * p.N * 4));
+    if (ksplit > max_by_k) ksplit = max_by_k;
+    if (ksplit > max_by_mem) ksplit = max_by_mem;
+    if (ksplit < 1) ksplit = 1;
+    p.ksplit = (int)ksplit;
+    p.partial = reinterpret_cast<float*>(h->ws + h->lay.cpart);
+    dim3 grid(col_tiles, row_blocks * p.ksplit, batches);
     small_linear_kernel<<<grid, 256, 0, st>>>(p);
     CUDA_TRY(cudaGetLastError());
     h->launches++;
+    if (p.ksplit > 1) {
+        dim3 g2((unsigned)(((size_t)p.rows * p.N + 255) / 256), 1, batches);
+        small_linear_finalize_kernel<<<g2, 256, 0, st>>>(p);
+        CUDA_TRY(cudaGetLastError());
+        h->launches++;
+    }
     return FITV2_OK;
 }
 

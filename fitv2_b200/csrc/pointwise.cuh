@@ -317,6 +317,8 @@ struct SmallLinear {
     float* out_silu;             // optional second output: silu(out) (same layout)
     int rows, N, K;
     int act_silu_in;             // apply SiLU to A on load
+    int ksplit;                  // > 1: K is split over blockIdx.y; raw partial sums go to `partial`, finalize adds the rest
+    float* partial;              // [batches][ksplit][rows][N]
 };
 
 __global__ void __launch_bounds__(256)
@@ -327,7 +329,13 @@ small_linear_kernel(SmallLinear p)
     const int z = blockIdx.z;
     const float* A = p.A + z * p.a_batch_stride;
     const float* W = p.W + z * p.w_batch_stride;
-    const int n0 = blockIdx.x * 64, r0 = blockIdx.y * 64;
+    const int ks = p.ksplit > 1 ? blockIdx.y % p.ksplit : 0;
+    const int n0 = blockIdx.x * 64, r0 = (p.ksplit > 1 ? blockIdx.y / p.ksplit : blockIdx.y) * 64;
+    // launches with few output tiles (N = 1152 .. 2304 at 64 rows) would run on a handful of SMs, each walking the whole
+    // K extent serially (latency bound): split K so that every launch fills the GPU; the split sums are added in a
+    // fixed order by small_linear_finalize_kernel (deterministic, no atomics).
+    const int kchunk = p.ksplit > 1 ? ((p.K + 16 * p.ksplit - 1) / (16 * p.ksplit)) * 16 : p.K;
+    const int k_begin = ks * kchunk, k_end = min(p.K, k_begin + kchunk);
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     float acc[4][4];
 #pragma unroll
@@ -337,16 +345,16 @@ small_linear_kernel(SmallLinear p)
 
     const int lr = threadIdx.x >> 2;            // 0..63 : row (A) / col (W) loaded by this thread
     const int lk = (threadIdx.x & 3) * 4;       // 0,4,8,12
-    for (int k0 = 0; k0 < p.K; k0 += 16) {
+    for (int k0 = k_begin; k0 < k_end; k0 += 16) {
         float4 av = make_float4(0.f, 0.f, 0.f, 0.f), wv = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (r0 + lr < p.rows && k0 + lk < p.K) {
+        if (r0 + lr < p.rows && k0 + lk < k_end) {
             av = *reinterpret_cast<const float4*>(A + (size_t)(r0 + lr) * p.lda + k0 + lk);
             if (p.act_silu_in) {
                 av.x = av.x / (1.f + expf(-av.x)); av.y = av.y / (1.f + expf(-av.y));
                 av.z = av.z / (1.f + expf(-av.z)); av.w = av.w / (1.f + expf(-av.w));
             }
         }
-        if (n0 + lr < p.N && k0 + lk < p.K)
+        if (n0 + lr < p.N && k0 + lk < k_end)
             wv = __ldg(reinterpret_cast<const float4*>(W + (size_t)(n0 + lr) * p.K + k0 + lk));
         __syncthreads();
         As[lk + 0][lr] = av.x; As[lk + 1][lr] = av.y; As[lk + 2][lr] = av.z; As[lk + 3][lr] = av.w;
@@ -363,6 +371,20 @@ small_linear_kernel(SmallLinear p)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
         }
+    }
+    if (p.ksplit > 1) {
+        float* part = p.partial + ((size_t)z * p.ksplit + ks) * p.rows * p.N;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int r = r0 + ty * 4 + i;
+            if (r >= p.rows) continue;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int n = n0 + tx * 4 + j;
+                if (n < p.N) part[(size_t)r * p.N + n] = acc[i][j];
+            }
+        }
+        return;
     }
     const float* bias = p.bias ? p.bias + z * p.bias_batch_stride : nullptr;
     float* out = p.out + z * p.out_batch_stride;
@@ -383,6 +405,24 @@ small_linear_kernel(SmallLinear p)
             if (out_silu) out_silu[(size_t)r * p.ldo + n] = v / (1.f + expf(-v));
         }
     }
+}
+
+// out = sum over K splits (fixed order) + bias (+ add) (+ embedding row); optional silu(out)
+__global__ void small_linear_finalize_kernel(SmallLinear p)
+{
+    const int z = blockIdx.z;
+    const size_t total = (size_t)p.rows * p.N;
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int r = (int)(i / p.N), n = (int)(i % p.N);
+    const float* part = p.partial + (size_t)z * p.ksplit * total + i;
+    float v = 0.f;
+    for (int s = 0; s < p.ksplit; ++s) v += part[(size_t)s * total];
+    if (p.bias) v += p.bias[z * p.bias_batch_stride + n];
+    if (p.add) v += p.add[(size_t)r * p.N + n];
+    if (p.emb) v += p.emb[(size_t)p.labels[r] * p.N + n];
+    p.out[z * p.out_batch_stride + (size_t)r * p.ldo + n] = v;
+    if (p.out_silu) p.out_silu[z * p.out_batch_stride + (size_t)r * p.ldo + n] = v / (1.f + expf(-v));
 }
 
 }  // namespace fitv2

@@ -216,7 +216,7 @@ def test_forward_stage_taps_depth1(lib):
         assert rel(m.debug_tap(name), want) < 8e-3, name
     assert rel(m.debug_tap("vt")[..., :256], taps["v"].transpose(-1, -2)) < 8e-3
     assert rel(m.debug_tap("x_res"), taps["x1"]) < 5e-3
-    assert m.kernel_launches() == 18
+    assert 18 <= m.kernel_launches() <= 24       # 18 kernels + one finalize per split-K conditioning linear
 
 
 @pytest.mark.parametrize("width,operand", [(B3, "bf16"), (XL, "fp16")])
