@@ -61,6 +61,15 @@ def measured_peaks():
     return dict(tflops_burst=1590.0, tflops_sustained=1400.0, hbm_gbs=6650.0, source="fallback (B200_PROFILING.md)")
 
 
+def ncu_traffic(workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu --set full summary."""
+    p = os.path.join(ROOT, "profiles", "r1_gateup_ncu_full.json")
+    if workload != "xl256" or not os.path.exists(p):
+        return None
+    with open(p) as f:
+        return json.load(f).get("traffic_bytes_per_launch")
+
+
 class ClockSampler:
     """nvidia-smi clock / throttle-reason samples during the timed region (B200_PROFILING.md recipe)."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
@@ -276,7 +285,7 @@ def run_ours(args):
         gpu_launches=int(launches),
         roofline=dict(bound="tensor", kernel="gemm_tc_kernel<256, EPI_SWIGLU> (fused gate/up GEMM + SwiGLU epilogue)",
                       achieved=gu_tflops, peak=peaks["tflops_sustained"], unit="TFLOP/s",
-                      frac=(gu_tflops / peaks["tflops_sustained"]) if gu_tflops else None, traffic=None,
+                      frac=(gu_tflops / peaks["tflops_sustained"]) if gu_tflops else None, traffic=ncu_traffic(args.workload),
                       peak_source=peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
                       launches_timed=gu_cnt, us_per_launch=(gu_ms / gu_cnt * 1e3) if gu_cnt else None),
         clocks=clocks.summary(),
