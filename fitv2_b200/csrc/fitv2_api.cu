@@ -10,6 +10,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -119,7 +120,7 @@ struct fitv2_handle {
     bool maps_valid = false;
     CUtensorMap map_h, map_ao, map_hidden;              // activations (A operands)
     CUtensorMap map_wqkv, map_wproj, map_wgu, map_wfc2; // stacked weights (B operands)
-    int bn_resid = 0;
+    int bn_proj = 0, bn_fc2 = 0;
     int num_sms = 148;
     int64_t launches = 0;
     // optional per-kernel-class CUDA-event timing (fitv2_profile_*)
@@ -254,7 +255,7 @@ int launch_gemm_bn(fitv2_handle* h, int bn, const CUtensorMap& ma, const CUtenso
 }
 
 // Tile width for the N = hidden_size projections: minimise (waves x per-tile cost) over the widths that divide N.
-int pick_bn(int M, int N, int num_sms) {
+int pick_bn(int M, int N, int num_sms, bool prefer_aligned) {
     const int cands[4] = {256, 192, 144, 128};
     int best = 0; long best_cost = 0;
     for (int bn : cands) {
@@ -262,7 +263,8 @@ int pick_bn(int M, int N, int num_sms) {
         const long m_tiles = (M + kGemmBM - 1) / kGemmBM;
         const long tiles = ((m_tiles + kGemmCluster - 1) / kGemmCluster) * kGemmCluster * (N / bn);
         const long waves = (tiles + num_sms - 1) / num_sms;
-        const long cost = waves * (bn + 16);
+        long cost = waves * (bn + 16);
+        if (prefer_aligned && (bn / 2) % 32 != 0) cost += cost / 4;    // tile halves not aligned to 128-byte lines of the fp32 residual
         if (!best || cost < best_cost) { best = bn; best_cost = cost; }
     }
     return best;
@@ -359,12 +361,19 @@ int ensure_maps(fitv2_handle* h) {
     if ((rc = make_map(&h->map_h, h->ws + l.h, c.operand_dtype, M, D, D, 128))) return rc;
     if ((rc = make_map(&h->map_ao, h->ws + l.ao, c.operand_dtype, M, D, D, 128))) return rc;
     if ((rc = make_map(&h->map_hidden, h->ws + l.hidden, c.operand_dtype, M, Hm, Hm, 128))) return rc;
-    h->bn_resid = pick_bn((int)M, (int)D, h->num_sms);
-    if (!h->bn_resid) return fail(FITV2_E_INVALID, "hidden_size %d has no supported tile width (multiple of 128/144/192/256)", (int)D);
+    // proj (K = D) is bound by its fp32 residual epilogue: prefer tile widths whose halves start on 128-byte lines;
+    // fc2 (K = mlp_hidden) is main-loop bound: pure wave / tile-size cost.
+    h->bn_proj = pick_bn((int)M, (int)D, h->num_sms, /*prefer_aligned=*/true);
+    h->bn_fc2 = pick_bn((int)M, (int)D, h->num_sms, /*prefer_aligned=*/false);
+    if (const char* e = getenv("FITV2_BN_RESID")) {             // tuning experiments only
+        const int v = atoi(e);
+        if ((v == 128 || v == 144 || v == 192 || v == 256) && D % v == 0) h->bn_proj = h->bn_fc2 = v;
+    }
+    if (!h->bn_proj || !h->bn_fc2) return fail(FITV2_E_INVALID, "hidden_size %d has no supported tile width (multiple of 128/144/192/256)", (int)D);
     if ((rc = make_map(&h->map_wqkv, h->w[FITV2_W_QKV_W], c.operand_dtype, L * 3 * D, D, D, 2 * c.head_dim / kGemmCluster))) return rc;
-    if ((rc = make_map(&h->map_wproj, h->w[FITV2_W_PROJ_W], c.operand_dtype, L * D, D, D, h->bn_resid / kGemmCluster))) return rc;
+    if ((rc = make_map(&h->map_wproj, h->w[FITV2_W_PROJ_W], c.operand_dtype, L * D, D, D, h->bn_proj / kGemmCluster))) return rc;
     if ((rc = make_map(&h->map_wgu, h->w[FITV2_W_GATEUP_W], c.operand_dtype, L * 2 * Hm, D, D, 256 / kGemmCluster))) return rc;
-    if ((rc = make_map(&h->map_wfc2, h->w[FITV2_W_FC2_W], c.operand_dtype, L * D, Hm, Hm, h->bn_resid / kGemmCluster))) return rc;
+    if ((rc = make_map(&h->map_wfc2, h->w[FITV2_W_FC2_W], c.operand_dtype, L * D, Hm, Hm, h->bn_fc2 / kGemmCluster))) return rc;
     h->maps_valid = true;
     return FITV2_OK;
 }
@@ -469,7 +478,7 @@ int forward_impl(fitv2_handle* h, const float* x, int x_rows, const float* t, co
         ep.bias = (const float*)h->w[FITV2_W_PROJ_B] + (size_t)layer * D;
         ep.tokens = tokens; ep.x = x_res; ep.gate = modl + 2 * D; ep.gate_ld = 6 * D;
         prof_begin(h, PC_PROJ, st);
-        if ((rc = launch_gemm_bn<EPI_RESID, OT>(h, h->bn_resid, h->map_ao, h->map_wproj, M, D, D, layer * D, ep, st))) return rc;
+        if ((rc = launch_gemm_bn<EPI_RESID, OT>(h, h->bn_proj, h->map_ao, h->map_wproj, M, D, D, layer * D, ep, st))) return rc;
         prof_end(h, st);
         // ---- SwiGLU branch (modules.py:273) ----
         prof_begin(h, PC_LNMOD, st);
@@ -485,7 +494,7 @@ int forward_impl(fitv2_handle* h, const float* x, int x_rows, const float* t, co
         ep.bias = (const float*)h->w[FITV2_W_FC2_B] + (size_t)layer * D;
         ep.tokens = tokens; ep.x = x_res; ep.gate = modl + 5 * D; ep.gate_ld = 6 * D;
         prof_begin(h, PC_FC2, st);
-        if ((rc = launch_gemm_bn<EPI_RESID, OT>(h, h->bn_resid, h->map_hidden, h->map_wfc2, M, D, Hm, layer * D, ep, st))) return rc;
+        if ((rc = launch_gemm_bn<EPI_RESID, OT>(h, h->bn_fc2, h->map_hidden, h->map_wfc2, M, D, Hm, layer * D, ep, st))) return rc;
         prof_end(h, st);
     }
 
