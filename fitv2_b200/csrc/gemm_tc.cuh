@@ -62,7 +62,10 @@ template <int BN, int EPI, int DH, int CL = 1> struct GemmCfg {
     static constexpr int kABytes = kGemmBM * kGemmBK * 2;
     static constexpr int kBRowsPerCta = BN / CL;                       // CL = 2: each CTA stages half of the weight tile
     static constexpr int kBBytes = kBRowsPerCta * kGemmBK * 2;
-    static constexpr int kStageBytes = kABytes + kBBytes;              // per CTA
+    // narrow tiles: one pipeline stage carries TWO 64-wide K blocks (8 UMMAs per barrier round trip); the UMMA issue /
+    // commit / wait overhead per stage, not the tensor pipe, bounded BN <= 192 tiles (70 % tensor-pipe utilisation)
+    static constexpr int kKSub = (kABytes + kBBytes) <= 28 * 1024 ? 2 : 1;
+    static constexpr int kStageBytes = (kABytes + kBBytes) * kKSub;    // per CTA
     static constexpr int kTxBytes = kStageBytes * CL;                  // credited to the (leader's) full barrier per stage
     static constexpr int kBarrierBytes = 1024;
     // epilogue staging: per warp 32 rows; QKV rows hold one head (16-bit) with a bank-conflict-free pitch,
@@ -100,7 +103,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;
-    uint8_t* smem_b = smem + STAGES * Cfg::kABytes;
+    constexpr int KSUB = Cfg::kKSub;
+    uint8_t* smem_b = smem + STAGES * Cfg::kABytes * KSUB;
     uint8_t* smem_epi = smem + STAGES * Cfg::kStageBytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + Cfg::kEpiBytes);
     uint64_t* full_bar = bars;
@@ -116,7 +120,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     // work items are groups of CL vertically adjacent 128-row tiles; CTA `cta_rank` of the cluster owns row tile
     // group * CL + cta_rank (a phantom tile past the M tail computes on zero-filled rows and stores nothing)
     const int num_groups = ((m_tiles + CL - 1) / CL) * n_tiles;
-    const int num_kb = (K + kGemmBK - 1) / kGemmBK;
+    const int num_kb = (K + kGemmBK * Cfg::kKSub - 1) / (kGemmBK * Cfg::kKSub);       // pipeline stages per tile
     const uint32_t cta_rank = CL > 1 ? cluster_ctarank() : 0u;
     const bool leader = cta_rank == 0;
     const int group0 = blockIdx.x / CL, group_stride = gridDim.x / CL;
@@ -147,18 +151,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             for (int kb = 0; kb < num_kb; ++kb) {
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 if (elect_one()) {
-                    uint8_t* sa = smem_a + stage * Cfg::kABytes;
-                    uint8_t* sb = smem_b + stage * Cfg::kBBytes;
-                    if constexpr (CL == 1) {
-                        mbar_arrive_expect_tx(&full_bar[stage], Cfg::kTxBytes);
-                        tma_load_2d(&tma_a, &full_bar[stage], sa, kb * kGemmBK, m_tile * kGemmBM);
-                        tma_load_2d(&tma_b, &full_bar[stage], sb, kb * kGemmBK, b_row_offset + n_tile * BN);
-                    } else {
-                        // both CTAs' loads are credited to the leader's barrier, which expects the pair's bytes
-                        if (leader) mbar_arrive_expect_tx(&full_bar[stage], Cfg::kTxBytes);
-                        tma_load_2d_2sm(&tma_a, &full_bar[stage], sa, kb * kGemmBK, m_tile * kGemmBM);
-                        tma_load_2d_2sm(&tma_b, &full_bar[stage], sb, kb * kGemmBK,
-                                        b_row_offset + n_tile * BN + (int)cta_rank * Cfg::kBRowsPerCta);
+                    uint8_t* sa = smem_a + stage * Cfg::kABytes * KSUB;
+                    uint8_t* sb = smem_b + stage * Cfg::kBBytes * KSUB;
+                    // both CTAs' loads are credited to the leader's barrier, which expects the pair's bytes
+                    if (CL == 1 || leader) mbar_arrive_expect_tx(&full_bar[stage], Cfg::kTxBytes);
+#pragma unroll
+                    for (int j = 0; j < KSUB; ++j) {               // a K block past the end of K is zero-filled by TMA
+                        const int kcol = (kb * KSUB + j) * kGemmBK;
+                        if constexpr (CL == 1) {
+                            tma_load_2d(&tma_a, &full_bar[stage], sa + j * Cfg::kABytes, kcol, m_tile * kGemmBM);
+                            tma_load_2d(&tma_b, &full_bar[stage], sb + j * Cfg::kBBytes, kcol, b_row_offset + n_tile * BN);
+                        } else {
+                            tma_load_2d_2sm(&tma_a, &full_bar[stage], sa + j * Cfg::kABytes, kcol, m_tile * kGemmBM);
+                            tma_load_2d_2sm(&tma_b, &full_bar[stage], sb + j * Cfg::kBBytes, kcol,
+                                            b_row_offset + n_tile * BN + (int)cta_rank * Cfg::kBRowsPerCta);
+                        }
                     }
                 }
                 __syncwarp();
@@ -182,12 +189,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     if (elect_one()) {
-                        const uint64_t da = da0 + (uint64_t)(stage * (Cfg::kABytes >> 4));   // start-address field is addr >> 4
-                        const uint64_t db = db0 + (uint64_t)(stage * (Cfg::kBBytes >> 4));
 #pragma unroll
-                        for (int kk = 0; kk < kGemmBK / 16; ++kk) {  // +32 bytes (>>4 = 2) per K=16 step inside the 128B atom
-                            if constexpr (CL == 1) umma_ss(d_tmem, da + 2 * kk, db + 2 * kk, idesc, (kb | kk) != 0);
-                            else umma_ss_2sm(d_tmem, da + 2 * kk, db + 2 * kk, idesc, (kb | kk) != 0);
+                        for (int j = 0; j < KSUB; ++j) {
+                            const uint64_t da = da0 + (uint64_t)((stage * KSUB + j) * (Cfg::kABytes >> 4));   // start-address field is addr >> 4
+                            const uint64_t db = db0 + (uint64_t)((stage * KSUB + j) * (Cfg::kBBytes >> 4));
+#pragma unroll
+                            for (int kk = 0; kk < kGemmBK / 16; ++kk) {  // +32 bytes (>>4 = 2) per K=16 step inside the 128B atom
+                                if constexpr (CL == 1) umma_ss(d_tmem, da + 2 * kk, db + 2 * kk, idesc, (kb | j | kk) != 0);
+                                else umma_ss_2sm(d_tmem, da + 2 * kk, db + 2 * kk, idesc, (kb | j | kk) != 0);
+                            }
                         }
                         // smem slot free (in both CTAs) once these MMAs retire; accumulator ready after the last k-block
                         if constexpr (CL == 1) {
