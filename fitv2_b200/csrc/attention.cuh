@@ -103,9 +103,12 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v);
         mbar_init(bar_s, 1); mbar_init(bar_o, 1); mbar_init(bar_k, 1); mbar_init(bar_v, 1);
         mbar_fence_init();
+        pdl_wait();                                                     // Q / K / V^T come from the QKV GEMM in front
         if ((int)blockIdx.x < num_items) { issue_qk0(blockIdx.x); issue_v(blockIdx.x / q_tiles, 0); }
     }
     if (warp == 1) tmem_alloc(tmem_slot, 256);
+    pdl_wait();
+    pdl_launch_dependents();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();

@@ -94,6 +94,26 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     __trap();
 }
 
+// Programmatic dependent launch: every kernel of the NFE chain is launched with programmatic stream serialization,
+// so its prologue (barrier init, TMEM allocation, descriptor prefetch, CTA placement) overlaps the tail of the
+// kernel in front of it.  pdl_wait() blocks until that kernel has completed and its writes are visible; it must
+// precede the first global-memory access.  pdl_launch_dependents() lets the NEXT kernel's CTAs be placed as soon
+// as SM resources free up (they block in their own pdl_wait()).  Both are no-ops without the launch attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// Non-blocking phase test (the polling tcgen05 issuer of attention_ws.cuh).
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, P;\n\t"
+        "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return done != 0;
+}
+
 // thread-block cluster helpers
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;

@@ -5,6 +5,7 @@
 #include "common.cuh"
 #include "gemm_tc.cuh"
 #include "attention.cuh"
+#include "attention_ws.cuh"
 #include "pointwise.cuh"
 
 #include <cstdarg>
@@ -25,6 +26,38 @@ constexpr size_t kCondPartialBytes = 24u << 20;
 constexpr int kGemmCluster = 2;
 
 thread_local std::string g_last_error;
+
+// Programmatic dependent launch for every kernel of the chain (see pdl_wait() in common.cuh); FITV2_PDL=0 turns it off
+// for A/B measurements.
+bool pdl_enabled() {
+    static const bool on = [] { const char* e = getenv("FITV2_PDL"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
+template <typename... KArgs, typename... Args>
+cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster, Args&&... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    unsigned n = 0;
+    if (cluster > 1) {
+        attr[n].id = cudaLaunchAttributeClusterDimension;
+        attr[n].val.clusterDim.x = cluster; attr[n].val.clusterDim.y = 1; attr[n].val.clusterDim.z = 1;
+        ++n;
+    }
+    if (pdl_enabled()) {
+        attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = n;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 
 int fail(int code, const char* fmt, ...) {
     char buf[1024];
@@ -95,6 +128,23 @@ int make_map3(CUtensorMap* map, const void* ptr, int operand_dtype, uint64_t d0,
     if (r != CUDA_SUCCESS)
         return fail(FITV2_E_CUDA, "cuTensorMapEncodeTiled(3d) failed (%d) dims=%llu,%llu,%llu box=%u,%u ptr=%p", (int)r,
                     (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2, box0, box1, ptr);
+    return FITV2_OK;
+}
+
+// 4-D output map of the attention kernel: (head_dim, heads, tokens, samples) over the (M, heads*head_dim) 16-bit matrix,
+// box = one (128 tokens x head_dim) tile of one head, no swizzle (dense staging rows).
+int make_map_attn_out(CUtensorMap* map, const void* ptr, int operand_dtype, uint64_t dh, uint64_t heads, uint64_t tokens,
+                      uint64_t samples) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return fail(FITV2_E_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+    cuuint64_t dims[4] = {dh, heads, tokens, samples};
+    cuuint64_t strides[3] = {dh * 2, heads * dh * 2, tokens * heads * dh * 2};
+    cuuint32_t box[4] = {(cuuint32_t)dh, 1, 128, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(map, operand_dtype == FITV2_OPERAND_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                    4, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(FITV2_E_CUDA, "cuTensorMapEncodeTiled(attention out) failed (%d)", (int)r);
     return FITV2_OK;
 }
 
@@ -225,18 +275,7 @@ int launch_gemm_t(fitv2_handle* h, const CUtensorMap& ma, const CUtensorMap& mb,
     const int groups = ((m_tiles + CL - 1) / CL) * (N / BN);
     const int max_clusters = h->num_sms / CL;
     const int grid = (groups < max_clusters ? groups : max_clusters) * CL;
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(kGemmThreads);
-    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ma, mb, M, N, K, b_row_off, ep));
+    CUDA_TRY(launch_k(kern, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, st, CL, ma, mb, M, N, K, b_row_off, ep));
     CUDA_TRY(cudaGetLastError());
     h->launches++;
     return FITV2_OK;
@@ -292,18 +331,49 @@ int launch_attention(fitv2_handle* h, const void* q, const void* k, const void* 
     if ((rc = make_map3(&mk, k, c.operand_dtype, DHu, tokens, BH, DHu * 2, (uint64_t)tokens * DHu * 2, 64, 128, 128))) return rc;
     if ((rc = make_map3(&mkt, k, c.operand_dtype, DHu, tokens, BH, DHu * 2, (uint64_t)tokens * DHu * 2, tail, 128, tail * 2))) return rc;
     if ((rc = make_map3(&mv, vt, c.operand_dtype, tokens_v, DHu, BH, (uint64_t)tokens_v * 2, DHu * tokens_v * 2, 64, dhp, 128))) return rc;
+    // production kernel: warp-specialised pipeline (attention_ws.cuh); the sequential kernel of attention.cuh serves the
+    // debug taps and FITV2_ATTN=v1 A/B runs
+    static const bool use_v1 = [] { const char* e = getenv("FITV2_ATTN"); return e && !strcmp(e, "v1"); }();
+    if (!use_v1 && !dbg_s && !dbg_o) {
+        const int q_pairs = ((tokens + 127) / 128 + 1) / 2;
+        const int items = q_pairs * c.num_heads * rows;
+        const int g = items < h->num_sms ? items : h->num_sms;
+        CUtensorMap mo;
+        if ((rc = make_map_attn_out(&mo, out, c.operand_dtype, DHu, c.num_heads, tokens, rows))) return rc;
+        if (c.head_dim == 72) {
+            using A = AttnWsCfg<72>;
+            auto kern = attention_ws_kernel<OT, 72>;
+            const int smem = A::smem_bytes(tokens);
+            if (smem > kSmemBudget) return fail(FITV2_E_INVALID, "tokens %d: attention shared memory %d exceeds %d", tokens, smem, kSmemBudget);
+            static int configured = 0;
+            if (configured < smem) { CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); configured = smem; }
+            CUDA_TRY(launch_k(kern, dim3(g), dim3(A::kThreads), smem, st, 1, mq, mqt, mk, mkt, mv, mo, seg, seg_uniform,
+                              c.num_heads, tokens, items, scale_log2e, bound_log2e));
+        } else {
+            using A = AttnWsCfg<96>;
+            auto kern = attention_ws_kernel<OT, 96>;
+            const int smem = A::smem_bytes(tokens);
+            if (smem > kSmemBudget) return fail(FITV2_E_INVALID, "tokens %d: attention shared memory %d exceeds %d", tokens, smem, kSmemBudget);
+            static int configured = 0;
+            if (configured < smem) { CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); configured = smem; }
+            CUDA_TRY(launch_k(kern, dim3(g), dim3(A::kThreads), smem, st, 1, mq, mqt, mk, mkt, mv, mo, seg, seg_uniform,
+                              c.num_heads, tokens, items, scale_log2e, bound_log2e));
+        }
+        h->launches++;
+        return FITV2_OK;
+    }
     if (c.head_dim == 72) {
         auto kern = attention_kernel<OT, 72>;
         static bool configured = false;
         if (!configured) { CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<72>::kSmemBytes)); configured = true; }
-        kern<<<grid, AttnCfg<72>::kThreads, AttnCfg<72>::kSmemBytes, st>>>(mq, mqt, mk, mkt, mv, seg, seg_uniform, (OT*)out,
-                                                        c.num_heads, tokens, num_items, scale_log2e, bound_log2e, dbg_s, dbg_o);
+        CUDA_TRY(launch_k(kern, grid, dim3(AttnCfg<72>::kThreads), AttnCfg<72>::kSmemBytes, st, 1, mq, mqt, mk, mkt, mv, seg, seg_uniform, (OT*)out,
+                                                        c.num_heads, tokens, num_items, scale_log2e, bound_log2e, dbg_s, dbg_o));
     } else if (c.head_dim == 96) {
         auto kern = attention_kernel<OT, 96>;
         static bool configured = false;
         if (!configured) { CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<96>::kSmemBytes)); configured = true; }
-        kern<<<grid, AttnCfg<96>::kThreads, AttnCfg<96>::kSmemBytes, st>>>(mq, mqt, mk, mkt, mv, seg, seg_uniform, (OT*)out,
-                                                        c.num_heads, tokens, num_items, scale_log2e, bound_log2e, dbg_s, dbg_o);
+        CUDA_TRY(launch_k(kern, grid, dim3(AttnCfg<96>::kThreads), AttnCfg<96>::kSmemBytes, st, 1, mq, mqt, mk, mkt, mv, seg, seg_uniform, (OT*)out,
+                                                        c.num_heads, tokens, num_items, scale_log2e, bound_log2e, dbg_s, dbg_o));
     } else {
         return fail(FITV2_E_INVALID, "head_dim %d not supported (72 or 96)", c.head_dim);
     }
@@ -317,10 +387,10 @@ int launch_ln_modulate(fitv2_handle* h, const float* x, const float* shift, cons
                        int M, int D, int tokens, cudaStream_t st) {
     const int nv = (D / 4 + 31) / 32;
     const int blocks = (M * 32 + 255) / 256;
-    if (nv <= 1) ln_modulate_kernel<OT, 1><<<blocks, 256, 0, st>>>(x, shift, scale, mod_ld, (OT*)out, M, D, tokens);
-    else if (nv <= 3) ln_modulate_kernel<OT, 3><<<blocks, 256, 0, st>>>(x, shift, scale, mod_ld, (OT*)out, M, D, tokens);
-    else if (nv <= 9) ln_modulate_kernel<OT, 9><<<blocks, 256, 0, st>>>(x, shift, scale, mod_ld, (OT*)out, M, D, tokens);
-    else if (nv <= 18) ln_modulate_kernel<OT, 18><<<blocks, 256, 0, st>>>(x, shift, scale, mod_ld, (OT*)out, M, D, tokens);
+    if (nv <= 1) CUDA_TRY(launch_k(ln_modulate_kernel<OT, 1>, dim3(blocks), dim3(256), 0, st, 1, x, shift, scale, mod_ld, (OT*)out, M, D, tokens));
+    else if (nv <= 3) CUDA_TRY(launch_k(ln_modulate_kernel<OT, 3>, dim3(blocks), dim3(256), 0, st, 1, x, shift, scale, mod_ld, (OT*)out, M, D, tokens));
+    else if (nv <= 9) CUDA_TRY(launch_k(ln_modulate_kernel<OT, 9>, dim3(blocks), dim3(256), 0, st, 1, x, shift, scale, mod_ld, (OT*)out, M, D, tokens));
+    else if (nv <= 18) CUDA_TRY(launch_k(ln_modulate_kernel<OT, 18>, dim3(blocks), dim3(256), 0, st, 1, x, shift, scale, mod_ld, (OT*)out, M, D, tokens));
     else return fail(FITV2_E_INVALID, "hidden_size %d too large for the LayerNorm kernel", D);
     CUDA_TRY(cudaGetLastError());
     h->launches++;
@@ -340,12 +410,12 @@ int launch_small_linear(fitv2_handle* h, SmallLinear p, int batches, cudaStream_
     p.ksplit = (int)ksplit;
     p.partial = reinterpret_cast<float*>(h->ws + h->lay.cpart);
     dim3 grid(col_tiles, row_blocks * p.ksplit, batches);
-    small_linear_kernel<<<grid, 256, 0, st>>>(p);
+    CUDA_TRY(launch_k(small_linear_kernel, grid, dim3(256), 0, st, 1, p));
     CUDA_TRY(cudaGetLastError());
     h->launches++;
     if (p.ksplit > 1) {
         dim3 g2((unsigned)(((size_t)p.rows * p.N + 255) / 256), 1, batches);
-        small_linear_finalize_kernel<<<g2, 256, 0, st>>>(p);
+        CUDA_TRY(launch_k(small_linear_finalize_kernel, g2, dim3(256), 0, st, 1, p));
         CUDA_TRY(cudaGetLastError());
         h->launches++;
     }
@@ -402,16 +472,16 @@ int forward_impl(fitv2_handle* h, const float* x, int x_rows, const float* t, co
 
     // ---- per-call tables: segment-uniformity flags, RoPE cos/sin (rope.py:308-333) ----
     prof_begin(h, PC_COND, st);
-    seg_uniform_kernel<<<rows, 128, 0, st>>>(mask, segu, tokens);
+    CUDA_TRY(launch_k(seg_uniform_kernel, dim3(rows), dim3(128), 0, st, 1, mask, segu, tokens));
     {
         const size_t total = (size_t)M * (DH / 2);
         const int blocks = (int)((total + 255) / 256);
-        rope_table_kernel<<<blocks, 256, 0, st>>>((const long long*)grid, (const float*)h->w[FITV2_W_ROPE_FREQS_H],
+        CUDA_TRY(launch_k(rope_table_kernel, dim3(blocks), dim3(256), 0, st, 1, (const long long*)grid, (const float*)h->w[FITV2_W_ROPE_FREQS_H],
                                                    (const float*)h->w[FITV2_W_ROPE_FREQS_W], c.rope_magnitude, rcos, rsin,
-                                                   rows, tokens, DH / 2);
+                                                   rows, tokens, DH / 2));
     }
     // ---- conditioning (fit_model.py:202-209,218-219; modules.py:52-76,101-106,259-264,287-293) ----
-    timestep_features_kernel<<<(rows * 128 + 255) / 256, 256, 0, st>>>(t, c.time_shifting, te, rows);
+    CUDA_TRY(launch_k(timestep_features_kernel, dim3((rows * 128 + 255) / 256), dim3(256), 0, st, 1, t, c.time_shifting, te, rows));
     CUDA_TRY(cudaGetLastError());
     h->launches += 3;
     SmallLinear p;
@@ -449,8 +519,8 @@ int forward_impl(fitv2_handle* h, const float* x, int x_rows, const float* t, co
     // ---- patch embedding (modules.py:34-37); implicit cat([z, z]) when x_rows == rows / 2 ----
     if (c.token_channels != 16) return fail(FITV2_E_INVALID, "token_channels %d not supported (16)", c.token_channels);
     prof_begin(h, PC_MISC, st);
-    patch_embed_kernel<16><<<(M + 7) / 8, 256, 0, st>>>(x, (const float*)h->w[FITV2_W_X_EMBED_W], (const float*)h->w[FITV2_W_X_EMBED_B],
-                                                       x_res, M, D, x_rows * tokens);
+    CUDA_TRY(launch_k(patch_embed_kernel<16>, dim3((M + 7) / 8), dim3(256), 0, st, 1, x, (const float*)h->w[FITV2_W_X_EMBED_W], (const float*)h->w[FITV2_W_X_EMBED_B],
+                                                       x_res, M, D, x_rows * tokens));
     CUDA_TRY(cudaGetLastError());
     h->launches++;
     prof_end(h, st);
@@ -508,14 +578,14 @@ int forward_impl(fitv2_handle* h, const float* x, int x_rows, const float* t, co
             auto kern = final_layer_kernel<9, 16>;
             static bool configured = false;
             if (!configured) { CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 1152 * 4)); configured = true; }
-            kern<<<blocks, 256, smem, st>>>(x_res, fmod, (const float*)h->w[FITV2_W_FINAL_LINEAR_W], (const float*)h->w[FITV2_W_FINAL_LINEAR_B],
-                                            mask, out, M, D, tokens);
+            CUDA_TRY(launch_k(kern, dim3(blocks), dim3(256), smem, st, 1, x_res, fmod, (const float*)h->w[FITV2_W_FINAL_LINEAR_W], (const float*)h->w[FITV2_W_FINAL_LINEAR_B],
+                                            mask, out, M, D, tokens));
         } else {
             auto kern = final_layer_kernel<18, 16>;
             static bool configured = false;
             if (!configured) { CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 2304 * 4)); configured = true; }
-            kern<<<blocks, 256, smem, st>>>(x_res, fmod, (const float*)h->w[FITV2_W_FINAL_LINEAR_W], (const float*)h->w[FITV2_W_FINAL_LINEAR_B],
-                                            mask, out, M, D, tokens);
+            CUDA_TRY(launch_k(kern, dim3(blocks), dim3(256), smem, st, 1, x_res, fmod, (const float*)h->w[FITV2_W_FINAL_LINEAR_W], (const float*)h->w[FITV2_W_FINAL_LINEAR_B],
+                                            mask, out, M, D, tokens));
         }
         CUDA_TRY(cudaGetLastError());
         h->launches++;
@@ -624,7 +694,7 @@ int fitv2_cfg_combine(float* out, const float* scale_per_sample, float scale, in
         return fail(FITV2_E_INVALID, "bad cfg_combine argument");
     const size_t total = (size_t)half_rows * tokens * channels;
     const int blocks = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
-    cfg_combine_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(out, scale_per_sample, scale, half_rows, tokens, channels, c_cfg);
+    CUDA_TRY(launch_k(cfg_combine_kernel, dim3(blocks), dim3(256), 0, static_cast<cudaStream_t>(stream), 1, out, scale_per_sample, scale, half_rows, tokens, channels, c_cfg));
     CUDA_TRY(cudaGetLastError());
     return FITV2_OK;
 }
@@ -637,7 +707,7 @@ int fitv2_cfg_euler(float* z, const float* v2, float cfg_scale, float dsigma, co
         return fail(FITV2_E_INVALID, "cfg_euler needs 16-byte aligned z / v2 and a multiple of 4 elements per half");
     const size_t nvec = half / 4;
     const int blocks = (int)((nvec + 255) / 256 < 1184 ? (nvec + 255) / 256 : 1184);
-    cfg_euler_kernel<<<blocks > 0 ? blocks : 1, 256, 0, static_cast<cudaStream_t>(stream)>>>(z, v2, cfg_scale, dsigma, dsigma_dev, half);
+    CUDA_TRY(launch_k(cfg_euler_kernel, dim3(blocks > 0 ? blocks : 1), dim3(256), 0, static_cast<cudaStream_t>(stream), 1, z, v2, cfg_scale, dsigma, dsigma_dev, half));
     CUDA_TRY(cudaGetLastError());
     return FITV2_OK;
 }
@@ -670,7 +740,7 @@ int fitv2_debug_attention(fitv2_handle* h, const void* q, const void* k, const v
     if (!h->ws) return fail(FITV2_E_UNBOUND, "workspace is not set");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int* segu = reinterpret_cast<int*>(h->ws);            // first bytes of the workspace as scratch
-    seg_uniform_kernel<<<rows, 128, 0, st>>>(mask, segu, tokens);
+    CUDA_TRY(launch_k(seg_uniform_kernel, dim3(rows), dim3(128), 0, st, 1, mask, segu, tokens));
     CUDA_TRY(cudaGetLastError());
     const int tokens_v = (tokens + 7) / 8 * 8;
     if (h->cfg.operand_dtype == FITV2_OPERAND_FP16)
@@ -705,6 +775,21 @@ int fitv2_debug_tap(fitv2_handle* h, int what, void* dst, int64_t bytes, void* s
     CUDA_TRY(cudaMemcpyAsync(dst, h->ws + off, have, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
     return FITV2_OK;
 }
+
+#ifdef FITV2_ATTN_TRACE
+// timing experiments only (not part of include/fitv2_b200.h)
+int fitv2_debug_attn_trace(unsigned long long* host_trace, unsigned int* host_n, int reset) {
+    if (reset) {
+        unsigned int z[20] = {0};
+        CUDA_TRY(cudaMemcpyToSymbol(g_attn_trace_n, z, sizeof(z)));
+        return FITV2_OK;
+    }
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpyFromSymbol(host_trace, g_attn_trace, sizeof(unsigned long long) * 20 * 512 * 2));
+    CUDA_TRY(cudaMemcpyFromSymbol(host_n, g_attn_trace_n, sizeof(unsigned int) * 20));
+    return FITV2_OK;
+}
+#endif
 
 int64_t fitv2_kernel_launches(const fitv2_handle* h) { return h ? h->launches : 0; }
 

@@ -139,6 +139,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     if constexpr (CL > 1) cluster_sync(); else __syncthreads();   // the peer's barriers must exist before anything signals them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();                       // everything above overlapped the previous kernel's tail
+    pdl_launch_dependents();
 
     // Producer and MMA loops are executed by the WHOLE warp (warp-uniform control flow lets the compiler keep the
     // descriptors / addresses in uniform registers, which the UTMALDG / UTCHMMA instructions consume directly);

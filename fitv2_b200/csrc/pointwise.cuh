@@ -14,6 +14,8 @@ namespace fitv2 {
 __global__ void cfg_euler_kernel(float* __restrict__ z, const float* __restrict__ v2, float cfg_scale, float dsigma,
                                  const float* __restrict__ dsigma_dev, size_t half_elems)
 {
+    pdl_wait();
+    pdl_launch_dependents();
     if (dsigma_dev) dsigma = *dsigma_dev;
     const size_t nvec = half_elems >> 2;
     const float4* cond = reinterpret_cast<const float4*>(v2);
@@ -42,6 +44,8 @@ __global__ void cfg_euler_kernel(float* __restrict__ z, const float* __restrict_
 __global__ void cfg_combine_kernel(float* __restrict__ out, const float* __restrict__ scale_per_sample, float scale,
                                    int B, int tokens, int C, int c_cfg)
 {
+    pdl_wait();
+    pdl_launch_dependents();
     const size_t per_sample = (size_t)tokens * C;
     const size_t total = (size_t)B * per_sample;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -65,6 +69,8 @@ __global__ void __launch_bounds__(256)
 patch_embed_kernel(const float* __restrict__ xin, const float* __restrict__ w, const float* __restrict__ b,
                    float* __restrict__ x, int M, int D, int rows_in_tokens /* tokens * rows_in */)
 {
+    pdl_wait();
+    pdl_launch_dependents();
     __shared__ float sx[8][CIN];
     const int m0 = blockIdx.x * 8;
     for (int i = threadIdx.x; i < 8 * CIN; i += blockDim.x) {
@@ -109,6 +115,8 @@ __global__ void __launch_bounds__(256)
 ln_modulate_kernel(const float* __restrict__ x, const float* __restrict__ shift, const float* __restrict__ scale,
                    int mod_ld, OT* __restrict__ h, int M, int D, int tokens)
 {
+    pdl_wait();
+    pdl_launch_dependents();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= M) return;
@@ -174,6 +182,8 @@ final_layer_kernel(const float* __restrict__ x, const float* __restrict__ fmod /
                    const float* __restrict__ w, const float* __restrict__ b, const float* __restrict__ mask,
                    float* __restrict__ out, int M, int D, int tokens)
 {
+    pdl_wait();
+    pdl_launch_dependents();
     extern __shared__ float sw[];                       // COUT * D
     for (int i = threadIdx.x; i < COUT * D; i += blockDim.x) sw[i] = w[i];
     __syncthreads();
@@ -250,6 +260,8 @@ __global__ void rope_table_kernel(const long long* __restrict__ grid, const floa
                                   const float* __restrict__ freqs_w, float mag, float* __restrict__ cos_t,
                                   float* __restrict__ sin_t, int samples, int tokens, int half /* dh/2 */)
 {
+    pdl_wait();
+    pdl_launch_dependents();
     const int quarter = half >> 1;
     const size_t total = (size_t)samples * tokens * half;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -273,6 +285,8 @@ __global__ void rope_table_kernel(const long long* __restrict__ grid, const floa
 // Per-sample flag: 1 when every segment id of the sample is identical (attention skips the compares).
 __global__ void seg_uniform_kernel(const float* __restrict__ seg, int* __restrict__ flag, int tokens)
 {
+    pdl_wait();
+    pdl_launch_dependents();
     const float* s = seg + (size_t)blockIdx.x * tokens;
     const float first = s[0];
     int same = 1;
@@ -288,6 +302,8 @@ __global__ void seg_uniform_kernel(const float* __restrict__ seg, int* __restric
 __global__ void timestep_features_kernel(const float* __restrict__ t, float time_shifting, float* __restrict__ te,
                                          int samples)
 {
+    pdl_wait();
+    pdl_launch_dependents();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= samples * 128) return;
     const int s = i >> 7, j = i & 127;
@@ -324,6 +340,8 @@ struct SmallLinear {
 __global__ void __launch_bounds__(256)
 small_linear_kernel(SmallLinear p)
 {
+    pdl_wait();
+    pdl_launch_dependents();
     __shared__ float As[16][64 + 4];
     __shared__ float Ws[16][64 + 4];
     const int z = blockIdx.z;
@@ -410,6 +428,8 @@ small_linear_kernel(SmallLinear p)
 // out = sum over K splits (fixed order) + bias (+ add) (+ embedding row); optional silu(out)
 __global__ void small_linear_finalize_kernel(SmallLinear p)
 {
+    pdl_wait();
+    pdl_launch_dependents();
     const int z = blockIdx.z;
     const size_t total = (size_t)p.rows * p.N;
     const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
