@@ -53,7 +53,7 @@ template <int DH> struct AttnWsCfg {
     static constexpr uint32_t kQKBytes = kQMain + kQTail;      // TMA transaction bytes of one Q or K tile
     static constexpr uint32_t kVBytes = 2 * kDHP * 128;
     static constexpr int kThreads = 32 * 19;
-    static constexpr int smem_bytes(int tokens) { return kOffSeg + ((tokens + 127) / 128 * 128) * 4 + 1024; }
+    static constexpr int smem_bytes(int tokens) { return kOffSeg + 2 * ((tokens + 127) / 128 * 128) * 4 + 1024; }
     static_assert(kTail == 16 || kTail == 32, "head_dim must be 72..80 or 88..96 (64 + 16/32 tail)");
 };
 
@@ -119,8 +119,8 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_qt); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_kt);
         tma_prefetch_desc(&map_v); tma_prefetch_desc(&map_o);
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 16);
-            mbar_init(&p_full[i], 16); mbar_init(&pv_done[i], 1); mbar_init(&o_free[i], 8);
+            mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 8);
+            mbar_init(&p_full[i], 8); mbar_init(&pv_done[i], 1); mbar_init(&o_free[i], 8);
         }
         for (int i = 0; i < C::kKStages; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 2); }
         for (int i = 0; i < C::kVStages; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 2); }
@@ -279,73 +279,69 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         s_step();
         while (pv.item < num_items) { s_step(); pv_step(); }
     } else {
-        // ------------------------------------- softmax warps (3..18) -------------------------------------
-        // All 16 warps work on ONE tile at a time and alternate between the streams: a(0) b(0) a(1) b(1) ...;
-        // four threads per query row, 32 key columns each.  The tensor-core work of a stream (its next S tile, its
-        // P V product) runs while the warps are busy with the other stream's exponentials.
-        const int wl = warp - 3;
-        const int cq = wl >> 2;                                         // which 32 key columns this thread owns
+        // ------------------------------------- softmax warp groups -------------------------------------
+        const int x = (warp - 3) >> 3;                                  // stream: 0 = first query tile of the pair, 1 = second
+        const int wl = (warp - 3) & 7;
+        const int half = wl >> 2;                                       // which 64 key columns / output half this thread owns
         const int quarter = warp & 3;                                   // TMEM lane quarter this warp may access
         const int row = quarter * 32 + lane;                            // query row inside the tile == TMEM lane
-        const int tid_sm = wl * 32 + lane;
-        const uint32_t t_row = tmem_base + (uint32_t(quarter * 32) << 16);
-        const uint32_t smem_p0 = smem_u32(smem + C::kOffP);
-        float* l_part = reinterpret_cast<float*>(smem + C::kOffSum);    // [stream][column quarter][row]
+        const int tid_wg = wl * 32 + lane;
+        const uint32_t t_s = tmem_base + (uint32_t(quarter * 32) << 16) + x * 128 + half * 64;
+        const uint32_t t_o = tmem_base + (uint32_t(quarter * 32) << 16) + 256 + x * 128;
+        const uint32_t smem_px = smem_u32(smem + C::kOffP) + x * C::kPTile;   // P_x; reused as the output staging tile
+        const uint32_t smem_p = smem_px + half * C::kPPanel;
+        float* l_part = reinterpret_cast<float*>(smem + C::kOffSum) + x * 256;
         const int seg_pad = (tokens + 127) / 128 * 128;
-        float* seg_s = reinterpret_cast<float*>(smem + C::kOffSeg);
-        uint32_t n_s[2] = {0, 0};
-        bool store_pending[2] = {false, false};                         // a TMA store may still be reading stream x's staging tile
+        float* seg_s = reinterpret_cast<float*>(smem + C::kOffSeg) + x * seg_pad;
+        uint32_t n_s = 0;
+        bool store_pending = false;                                     // a TMA store may still be reading the staging tile
         // per-item scalars are fetched one item ahead (two dependent global loads would otherwise sit on the item start)
-        int uni_nx = 1; float seg_nx[2] = {0.f, 0.f};
+        int uni_nx = 1; float seg_nx = 0.f;
         auto fetch_meta = [&](int item) {
             if (item < num_items) {
                 const int bh = item / q_pairs, qp = item - bh * q_pairs;
-                const int sample = bh / heads;
+                const int sample = bh / heads, qi = (2 * qp + x) * 128 + row;
                 uni_nx = __ldg(seg_uniform + sample);
-#pragma unroll
-                for (int x = 0; x < 2; ++x) {
-                    const int qi = (2 * qp + x) * 128 + row;
-                    seg_nx[x] = qi < tokens ? __ldg(seg + (size_t)sample * tokens + qi) : 0.f;
-                }
+                seg_nx = qi < tokens ? __ldg(seg + (size_t)sample * tokens + qi) : 0.f;
             }
         };
         fetch_meta(blockIdx.x);
         for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
             const bool uniform = uni_nx != 0;
-            const float my_seg[2] = {seg_nx[0], seg_nx[1]};
+            const float my_seg = seg_nx;
             fetch_meta(item + gridDim.x);
             const int bh = item / q_pairs, qp = item - bh * q_pairs;
-            const int nstreams = (2 * qp + 1 < q_tiles) ? 2 : 1;
+            const int qt = 2 * qp + x;
+            if (qt >= q_tiles) continue;                                // odd number of query tiles: stream b idles
             const int sample = bh / heads, head = bh - sample * heads;
             if (!uniform) {                                             // masked path: key segment ids of the sample in smem
-                // (the readers of the previous item's ids have all passed that item's epilogue barrier)
+                // (the readers of the previous item's ids have all passed that item's epilogue barriers)
                 const float* segb = seg + (size_t)sample * tokens;
-                for (int i = tid_sm; i < seg_pad; i += 512) seg_s[i] = i < tokens ? __ldg(segb + i) : 0.f;
-                named_bar_sync(1, 512);
+                for (int i = tid_wg; i < seg_pad; i += 256) seg_s[i] = i < tokens ? __ldg(segb + i) : 0.f;
+                named_bar_sync(1 + x, 256);
             }
-            float l_run[2] = {0.f, 0.f};
-            uint32_t v[32];
-            bool have = false;                                          // v already holds (a load in flight for) the next S tile
-            for (int t = 0; t < kv_tiles; ++t) {
+            float l_run = 0.f;
+            for (int t = 0; t < kv_tiles; ++t, ++n_s) {
                 const int kv0 = t * 128;
                 const int kv_valid = min(128, tokens - kv0);
                 const int mode = (uniform && kv_valid == 128) ? 0 : (uniform ? 1 : 2);   // dense / key-tail bound / segment compare
+                ATTN_TRACE(warp, 400 + t);
+                mbar_wait(&s_full[x], n_s & 1);
+                tc_fence_after();
+                ATTN_TRACE(warp, 410 + t);
+                uint32_t packed[32];
+                float lsum = 0.f;
 #pragma unroll
-                for (int x = 0; x < 2; ++x) {
-                    if (x >= nstreams) break;
-                    ATTN_TRACE(warp, 400 + x * 10 + t);
-                    if (!have) {
-                        mbar_wait(&s_full[x], n_s[x] & 1);
-                        tc_fence_after();
-                        tmem_ld32(t_row + x * 128 + cq * 32, v);
-                    }
+                for (int c = 0; c < 2; ++c) {
+                    uint32_t v[32];
+                    tmem_ld32(t_s + c * 32, v);
                     tmem_ld_wait();
-                    tc_fence_before();                                  // S_x is in registers: the next Q K^T may overwrite it
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&s_free[x]);
-                    ATTN_TRACE(warp, 420 + x * 10 + t);
-                    uint32_t packed[16];
-                    float lsum = 0.f;
+                    if (c == 1) {                                       // S_x is in registers: the next Q K^T may overwrite it
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&s_free[x]);
+                        ATTN_TRACE(warp, 420 + t);
+                    }
                     auto soft32 = [&](auto mode_c) {                    // mode is a compile-time constant inside
                         constexpr int kMode = decltype(mode_c)::value;
 #pragma unroll
@@ -358,82 +354,64 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                             float p1 = fast_exp2(fmaf(__uint_as_float(v[2 * j + 1]), scale_log2e, -bound_log2e));
 #endif
                             if constexpr (kMode != 0) {
-                                const int col = cq * 32 + 2 * j;
+                                const int col = half * 64 + c * 32 + 2 * j;
                                 bool ok0 = col < kv_valid, ok1 = col + 1 < kv_valid;
                                 if constexpr (kMode == 2) {
-                                    ok0 = ok0 && seg_s[kv0 + col] == my_seg[x];
-                                    ok1 = ok1 && seg_s[kv0 + col + 1] == my_seg[x];
+                                    ok0 = ok0 && seg_s[kv0 + col] == my_seg;
+                                    ok1 = ok1 && seg_s[kv0 + col + 1] == my_seg;
                                 }
                                 p0 = ok0 ? p0 : 0.f;
                                 p1 = ok1 ? p1 : 0.f;
                             }
-                            packed[j] = Op16<OT>::pack(p0, p1);
+                            packed[c * 16 + j] = Op16<OT>::pack(p0, p1);
                             lsum += p0 + p1;
                         }
                     };
                     if (mode == 0) soft32(std::integral_constant<int, 0>{});
                     else if (mode == 1) soft32(std::integral_constant<int, 1>{});
                     else soft32(std::integral_constant<int, 2>{});
-                    l_run[x] += lsum;
-                    ATTN_TRACE(warp, 430 + x * 10 + t);
-                    // the S tile that follows inside this item (other stream, or next key tile) is normally complete by
-                    // now: start its TMEM load so that the latency hides behind the P store below
-                    {
-                        const int nx = (x + 1 < nstreams) ? x + 1 : 0;
-                        const bool more = (x + 1 < nstreams) || (t + 1 < kv_tiles);
-                        have = more;
-                        if (more) {
-                            mbar_wait(&s_full[nx], (n_s[nx] + (nx == x ? 1u : 0u)) & 1);   // n_s[x] is bumped at the end of this step
-                            tc_fence_after();
-                            tmem_ld32(t_row + nx * 128 + cq * 32, v);
-                        }
-                    }
-                    if (n_s[x] > 0) mbar_wait(&pv_done[x], (n_s[x] - 1) & 1);   // the previous P V of this stream has read the P buffer
-                    if (t == 0 && store_pending[x]) {                   // ... and so has the TMA store of its previous output tile
-                        if (tid_sm == x * 256) tma_store_wait_read();
-                        named_bar_sync(1, 512);
-                        store_pending[x] = false;
-                    }
-                    ATTN_TRACE(warp, 440 + x * 10 + t);
-                    const uint32_t pdst = smem_p0 + x * C::kPTile + (cq >> 1) * C::kPPanel;
-#pragma unroll
-                    for (int g = 0; g < 4; ++g)                         // 4 chunks of 8 keys inside the 64-key panel row
-                        sts128(pdst + swz_offset<128>(row, (cq & 1) * 4 + g),
-                               make_uint4(packed[g * 4], packed[g * 4 + 1], packed[g * 4 + 2], packed[g * 4 + 3]));
-                    fence_proxy_async_smem();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&p_full[x]);
-                    ++n_s[x];
-                    ATTN_TRACE(warp, 450 + x * 10 + t);
                 }
+                l_run += lsum;
+                ATTN_TRACE(warp, 430 + t);
+                if (n_s > 0) mbar_wait(&pv_done[x], (n_s - 1) & 1);     // the previous P V of this stream has read the P buffer
+                if (t == 0 && store_pending) {                          // ... and so has the TMA store of the previous output tile
+                    if (tid_wg == 0) tma_store_wait_read();
+                    named_bar_sync(1 + x, 256);
+                    store_pending = false;
+                }
+                ATTN_TRACE(warp, 440 + t);
+#pragma unroll
+                for (int g = 0; g < 8; ++g)                             // 8 chunks of 8 keys: this thread's 64-key panel row
+                    sts128(smem_p + swz_offset<128>(row, g),
+                           make_uint4(packed[g * 4], packed[g * 4 + 1], packed[g * 4 + 2], packed[g * 4 + 3]));
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&p_full[x]);
+                ATTN_TRACE(warp, 450 + t);
             }
 
             // ---- O / l, zero padded queries (mask != 0): (128, DH) tile -> staging -> one TMA store into the
-            //      (M, heads*DH) rows that feed the proj GEMM.  Warps 3-10 finish stream a, warps 11-18 stream b. ----
-            l_part[0 * 512 + cq * 128 + row] = l_run[0];
-            l_part[1 * 512 + cq * 128 + row] = l_run[1];
-            named_bar_sync(1, 512);
-            const int xe = cq >> 1, half = cq & 1;                      // stream / output column half of this thread's epilogue
-            if (xe < nstreams) {
-                const float l_tot = (l_part[xe * 512 + row] + l_part[xe * 512 + 128 + row]) +
-                                    (l_part[xe * 512 + 256 + row] + l_part[xe * 512 + 384 + row]);
-                mbar_wait(&pv_done[xe], (n_s[xe] - 1) & 1);             // last P V retired: O_x is final, P_x is free
-                tc_fence_after();
-                ATTN_TRACE(warp, 500);
-                constexpr int OH = C::kDHP / 2;                        // output columns per thread: 40 or 48
-                float o[OH];
-                const uint32_t t_o = t_row + 256 + xe * 128 + half * OH;
-                tmem_ld32(t_o, reinterpret_cast<uint32_t*>(o));
-                if constexpr (OH == 40) tmem_ld8(t_o + 32, reinterpret_cast<uint32_t*>(o) + 32);
-                else tmem_ld16(t_o + 32, reinterpret_cast<uint32_t*>(o) + 32);
-                tmem_ld_wait();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&o_free[xe]);
-                ATTN_TRACE(warp, 510);
-                const float inv = (my_seg[xe] != 0.f && l_tot > 0.f) ? 1.0f / l_tot : 0.f;
-                const uint32_t stage = smem_p0 + xe * C::kPTile;
-                const uint32_t dst = stage + row * (DH * 2) + half * (OH * 2);
+            //      (M, heads*DH) rows that feed the proj GEMM ----
+            l_part[half * 128 + row] = l_run;
+            mbar_wait(&pv_done[x], (n_s - 1) & 1);                      // last P V retired: O_x is final, P_x is free
+            tc_fence_after();
+            ATTN_TRACE(warp, 500);
+            constexpr int OH = C::kDHP / 2;                            // output columns per thread: 40 or 48
+            float o[OH];
+            tmem_ld32(t_o + half * OH, reinterpret_cast<uint32_t*>(o));
+            if constexpr (OH == 40) tmem_ld8(t_o + half * OH + 32, reinterpret_cast<uint32_t*>(o) + 32);
+            else tmem_ld16(t_o + half * OH + 32, reinterpret_cast<uint32_t*>(o) + 32);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&o_free[x]);
+            ATTN_TRACE(warp, 510);
+            named_bar_sync(1 + x, 256);                                 // both halves' row sums are in l_part
+            const float l_tot = l_part[row] + l_part[row + 128];
+            ATTN_TRACE(warp, 520);
+            {
+                const float inv = (my_seg != 0.f && l_tot > 0.f) ? 1.0f / l_tot : 0.f;
+                const uint32_t dst = smem_px + row * (DH * 2) + half * (OH * 2);
 #pragma unroll
                 for (int c = 0; c < OH / 8; ++c) {
                     if (half * OH + c * 8 < DH) {                      // skip the zero-pad columns 72..79
@@ -443,17 +421,16 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                         sts128(dst + c * 16, make_uint4(pk[0], pk[1], pk[2], pk[3]));
                     }
                 }
-                fence_proxy_async_smem();
-                named_bar_sync(2 + xe, 256);
-#ifndef FITV2_ATTN_DBG_NOSTORE
-                if (tid_sm == xe * 256) tma_store_4d(&map_o, stage, 0, head, (2 * qp + xe) * 128, sample);   // rows >= tokens are clipped
-#endif
-                ATTN_TRACE(warp, 530);
             }
-            store_pending[0] = true;
-            store_pending[1] = nstreams > 1;
+            fence_proxy_async_smem();
+            named_bar_sync(1 + x, 256);
+#ifndef FITV2_ATTN_DBG_NOSTORE
+            if (tid_wg == 0) tma_store_4d(&map_o, smem_px, 0, head, qt * 128, sample);   // rows >= tokens are clipped
+#endif
+            store_pending = true;
+            ATTN_TRACE(warp, 530);
         }
-        if (tid_sm == 0 || tid_sm == 256) tma_store_wait_all();         // global writes complete before the CTA retires
+        if (store_pending && tid_wg == 0) tma_store_wait_all();         // global writes complete before the CTA retires
     }
     tc_fence_before();
     __syncthreads();
