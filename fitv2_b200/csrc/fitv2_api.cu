@@ -712,6 +712,46 @@ int fitv2_cfg_euler(float* z, const float* v2, float cfg_scale, float dsigma, co
     return FITV2_OK;
 }
 
+// ---- transport sampler updates (elementwise, fp32, bit-exact with the reference expressions) ----
+namespace {
+int elementwise_grid(int64_t n) {
+    const int64_t blocks = (n / 4 + 255) / 256;
+    return (int)(blocks < 1 ? 1 : (blocks > 1184 ? 1184 : blocks));
+}
+bool aligned16(const void* p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; }
+}  // namespace
+
+int fitv2_sde_step(float* x, const float* v, const float* w, const float* coef_dev, int64_t n, void* stream) {
+    if (!x || !v || !coef_dev || n <= 0) return fail(FITV2_E_INVALID, "bad sde_step argument");
+    if (!aligned16(x) || !aligned16(v) || (w && !aligned16(w))) return fail(FITV2_E_INVALID, "sde_step needs 16-byte aligned tensors");
+    CUDA_TRY(launch_k(sde_em_step_kernel, dim3(elementwise_grid(n)), dim3(256), 0, static_cast<cudaStream_t>(stream), 1, x, v, w, coef_dev, (size_t)n));
+    return FITV2_OK;
+}
+
+int fitv2_sde_drift(float* out, const float* x, const float* v, const float* coef_dev, int64_t n, void* stream) {
+    if (!out || !x || !v || !coef_dev || n <= 0) return fail(FITV2_E_INVALID, "bad sde_drift argument");
+    CUDA_TRY(launch_k(sde_drift_kernel, dim3(elementwise_grid(n * 4)), dim3(256), 0, static_cast<cudaStream_t>(stream), 1, out, x, v, coef_dev, (size_t)n));
+    return FITV2_OK;
+}
+
+int fitv2_scaled_add(float* out, const float* a, const float* b, const float* s_dev, int64_t n, void* stream) {
+    if (!out || !a || !b || !s_dev || n <= 0) return fail(FITV2_E_INVALID, "bad scaled_add argument");
+    CUDA_TRY(launch_k(scaled_add_kernel, dim3(elementwise_grid(n * 4)), dim3(256), 0, static_cast<cudaStream_t>(stream), 1, out, a, b, s_dev, (size_t)n));
+    return FITV2_OK;
+}
+
+int fitv2_heun_combine(float* out, const float* xhat, const float* k1, const float* k2, const float* c_dev, int64_t n, void* stream) {
+    if (!out || !xhat || !k1 || !k2 || !c_dev || n <= 0) return fail(FITV2_E_INVALID, "bad heun_combine argument");
+    CUDA_TRY(launch_k(heun_combine_kernel, dim3(elementwise_grid(n * 4)), dim3(256), 0, static_cast<cudaStream_t>(stream), 1, out, xhat, k1, k2, c_dev, (size_t)n));
+    return FITV2_OK;
+}
+
+int fitv2_tweedie(float* out, const float* x, const float* v, const float* coef_dev, int64_t n, void* stream) {
+    if (!out || !x || !v || !coef_dev || n <= 0) return fail(FITV2_E_INVALID, "bad tweedie argument");
+    CUDA_TRY(launch_k(tweedie_kernel, dim3(elementwise_grid(n * 4)), dim3(256), 0, static_cast<cudaStream_t>(stream), 1, out, x, v, coef_dev, (size_t)n));
+    return FITV2_OK;
+}
+
 int fitv2_debug_gemm(fitv2_handle* h, int epilogue, const void* a, const void* w, const float* bias, float* out32, int M,
                      int N, int K, int bn, void* stream) {
     if (!h || !a || !w || !bias || !out32) return fail(FITV2_E_INVALID, "null argument");

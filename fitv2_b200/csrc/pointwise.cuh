@@ -38,6 +38,98 @@ __global__ void cfg_euler_kernel(float* __restrict__ z, const float* __restrict_
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Transport sampler updates (fit/scheduler/transport/integrators.py:29-48, transport.py:256-292, path.py:71-85),
+// velocity model on the linear path.  All per-step scalars are computed on the host in fp32 with the reference's
+// own expression order and read from a small device array (graph-replay friendly):
+//   coef[0] rar      = alpha_t / d_alpha_t (= t)          coef[4] sqrt(2 * diffusion)
+//   coef[1] var      = sigma^2 - rar * d_sigma * sigma    coef[5] sqrt(dt)
+//   coef[2] diffusion(t)                                  coef[6] alpha_t          (Tweedie last step)
+//   coef[3] dt  (or the last-step size)                   coef[7] sigma_t^2 / alpha_t
+// Every product / sum below is a separate rounded fp32 operation in the order PyTorch evaluates the reference's
+// expressions (no FMA contraction), so the results are bit-identical to it given the same velocity and noise.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sde_drift_elem(float x, float v, float rar, float var, float diff) {
+    const float score = __fdiv_rn(__fsub_rn(__fmul_rn(rar, v), x), var);                // path.py:84
+    return __fadd_rn(v, __fmul_rn(diff, score));                                        // transport.py:256-258
+}
+
+// Euler-Maruyama step, in place:  x <- (x + drift * dt) + sqrt(2 D) * (w * sqrt(dt))     (integrators.py:29-37)
+// w == nullptr: the noise-free "Mean" last step  x <- x + drift * h                      (transport.py:277-280)
+__global__ void sde_em_step_kernel(float* __restrict__ x, const float* __restrict__ v, const float* __restrict__ w,
+                                   const float* __restrict__ coef, size_t n)
+{
+    pdl_wait();
+    pdl_launch_dependents();
+    const float rar = coef[0], var = coef[1], diff = coef[2], dt = coef[3], s2d = coef[4], sdt = coef[5];
+    const size_t nvec = n >> 2;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
+        float4 xv = reinterpret_cast<const float4*>(x)[i];
+        const float4 vv = reinterpret_cast<const float4*>(v)[i];
+        float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (w) wv = reinterpret_cast<const float4*>(w)[i];
+        float* xe = reinterpret_cast<float*>(&xv);
+        const float* ve = reinterpret_cast<const float*>(&vv);
+        const float* we = reinterpret_cast<const float*>(&wv);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float mean = __fadd_rn(xe[j], __fmul_rn(sde_drift_elem(xe[j], ve[j], rar, var, diff), dt));
+            xe[j] = w ? __fadd_rn(mean, __fmul_rn(s2d, __fmul_rn(we[j], sdt))) : mean;
+        }
+        reinterpret_cast<float4*>(x)[i] = xv;
+    }
+    for (size_t i = (nvec << 2) + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float mean = __fadd_rn(x[i], __fmul_rn(sde_drift_elem(x[i], v[i], rar, var, diff), dt));
+        x[i] = w ? __fadd_rn(mean, __fmul_rn(s2d, __fmul_rn(w[i], sdt))) : mean;
+    }
+}
+
+// out = v + D * score(v, x, t)   (the SDE drift; K1 / K2 of the Heun step, integrators.py:45-47)
+__global__ void sde_drift_kernel(float* __restrict__ out, const float* __restrict__ x, const float* __restrict__ v,
+                                 const float* __restrict__ coef, size_t n)
+{
+    pdl_wait();
+    pdl_launch_dependents();
+    const float rar = coef[0], var = coef[1], diff = coef[2];
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = sde_drift_elem(x[i], v[i], rar, var, diff);
+}
+
+// out = a + s2 * (s1 * b)      (xhat = x + sqrt(2D) * (w * sqrt(dt)); xp = xhat + dt * K1; ODE Euler y + dt * f; "Euler" last step)
+__global__ void scaled_add_kernel(float* __restrict__ out, const float* __restrict__ a, const float* __restrict__ b,
+                                  const float* __restrict__ s, size_t n)
+{
+    pdl_wait();
+    pdl_launch_dependents();
+    const float s1 = s[0], s2 = s[1];
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = __fadd_rn(a[i], __fmul_rn(s2, __fmul_rn(s1, b[i])));
+}
+
+// out = xhat + c * (k1 + k2),  c = 0.5 * dt                                              (integrators.py:48)
+__global__ void heun_combine_kernel(float* __restrict__ out, const float* __restrict__ xhat, const float* __restrict__ k1,
+                                    const float* __restrict__ k2, const float* __restrict__ c, size_t n)
+{
+    pdl_wait();
+    pdl_launch_dependents();
+    const float cc = c[0];
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = __fadd_rn(xhat[i], __fmul_rn(cc, __fadd_rn(k1[i], k2[i])));
+}
+
+// "Tweedie" last step: out = x / alpha + (sigma^2 / alpha) * score(v, x, t)                (transport.py:281-286)
+__global__ void tweedie_kernel(float* __restrict__ out, const float* __restrict__ x, const float* __restrict__ v,
+                               const float* __restrict__ coef, size_t n)
+{
+    pdl_wait();
+    pdl_launch_dependents();
+    const float rar = coef[0], var = coef[1], a = coef[6], c2 = coef[7];
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float score = __fdiv_rn(__fsub_rn(__fmul_rn(rar, v[i]), x[i]), var);
+        out[i] = __fadd_rn(__fdiv_rn(x[i], a), __fmul_rn(c2, score));
+    }
+}
+
 // forward_with_cfg channel-limited guidance (fit_model.py:253-275): channels [0, c_cfg) of BOTH halves become
 // uncond + s_b * (cond - uncond); channels >= c_cfg pass through.  out: (2B, tokens, C) in place.
 // scale_per_sample may be null (then `scale` is used for every sample).

@@ -1,0 +1,246 @@
+"""Transport ``Sampler`` of the reference (SiT-style ODE / SDE integrators) on the B200 path.
+
+Mirrors ``fit/scheduler/transport`` of the reference for the configuration FiTv2 uses
+(``configs/fitv2/config_fitv2_xl.yaml:3-9``: path ``Linear``, prediction ``velocity``):
+
+    transport = create_transport(path_type="Linear", prediction="velocity")      # __init__.py:5-71
+    sampler = Sampler(transport)                                                  # transport.py:230-243
+    sample_fn = sampler.sample_sde(sampling_method="Euler", diffusion_form="sigma", last_step="Mean",
+                                   last_step_size=0.04, num_steps=250)            # transport.py:296-356
+    xs = sample_fn(z, model.forward_with_cfg, **model_kwargs)                     # list of num_steps tensors
+
+Same names, keyword arguments, return values (the list of intermediate samples) and errors as the reference.
+What differs is the execution: every update is ONE fused elementwise CUDA kernel called through the C ABI
+(``fitv2_sde_step`` & co, bit-exact with the reference's PyTorch expressions), and the SDE drift shares a single
+network evaluation between the velocity and the score term (the reference calls the network twice per step,
+transport.py:256-258).  The per-step scalars (score variance, diffusion coefficient, step sizes) are computed once
+on the host in fp32 with the reference's expression order and kept in a device table.
+
+Not built: adaptive ``dopri5`` (data-dependent number of network evaluations; ``torchdiffeq`` is an un-vendored
+dependency of the reference) and the likelihood ODE — both raise ``NotImplementedError``.  Paths / predictions
+other than Linear / velocity raise at ``create_transport``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Callable, List, Optional
+
+import torch as th
+
+from . import _lib
+
+_DIFFUSION_FORMS = ("constant", "SBDM", "sigma", "linear", "decreasing", "increasing-decreasing")
+
+
+class Transport:
+    """Subset of transport.py:37-108 that sampling needs (Linear path, velocity prediction)."""
+
+    def __init__(self, *, path_type="Linear", prediction="velocity", train_eps=0, sample_eps=0, snr_type="uniform",
+                 loss_weight=None):
+        self.path_type, self.prediction = path_type, prediction
+        self.train_eps, self.sample_eps, self.snr_type, self.loss_weight = train_eps, sample_eps, snr_type, loss_weight
+
+    def check_interval(self, train_eps, sample_eps, *, diffusion_form="SBDM", sde=False, reverse=False, eval=False,
+                       last_step_size=0.0):
+        """transport.py:81-108 (ICPlan, ModelType.VELOCITY)."""
+        t0, t1 = 0, 1
+        eps = train_eps if not eval else sample_eps
+        if sde:
+            t0 = eps if (diffusion_form == "SBDM" and sde) else 0
+            t1 = 1 - eps if (not sde or last_step_size == 0) else 1 - last_step_size
+        if reverse:
+            t0, t1 = 1 - t0, 1 - t1
+        return t0, t1
+
+
+def create_transport(path_type="Linear", prediction="velocity", loss_weight=None, train_eps=None, sample_eps=None,
+                     snr_type="uniform") -> Transport:
+    """__init__.py:5-71.  Velocity on the Linear path is stable everywhere: both eps are 0 (lines 57-60)."""
+    if path_type != "Linear" or prediction not in ("velocity", None):
+        raise NotImplementedError(f"fitv2_b200 implements the FiTv2 transport (Linear path, velocity prediction), got {path_type}/{prediction}")
+    if snr_type not in ("uniform", "lognorm"):
+        raise ValueError(f"Invalid snr type {snr_type}")
+    return Transport(path_type=path_type, prediction="velocity", train_eps=0, sample_eps=0, snr_type=snr_type, loss_weight=loss_weight)
+
+
+def _f32(v) -> th.Tensor:
+    return th.as_tensor(v, dtype=th.float32)
+
+
+def _coef_row(t: th.Tensor, dt: th.Tensor, form: str, norm: float) -> th.Tensor:
+    """The 8 per-step scalars of include/fitv2_b200.h, evaluated on 0-dim fp32 CPU tensors in the reference's own
+    expression order (path.py:20-85), so that they carry the same roundings as its (B,1,1) tensors."""
+    alpha, d_alpha = t, 1
+    sigma, d_sigma = 1 - t, -1
+    rar = alpha / d_alpha
+    var = sigma ** 2 - rar * d_sigma * sigma
+    if form == "constant":
+        diff = th.tensor(norm)
+    elif form == "SBDM":
+        alpha_ratio = 1 / t
+        diff = norm * (alpha_ratio * (sigma ** 2) - sigma * d_sigma)
+    elif form == "sigma":
+        diff = norm * sigma
+    elif form == "linear":
+        diff = norm * (1 - t)
+    elif form == "decreasing":
+        diff = 0.25 * (norm * th.cos(math.pi * t) + 1) ** 2
+    elif form == "increasing-decreasing":
+        diff = norm * th.sin(math.pi * t) ** 2
+    else:
+        raise NotImplementedError(f"Diffusion form {form} not implemented")
+    return th.stack([_f32(rar), _f32(var), _f32(diff), _f32(dt), th.sqrt(2 * _f32(diff)), th.sqrt(_f32(dt)),
+                     _f32(alpha), _f32((sigma ** 2) / alpha)])
+
+
+def _p(t: Optional[th.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream(dev) -> C.c_void_p:
+    return C.c_void_p(th.cuda.current_stream(dev).cuda_stream)
+
+
+def _check_state(x: th.Tensor, what: str) -> th.Tensor:
+    if not isinstance(x, th.Tensor) or not x.is_cuda:
+        raise _lib.FitV2Error(f"{what} must be a CUDA tensor: fitv2_b200 has no CPU path")
+    if x.dtype != th.float32:
+        raise _lib.FitV2Error(f"{what} must be float32 (the sampler state is integrated in fp32), got {x.dtype}")
+    return x.contiguous()
+
+
+class Sampler:
+    """transport.py:230-401."""
+
+    def __init__(self, transport: Transport):
+        self.transport = transport
+
+    # ------------------------------------------------------------------ SDE
+    def sample_sde(self, *, sampling_method="Euler", diffusion_form="SBDM", diffusion_norm=1.0, last_step="Mean",
+                   last_step_size=0.04, num_steps=250, noise: str = "device",
+                   generator: Optional[th.Generator] = None) -> Callable[..., List[th.Tensor]]:
+        """transport.py:296-356.  ``noise``: "device" draws the Wiener increments on the GPU (``generator`` optional);
+        "reference" draws them exactly like the reference, ``th.randn(x.size())`` from the default CPU generator, and
+        copies them over (bit-parity runs)."""
+        if sampling_method not in ("Euler", "Heun"):
+            raise NotImplementedError("Smapler type not implemented.")           # integrators.py:58-59 (sic)
+        if diffusion_form not in _DIFFUSION_FORMS:
+            raise NotImplementedError(f"Diffusion form {diffusion_form} not implemented")
+        if last_step not in (None, "Mean", "Tweedie", "Euler"):
+            raise NotImplementedError()
+        if noise not in ("device", "reference"):
+            raise ValueError("noise must be 'device' or 'reference'")
+        if last_step is None:
+            last_step_size = 0.0
+        tr = self.transport
+        t0, t1 = tr.check_interval(tr.train_eps, tr.sample_eps, diffusion_form=diffusion_form, sde=True, eval=True,
+                                   reverse=False, last_step_size=last_step_size)
+        ts = th.linspace(t0, t1, num_steps)                                      # integrators.py:22-23 (CPU fp32)
+        dt = ts[1] - ts[0]
+        norm = diffusion_norm
+        rows = [_coef_row(ti, dt, diffusion_form, norm) for ti in ts[:-1]]
+        rows2 = [_coef_row(ti + dt, dt, diffusion_form, norm) for ti in ts[:-1]] if sampling_method == "Heun" else []
+        t1f = th.ones(1) * t1                                                    # transport.py:347
+        last = _coef_row(t1f[0], _f32(last_step_size), diffusion_form, norm)
+        half_dt = 0.5 * dt
+        lib = _lib.load()
+
+        def _sample(init: th.Tensor, model: Callable, **model_kwargs) -> List[th.Tensor]:
+            x = _check_state(init, "init").clone()
+            dev, n, B = x.device, x.numel(), x.size(0)
+            coef = th.stack(rows).to(dev)
+            coef2 = th.stack(rows2).to(dev) if rows2 else None
+            coef_last = last.to(dev)
+            sc = th.stack([th.stack([th.sqrt(dt), r[4]]) for r in rows]).to(dev)             # (w * sqrt(dt)) * sqrt(2D)
+            sc_dt = th.stack([_f32(1.0), dt]).to(dev)
+            sc_last = th.stack([_f32(1.0), _f32(last_step_size)]).to(dev)
+            c_half = half_dt.reshape(1).to(dev)
+            xs: List[th.Tensor] = []
+            with th.cuda.device(dev), th.no_grad():
+                st = _stream(dev)
+                for i, ti in enumerate(ts[:-1]):
+                    if noise == "reference":
+                        w = th.randn(x.size()).to(x)                             # integrators.py:30 / :40
+                    else:
+                        w = th.randn(x.shape, device=dev, dtype=th.float32, generator=generator)
+                    t = th.full((B,), float(ti), device=dev, dtype=th.float32)
+                    if sampling_method == "Euler":
+                        v = _check_state(model(x, t, **model_kwargs), "model output")
+                        _lib.check(lib.fitv2_sde_step(_p(x), _p(v), _p(w), _p(coef[i]), n, st), "fitv2_sde_step")
+                    else:
+                        xhat = th.empty_like(x)
+                        _lib.check(lib.fitv2_scaled_add(_p(xhat), _p(x), _p(w), _p(sc[i]), n, st), "fitv2_scaled_add")
+                        v1 = _check_state(model(xhat, t, **model_kwargs), "model output")
+                        k1 = th.empty_like(x)
+                        _lib.check(lib.fitv2_sde_drift(_p(k1), _p(xhat), _p(v1), _p(coef[i]), n, st), "fitv2_sde_drift")
+                        xp = th.empty_like(x)
+                        _lib.check(lib.fitv2_scaled_add(_p(xp), _p(xhat), _p(k1), _p(sc_dt), n, st), "fitv2_scaled_add")
+                        t2 = th.full((B,), float(ti + dt), device=dev, dtype=th.float32)
+                        v2 = _check_state(model(xp, t2, **model_kwargs), "model output")
+                        k2 = th.empty_like(x)
+                        _lib.check(lib.fitv2_sde_drift(_p(k2), _p(xp), _p(v2), _p(coef2[i]), n, st), "fitv2_sde_drift")
+                        _lib.check(lib.fitv2_heun_combine(_p(x), _p(xhat), _p(k1), _p(k2), _p(c_half), n, st), "fitv2_heun_combine")
+                    xs.append(x.clone())
+                # ---- last step (transport.py:268-292, 346-349) ----
+                if last_step is not None:
+                    tl = th.full((B,), float(t1f[0]), device=dev, dtype=th.float32)
+                    v = _check_state(model(x, tl, **model_kwargs), "model output")
+                    if last_step == "Mean":
+                        _lib.check(lib.fitv2_sde_step(_p(x), _p(v), None, _p(coef_last), n, st), "fitv2_sde_step")
+                    elif last_step == "Euler":
+                        _lib.check(lib.fitv2_scaled_add(_p(x), _p(x), _p(v), _p(sc_last), n, st), "fitv2_scaled_add")
+                    else:
+                        _lib.check(lib.fitv2_tweedie(_p(x), _p(x), _p(v), _p(coef_last), n, st), "fitv2_tweedie")
+                xs.append(x)
+            assert len(xs) == num_steps, "Samples does not match the number of steps"
+            return xs
+
+        return _sample
+
+    # ------------------------------------------------------------------ ODE
+    def sample_ode(self, *, sampling_method="dopri5", num_steps=50, atol=1e-6, rtol=1e-3, reverse=False
+                   ) -> Callable[..., List[th.Tensor]]:
+        """transport.py:358-401 with the fixed-grid methods of ``torchdiffeq.odeint`` ("euler", "midpoint") on
+        ``linspace(t0, t1, num_steps)`` (integrators.py:95-116); returns the solution at every grid point."""
+        if sampling_method not in ("euler", "midpoint"):
+            raise NotImplementedError(f"ODE method {sampling_method!r}: only the fixed-grid 'euler' and 'midpoint' solvers are built "
+                                      "(adaptive solvers have a data-dependent number of network evaluations)")
+        tr = self.transport
+        t0, t1 = tr.check_interval(tr.train_eps, tr.sample_eps, sde=False, eval=True, reverse=reverse, last_step_size=0.0)
+        ts = th.linspace(t0, t1, num_steps)
+        lib = _lib.load()
+
+        def _sample(x: th.Tensor, model: Callable, **model_kwargs) -> List[th.Tensor]:
+            y = _check_state(x, "x").clone()
+            dev, n, B = y.device, y.numel(), y.size(0)
+            ys = [y.clone()]
+
+            def f(tval: th.Tensor, state: th.Tensor) -> th.Tensor:
+                tv = th.ones(B) * tval                                           # integrators.py:102
+                if reverse:
+                    tv = th.ones_like(tv) * (1 - tv)                             # transport.py:376-377
+                return _check_state(model(state, tv.to(dev), **model_kwargs), "model output")
+
+            with th.cuda.device(dev), th.no_grad():
+                st = _stream(dev)
+                for i in range(num_steps - 1):
+                    ta, tb = ts[i], ts[i + 1]
+                    dt = tb - ta
+                    if sampling_method == "euler":
+                        s = th.stack([_f32(1.0), dt]).to(dev)
+                        _lib.check(lib.fitv2_scaled_add(_p(y), _p(y), _p(f(ta, y)), _p(s), n, st), "fitv2_scaled_add")
+                    else:
+                        half = 0.5 * dt
+                        y_mid = th.empty_like(y)
+                        s1 = th.stack([_f32(1.0), half]).to(dev)
+                        _lib.check(lib.fitv2_scaled_add(_p(y_mid), _p(y), _p(f(ta, y)), _p(s1), n, st), "fitv2_scaled_add")
+                        s2 = th.stack([_f32(1.0), dt]).to(dev)
+                        _lib.check(lib.fitv2_scaled_add(_p(y), _p(y), _p(f(ta + half, y_mid)), _p(s2), n, st), "fitv2_scaled_add")
+                    ys.append(y.clone())
+            return ys
+
+        return _sample
+
+    def sample_ode_likelihood(self, **kw):
+        raise NotImplementedError("the likelihood ODE differentiates through the network (autograd); fitv2_b200 is inference only")

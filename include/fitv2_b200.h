@@ -124,6 +124,27 @@ int fitv2_cfg_combine(float* out, const float* scale_per_sample, float scale, in
 int fitv2_cfg_euler(float* z, const float* v2, float cfg_scale, float dsigma, const float* dsigma_dev,
                     int half_rows, int tokens, int channels, void* stream);
 
+/* ---- transport Sampler updates (reference: fit/scheduler/transport/{transport,integrators,path}.py), velocity model,
+ * linear path.  Elementwise fp32 over n elements, bit-exact with the PyTorch expressions of the reference.
+ * coef_dev: 8 device floats computed by the host per step with the reference's expression order:
+ *   [0] alpha_t/d_alpha_t  [1] sigma_t^2 - [0]*d_sigma_t*sigma_t  [2] diffusion(t)  [3] dt (or last-step size)
+ *   [4] sqrt(2*diffusion)  [5] sqrt(dt)  [6] alpha_t  [7] sigma_t^2/alpha_t                                  */
+
+/* Replaces sde.__Euler_Maruyama_step (integrators.py:29-37) with ONE model evaluation shared by drift and score
+ * (the reference evaluates the network twice, transport.py:256-258):
+ *   x <- (x + (v + D*score(v,x,t))*dt) + sqrt(2D) * (w*sqrt(dt)),   score = ([0]*v - x)/[1]   (path.py:71-85).
+ * w == NULL: the noise-free "Mean" last step x <- x + drift*[3] (transport.py:277-280). */
+int fitv2_sde_step(float* x, const float* v, const float* w, const float* coef_dev, int64_t n, void* stream);
+/* out = v + D*score(v, x, t): the SDE drift (K1, K2 of sde.__Heun_step, integrators.py:45-47). */
+int fitv2_sde_drift(float* out, const float* x, const float* v, const float* coef_dev, int64_t n, void* stream);
+/* out = a + s[1]*(s[0]*b) (s_dev: 2 device floats): xhat = x + sqrt(2D)*(w*sqrt(dt)), xp = xhat + dt*K1 (integrators.py:43,46),
+ * the fixed-grid ODE Euler / midpoint updates (integrators.py:109-116) and the "Euler" last step (transport.py:287-290). */
+int fitv2_scaled_add(float* out, const float* a, const float* b, const float* s_dev, int64_t n, void* stream);
+/* out = xhat + c*(k1 + k2), c_dev[0] = 0.5*dt (integrators.py:48). */
+int fitv2_heun_combine(float* out, const float* xhat, const float* k1, const float* k2, const float* c_dev, int64_t n, void* stream);
+/* "Tweedie" last step (transport.py:281-286): out = x/[6] + [7]*score(v, x, t). */
+int fitv2_tweedie(float* out, const float* x, const float* v, const float* coef_dev, int64_t n, void* stream);
+
 /* Component entry points (same kernels the forward uses) — exercised by the parity tests. */
 int fitv2_debug_gemm(fitv2_handle* h, int epilogue /*3 = plain*/, const void* a, const void* w, const float* bias,
                      float* out32, int M, int N, int K, int bn, void* stream);

@@ -1,0 +1,202 @@
+"""CPU restatement of the reference's transport ``Sampler`` (SiT-style ODE / SDE integrators) for the
+configuration FiTv2 uses (``configs/fitv2/config_fitv2_xl.yaml:3-9``: path Linear, prediction velocity).
+
+TEST INFRASTRUCTURE ONLY: imported by ``tests/`` (and ``oracle/make_transport_golden.py``), never by the
+product package ``fitv2_b200``.  Plain PyTorch fp32 on the CPU, same expression order as the reference so that
+the results are bit-equal to it (``oracle/make_transport_golden.py`` asserts that against the real classes of
+/root/reference and writes ``tests/golden/transport_kat.pt``).
+
+Reference lines restated (paths relative to the reference repo):
+  fit/scheduler/transport/__init__.py:5-71     create_transport (eps defaults)
+  fit/scheduler/transport/transport.py:81-108  Transport.check_interval
+  fit/scheduler/transport/transport.py:194-228 get_drift (velocity_ode) / get_score (velocity -> score)
+  fit/scheduler/transport/transport.py:245-356 Sampler: SDE drift/diffusion, last step, sample_sde
+  fit/scheduler/transport/transport.py:358-401 Sampler.sample_ode
+  fit/scheduler/transport/path.py:20-100       ICPlan: alpha/sigma, compute_drift, compute_diffusion, score from velocity
+  fit/scheduler/transport/integrators.py:8-75  sde: Euler-Maruyama / Heun steps and the forward loop
+  fit/scheduler/transport/integrators.py:77-116 ode: torchdiffeq.odeint on linspace(t0, t1, num_steps)
+
+``torchdiffeq`` (requirements.txt, unpinned, NOT vendored and not installed here) supplies ``odeint``; for the
+fixed-grid methods its published algorithm is  y_{i+1} = y_i + (t_{i+1} - t_i) * f(t_i, y_i)  ("euler") and
+y_{i+1} = y_i + dt * f(t_i + dt/2, y_i + dt/2 * f(t_i, y_i))  ("midpoint"), evaluated on exactly the grid passed in
+(no ``step_size`` option is given by the reference).  Those two are restated here; parity of the ODE integrator
+itself is therefore anchored on the reference's call site only ("parity unpinned" for that one function), while
+everything on the SDE route is pinned against the reference's own code.
+"""
+from __future__ import annotations
+
+import math
+from typing import Callable, List, Optional, Sequence
+
+import torch as th
+
+
+def expand_t_like_x(t: th.Tensor, x: th.Tensor) -> th.Tensor:
+    """path.py:5-13."""
+    return t.view(t.size(0), *([1] * (x.dim() - 1)))
+
+
+# ------------------------------------------------------------------------------------------------
+# ICPlan (path.py:17-100), linear coupling  x_t = t * x1 + (1 - t) * x0
+# ------------------------------------------------------------------------------------------------
+def alpha_t(t):
+    return t, 1
+
+
+def sigma_t(t):
+    return 1 - t, -1
+
+
+def compute_drift(x, t):
+    """path.py:35-43 (t already broadcastable): returns (-drift, diffusion)."""
+    alpha_ratio = 1 / t
+    s, ds = sigma_t(t)
+    drift = alpha_ratio * x
+    diffusion = alpha_ratio * (s ** 2) - s * ds
+    return -drift, diffusion
+
+
+def compute_diffusion(x, t, form="constant", norm=1.0):
+    """path.py:45-69; t is the (B,) time vector."""
+    t = expand_t_like_x(t, x)
+    if form == "constant":
+        return th.tensor(norm).to(x)
+    if form == "SBDM":
+        return norm * compute_drift(x, t)[1]
+    if form == "sigma":
+        return norm * sigma_t(t)[0]
+    if form == "linear":
+        return norm * (1 - t)
+    if form == "decreasing":
+        return 0.25 * (norm * th.cos(math.pi * t) + 1) ** 2
+    if form == "increasing-decreasing":
+        return norm * th.sin(math.pi * t) ** 2
+    raise NotImplementedError(f"Diffusion form {form} not implemented")
+
+
+def score_from_velocity(velocity, x, t):
+    """path.py:71-85."""
+    t = expand_t_like_x(t, x)
+    a, da = alpha_t(t)
+    s, ds = sigma_t(t)
+    reverse_alpha_ratio = a / da
+    var = s ** 2 - reverse_alpha_ratio * ds * s
+    return (reverse_alpha_ratio * velocity - x) / var
+
+
+def create_transport_eps(path_type="Linear", prediction="velocity", train_eps=None, sample_eps=None):
+    """__init__.py:50-60: velocity on a Linear / GVP path is stable everywhere -> both eps are 0."""
+    if path_type != "Linear" or prediction != "velocity":
+        raise NotImplementedError("oracle restates the FiTv2 configuration: Linear path, velocity prediction")
+    return 0, 0
+
+
+def check_interval(sample_eps=0, *, diffusion_form="SBDM", sde=False, reverse=False, last_step_size=0.0):
+    """transport.py:81-108 for ICPlan + ModelType.VELOCITY, eval=True."""
+    t0, t1 = 0, 1
+    eps = sample_eps
+    if sde:                                       # `self.model_type != VELOCITY or sde`
+        t0 = eps if (diffusion_form == "SBDM" and sde) else 0
+        t1 = 1 - eps if (not sde or last_step_size == 0) else 1 - last_step_size
+    if reverse:
+        t0, t1 = 1 - t0, 1 - t1
+    return t0, t1
+
+
+# ------------------------------------------------------------------------------------------------
+# SDE (transport.py:245-356, integrators.py:8-75)
+# ------------------------------------------------------------------------------------------------
+def sde_drift(model, x, t, diffusion_form, diffusion_norm, **kw):
+    """transport.py:256-258.  The reference evaluates the model twice (drift and score); the outputs are identical."""
+    v = model(x, t, **kw)
+    return v + compute_diffusion(x, t, form=diffusion_form, norm=diffusion_norm) * score_from_velocity(v, x, t)
+
+
+def sample_sde(model: Callable, init: th.Tensor, *, sampling_method="Euler", diffusion_form="SBDM", diffusion_norm=1.0,
+               last_step: Optional[str] = "Mean", last_step_size=0.04, num_steps=250,
+               noises: Optional[Sequence[th.Tensor]] = None, sample_eps=0, **model_kwargs) -> List[th.Tensor]:
+    """transport.py:296-356 + integrators.py:64-75.  `noises` (one tensor per step) replaces the reference's
+    ``th.randn(x.size())`` draws from the default CPU generator, in the same order."""
+    if last_step is None:
+        last_step_size = 0.0
+    t0, t1 = check_interval(sample_eps, diffusion_form=diffusion_form, sde=True, last_step_size=last_step_size)
+    ts = th.linspace(t0, t1, num_steps)
+    dt = ts[1] - ts[0]
+    drift = lambda x, t: sde_drift(model, x, t, diffusion_form, diffusion_norm, **model_kwargs)
+    x = init
+    xs = []
+    for i, ti in enumerate(ts[:-1]):
+        w_cur = (noises[i] if noises is not None else th.randn(x.size())).to(x)
+        dw = w_cur * th.sqrt(dt)
+        if sampling_method == "Euler":                                  # integrators.py:29-37
+            t = th.ones(x.size(0)).to(x) * ti
+            d = drift(x, t)
+            diffusion = compute_diffusion(x, t, form=diffusion_form, norm=diffusion_norm)
+            mean_x = x + d * dt
+            x = mean_x + th.sqrt(2 * diffusion) * dw
+        elif sampling_method == "Heun":                                 # integrators.py:39-48
+            t_cur = th.ones(x.size(0)).to(x) * ti
+            diffusion = compute_diffusion(x, t_cur, form=diffusion_form, norm=diffusion_norm)
+            xhat = x + th.sqrt(2 * diffusion) * dw
+            k1 = drift(xhat, t_cur)
+            xp = xhat + dt * k1
+            k2 = drift(xp, t_cur + dt)
+            x = xhat + 0.5 * dt * (k1 + k2)
+        else:
+            raise NotImplementedError("Smapler type not implemented.")
+        xs.append(x)
+    t_last = th.ones(init.size(0), device=init.device) * t1
+    if last_step is None:                                               # transport.py:268-292
+        x = xs[-1]
+    elif last_step == "Mean":
+        x = xs[-1] + drift(xs[-1], t_last) * last_step_size
+    elif last_step == "Tweedie":
+        v = model(xs[-1], t_last, **model_kwargs)
+        a = alpha_t(t_last)[0][0]
+        s = sigma_t(t_last)[0][0]
+        x = xs[-1] / a + (s ** 2) / a * score_from_velocity(v, xs[-1], t_last)
+    elif last_step == "Euler":
+        x = xs[-1] + model(xs[-1], t_last, **model_kwargs) * last_step_size
+    else:
+        raise NotImplementedError()
+    xs.append(x)
+    assert len(xs) == num_steps, "Samples does not match the number of steps"
+    return xs
+
+
+# ------------------------------------------------------------------------------------------------
+# ODE (transport.py:358-401, integrators.py:77-116): fixed-grid methods of torchdiffeq.odeint
+# ------------------------------------------------------------------------------------------------
+def sample_ode(model: Callable, x: th.Tensor, *, sampling_method="euler", num_steps=50, reverse=False,
+               **model_kwargs) -> List[th.Tensor]:
+    """Returns the solution at every grid point (odeint returns a (num_steps, ...) tensor; the script takes [-1])."""
+    t0, t1 = check_interval(0, sde=False, reverse=reverse)
+    ts = th.linspace(t0, t1, num_steps)
+
+    def f(t, y):
+        tv = th.ones(y.size(0)).to(y) * t
+        if reverse:
+            tv = th.ones_like(tv) * (1 - tv)
+        return model(y, tv, **model_kwargs)
+
+    ys = [x]
+    y = x
+    for i in range(num_steps - 1):
+        ta, tb = ts[i], ts[i + 1]
+        dt = tb - ta
+        if sampling_method == "euler":
+            y = y + dt * f(ta, y)
+        elif sampling_method == "midpoint":
+            half_dt = 0.5 * dt
+            y_mid = y + f(ta, y) * half_dt
+            y = y + dt * f(ta + half_dt, y_mid)
+        else:
+            raise NotImplementedError(f"fixed-grid ODE method {sampling_method!r} not restated (adaptive dopri5 has data-dependent NFE)")
+        ys.append(y)
+    return ys
+
+
+def toy_velocity_model(x, t, **kw):
+    """Polynomial stand-in for the network (+, -, * only: bit-reproducible on any CPU); used by the golden vectors."""
+    tt = expand_t_like_x(t, x)
+    return 0.5 * x * (1 + tt) - 0.125 * x * x * x + 0.3 * tt
