@@ -22,6 +22,9 @@ namespace {
 // scratch for the split-K partial sums of the conditioning linears
 constexpr size_t kCondPartialBytes = 24u << 20;
 
+// per-GEMM tile schedule table (clusters x items int2), see build_schedule
+constexpr size_t kSchedBytes = 64u << 10;
+
 // Thread-block cluster size of the production GEMMs (weight-tile TMA multicast across the cluster).
 constexpr int kGemmCluster = 2;
 
@@ -152,7 +155,7 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct Layout {
     int rows = 0, tokens = 0, tokens_v = 0;
-    size_t x_res, h, ao, q, k, vt, hidden, te, t0, c, sc, lmid, gmod, mod, fmod, rope_cos, rope_sin, seg_uniform, cpart, total;
+    size_t x_res, h, ao, q, k, vt, hidden, te, t0, c, sc, lmid, gmod, mod, fmod, rope_cos, rope_sin, seg_uniform, cpart, sched_proj, sched_fc2, total;
 };
 
 }  // namespace
@@ -171,6 +174,8 @@ struct fitv2_handle {
     CUtensorMap map_h, map_ao, map_hidden;              // activations (A operands)
     CUtensorMap map_wqkv, map_wproj, map_wgu, map_wfc2; // stacked weights (B operands)
     int bn_proj = 0, bn_fc2 = 0;
+    int sched_stride_proj = 0, sched_stride_fc2 = 0;     // > 0: ragged tiling (BN-wide tiles + one narrower tail tile per row group)
+    std::vector<int2> sched_host;
     int num_sms = 148;
     int64_t launches = 0;
     // optional per-kernel-class CUDA-event timing (fitv2_profile_*)
@@ -241,6 +246,8 @@ Layout make_layout(const fitv2_config& c, int rows, int tokens) {
     l.rope_sin = take(M * (c.head_dim / 2) * 4);
     l.seg_uniform = take((size_t)rows * 4);
     l.cpart = take(kCondPartialBytes);
+    l.sched_proj = take(kSchedBytes);
+    l.sched_fc2 = take(kSchedBytes);
     l.total = off;
     return l;
 }
@@ -262,7 +269,7 @@ inline void prof_end(fitv2_handle* h, cudaStream_t st) {
 
 template <int BN, int EPI, typename OT, int DH, int CL = kGemmCluster>
 int launch_gemm_t(fitv2_handle* h, const CUtensorMap& ma, const CUtensorMap& mb, int M, int N, int K, int b_row_off,
-                  const GemmEpi& ep, cudaStream_t st) {
+                  const GemmEpi& ep, cudaStream_t st, const int2* sched = nullptr, int sched_stride = 0) {
     using Cfg = GemmCfg<BN, EPI, DH, CL>;
     auto kern = gemm_tc_kernel<BN, EPI, OT, DH, CL>;
     static bool configured = false;
@@ -270,12 +277,13 @@ int launch_gemm_t(fitv2_handle* h, const CUtensorMap& ma, const CUtensorMap& mb,
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
         configured = true;
     }
-    if (N % BN != 0) return fail(FITV2_E_INVALID, "GEMM N=%d is not a multiple of the tile width %d", N, BN);
+    if (N % BN != 0 && !(sched && EPI == EPI_RESID && (N % BN) % 32 == 0))
+        return fail(FITV2_E_INVALID, "GEMM N=%d is not a multiple of the tile width %d", N, BN);
     const int m_tiles = (M + kGemmBM - 1) / kGemmBM;
-    const int groups = ((m_tiles + CL - 1) / CL) * (N / BN);
+    const int groups = ((m_tiles + CL - 1) / CL) * ((N + BN - 1) / BN);
     const int max_clusters = h->num_sms / CL;
     const int grid = (groups < max_clusters ? groups : max_clusters) * CL;
-    CUDA_TRY(launch_k(kern, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, st, CL, ma, mb, M, N, K, b_row_off, ep));
+    CUDA_TRY(launch_k(kern, dim3(grid), dim3(Cfg::kThreads), Cfg::kSmemBytes, st, CL, ma, mb, M, N, K, b_row_off, ep, sched, sched_stride));
     CUDA_TRY(cudaGetLastError());
     h->launches++;
     return FITV2_OK;
@@ -283,17 +291,57 @@ int launch_gemm_t(fitv2_handle* h, const CUtensorMap& ma, const CUtensorMap& mb,
 
 template <int EPI, typename OT, int CL = kGemmCluster>
 int launch_gemm_bn(fitv2_handle* h, int bn, const CUtensorMap& ma, const CUtensorMap& mb, int M, int N, int K,
-                   int b_row_off, const GemmEpi& ep, cudaStream_t st) {
+                   int b_row_off, const GemmEpi& ep, cudaStream_t st, const int2* sched = nullptr, int sched_stride = 0) {
     switch (bn) {
-        case 128: return launch_gemm_t<128, EPI, OT, 0, CL>(h, ma, mb, M, N, K, b_row_off, ep, st);
-        case 144: return launch_gemm_t<144, EPI, OT, 0, CL>(h, ma, mb, M, N, K, b_row_off, ep, st);
-        case 192: return launch_gemm_t<192, EPI, OT, 0, CL>(h, ma, mb, M, N, K, b_row_off, ep, st);
-        case 256: return launch_gemm_t<256, EPI, OT, 0, CL>(h, ma, mb, M, N, K, b_row_off, ep, st);
+        case 128: return launch_gemm_t<128, EPI, OT, 0, CL>(h, ma, mb, M, N, K, b_row_off, ep, st, sched, sched_stride);
+        case 144: return launch_gemm_t<144, EPI, OT, 0, CL>(h, ma, mb, M, N, K, b_row_off, ep, st, sched, sched_stride);
+        case 192: return launch_gemm_t<192, EPI, OT, 0, CL>(h, ma, mb, M, N, K, b_row_off, ep, st, sched, sched_stride);
+        case 256: return launch_gemm_t<256, EPI, OT, 0, CL>(h, ma, mb, M, N, K, b_row_off, ep, st, sched, sched_stride);
     }
     return fail(FITV2_E_INVALID, "unsupported GEMM tile width %d", bn);
 }
 
-// Tile width for the N = hidden_size projections: minimise (waves x per-tile cost) over the widths that divide N.
+// Cost of one 64-deep K block of a (128 rows per CTA) x bn tile in SM clocks: the tensor pipe needs 2*bn, the shared
+// memory pipe (TMA writes + UMMA operand reads share 128 B/clk) needs (16384 + 64*bn) * 2 / 128 = 256 + bn: tiles
+// narrower than 256 columns are shared-memory bound (measured: 72 % tensor-pipe ceiling at bn = 144).
+long tile_cost(int bn) { return (2L * bn > 256L + bn ? 2L * bn : 256L + bn) + 24; }
+
+// LPT schedule of (row-tile group, column tile) items over `clusters` persistent clusters: full bn-wide tiles in
+// n-fastest order first, then one narrower tail tile per row group.  Returns the makespan in tile_cost units and,
+// when `out` is given, the per-cluster item lists (stride entries each, terminated by {-1, 0}).
+long build_schedule(int M, int N, int bn, int clusters, std::vector<int2>* out, int* stride_out) {
+    const int m_tiles = (M + kGemmBM - 1) / kGemmBM;
+    const int m_groups = (m_tiles + kGemmCluster - 1) / kGemmCluster;
+    const int n_full = N / bn, tail = N % bn;
+    std::vector<long> load(clusters, 0);
+    std::vector<std::vector<int2>> items(clusters);
+    auto place = [&](int mg, int n0, int width) {
+        int best = 0;
+        for (int c = 1; c < clusters; ++c) if (load[c] < load[best]) best = c;
+        load[best] += tile_cost(width);
+        items[best].push_back(make_int2(mg, n0 | (width << 20)));
+    };
+    for (int mg = 0; mg < m_groups; ++mg)
+        for (int n = 0; n < n_full; ++n) place(mg, n * bn, bn);
+    if (tail)
+        for (int mg = 0; mg < m_groups; ++mg) place(mg, n_full * bn, tail);
+    long makespan = 0;
+    size_t longest = 0;
+    for (int c = 0; c < clusters; ++c) { if (load[c] > makespan) makespan = load[c]; if (items[c].size() > longest) longest = items[c].size(); }
+    if (out) {
+        const int stride = (int)longest + 2;                            // terminator + one readable entry for the lookahead
+        out->assign((size_t)clusters * stride, make_int2(-1, 0));
+        for (int c = 0; c < clusters; ++c)
+            for (size_t i = 0; i < items[c].size(); ++i) (*out)[(size_t)c * stride + i] = items[c][i];
+        *stride_out = stride;
+    }
+    return makespan;
+}
+
+// Tile width for the N = hidden_size projections among the uniform widths that divide N: minimise (waves x per-tile cost).
+// Measured (profiles/README.md): these two GEMMs are bound by their fp32 read-modify-write residual epilogue, not by the
+// main loop, so the wider, better-scheduling ragged 256 + tail tiling (build_schedule; FITV2_RAGGED=1) is SLOWER for them
+// (proj 66 -> 100 us, fc2 111 -> 121 us) although it lifts the shared-memory ceiling of the main loop from 72 % to 100 %.
 int pick_bn(int M, int N, int num_sms, bool prefer_aligned) {
     const int cands[4] = {256, 192, 144, 128};
     int best = 0; long best_cost = 0;
@@ -432,7 +480,7 @@ int ensure_maps(fitv2_handle* h) {
     if ((rc = make_map(&h->map_ao, h->ws + l.ao, c.operand_dtype, M, D, D, 128))) return rc;
     if ((rc = make_map(&h->map_hidden, h->ws + l.hidden, c.operand_dtype, M, Hm, Hm, 128))) return rc;
     // proj (K = D) is bound by its fp32 residual epilogue: prefer tile widths whose halves start on 128-byte lines;
-    // fc2 (K = mlp_hidden) is main-loop bound: pure wave / tile-size cost.
+    // fc2 (K = mlp_hidden) has the longer main loop: pure wave / tile-size cost.
     h->bn_proj = pick_bn((int)M, (int)D, h->num_sms, /*prefer_aligned=*/true);
     h->bn_fc2 = pick_bn((int)M, (int)D, h->num_sms, /*prefer_aligned=*/false);
     if (const char* e = getenv("FITV2_BN_RESID")) {             // tuning experiments only
@@ -440,6 +488,18 @@ int ensure_maps(fitv2_handle* h) {
         if ((v == 128 || v == 144 || v == 192 || v == 256) && D % v == 0) h->bn_proj = h->bn_fc2 = v;
     }
     if (!h->bn_proj || !h->bn_fc2) return fail(FITV2_E_INVALID, "hidden_size %d has no supported tile width (multiple of 128/144/192/256)", (int)D);
+    h->sched_stride_proj = h->sched_stride_fc2 = 0;
+    if (const char* e = getenv("FITV2_RAGGED")) {               // tuning experiments only: 256-wide tiles + tail tile, LPT schedule
+        if (atoi(e) == 1 && D % 256 != 0 && (D % 256) % 32 == 0 && D > 256) {
+            int stride = 0;
+            build_schedule((int)M, (int)D, 256, h->num_sms / kGemmCluster, &h->sched_host, &stride);
+            if (h->sched_host.size() * sizeof(int2) > kSchedBytes) return fail(FITV2_E_WORKSPACE, "tile schedule does not fit its workspace slot");
+            CUDA_TRY(cudaMemcpy(h->ws + l.sched_proj, h->sched_host.data(), h->sched_host.size() * sizeof(int2), cudaMemcpyHostToDevice));
+            CUDA_TRY(cudaMemcpy(h->ws + l.sched_fc2, h->sched_host.data(), h->sched_host.size() * sizeof(int2), cudaMemcpyHostToDevice));
+            h->bn_proj = h->bn_fc2 = 256;
+            h->sched_stride_proj = h->sched_stride_fc2 = stride;
+        }
+    }
     if ((rc = make_map(&h->map_wqkv, h->w[FITV2_W_QKV_W], c.operand_dtype, L * 3 * D, D, D, 2 * c.head_dim / kGemmCluster))) return rc;
     if ((rc = make_map(&h->map_wproj, h->w[FITV2_W_PROJ_W], c.operand_dtype, L * D, D, D, h->bn_proj / kGemmCluster))) return rc;
     if ((rc = make_map(&h->map_wgu, h->w[FITV2_W_GATEUP_W], c.operand_dtype, L * 2 * Hm, D, D, 256 / kGemmCluster))) return rc;
@@ -548,7 +608,8 @@ int forward_impl(fitv2_handle* h, const float* x, int x_rows, const float* t, co
         ep.bias = (const float*)h->w[FITV2_W_PROJ_B] + (size_t)layer * D;
         ep.tokens = tokens; ep.x = x_res; ep.gate = modl + 2 * D; ep.gate_ld = 6 * D;
         prof_begin(h, PC_PROJ, st);
-        if ((rc = launch_gemm_bn<EPI_RESID, OT>(h, h->bn_proj, h->map_ao, h->map_wproj, M, D, D, layer * D, ep, st))) return rc;
+        if ((rc = launch_gemm_bn<EPI_RESID, OT>(h, h->bn_proj, h->map_ao, h->map_wproj, M, D, D, layer * D, ep, st,
+                                               h->sched_stride_proj ? (const int2*)(ws + l.sched_proj) : nullptr, h->sched_stride_proj))) return rc;
         prof_end(h, st);
         // ---- SwiGLU branch (modules.py:273) ----
         prof_begin(h, PC_LNMOD, st);
@@ -564,7 +625,8 @@ int forward_impl(fitv2_handle* h, const float* x, int x_rows, const float* t, co
         ep.bias = (const float*)h->w[FITV2_W_FC2_B] + (size_t)layer * D;
         ep.tokens = tokens; ep.x = x_res; ep.gate = modl + 5 * D; ep.gate_ld = 6 * D;
         prof_begin(h, PC_FC2, st);
-        if ((rc = launch_gemm_bn<EPI_RESID, OT>(h, h->bn_fc2, h->map_hidden, h->map_wfc2, M, D, Hm, layer * D, ep, st))) return rc;
+        if ((rc = launch_gemm_bn<EPI_RESID, OT>(h, h->bn_fc2, h->map_hidden, h->map_wfc2, M, D, Hm, layer * D, ep, st,
+                                               h->sched_stride_fc2 ? (const int2*)(ws + l.sched_fc2) : nullptr, h->sched_stride_fc2))) return rc;
         prof_end(h, st);
     }
 

@@ -54,7 +54,7 @@ struct GemmEpi {
 
 constexpr int kGemmBM = 128;          // rows per CTA
 constexpr int kGemmBK = 64;
-constexpr int kGemmThreads = 320;     // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
+constexpr int kGemmThreads = 320;     // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (GemmCfg::kThreads: the RESID epilogue may use 16 warps)
 constexpr int kSmemBudget = 227 * 1024;
 
 template <int BN, int EPI, int DH, int CL = 1> struct GemmCfg {
@@ -65,6 +65,11 @@ template <int BN, int EPI, int DH, int CL = 1> struct GemmCfg {
     // narrow tiles: one pipeline stage carries TWO 64-wide K blocks (8 UMMAs per barrier round trip); the UMMA issue /
     // commit / wait overhead per stage, not the tensor pipe, bounded BN <= 192 tiles (70 % tensor-pipe utilisation)
     static constexpr int kKSub = (kABytes + kBBytes) <= 28 * 1024 ? 2 : 1;
+    // epilogue warps per TMEM lane quarter (each takes BN / kParts tile columns).  Four per quarter (16 epilogue warps)
+    // only pay for the 256-wide residual tiles of the ragged-tiling experiments (proj 100 -> 79 us); at BN = 128 they
+    // measured slightly slower than two (61.5 vs 57.3 us), so the production widths keep 8 epilogue warps.
+    static constexpr int kParts = (EPI == EPI_RESID && BN == 256) ? 4 : 2;
+    static constexpr int kThreads = 64 + kParts * 128;
     static constexpr int kStageBytes = (kABytes + kBBytes) * kKSub;    // per CTA
     static constexpr int kTxBytes = kStageBytes * CL;                  // credited to the (leader's) full barrier per stage
     static constexpr int kBarrierBytes = 1024;
@@ -72,7 +77,7 @@ template <int BN, int EPI, int DH, int CL = 1> struct GemmCfg {
     // the other epilogues use 128-byte XOR-swizzled rows.
     static constexpr int kEpiPitch = EPI == EPI_QKV ? ((DH * 2 / 4) % 8 == 4 ? DH * 2 : DH * 2 + 16) : 128;
     static constexpr int kEpiWarpBytes = 32 * kEpiPitch;
-    static constexpr int kEpiBytes = (EPI == EPI_PLAIN ? 0 : 8 * kEpiWarpBytes);
+    static constexpr int kEpiBytes = (EPI == EPI_PLAIN ? 0 : 4 * kParts * kEpiWarpBytes);
     static constexpr int kStagesRaw = (kSmemBudget - kBarrierBytes - 1024 - kEpiBytes) / kStageBytes;
     static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
     static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + kBarrierBytes + 1024;   // +1024 alignment slack
@@ -93,10 +98,33 @@ template <int CPR> __device__ __forceinline__ void slab_task(int i, int lane, in
     c = task % CPR;
 }
 
+// Work items of one cluster.  Uniform tiling (sched == nullptr): item i of cluster c is tile c + i * clusters in
+// n-fastest order.  Ragged tiling (EPI_RESID with N not a multiple of BN): the host builds an LPT schedule per
+// cluster, entries {row-tile group, n0 | width << 20}, terminated by a negative group: full BN-wide tiles first,
+// the narrower tail tiles fill the gaps of the last wave (fitv2_api.cu: build_schedule).
+struct TileWalk {
+    const int2* sched; int grp, num_groups, stride, n_tiles, bn;
+    int2 ahead;                                                         // table mode: the entry after the current one (prefetched)
+    __device__ __forceinline__ void start() { if (sched) ahead = __ldg(sched++); }
+    __device__ __forceinline__ bool next(int& m_group, int& n0, int& bn_t) {
+        if (sched) {
+            const int2 w = ahead;
+            if (w.x < 0) return false;
+            ahead = __ldg(sched++);                                     // the terminator is always followed by readable entries
+            m_group = w.x; n0 = w.y & 0xFFFFF; bn_t = w.y >> 20;
+            return true;
+        }
+        if (grp >= num_groups) return false;
+        m_group = grp / n_tiles; n0 = (grp % n_tiles) * bn; bn_t = bn;      // n fastest: a wave shares few A tiles
+        grp += stride;
+        return true;
+    }
+};
+
 template <int BN, int EPI, typename OT, int DH, int CL>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__((GemmCfg<BN, EPI, DH, CL>::kThreads), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-               int M, int N, int K, int b_row_offset, GemmEpi ep)
+               int M, int N, int K, int b_row_offset, GemmEpi ep, const int2* __restrict__ sched, int sched_stride)
 {
     using Cfg = GemmCfg<BN, EPI, DH, CL>;
     constexpr int STAGES = Cfg::kStages;
@@ -124,12 +152,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     const uint32_t cta_rank = CL > 1 ? cluster_ctarank() : 0u;
     const bool leader = cta_rank == 0;
     const int group0 = blockIdx.x / CL, group_stride = gridDim.x / CL;
+    const TileWalk walk0 = {sched ? sched + (size_t)group0 * sched_stride : nullptr, group0, num_groups, group_stride, n_tiles, BN, make_int2(-1, 0)};
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tma_a);
         tma_prefetch_desc(&tma_b);
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 256 * CL); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], Cfg::kParts * 128 * CL); }
         mbar_fence_init();
     }
     if (warp == 1) {
@@ -148,8 +177,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     if (warp == 0) {
         // ------------------------------ TMA producer (every CTA) ------------------------------
         int stage = 0; uint32_t phase = 0;
-        for (int grp = group0; grp < num_groups; grp += group_stride) {
-            const int m_tile = (grp / n_tiles) * CL + (int)cta_rank, n_tile = grp % n_tiles;   // n fastest: a wave shares few A tiles
+        TileWalk walk = walk0;
+        walk.start();
+        int m_group, n0, bn_t;
+        while (walk.next(m_group, n0, bn_t)) {
+            const int m_tile = m_group * CL + (int)cta_rank;
             for (int kb = 0; kb < num_kb; ++kb) {
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 if (elect_one()) {
@@ -162,11 +194,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                         const int kcol = (kb * KSUB + j) * kGemmBK;
                         if constexpr (CL == 1) {
                             tma_load_2d(&tma_a, &full_bar[stage], sa + j * Cfg::kABytes, kcol, m_tile * kGemmBM);
-                            tma_load_2d(&tma_b, &full_bar[stage], sb + j * Cfg::kBBytes, kcol, b_row_offset + n_tile * BN);
+                            tma_load_2d(&tma_b, &full_bar[stage], sb + j * Cfg::kBBytes, kcol, b_row_offset + n0);
                         } else {
                             tma_load_2d_2sm(&tma_a, &full_bar[stage], sa + j * Cfg::kABytes, kcol, m_tile * kGemmBM);
+                            // a narrower (tail) tile still fetches the full box; the UMMA reads bn_t / CL rows of it
                             tma_load_2d_2sm(&tma_b, &full_bar[stage], sb + j * Cfg::kBBytes, kcol,
-                                            b_row_offset + n_tile * BN + (int)cta_rank * Cfg::kBRowsPerCta);
+                                            b_row_offset + n0 + (int)cta_rank * (bn_t / CL));
                         }
                     }
                 }
@@ -181,7 +214,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             const uint64_t da0 = umma_desc_kmajor(smem_u32(smem_a), 128);
             const uint64_t db0 = umma_desc_kmajor(smem_u32(smem_b), 128);
             int stage = 0; uint32_t phase = 0; int it = 0;
-            for (int grp = group0; grp < num_groups; grp += group_stride, ++it) {
+            TileWalk walk = walk0;
+            walk.start();
+            int m_group, n0, bn_t;
+            for (; walk.next(m_group, n0, bn_t); ++it) {
+                const uint32_t idesc_t = bn_t == BN ? idesc : umma_idesc(Op16<OT>::kUmmaFormat, kGemmBM * CL, bn_t);
                 const int acc = it & 1;
                 const uint32_t acc_phase = (it >> 1) & 1;
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);          // CL = 2: both CTAs' epilogues have drained it
@@ -197,8 +234,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                             const uint64_t db = db0 + (uint64_t)((stage * KSUB + j) * (Cfg::kBBytes >> 4));
 #pragma unroll
                             for (int kk = 0; kk < kGemmBK / 16; ++kk) {  // +32 bytes (>>4 = 2) per K=16 step inside the 128B atom
-                                if constexpr (CL == 1) umma_ss(d_tmem, da + 2 * kk, db + 2 * kk, idesc, (kb | j | kk) != 0);
-                                else umma_ss_2sm(d_tmem, da + 2 * kk, db + 2 * kk, idesc, (kb | j | kk) != 0);
+                                if constexpr (CL == 1) umma_ss(d_tmem, da + 2 * kk, db + 2 * kk, idesc_t, (kb | j | kk) != 0);
+                                else umma_ss_2sm(d_tmem, da + 2 * kk, db + 2 * kk, idesc_t, (kb | j | kk) != 0);
                             }
                         }
                         // smem slot free (in both CTAs) once these MMAs retire; accumulator ready after the last k-block
@@ -218,7 +255,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     } else {
         // ------------------------------ epilogue warps (every CTA: its own 128 rows) ------------------------------
         const int quarter = warp & 3;                                 // TMEM lane quarter this warp may access
-        const int half = (warp - 2) >> 2;                             // 0: left half of the tile columns, 1: right half
+        const int half = (warp - 2) >> 2;                             // which BN / kParts column range of the tile this warp owns
         const uint32_t stg = smem_u32(smem_epi) + (warp - 2) * Cfg::kEpiWarpBytes;   // warp-private staging slab (shared-space address)
         // hand the accumulator back to the MMA issuer (which lives in the leader CTA)
         auto release_acc = [&](int acc) {
@@ -227,8 +264,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             else mbar_arrive_remote(&tempty_bar[acc], 0);
         };
         int it = 0;
-        for (int grp = group0; grp < num_groups; grp += group_stride, ++it) {
-            const int m_tile = (grp / n_tiles) * CL + (int)cta_rank, n_tile = grp % n_tiles;
+        TileWalk walk = walk0;
+        walk.start();
+        int m_group, n0, bn_t;
+        for (; walk.next(m_group, n0, bn_t); ++it) {
+            const int m_tile = m_group * CL + (int)cta_rank, n_tile = n0 / BN;
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
             const uint32_t t_row = tmem_base + acc * Cfg::kAccStride + (uint32_t(quarter * 32) << 16);
@@ -236,17 +276,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             const int rows_valid = min(32, M - m_warp);               // <= 0 when the whole warp is past the M tail
             const int m = m_warp + lane;
             const bool row_ok = lane < rows_valid;
-            const int n0 = n_tile * BN;
             const int s_first = m_warp / ep.tokens;
             const bool one_sample = rows_valid > 0 && (m_warp + rows_valid - 1) / ep.tokens == s_first;
 
             if constexpr (EPI == EPI_RESID) {
-                constexpr int HALF = BN / 2;                          // columns per warp
+                constexpr int HALF = BN / Cfg::kParts;                // columns per warp
                 constexpr int NFULL = HALF / 32, REM = HALF % 32;     // 32-column slabs + one remainder slab
                 constexpr int NS = NFULL + (REM ? 1 : 0);
                 constexpr int NPF = NS < 3 ? NS : 3;                  // slabs of x kept in flight (register ring)
                 static_assert(REM == 0 || REM == 8 || REM == 16, "unsupported tile half width");
                 const int col0 = n0 + half * HALF;
+                // slabs of this warp inside the (possibly narrower, multiple-of-32 wide) tile
+                const int ns_valid = REM == 0 ? max(0, min(NS, (bn_t - half * HALF) / 32)) : NS;
                 float* xbase = ep.x + (size_t)m_warp * N + col0;
                 // The residual does not depend on the accumulator: the x values of (up to) the whole tile half are
                 // requested, in the coalesced mapping, BEFORE waiting for the MMAs of this tile, so the HBM latency
@@ -258,7 +299,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     for (int i = 0; i < 8; ++i) {
                         if (i < cpr) {
                             const int task = i * 32 + lane, r = task / cpr, c = task - r * cpr;
-                            if (r < rows_valid) xr[slot][i] = *reinterpret_cast<const float4*>(xbase + (size_t)r * N + sl * 32 + c * 4);
+                            if (r < rows_valid && sl < ns_valid) xr[slot][i] = *reinterpret_cast<const float4*>(xbase + (size_t)r * N + sl * 32 + c * 4);
                         }
                     }
                 };
@@ -266,8 +307,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 for (int sl = 0; sl < NPF; ++sl) load_x(sl, sl);
                 mbar_wait(&tfull_bar[acc], acc_phase);
                 tc_fence_after();
+                if (ns_valid == 0) release_acc(acc);
 #pragma unroll
                 for (int sl = 0; sl < NS; ++sl) {
+                    if (sl < ns_valid) {
                     const int cpr = sl < NFULL ? 8 : REM / 4;
                     const int s0 = sl * 32;
                     uint32_t v[32];
@@ -275,7 +318,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     else if (cpr == 4) tmem_ld16(t_row + half * HALF + s0, v);
                     else tmem_ld8(t_row + half * HALF + s0, v);
                     tmem_ld_wait();
-                    if (sl == NS - 1) release_acc(acc);
+                    if (sl == ns_valid - 1) release_acc(acc);
 #pragma unroll
                     for (int c = 0; c < 8; ++c)
                         if (c < cpr) sts128(stg + slab_off(lane, c), make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]));
@@ -304,6 +347,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     }
                     __syncwarp();
                     if (sl + NPF < NS) load_x(sl % NPF, sl + NPF);    // refill the ring slot (only tiles wider than 3 slabs)
+                    }
                 }
             } else if constexpr (EPI == EPI_SWIGLU) {
                 // tile columns: [0, BN/2) = gate rows of W, [BN/2, BN) = matching up rows (host packs W this way)
