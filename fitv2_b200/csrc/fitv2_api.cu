@@ -37,6 +37,12 @@ bool pdl_enabled() {
     return on;
 }
 
+// L2 residency window of the fp32 residual stream (set per forward): kernels launched while it is active carry an
+// access-policy window that marks `hit_ratio` of its lines persisting in L2 and everything else streaming, so that the
+// residual written by one kernel is still in L2 when the next one reads it (it is touched six times per block).
+struct L2Window { void* base = nullptr; size_t bytes = 0; float hit_ratio = 0.f; };
+thread_local L2Window g_l2_window;
+
 template <typename... KArgs, typename... Args>
 cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster, Args&&... args) {
     cudaLaunchConfig_t cfg;
@@ -45,8 +51,17 @@ cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
     cfg.blockDim = block;
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[2];
+    cudaLaunchAttribute attr[3];
     unsigned n = 0;
+    if (g_l2_window.base) {
+        attr[n].id = cudaLaunchAttributeAccessPolicyWindow;
+        attr[n].val.accessPolicyWindow.base_ptr = g_l2_window.base;
+        attr[n].val.accessPolicyWindow.num_bytes = g_l2_window.bytes;
+        attr[n].val.accessPolicyWindow.hitRatio = g_l2_window.hit_ratio;
+        attr[n].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr[n].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        ++n;
+    }
     if (cluster > 1) {
         attr[n].id = cudaLaunchAttributeClusterDimension;
         attr[n].val.clusterDim.x = cluster; attr[n].val.clusterDim.y = 1; attr[n].val.clusterDim.z = 1;
@@ -177,6 +192,7 @@ struct fitv2_handle {
     int sched_stride_proj = 0, sched_stride_fc2 = 0;     // > 0: ragged tiling (BN-wide tiles + one narrower tail tile per row group)
     std::vector<int2> sched_host;
     int num_sms = 148;
+    int64_t l2_persist_bytes = 0, l2_window_max = 0;     // persisting-L2 carve-out used for the residual stream (0 = off)
     int64_t launches = 0;
     // optional per-kernel-class CUDA-event timing (fitv2_profile_*)
     uint32_t prof_mask = 0;
@@ -529,6 +545,14 @@ int forward_impl(fitv2_handle* h, const float* x, int x_rows, const float* t, co
     float* rsin = (float*)(ws + l.rope_sin);
     int* segu = (int*)(ws + l.seg_uniform);
     int rc;
+    struct WindowGuard { ~WindowGuard() { g_l2_window = L2Window(); } } window_guard;
+    if (h->l2_persist_bytes > 0) {
+        const size_t xb = (size_t)M * D * 4;
+        g_l2_window.base = x_res;
+        g_l2_window.bytes = xb < (size_t)h->l2_window_max ? xb : (size_t)h->l2_window_max;
+        const float r = (float)h->l2_persist_bytes / (float)g_l2_window.bytes;
+        g_l2_window.hit_ratio = r < 1.f ? r : 1.f;
+    }
 
     // ---- per-call tables: segment-uniformity flags, RoPE cos/sin (rope.py:308-333) ----
     prof_begin(h, PC_COND, st);
@@ -690,6 +714,22 @@ int fitv2_create(const fitv2_config* cfg, fitv2_handle** out) {
     memset(h->w, 0, sizeof(h->w));
     memset(h->w_numel, 0, sizeof(h->w_numel));
     h->num_sms = sms;
+    {   // persisting L2 for the fp32 residual stream: FITV2_L2_PERSIST_MB (default 0 = off)
+        int max_persist = 0, max_window = 0;
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+        const char* e = getenv("FITV2_L2_PERSIST_MB");
+        long want = e ? atol(e) : 0;
+        if (want > 0 && max_persist > 0) {
+            long bytes = want << 20;
+            if (bytes > max_persist) bytes = max_persist;
+            if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)bytes) == cudaSuccess) {
+                h->l2_persist_bytes = bytes;
+                h->l2_window_max = max_window;
+            }
+        }
+        if (getenv("FITV2_VERBOSE")) fprintf(stderr, "[fitv2] L2 persist max %d MB, window max %d MB, using %lld MB\n", max_persist >> 20, max_window >> 20, (long long)(h->l2_persist_bytes >> 20));
+    }
     *out = h;
     return FITV2_OK;
 }

@@ -24,4 +24,14 @@ grid, mask = make_grid(R, hp, wp).cuda(), torch.ones(R, N).cuda()
 for _ in range(2):
     out = m(x, t, y, grid, mask)
 torch.cuda.synchronize()
-print("ok", float(out.abs().max()))
+# the sampler-side elementwise kernels (fused CFG + Euler update; SDE Euler-Maruyama step), at the headline state size
+from fitv2_b200 import EulerCFGSampler, Sampler, create_transport
+n = R // 2
+smp = EulerCFGSampler(m, y[:n], grid[:n], mask[:n], 250, 1.5)
+z = torch.randn(n, N, 16, device="cuda")
+for i in range(2):
+    smp._step(z, smp.t_table[i], smp.dsig[i:i + 1])
+fn = Sampler(create_transport()).sample_sde(diffusion_form="sigma", num_steps=3)
+xs = fn(torch.randn(R, N, 16, device="cuda"), lambda xx, tt, **k: xx * 0.5)
+torch.cuda.synchronize()
+print("ok", float(out.abs().max()), float(z.abs().max()), float(xs[-1].abs().max()))
