@@ -854,6 +854,23 @@ int fitv2_tweedie(float* out, const float* x, const float* v, const float* coef_
     return FITV2_OK;
 }
 
+int fitv2_unpatchify_scale(const float* z, float* out, float scaling_factor, int batch, int hp, int wp, int channels, int patch, void* stream) {
+    if (!z || !out || batch <= 0 || hp <= 0 || wp <= 0 || channels <= 0 || patch <= 0 || scaling_factor == 0.0f)
+        return fail(FITV2_E_INVALID, "bad unpatchify_scale argument");
+    const int64_t n = (int64_t)batch * channels * hp * wp * patch * patch;
+    CUDA_TRY(launch_k(unpatchify_scale_kernel, dim3(elementwise_grid(n * 4)), dim3(256), 0, static_cast<cudaStream_t>(stream), 1,
+                      z, out, scaling_factor, batch, hp, wp, channels, patch));
+    return FITV2_OK;
+}
+
+int fitv2_pack_uint8(const float* img, unsigned char* out, int batch, int channels, int height, int width, void* stream) {
+    if (!img || !out || batch <= 0 || channels <= 0 || height <= 0 || width <= 0) return fail(FITV2_E_INVALID, "bad pack_uint8 argument");
+    const int64_t n = (int64_t)batch * channels * height * width;
+    CUDA_TRY(launch_k(pack_uint8_kernel, dim3(elementwise_grid(n * 4)), dim3(256), 0, static_cast<cudaStream_t>(stream), 1,
+                      img, out, batch, channels, height, width));
+    return FITV2_OK;
+}
+
 int fitv2_debug_gemm(fitv2_handle* h, int epilogue, const void* a, const void* w, const float* bias, float* out32, int M,
                      int N, int K, int bn, void* stream) {
     if (!h || !a || !w || !bias || !out32) return fail(FITV2_E_INVALID, "null argument");

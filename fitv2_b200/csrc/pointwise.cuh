@@ -130,6 +130,48 @@ __global__ void tweedie_kernel(float* __restrict__ out, const float* __restrict_
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// After the trajectory (sample_fitv2_ddp.py:319-324):
+//   latents = unpatchify(z) / scaling_factor    (fit_model.py:171-187: "b (h w) (c p1 p2) -> b c (h p1) (w p2)")
+//   ... vae.decode (reference PyTorch, outside this path) ...
+//   images  = clamp(127.5 * clamp(s, -1, 1) + 128, 0, 255).permute(0, 2, 3, 1).to(uint8)
+// Both are pure index permutations with one correctly rounded fp32 operation per element (IEEE division; multiply
+// then add, no FMA; float -> uint8 truncation), so they are bit-identical to the PyTorch expressions.
+// ---------------------------------------------------------------------------------------------
+// z: (B, hp*wp, C*p*p) fp32 -> out: (B, C, hp*p, wp*p) fp32.  One thread per output element: consecutive threads write
+// consecutive W positions; the matching reads are p-strided inside one token row (64 bytes for p = 2, C = 4).
+__global__ void unpatchify_scale_kernel(const float* __restrict__ z, float* __restrict__ out, float scaling_factor,
+                                        int B, int hp, int wp, int C, int p)
+{
+    pdl_wait();
+    pdl_launch_dependents();
+    const int H = hp * p, W = wp * p;
+    const size_t total = (size_t)B * C * H * W;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int x = (int)(i % W), y = (int)((i / W) % H), c = (int)((i / ((size_t)W * H)) % C), b = (int)(i / ((size_t)W * H * C));
+        const int token = (y / p) * wp + (x / p);
+        const int ch = (c * p + (y % p)) * p + (x % p);
+        const float v = z[((size_t)b * hp * wp + token) * (C * p * p) + ch];
+        out[i] = scaling_factor == 1.0f ? v : __fdiv_rn(v, scaling_factor);
+    }
+}
+
+// img: (B, C, H, W) fp32 -> out: (B, H, W, C) uint8
+__global__ void pack_uint8_kernel(const float* __restrict__ img, unsigned char* __restrict__ out, int B, int C, int H, int W)
+{
+    pdl_wait();
+    pdl_launch_dependents();
+    const size_t total = (size_t)B * C * H * W;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C), x = (int)((i / C) % W), y = (int)((i / ((size_t)C * W)) % H), b = (int)(i / ((size_t)C * W * H));
+        float s = img[(((size_t)b * C + c) * H + y) * W + x];
+        s = fminf(fmaxf(s, -1.0f), 1.0f);                                               // samples.clamp(-1, 1)
+        s = __fadd_rn(__fmul_rn(127.5f, s), 128.0f);
+        s = fminf(fmaxf(s, 0.0f), 255.0f);                                              // torch.clamp(..., 0, 255)
+        out[i] = (unsigned char)(int)s;                                                 // .to(torch.uint8): truncation
+    }
+}
+
 // forward_with_cfg channel-limited guidance (fit_model.py:253-275): channels [0, c_cfg) of BOTH halves become
 // uncond + s_b * (cond - uncond); channels >= c_cfg pass through.  out: (2B, tokens, C) in place.
 // scale_per_sample may be null (then `scale` is used for every sample).

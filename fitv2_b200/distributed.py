@@ -56,6 +56,12 @@ def gather_latents(z: torch.Tensor) -> torch.Tensor:
     return torch.cat(out, dim=0)
 
 
+def gather_images(images: torch.Tensor) -> torch.Tensor:
+    """All-gather of the decoded uint8 images (n, H, W, 3) of every rank, the reference's own format for this step
+    (sample_fit_ddp.py:185-186; commented out in sample_fitv2_ddp.py:328-329) -> (world*n, H, W, 3), rank-major."""
+    return gather_latents(images)
+
+
 def max_over_ranks(value: float, device) -> float:
     if not dist.is_initialized() or dist.get_world_size() == 1:
         return value

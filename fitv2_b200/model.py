@@ -312,14 +312,25 @@ class FiT(nn.Module):
                                              c_cfg, C.c_void_p(st)), "fitv2_cfg_combine")
         return out if x.dtype == torch.float32 else out.to(x.dtype)
 
-    def unpatchify(self, x, hw):
-        """fit_model.py:171-187 (use_sit): (B,(h w),(c p1 p2)) -> (B,c,h*p1,w*p2).  Pure permutation, outside
-        the timed path."""
+    def unpatchify(self, x, hw, scaling_factor: float = 1.0):
+        """fit_model.py:171-187 (use_sit): (B,(h w),(c p1 p2)) -> (B,c,h*p1,w*p2), optionally fused with the latent
+        scaling ``samples / vae.config.scaling_factor`` of sample_fitv2_ddp.py:320-321 (one kernel, bit-exact).
+        CUDA fp32 tensors go through the C ABI (``fitv2_unpatchify_scale``); anything else (the reference also calls
+        this on CPU tensors in its data tools) is the same index permutation as a tensor view."""
         h, w = hw
         p = self.patch_size
         B = x.shape[0]
-        x = x.reshape(B, h // p, w // p, -1, p, p)
-        return x.permute(0, 3, 1, 4, 2, 5).reshape(B, -1, h, w)
+        if x.is_cuda and x.dtype == torch.float32:
+            x = x.contiguous()
+            ch = x.shape[2] // (p * p)
+            out = torch.empty(B, ch, h, w, dtype=torch.float32, device=x.device)
+            with torch.cuda.device(x.device):
+                st = torch.cuda.current_stream(x.device).cuda_stream
+                _lib.check(_lib.load().fitv2_unpatchify_scale(C.c_void_p(x.data_ptr()), C.c_void_p(out.data_ptr()), float(scaling_factor),
+                                                              B, h // p, w // p, ch, p, C.c_void_p(st)), "fitv2_unpatchify_scale")
+            return out
+        x = x.reshape(B, h // p, w // p, -1, p, p).permute(0, 3, 1, 4, 2, 5).reshape(B, -1, h, w)
+        return x if scaling_factor == 1.0 else x / scaling_factor
 
     # ------------------------------------------------------------------------------------------
     # introspection used by tests / bench

@@ -94,3 +94,18 @@ def euler_cfg_sample(model: FiT, z, y, grid, mask, size=None, num_steps: int = 2
                      use_cuda_graph: bool = False, first_steps: Optional[int] = None) -> torch.Tensor:
     """Functional form of the script's loop: z (n,N,C), y (n,), grid (n,2,N), mask (n,N)."""
     return EulerCFGSampler(model, y, grid, mask, num_steps, cfg_scale, use_cuda_graph).sample(z, first_steps)
+
+
+def pack_images_uint8(samples: torch.Tensor) -> torch.Tensor:
+    """sample_fitv2_ddp.py:321-323 in one kernel: decoded images (B, C, H, W) fp32 on the GPU ->
+    ``clamp(127.5 * samples.clamp(-1, 1) + 128, 0, 255).permute(0, 2, 3, 1).to(uint8)`` (B, H, W, C), bit-exact."""
+    if not samples.is_cuda:
+        raise _lib.FitV2Error("pack_images_uint8 needs a CUDA tensor: fitv2_b200 has no CPU path")
+    x = samples.to(torch.float32).contiguous()
+    B, Cc, H, W = x.shape
+    out = torch.empty(B, H, W, Cc, dtype=torch.uint8, device=x.device)
+    with torch.cuda.device(x.device):
+        st = torch.cuda.current_stream(x.device).cuda_stream
+        _lib.check(_lib.load().fitv2_pack_uint8(C.c_void_p(x.data_ptr()), C.c_void_p(out.data_ptr()), B, Cc, H, W, C.c_void_p(st)),
+                   "fitv2_pack_uint8")
+    return out

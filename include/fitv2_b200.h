@@ -145,6 +145,15 @@ int fitv2_heun_combine(float* out, const float* xhat, const float* k1, const flo
 /* "Tweedie" last step (transport.py:281-286): out = x/[6] + [7]*score(v, x, t). */
 int fitv2_tweedie(float* out, const float* x, const float* v, const float* coef_dev, int64_t n, void* stream);
 
+/* ---- after the trajectory (sample_fitv2_ddp.py:319-324) ----
+ * Replaces FiT.unpatchify (fit_model.py:171-187, use_sit layout) fused with the latent scaling `samples / vae.config.scaling_factor`:
+ *   z (batch, hp*wp, channels*patch*patch) fp32 -> out (batch, channels, hp*patch, wp*patch) fp32, out = unpatchify(z) / scaling_factor
+ * (scaling_factor 1 = plain unpatchify).  Bit-exact (one IEEE division per element). */
+int fitv2_unpatchify_scale(const float* z, float* out, float scaling_factor, int batch, int hp, int wp, int channels, int patch, void* stream);
+/* Replaces `samples.clamp(-1,1)` ... `torch.clamp(127.5*samples + 128.0, 0, 255).permute(0,2,3,1).to(torch.uint8)`
+ * (sample_fitv2_ddp.py:321-323): img (batch, channels, H, W) fp32 -> out (batch, H, W, channels) uint8.  Bit-exact. */
+int fitv2_pack_uint8(const float* img, unsigned char* out, int batch, int channels, int height, int width, void* stream);
+
 /* Component entry points (same kernels the forward uses) — exercised by the parity tests. */
 int fitv2_debug_gemm(fitv2_handle* h, int epilogue /*3 = plain*/, const void* a, const void* w, const float* bias,
                      float* out32, int M, int N, int K, int bn, void* stream);

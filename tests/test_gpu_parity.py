@@ -283,3 +283,28 @@ def test_errors_are_loud(lib):
     rc = lib.fitv2_forward(h, _p(x), 2, _p(t), _p(y), _p(grid), _p(mask.float()), _p(out), 2, 16, None)
     assert rc == -2 and b"not bound" in lib.fitv2_last_error()             # unbound weights: error, no fallback
     lib.fitv2_destroy(h)
+
+
+# ------------------------------------------------------------------------------------------------
+# after the trajectory: unpatchify + latent scaling, uint8 image pack (sample_fitv2_ddp.py:319-324)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,hp,wp", [(2, 16, 16), (3, 10, 20), (1, 32, 32), (2, 1, 3)])
+def test_unpatchify_scale_bit_exact(lib, B, hp, wp):
+    cfg = O.FiTConfig(hidden_size=1152, num_heads=16, depth=1)
+    m = FiT(**KW, depth=1, **XL)
+    g = torch.Generator().manual_seed(B * 100 + hp)
+    z = torch.randn(B, hp * wp, 16, generator=g)
+    ref = O.unpatchify(cfg, z, (hp * 2, wp * 2))
+    assert torch.equal(m.unpatchify(z, (hp * 2, wp * 2)), ref)                      # CPU view path == oracle
+    assert torch.equal(m.unpatchify(z.cuda(), (hp * 2, wp * 2)).cpu(), ref)          # CUDA kernel, bit-exact
+    assert torch.equal(m.unpatchify(z.cuda(), (hp * 2, wp * 2), scaling_factor=0.18215).cpu(), ref / 0.18215)
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 256, 256), (1, 160, 320), (3, 8, 24)])
+def test_pack_uint8_bit_exact(lib, B, H, W):
+    from fitv2_b200 import pack_images_uint8
+    g = torch.Generator().manual_seed(H + W)
+    s = torch.randn(B, 3, H, W, generator=g) * 0.8
+    s[0, 0, 0, :4] = torch.tensor([-1.0, 1.0, 0.0, 0.99999994])
+    ref = torch.clamp(127.5 * s.clamp(-1, 1) + 128.0, 0, 255).permute(0, 2, 3, 1).to(torch.uint8).contiguous()
+    assert torch.equal(pack_images_uint8(s.cuda()).cpu(), ref)
