@@ -63,6 +63,7 @@ def load():
     lib.fitv2_destroy.argtypes = [vp]
     lib.fitv2_destroy.restype = None
     lib.fitv2_bind_weight.argtypes = [vp, i32, vp, i64]
+    lib.fitv2_set_online_rope.argtypes = [vp, vp, vp, i32]
     lib.fitv2_workspace_bytes.argtypes = [vp, i32, i32]
     lib.fitv2_workspace_bytes.restype = i64
     lib.fitv2_set_workspace.argtypes = [vp, vp, i64]
@@ -95,7 +96,7 @@ def check(rc: int, what: str = ""):
 
 EXPORTED_SYMBOLS = [
     "fitv2_last_error", "fitv2_version", "fitv2_create", "fitv2_destroy", "fitv2_bind_weight",
-    "fitv2_workspace_bytes", "fitv2_set_workspace", "fitv2_forward", "fitv2_cfg_combine", "fitv2_cfg_euler",
+    "fitv2_set_online_rope", "fitv2_workspace_bytes", "fitv2_set_workspace", "fitv2_forward", "fitv2_cfg_combine", "fitv2_cfg_euler",
     "fitv2_sde_step", "fitv2_sde_drift", "fitv2_scaled_add", "fitv2_heun_combine", "fitv2_tweedie", "fitv2_unpatchify_scale", "fitv2_pack_uint8",
     "fitv2_debug_gemm", "fitv2_debug_attention", "fitv2_debug_tap", "fitv2_kernel_launches",
     "fitv2_profile_set", "fitv2_profile_read",

@@ -192,6 +192,9 @@ struct fitv2_handle {
     int sched_stride_proj = 0, sched_stride_fc2 = 0;     // > 0: ragged tiling (BN-wide tiles + one narrower tail tile per row group)
     std::vector<int2> sched_host;
     int num_sms = 148;
+    const float* online_fh = nullptr;                    // per-row RoPE frequencies (rows, head_dim/4), online_rope mode
+    const float* online_fw = nullptr;
+    int online_rows = 0;
     int64_t l2_persist_bytes = 0, l2_window_max = 0;     // persisting-L2 carve-out used for the residual stream (0 = off)
     int64_t launches = 0;
     // optional per-kernel-class CUDA-event timing (fitv2_profile_*)
@@ -560,8 +563,14 @@ int forward_impl(fitv2_handle* h, const float* x, int x_rows, const float* t, co
     {
         const size_t total = (size_t)M * (DH / 2);
         const int blocks = (int)((total + 255) / 256);
+        if (h->online_fh && h->online_rows != rows)
+            return fail(FITV2_E_INVALID, "online RoPE frequencies were set for %d rows, forward has %d", h->online_rows, rows);
+        if (h->online_fh)
+            CUDA_TRY(launch_k(rope_table_kernel, dim3(blocks), dim3(256), 0, st, 1, (const long long*)grid, h->online_fh, h->online_fw, DH / 4,
+                              1.0f, rcos, rsin, rows, tokens, DH / 2));
+        else
         CUDA_TRY(launch_k(rope_table_kernel, dim3(blocks), dim3(256), 0, st, 1, (const long long*)grid, (const float*)h->w[FITV2_W_ROPE_FREQS_H],
-                                                   (const float*)h->w[FITV2_W_ROPE_FREQS_W], c.rope_magnitude, rcos, rsin,
+                                                   (const float*)h->w[FITV2_W_ROPE_FREQS_W], 0, c.rope_magnitude, rcos, rsin,
                                                    rows, tokens, DH / 2));
     }
     // ---- conditioning (fit_model.py:202-209,218-219; modules.py:52-76,101-106,259-264,287-293) ----
@@ -748,6 +757,16 @@ int fitv2_bind_weight(fitv2_handle* h, int slot, const void* dev_ptr, int64_t nu
     h->w[slot] = dev_ptr;
     h->w_numel[slot] = numel;
     h->maps_valid = false;
+    return FITV2_OK;
+}
+
+int fitv2_set_online_rope(fitv2_handle* h, const float* freqs_h_rows, const float* freqs_w_rows, int rows) {
+    if (!h) return fail(FITV2_E_INVALID, "null handle");
+    if ((freqs_h_rows == nullptr) != (freqs_w_rows == nullptr) || (freqs_h_rows && rows <= 0))
+        return fail(FITV2_E_INVALID, "bad online RoPE argument");
+    h->online_fh = freqs_h_rows;
+    h->online_fw = freqs_w_rows;
+    h->online_rows = freqs_h_rows ? rows : 0;
     return FITV2_OK;
 }
 

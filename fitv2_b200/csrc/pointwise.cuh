@@ -392,8 +392,10 @@ final_layer_kernel(const float* __restrict__ x, const float* __restrict__ fmod /
 //   pair i >= dh/4 : angle = float(grid[s,0,n]) * freqs_w[i - dh/4]     (w position)
 //   cos/sin tables (dh/2, M) fp32 (pair-major), optionally scaled by the yarn / ntk-pro magnitude.
 // ---------------------------------------------------------------------------------------------
+// freq_stride = 0: one frequency vector per axis for the whole batch (cached mode); freq_stride = dh/4: per-sample
+// vectors (online mode, rope.py:234-274: dynamic NTK scale from each sample's own size).
 __global__ void rope_table_kernel(const long long* __restrict__ grid, const float* __restrict__ freqs_h,
-                                  const float* __restrict__ freqs_w, float mag, float* __restrict__ cos_t,
+                                  const float* __restrict__ freqs_w, int freq_stride, float mag, float* __restrict__ cos_t,
                                   float* __restrict__ sin_t, int samples, int tokens, int half /* dh/2 */)
 {
     pdl_wait();
@@ -408,8 +410,8 @@ __global__ void rope_table_kernel(const long long* __restrict__ grid, const floa
         const int s = (int)(m / tokens);
         const long long* g = grid + (size_t)s * 2 * tokens;
         float ang;
-        if (p < quarter) ang = __fmul_rn((float)g[tokens + n], freqs_h[p]);
-        else             ang = __fmul_rn((float)g[n], freqs_w[p - quarter]);
+        if (p < quarter) ang = __fmul_rn((float)g[tokens + n], freqs_h[(size_t)s * freq_stride + p]);
+        else             ang = __fmul_rn((float)g[n], freqs_w[(size_t)s * freq_stride + p - quarter]);
         float sv, cv;
         sincosf(ang, &sv, &cv);
         if (mag != 1.0f) { cv = __fmul_rn(cv, mag); sv = __fmul_rn(sv, mag); }

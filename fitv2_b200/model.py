@@ -16,7 +16,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .rope import rope_frequencies
+from .rope import rope_frequencies, online_rope_frequencies, _ONLINE_RULES
 
 
 class _Holder(nn.Module):
@@ -53,7 +53,9 @@ class FiT(nn.Module):
         if norm_type != "layernorm": unsupported.append("norm_type must be 'layernorm'")
         if q_norm != "layernorm" or k_norm != "layernorm" or qk_norm_weight: unsupported.append("q_norm/k_norm must be 'layernorm' without weight")
         if not (qkv_bias and ffn_bias and adaln_bias): unsupported.append("qkv_bias/ffn_bias/adaln_bias must be True")
-        if online_rope: unsupported.append("online_rope=True")
+        if online_rope and (custom_freqs.lower() not in _ONLINE_RULES or not isinstance(ori_max_pe_len, int)):
+            unsupported.append("online_rope=True needs custom_freqs in ('linear', 'ntk-aware', 'ntk-by-parts') and ori_max_pe_len "
+                               "(the reference's online mode has no 'normal' branch and never sets the yarn / ntk-aware-pro magnitudes)")
         if add_rel_pe_to_v: unsupported.append("add_rel_pe_to_v=True")
         if use_checkpoint: unsupported.append("use_checkpoint=True (inference only)")
         if finetune is not None or pretrain_ckpt is not None: unsupported.append("pretrain_ckpt/finetune (load weights with load_state_dict)")
@@ -78,7 +80,10 @@ class FiT(nn.Module):
         self.rope_args = dict(head_dim=self.head_dim, custom_freqs=custom_freqs, theta=rope_theta,
                               max_pe_len_h=max_pe_len_h, max_pe_len_w=max_pe_len_w, decouple=decouple,
                               ori_max_pe_len=ori_max_pe_len)
+        if online_rope:                                                     # frequencies come from `size` at call time
+            self.rope_args.update(max_pe_len_h=max_pe_len_h or ori_max_pe_len, max_pe_len_w=max_pe_len_w or ori_max_pe_len)
         rope_frequencies(**self.rope_args)                                  # validate early
+        self._online_key, self._online_freqs = None, None
 
         # ---- parameters: same names / shapes / creation order as the reference (fit_model.py:84-112) ----
         D, C = hidden_size, in_channels * patch_size ** 2
@@ -283,11 +288,32 @@ class FiT(nn.Module):
     # ------------------------------------------------------------------------------------------
     # reference-facing API
     # ------------------------------------------------------------------------------------------
+    def _set_online_rope(self, size, rows: int):
+        """online_rope (fit_model.py:212-214): per-sample frequencies from ``size`` (B,1,2), recomputed only when the
+        caller hands in a different tensor (a sampling loop passes the same one every step)."""
+        if not self.online_rope:
+            return
+        if size is None:
+            raise ValueError("online_rope=True needs `size` (B, 1, 2) = (h, w) patches per sample (fit_model.py:212-213)")
+        if size.reshape(-1, 2).shape[0] != rows:
+            raise ValueError(f"size has {size.reshape(-1, 2).shape[0]} rows, the batch {rows}")
+        self._ensure_packed()
+        key = (size.data_ptr(), size._version, tuple(size.shape), str(size.device))
+        if key != self._online_key:
+            a = self.rope_args
+            fh, fw = online_rope_frequencies(a["head_dim"], a["custom_freqs"], a["theta"], a["decouple"], a["ori_max_pe_len"], size)
+            self._online_freqs = (fh.to(self.device), fw.to(self.device))
+            self._online_key = key
+        fh, fw = self._online_freqs
+        _lib.check(_lib.load().fitv2_set_online_rope(self._handle, C.c_void_p(fh.data_ptr()), C.c_void_p(fw.data_ptr()), rows),
+                   "fitv2_set_online_rope")
+
     @torch.no_grad()
     def forward(self, x, t, y, grid, mask, size=None):
-        """fit_model.py:189-233.  x (B,N,p*p*C), t (B,), y (B,), grid (B,2,N), mask (B,N); ``size`` is unused
-        (online_rope=False).  Returns the velocity (B,N,p*p*C) in x.dtype."""
+        """fit_model.py:189-233.  x (B,N,p*p*C), t (B,), y (B,), grid (B,2,N), mask (B,N); ``size`` (B,1,2) is read only
+        with online_rope=True.  Returns the velocity (B,N,p*p*C) in x.dtype."""
         xf = x.to(torch.float32).contiguous()
+        self._set_online_rope(size, x.shape[0])
         out = self._run(xf, t, y, grid, mask, rows=x.shape[0])
         return out if x.dtype == torch.float32 else out.to(x.dtype)
 
@@ -297,6 +323,7 @@ class FiT(nn.Module):
         rows = x.shape[0]
         half = rows // 2
         xf = x[:half].to(torch.float32).contiguous()
+        self._set_online_rope(size, rows)
         out = self._run(xf, t, y, grid, mask, rows=rows)               # implicit cat([half, half])
         c_cfg = 3 * self.patch_size * self.patch_size
         scale_ptr, scale = None, float(cfg_scale)

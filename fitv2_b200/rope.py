@@ -98,3 +98,45 @@ def rope_frequencies(head_dim: int, custom_freqs: str = "normal", theta: float =
         mag = float(torch.where(torch.tensor(l_test / l_train) <= 1.0, torch.tensor(1.0),
                                 torch.sqrt(torch.log(torch.tensor(l_test)) / torch.log(torch.tensor(l_train)))))
     return fh.float(), fw.float(), mag
+
+
+_ONLINE_RULES = ("linear", "ntk-aware", "ntk-by-parts")
+
+
+def online_axis_freqs(rule: str, theta: float, dim: int, sizes: torch.Tensor, ori_max_pe_len: int) -> torch.Tensor:
+    """rope.py:173-231 with a tensor ``max_pe_len``: per-sample axis lengths (B,) -> inverse frequencies (B, dim // 2),
+    fp32 on the CPU in the reference's operation order (the rules its online mode supports, rope.py:234-274)."""
+    if not isinstance(ori_max_pe_len, int):
+        raise TypeError("ori_max_pe_len must be an int (rope.py:175)")
+    if rule not in _ONLINE_RULES:
+        raise ValueError(f"Unknown modality {rule}. online_rope supports {_ONLINE_RULES}")
+    scale = torch.clamp_min(sizes / ori_max_pe_len, 1.0)
+    expo = torch.arange(0, dim, 2).float() / dim
+    base_pow = theta ** expo
+    f_lin = 1.0 / (scale[:, None] * base_pow[None, :])
+    if rule == "linear":
+        return f_lin
+    newbase = theta * scale ** (dim / (dim - 2))
+    f_ntk = (1.0 / torch.pow(newbase.view(-1, 1), expo.to(scale).float())).reshape(sizes.shape[0], -1)
+    if rule == "ntk-aware":
+        return f_ntk
+    f_base = 1.0 / base_pow
+    lo, hi = _correction_range(1.25, 0.75, dim, theta, ori_max_pe_len)
+    m = (1 - _ramp(lo, hi, dim // 2).to(scale)) * 1
+    f = f_lin * (1 - m) + f_ntk * m
+    lo, hi = _correction_range(16, 2, dim, theta, ori_max_pe_len)
+    m = (1 - _ramp(lo, hi, dim // 2).to(scale)) * 1
+    return f * (1 - m) + f_base * m
+
+
+def online_rope_frequencies(head_dim: int, custom_freqs: str, theta: float, decouple: bool, ori_max_pe_len: int,
+                            size: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """rope.py:243-253: per-sample (freqs_h, freqs_w), each (B, head_dim // 4) fp32 CPU, from size (B,1,2) = (h, w)."""
+    dim = head_dim // 2
+    size = size.detach().to("cpu", torch.int64).reshape(-1, 2)
+    rule = custom_freqs.lower()
+    if decouple:
+        return (online_axis_freqs(rule, theta, dim, size[:, 0], ori_max_pe_len).float().contiguous(),
+                online_axis_freqs(rule, theta, dim, size[:, 1], ori_max_pe_len).float().contiguous())
+    f = online_axis_freqs(rule, theta, dim, torch.max(size[:, 0], size[:, 1]), ori_max_pe_len).float().contiguous()
+    return f, f.clone()

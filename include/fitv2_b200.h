@@ -96,6 +96,11 @@ void fitv2_destroy(fitv2_handle* h);
  * pointer of one packed weight.  `numel` is checked against the slot's expected element count. */
 int fitv2_bind_weight(fitv2_handle* h, int slot, const void* dev_ptr, int64_t numel);
 
+/* online_rope mode (fit_model.py:212-214, rope.py:234-274): per-row inverse frequencies, two device arrays of
+ * (rows, head_dim/4) fp32 computed by the host from each sample's `size` (dynamic NTK scale), used instead of the bound
+ * ROPE_FREQS_H/W vectors by the following forward calls (which must use the same `rows`).  NULL, NULL switches back. */
+int fitv2_set_online_rope(fitv2_handle* h, const float* freqs_h_rows, const float* freqs_w_rows, int rows);
+
 /* Bytes of scratch the forward needs for (rows = batch incl. CFG duplication, tokens per row). */
 int64_t fitv2_workspace_bytes(const fitv2_handle* h, int rows, int tokens);
 int fitv2_set_workspace(fitv2_handle* h, void* dev_ptr, int64_t bytes);

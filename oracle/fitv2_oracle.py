@@ -67,6 +67,7 @@ class FiTConfig:
     ori_max_pe_len: Optional[int] = None
     time_shifting: int = 1
     max_cached_len: int = 256  # rope.py:126
+    online_rope: bool = False  # fit_model.py:57,212-214: per-sample frequencies from `size`
 
     @property
     def head_dim(self) -> int:
@@ -193,6 +194,52 @@ def rope_cos_sin(cfg: FiTConfig, grid: torch.Tensor) -> Tuple[torch.Tensor, torc
         # the reference multiplies by a 0-dim fp32 tensor (rope.py:320-328)
         cos, sin = cos * torch.tensor(mag), sin * torch.tensor(mag)
     return cos, sin
+
+
+def rope_1d_freqs_online(custom_freqs: str, theta: float, dim: int, sizes: torch.Tensor, ori_max_pe_len: int) -> torch.Tensor:
+    """rope.py:173-231 (get_1d_rope_freqs) with a TENSOR ``max_pe_len`` of per-sample lengths (B,) -> (B, dim//2).
+    Only the rules that work in the reference's online mode: 'normal' has no branch there (ValueError) and the
+    magnitude rules (yarn, ntk-aware-pro1/2) read attributes the online constructor never sets (rope.py:143-160)."""
+    assert isinstance(ori_max_pe_len, int)
+    scale = torch.clamp_min(sizes / ori_max_pe_len, 1.0)                      # (B,) fp32
+    ar = torch.arange(0, dim, 2).float() / dim
+    if custom_freqs == "linear":
+        return 1.0 / (scale[:, None] * (theta ** ar)[None, :])               # einsum('..., f -> ... f') outer product
+    newbase = theta * scale ** (dim / (dim - 2))                              # rope.py:40-42
+    freqs_ntk = (1.0 / torch.pow(newbase.view(-1, 1), ar.to(scale).float())).squeeze()
+    if custom_freqs == "ntk-aware":
+        return freqs_ntk.reshape(sizes.shape[0], -1)
+    if custom_freqs == "ntk-by-parts":
+        beta_0, beta_1, gamma_0, gamma_1 = 1.25, 0.75, 16, 2
+        freqs_base = 1.0 / (theta ** ar)
+        freqs_linear = 1.0 / (scale[:, None] * (theta ** ar.to(scale).float())[None, :])
+        low, high = _find_correction_range(beta_0, beta_1, dim, theta, ori_max_pe_len)
+        m = (1 - _linear_ramp_mask(low, high, dim // 2).to(scale)) * 1
+        freqs = freqs_linear * (1 - m) + freqs_ntk * m
+        low, high = _find_correction_range(gamma_0, gamma_1, dim, theta, ori_max_pe_len)
+        m = (1 - _linear_ramp_mask(low, high, dim // 2).to(scale)) * 1
+        return (freqs * (1 - m) + freqs_base * m).reshape(sizes.shape[0], -1)
+    raise ValueError(f"Unknown modality {custom_freqs}. online_rope supports linear, ntk-aware, ntk-by-parts")
+
+
+def rope_cos_sin_online(cfg: FiTConfig, grid: torch.Tensor, size: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """rope.py:234-274 (online_get_2d_rope_from_grid).  size (B,1,2) int64, h first, w last."""
+    dim = cfg.head_dim // 2
+    cf = cfg.custom_freqs.lower()
+    size = size.squeeze()
+    if size.dim() == 1:
+        size = size[None]
+    if cfg.decouple:
+        fh = rope_1d_freqs_online(cf, cfg.rope_theta, dim, size[:, 0], cfg.ori_max_pe_len)
+        fw = rope_1d_freqs_online(cf, cfg.rope_theta, dim, size[:, 1], cfg.ori_max_pe_len)
+    else:
+        smax = torch.max(size[:, 0], size[:, 1])
+        fh = rope_1d_freqs_online(cf, cfg.rope_theta, dim, smax, cfg.ori_max_pe_len)
+        fw = fh
+    tw = (grid[:, 0][..., None] * fw[:, None, :]).repeat_interleave(2, dim=-1)
+    th = (grid[:, 1][..., None] * fh[:, None, :]).repeat_interleave(2, dim=-1)
+    freqs = torch.cat([th, tw], dim=-1)
+    return freqs.cos(), freqs.sin()
 
 
 def rotate_half(x: torch.Tensor) -> torch.Tensor:
@@ -397,7 +444,7 @@ def swiglu(cfg: FiTConfig, sd, i: int, x, quant=None):
 
 
 def forward(cfg: FiTConfig, sd, x, t, y, grid, mask, size=None, quant: Optional[str] = None, taps=None):
-    """fit_model.py:189-233 with use_sit=True, adaln_type='lora', online_rope=False.
+    """fit_model.py:189-233 with use_sit=True, adaln_type='lora' (online_rope per cfg).
 
     x (B,N,p*p*C) float, t (B,) float, y (B,) int64, grid (B,2,N) int64,
     mask (B,N) float/bool segment ids.  Returns (B,N,p*p*C)."""
@@ -405,7 +452,10 @@ def forward(cfg: FiTConfig, sd, x, t, y, grid, mask, size=None, quant: Optional[
     maskf = mask.to(x.dtype) if mask.dtype != torch.bool else mask
     c = conditioning(cfg, sd, t.to(x.dtype), y)
     h = _linear(x, sd, "x_embedder.proj")                                # :206
-    cos, sin = rope_cos_sin(cfg, grid)                                   # :216
+    if cfg.online_rope:
+        cos, sin = rope_cos_sin_online(cfg, grid, size)                  # :212-214
+    else:
+        cos, sin = rope_cos_sin(cfg, grid)                               # :216
     cos, sin = cos.unsqueeze(1), sin.unsqueeze(1)
     g_adaln = _linear(F.silu(c), sd, "global_adaLN_modulation.1")        # :218-219
     if taps is not None:

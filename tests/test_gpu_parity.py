@@ -308,3 +308,28 @@ def test_pack_uint8_bit_exact(lib, B, H, W):
     s[0, 0, 0, :4] = torch.tensor([-1.0, 1.0, 0.0, 0.99999994])
     ref = torch.clamp(127.5 * s.clamp(-1, 1) + 128.0, 0, 255).permute(0, 2, 3, 1).to(torch.uint8).contiguous()
     assert torch.equal(pack_images_uint8(s.cuda()).cpu(), ref)
+
+
+# ------------------------------------------------------------------------------------------------
+# online_rope: per-sample dynamic NTK frequencies from `size` (fit_model.py:212-214, rope.py:234-274)
+# ------------------------------------------------------------------------------------------------
+def test_online_rope_forward_golden(lib, golden_dir):
+    fx = torch.load(os.path.join(golden_dir, "xl_depth2_online.pt"))
+    extra = dict(custom_freqs="ntk-aware", decouple=True, ori_max_pe_len=16, max_pe_len_h=16, max_pe_len_w=16, online_rope=True)
+    m, sd, cfg = build_model(2, **extra)
+    a = [fx[k].cuda() for k in ("x", "t", "y", "grid", "mask", "size")]
+    out = m(*a).cpu()
+    assert rel(out, fx["out"]) < V_TOL                                      # vs the REAL reference's online_rope forward
+    assert bool((out[fx["mask"] == 0] == 0).all())
+    cos, sin = O.rope_cos_sin_online(cfg, fx["grid"], fx["size"])
+    assert float((m.debug_tap("rope_cos").cpu() - cos[..., 0::2].permute(2, 0, 1)).abs().max()) < 1e-6
+    assert float((m.debug_tap("rope_sin").cpu() - sin[..., 0::2].permute(2, 0, 1)).abs().max()) < 1e-6
+    # a different size tensor is picked up (different per-sample scale -> different output), the same one is cached
+    size2 = fx["size"].clone(); size2[0, 0, 1] = 32
+    assert rel(m(*a[:5], size2.cuda()).cpu(), out) > 1e-4
+    with pytest.raises(ValueError):
+        m(*a[:5], None)
+    with pytest.raises(NotImplementedError):
+        FiT(**KW, depth=1, **XL, custom_freqs="yarn", ori_max_pe_len=16, max_pe_len_h=16, max_pe_len_w=16, online_rope=True)
+    with pytest.raises(NotImplementedError):
+        FiT(**KW, depth=1, **XL, online_rope=True)                          # 'normal' has no online branch in the reference

@@ -142,3 +142,22 @@ def test_flops_formula():
     assert O.flops_per_forward_row(xl, 200) / 1e9 == pytest.approx(236.17, abs=0.01)
     assert O.flops_per_forward_row(xl, 1024) / 1e9 == pytest.approx(1348.35, abs=0.01)
     assert O.flops_per_forward_row(b3, 256) / 1e9 == pytest.approx(1329.63, abs=0.01)
+
+
+def test_online_rope_forward_golden(golden_dir):
+    """oracle online_rope path == the real reference's output (oracle/make_online_rope_golden.py)."""
+    fx = torch.load(os.path.join(golden_dir, "xl_depth2_online.pt"))
+    cfg = O.FiTConfig(hidden_size=1152, depth=2, num_heads=16, adaln_lora_dim=288, custom_freqs="ntk-aware", decouple=True,
+                      ori_max_pe_len=16, max_pe_len_h=16, max_pe_len_w=16, online_rope=True)
+    sd = O.synthetic_state_dict(cfg)
+    out = O.forward(cfg, sd, fx["x"], fx["t"], fx["y"], fx["grid"], fx["mask"], fx["size"])
+    assert rel(out, fx["out"]) < TOL
+    # the product's host-side frequency rule == the oracle's
+    from fitv2_b200.rope import online_rope_frequencies
+    for cf in ("linear", "ntk-aware", "ntk-by-parts"):
+        for dec in (False, True):
+            fh, fw = online_rope_frequencies(72, cf, 10000.0, dec, 16, fx["size"])
+            s = fx["size"].reshape(-1, 2)
+            sh, sw = (s[:, 0], s[:, 1]) if dec else (torch.max(s[:, 0], s[:, 1]),) * 2
+            assert torch.equal(fh, O.rope_1d_freqs_online(cf, 10000.0, 36, sh, 16).float())
+            assert torch.equal(fw, O.rope_1d_freqs_online(cf, 10000.0, 36, sw, 16).float())
