@@ -2,7 +2,8 @@
 from .model import FiT
 from .sampler import EulerCFGSampler, euler_cfg_sample, make_grid, pack_images_uint8
 from .transport import Sampler, Transport, create_transport
+from .checkpoint import init_from_ckpt
 from ._lib import FitV2Error
 
 __all__ = ["FiT", "EulerCFGSampler", "euler_cfg_sample", "make_grid", "pack_images_uint8", "FitV2Error", "Sampler", "Transport",
-           "create_transport"]
+           "create_transport", "init_from_ckpt"]

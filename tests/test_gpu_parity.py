@@ -333,3 +333,19 @@ def test_online_rope_forward_golden(lib, golden_dir):
         FiT(**KW, depth=1, **XL, custom_freqs="yarn", ori_max_pe_len=16, max_pe_len_h=16, max_pe_len_w=16, online_rope=True)
     with pytest.raises(NotImplementedError):
         FiT(**KW, depth=1, **XL, online_rope=True)                          # 'normal' has no online branch in the reference
+
+
+def test_checkpoint_ingestion_repacks_kernel_weights(lib, tmp_path):
+    """init_from_ckpt (eval_utils.py:12-71) after the model has already run: the packed kernel layouts follow the new weights."""
+    from safetensors.torch import save_file
+    from fitv2_b200 import init_from_ckpt
+    m_a, _, _ = build_model(1)
+    torch.manual_seed(123)
+    m_b = FiT(**KW, depth=1, **XL).randomize_zero_init_(7).cuda().eval()
+    a = inputs(2, 8, 8)
+    out_a, out_b = run(m_a, *a), run(m_b, *a)
+    assert rel(out_a, out_b) > 1e-2
+    f = str(tmp_path / "model_ema.safetensors")
+    save_file({f"_orig_mod.{k}": v.detach().cpu().contiguous() for k, v in m_b.state_dict().items()}, f)
+    assert init_from_ckpt(m_a, f) == ([], [])
+    assert torch.equal(run(m_a, *a), out_b)

@@ -123,3 +123,38 @@ def test_c_abi_argument_errors(built_lib):
     if not torch.cuda.is_available():
         ok = _lib.FitV2Config(1152, 1, 16, 72, 3072, 288, 16, 1001, 0, 1.0, 1.0)
         assert lib.fitv2_create(ctypes.byref(ok), ctypes.byref(h)) == -3              # no device: CUDA error, not a fallback
+
+
+def test_init_from_ckpt_rules(tmp_path):
+    """fit/utils/eval_utils.py:12-71: safetensors / torch files, `_orig_mod.` prefix handling, ignore_keys, strict=False."""
+    import torch
+    from safetensors.torch import save_file
+    from fitv2_b200 import FiT, init_from_ckpt
+    kw = dict(learn_sigma=False, use_sit=True, use_swiglu=True, q_norm="layernorm", k_norm="layernorm", adaln_type="lora",
+              hidden_size=144, depth=1, num_heads=2, adaln_lora_dim=8)
+    torch.manual_seed(0)
+    src = FiT(**kw).randomize_zero_init_(1)
+    sd = {k: v.detach().clone().contiguous() for k, v in src.state_dict().items()}
+    # 1. plain safetensors (model_ema.safetensors of the released checkpoints)
+    f1 = str(tmp_path / "model_ema.safetensors")
+    save_file(sd, f1)
+    torch.manual_seed(5)
+    m = FiT(**kw)
+    missing, unexpected = init_from_ckpt(m, f1, ignore_keys=None, verbose=True)
+    assert missing == [] and unexpected == []
+    assert all(torch.equal(v, sd[k]) for k, v in m.state_dict().items())
+    # 2. checkpoint saved from a torch.compile'd model: `_orig_mod.` prefix is stripped
+    f2 = str(tmp_path / "compiled.safetensors")
+    save_file({f"_orig_mod.{k}": v for k, v in sd.items()}, f2)
+    m2 = FiT(**kw)
+    assert init_from_ckpt(m2, f2) == ([], [])
+    assert all(torch.equal(v, sd[k]) for k, v in m2.state_dict().items())
+    # 3. torch.save file, ignore_keys as regular expressions, strict=False semantics
+    f3 = str(tmp_path / "ckpt.pt")
+    torch.save(dict(sd, extra_buffer=torch.zeros(1)), f3)
+    m3 = FiT(**kw)
+    before = m3.final_layer.linear.weight.detach().clone()
+    missing, unexpected = init_from_ckpt(m3, f3, ignore_keys=[r"final_layer\.linear"])
+    assert sorted(missing) == ["final_layer.linear.bias", "final_layer.linear.weight"] and unexpected == ["extra_buffer"]
+    assert torch.equal(m3.final_layer.linear.weight, before)
+    assert torch.equal(m3.x_embedder.proj.weight, sd["x_embedder.proj.weight"])
