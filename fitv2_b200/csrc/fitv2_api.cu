@@ -457,7 +457,11 @@ int launch_ln_modulate(fitv2_handle* h, const float* x, const float* shift, cons
     if (nv <= 1) CUDA_TRY(launch_k(ln_modulate_kernel<OT, 1>, dim3(blocks), dim3(256), 0, st, 1, x, shift, scale, mod_ld, (OT*)out, M, D, tokens));
     else if (nv <= 3) CUDA_TRY(launch_k(ln_modulate_kernel<OT, 3>, dim3(blocks), dim3(256), 0, st, 1, x, shift, scale, mod_ld, (OT*)out, M, D, tokens));
     else if (nv <= 9) CUDA_TRY(launch_k(ln_modulate_kernel<OT, 9>, dim3(blocks), dim3(256), 0, st, 1, x, shift, scale, mod_ld, (OT*)out, M, D, tokens));
-    else if (nv <= 18) CUDA_TRY(launch_k(ln_modulate_kernel<OT, 18>, dim3(blocks), dim3(256), 0, st, 1, x, shift, scale, mod_ld, (OT*)out, M, D, tokens));
+    else if (nv <= 18) {                                             // wide rows: one row per warp pair (4 rows per CTA)
+        static const bool single = [] { const char* e = getenv("FITV2_LN_WIDE_SINGLE"); return e && e[0] == '1'; }();
+        if (single) CUDA_TRY(launch_k(ln_modulate_kernel<OT, 18>, dim3(blocks), dim3(256), 0, st, 1, x, shift, scale, mod_ld, (OT*)out, M, D, tokens));
+        else CUDA_TRY(launch_k(ln_modulate_pair_kernel<OT, 9>, dim3((M + 3) / 4), dim3(256), 0, st, 1, x, shift, scale, mod_ld, (OT*)out, M, D, tokens));
+    }
     else return fail(FITV2_E_INVALID, "hidden_size %d too large for the LayerNorm kernel", D);
     CUDA_TRY(cudaGetLastError());
     h->launches++;
