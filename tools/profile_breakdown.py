@@ -53,7 +53,7 @@ for name, (ms, cnt) in prof.items():
     row = dict(ms_per_nfe=round(per_nfe, 4), launches_per_nfe=cnt // reps, us_per_launch=round(us, 2))
     if name in flops:
         row["tflops"] = round(flops[name] / (us * 1e-6) / 1e12, 1)
-    if name == "ln_modulate":
+    if name == "ln_modulate" and us > 0:
         row["gbs"] = round(M * D * 6 / (us * 1e-6) / 1e9, 1)      # read fp32 + write 16-bit
     out["classes"][name] = row
 out["sum_of_classes_ms"] = tot
