@@ -349,3 +349,16 @@ def test_checkpoint_ingestion_repacks_kernel_weights(lib, tmp_path):
     save_file({f"_orig_mod.{k}": v.detach().cpu().contiguous() for k, v in m_b.state_dict().items()}, f)
     assert init_from_ckpt(m_a, f) == ([], [])
     assert torch.equal(run(m_a, *a), out_b)
+
+
+def test_ragged_residual_tiling_matches_uniform(lib, monkeypatch):
+    """The experimental 256-wide + tail-tile residual tiling with its host-built LPT schedule table (FITV2_RAGGED=1, see
+    profiles/README.md) computes the same function as the production uniform tiling."""
+    a = inputs(3, 10, 20)                                                    # 200 tokens: M tail inside a row-tile pair
+    m0, _, _ = build_model(2)
+    ref = run(m0, *a)
+    monkeypatch.setenv("FITV2_RAGGED", "1")
+    m1, _, _ = build_model(2)
+    out = run(m1, *a)
+    assert rel(out, ref) < 2e-5                                              # same operands; only the fp32 summation tiling differs
+    assert torch.equal(run(m1, *a), out)
