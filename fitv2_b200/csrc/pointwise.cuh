@@ -568,8 +568,9 @@ small_linear_kernel(SmallLinear p)
 
     const int lr = threadIdx.x >> 2;            // 0..63 : row (A) / col (W) loaded by this thread
     const int lk = (threadIdx.x & 3) * 4;       // 0,4,8,12
-    for (int k0 = k_begin; k0 < k_end; k0 += 16) {
-        float4 av = make_float4(0.f, 0.f, 0.f, 0.f), wv = make_float4(0.f, 0.f, 0.f, 0.f);
+    // register double buffering: the global loads of chunk k + 1 are in flight while chunk k is multiplied out of shared memory
+    auto load_chunk = [&](int k0, float4& av, float4& wv) {
+        av = make_float4(0.f, 0.f, 0.f, 0.f); wv = make_float4(0.f, 0.f, 0.f, 0.f);
         if (r0 + lr < p.rows && k0 + lk < k_end) {
             av = *reinterpret_cast<const float4*>(A + (size_t)(r0 + lr) * p.lda + k0 + lk);
             if (p.act_silu_in) {
@@ -579,10 +580,15 @@ small_linear_kernel(SmallLinear p)
         }
         if (n0 + lr < p.N && k0 + lk < k_end)
             wv = __ldg(reinterpret_cast<const float4*>(W + (size_t)(n0 + lr) * p.K + k0 + lk));
+    };
+    float4 av, wv;
+    if (k_begin < k_end) load_chunk(k_begin, av, wv);
+    for (int k0 = k_begin; k0 < k_end; k0 += 16) {
         __syncthreads();
         As[lk + 0][lr] = av.x; As[lk + 1][lr] = av.y; As[lk + 2][lr] = av.z; As[lk + 3][lr] = av.w;
         Ws[lk + 0][lr] = wv.x; Ws[lk + 1][lr] = wv.y; Ws[lk + 2][lr] = wv.z; Ws[lk + 3][lr] = wv.w;
         __syncthreads();
+        if (k0 + 16 < k_end) load_chunk(k0 + 16, av, wv);
 #pragma unroll
         for (int kk = 0; kk < 16; ++kk) {
             const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
