@@ -6,6 +6,7 @@
 #include "gemm_tc.cuh"
 #include "attention.cuh"
 #include "attention_ws.cuh"
+#include "attention_tm.cuh"
 #include "pointwise.cuh"
 
 #include <cstdarg>
@@ -401,13 +402,23 @@ int launch_attention(fitv2_handle* h, const void* q, const void* k, const void* 
     // production kernel: warp-specialised pipeline (attention_ws.cuh); the sequential kernel of attention.cuh serves the
     // debug taps and FITV2_ATTN=v1 A/B runs
     static const bool use_v1 = [] { const char* e = getenv("FITV2_ATTN"); return e && !strcmp(e, "v1"); }();
+    static const bool use_tm = [] { const char* e = getenv("FITV2_ATTN"); return e && !strcmp(e, "tm"); }();
     if (!use_v1 && !dbg_s && !dbg_o) {
         const int q_pairs = ((tokens + 127) / 128 + 1) / 2;
         const int items = q_pairs * c.num_heads * rows;
         const int g = items < h->num_sms ? items : h->num_sms;
         CUtensorMap mo;
         if ((rc = make_map_attn_out(&mo, out, c.operand_dtype, DHu, c.num_heads, tokens, rows))) return rc;
-        if (c.head_dim == 72) {
+        if (use_tm && c.head_dim == 72) {                          // experiment: P kept in tensor memory (attention_tm.cuh)
+            using A = AttnTmCfg<72>;
+            auto kern = attention_tm_kernel<OT, 72>;
+            const int smem = A::smem_bytes(tokens);
+            if (smem > kSmemBudget) return fail(FITV2_E_INVALID, "tokens %d: attention shared memory %d exceeds %d", tokens, smem, kSmemBudget);
+            static int configured = 0;
+            if (configured < smem) { CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); configured = smem; }
+            CUDA_TRY(launch_k(kern, dim3(g), dim3(A::kThreads), smem, st, 1, mq, mqt, mk, mkt, mv, mo, seg, seg_uniform,
+                              c.num_heads, tokens, items, scale_log2e, bound_log2e));
+        } else if (c.head_dim == 72) {
             using A = AttnWsCfg<72>;
             auto kern = attention_ws_kernel<OT, 72>;
             const int smem = A::smem_bytes(tokens);
