@@ -27,7 +27,11 @@ tv = (T + 7) // 8 * 8
 vt = torch.zeros(R, H, dh, tv, dtype=torch.bfloat16)
 vt[..., :T] = torch.randn(R, H, dh, T, generator=g).bfloat16()
 vt = vt.cuda()
-mask = torch.ones(R, T, device="cuda")
+mask = torch.ones(R, T)
+if os.environ.get("ATTN_MASKED"):                      # mixed-aspect padded batch: lengths 200 / 256 / 192 / 200, pad id 0
+    for r in range(R):
+        mask[r, (200, 256, 192, 200)[r % 4]:] = 0
+mask = mask.cuda()
 out = torch.empty(R, T, H * dh, dtype=torch.bfloat16, device="cuda")
 p = lambda t: C.c_void_p(t.data_ptr())
 call = lambda: _lib.check(lib.fitv2_debug_attention(h, p(q), p(k), p(vt), p(mask), p(out), R, T, None, None, None))
