@@ -6,7 +6,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from fitv2_b200.distributed import draw_rank_inputs, gather_latents, max_over_ranks, rank_seed, shard_range
+from fitv2_b200.distributed import draw_rank_inputs, gather_images, gather_latents, max_over_ranks, rank_seed, shard_range
 
 
 def _free_port():
@@ -22,7 +22,8 @@ def _worker(rank, world, port, ret):
     z_final = z * 2 + rank                                  # stand-in for an independent trajectory
     allz = gather_latents(z_final)
     slow = max_over_ranks(10.0 + rank, torch.device("cpu"))
-    ret[rank] = (allz.clone(), z_final.clone(), y.clone(), slow)
+    imgs = gather_images(torch.full((3, 4, 4, 3), 10 * rank + 1, dtype=torch.uint8))   # the reference's uint8 (n, H, W, 3) format
+    ret[rank] = (allz.clone(), z_final.clone(), y.clone(), slow, imgs.clone())
     dist.barrier()
     dist.destroy_process_group()
 
@@ -36,6 +37,8 @@ def test_two_rank_shard_and_gather():
     assert r0[0].shape == (6, 8, 16) and torch.equal(r0[0], r1[0])              # every rank holds the same gather
     assert torch.equal(r0[0][:3], r0[1]) and torch.equal(r0[0][3:], r1[1])      # rank-major order
     assert not torch.equal(r0[1], r1[1]) and r0[3] == r1[3] == 11.0             # different seeds; MAX over ranks
+    assert r0[4].dtype == torch.uint8 and r0[4].shape == (6, 4, 4, 3) and torch.equal(r0[4], r1[4])
+    assert int(r0[4][0, 0, 0, 0]) == 1 and int(r0[4][3, 0, 0, 0]) == 11         # rank-major image order
     g = torch.Generator().manual_seed(rank_seed(0, 2, 1))
     assert torch.equal(torch.randn(3, 8, 16, generator=g) * 2 + 1, r1[1])       # seed = global*world + rank
 
