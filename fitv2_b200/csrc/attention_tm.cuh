@@ -148,7 +148,7 @@ attention_tm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         struct Seq { int item, j; uint32_t n, n_item, stage, phase; };   // j: 64-key sub-tile inside the item; n: active sub-tiles issued
         Seq sq = {(int)blockIdx.x, 0, 0u, 0u, 0u, 0u}, pv = sq;
         auto s_step = [&]() {
-            while (sq.item < num_items) {
+            if (sq.item < num_items) {
                 const bool act = active(sq.item);
                 const int sub = sq.j & 1;
                 if (sub == 0) mbar_wait(&k_full[sq.stage], sq.phase);
@@ -178,11 +178,11 @@ attention_tm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                 }
                 if (sub == 1) { if (++sq.stage == C::kKStages) { sq.stage = 0; sq.phase ^= 1; } }
                 if (++sq.j == sub_tiles) { sq.j = 0; sq.item += gridDim.x; if (act) ++sq.n_item; }
-                if (act) return;
-            }
+                return;                                                 // one tile per call, also for an idle stream: K and V stages must be
+            }                                                           // handed back in the producer's order or the rings deadlock
         };
         auto pv_step = [&]() {
-            while (pv.item < num_items) {
+            if (pv.item < num_items) {
                 const bool act = active(pv.item);
                 const int sub = pv.j & 1;
                 if (sub == 0) mbar_wait(&v_full[pv.stage], pv.phase);
@@ -208,8 +208,8 @@ attention_tm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                 }
                 if (sub == 1) { if (++pv.stage == C::kVStages) { pv.stage = 0; pv.phase ^= 1; } }
                 if (++pv.j == sub_tiles) { pv.j = 0; pv.item += gridDim.x; if (act) ++pv.n_item; }
-                if (act) return;
-            }
+                return;                                                 // one tile per call, also for an idle stream: K and V stages must be
+            }                                                           // handed back in the producer's order or the rings deadlock
         };
         s_step(); s_step();                                             // S runs two sub-tiles ahead of P V
         while (pv.item < num_items) { pv_step(); s_step(); }

@@ -214,7 +214,7 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         struct Seq { int item, t; uint32_t n, n_item, stage, phase; };
         Seq sq = {(int)blockIdx.x, 0, 0u, 0u, 0u, 0u}, pv = sq;
         auto s_step = [&]() {                                           // issue the next S tile of this stream (if any)
-            while (sq.item < num_items) {
+            if (sq.item < num_items) {
                 mbar_wait(&k_full[sq.stage], sq.phase);
                 const bool act = active(sq.item);
                 if (act) {
@@ -243,11 +243,11 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                 }
                 if (++sq.stage == C::kKStages) { sq.stage = 0; sq.phase ^= 1; }
                 if (++sq.t == kv_tiles) { sq.t = 0; sq.item += gridDim.x; if (act) ++sq.n_item; }
-                if (act) return;
-            }
+                return;                                                 // one tile per call, also for an idle stream: K and V stages must be
+            }                                                           // handed back in the producer's order or the rings deadlock
         };
         auto pv_step = [&]() {
-            while (pv.item < num_items) {
+            if (pv.item < num_items) {
                 mbar_wait(&v_full[pv.stage], pv.phase);
                 const bool act = active(pv.item);
                 if (act) {
@@ -273,8 +273,8 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                 }
                 if (++pv.stage == C::kVStages) { pv.stage = 0; pv.phase ^= 1; }
                 if (++pv.t == kv_tiles) { pv.t = 0; pv.item += gridDim.x; if (act) ++pv.n_item; }
-                if (act) return;
-            }
+                return;                                                 // one tile per call, also for an idle stream: K and V stages must be
+            }                                                           // handed back in the producer's order or the rings deadlock
         };
         s_step();
         while (pv.item < num_items) { s_step(); pv_step(); }

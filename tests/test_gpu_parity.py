@@ -136,7 +136,11 @@ def _attention_oracle(q, k, v, mask):
 
 @pytest.mark.parametrize("R,T,dh,H,masked", [(1, 128, 72, 16, False), (2, 256, 72, 16, False), (2, 200, 72, 16, False), (2, 256, 72, 16, True),
                                              (1, 1024, 72, 16, False), (3, 100, 72, 16, True), (2, 256, 96, 24, True), (1, 1, 72, 16, False),
-                                             (2, 77, 96, 24, True)])
+                                             (2, 77, 96, 24, True),
+                                             # odd number of 128-row query tiles AND more work items than SMs: the second stream of the
+                                             # pipelined kernel idles for whole items while its CTA keeps cycling the K / V rings
+                                             (10, 128, 72, 16, False), (3, 777, 72, 16, True), (12, 384, 72, 16, False), (8, 100, 96, 24, True),
+                                             (24, 256, 72, 16, True), (20, 200, 72, 16, True)])   # several masked items per CTA
 def test_attention_matches_oracle(lib, R, T, dh, H, masked):
     h, ws = _handle(lib, 0, D=H * dh, H=H, dh=dh, Hm=3072 if dh == 72 else 6144, lora=288 if dh == 72 else 576)
     g = torch.Generator().manual_seed(R * 7 + T)
@@ -146,6 +150,11 @@ def test_attention_matches_oracle(lib, R, T, dh, H, masked):
         mask[0, T - T // 4:] = 0
         if R > 1:
             mask[1, : T // 3] = 2
+        for r in range(2, R):                    # larger batches: a different padding length / packing per sample
+            if r % 3 == 0:
+                mask[r, T - (r * 7) % (T // 2) - 1:] = 0
+            elif r % 3 == 1:
+                mask[r, : (r * 5) % (T // 2) + 1] = 3
     tv = (T + 7) // 8 * 8
     vt = torch.zeros(R, H, dh, tv, dtype=torch.bfloat16)
     vt[..., :T] = v.transpose(-1, -2)
