@@ -371,3 +371,15 @@ def test_ragged_residual_tiling_matches_uniform(lib, monkeypatch):
     out = run(m1, *a)
     assert rel(out, ref) < 2e-5                                              # same operands; only the fp32 summation tiling differs
     assert torch.equal(run(m1, *a), out)
+
+
+@pytest.mark.parametrize("R,hp,wp", [(40, 8, 8), (20, 10, 20), (12, 12, 24)])
+def test_forward_many_rows_odd_tile_counts(lib, R, hp, wp):
+    """Whole forward where every CTA of the attention kernel owns several work items and the number of 128-row query tiles
+    is odd (64 / 288 tokens) or the last tile is ragged (200 tokens)."""
+    m, sd, cfg = build_model(1)
+    a = inputs(R, hp, wp, seed=11)
+    out = run(m, *a)
+    ref = O.forward(cfg, sd, *a)
+    assert rel(out, ref) < V_TOL
+    assert torch.equal(run(m, *a), out)
