@@ -398,7 +398,9 @@ int launch_attention(fitv2_handle* h, const void* q, const void* k, const void* 
     if ((rc = make_map3(&mqt, q, c.operand_dtype, DHu, tokens, BH, DHu * 2, (uint64_t)tokens * DHu * 2, tail, 128, tail * 2))) return rc;
     if ((rc = make_map3(&mk, k, c.operand_dtype, DHu, tokens, BH, DHu * 2, (uint64_t)tokens * DHu * 2, 64, 128, 128))) return rc;
     if ((rc = make_map3(&mkt, k, c.operand_dtype, DHu, tokens, BH, DHu * 2, (uint64_t)tokens * DHu * 2, tail, 128, tail * 2))) return rc;
-    if ((rc = make_map3(&mv, vt, c.operand_dtype, tokens_v, DHu, BH, (uint64_t)tokens_v * 2, DHu * tokens_v * 2, 64, dhp, 128))) return rc;
+    // V^T rows are tokens_v (a multiple of 8) long in memory, but only `tokens` keys exist: the map ends at `tokens`, so the pad
+    // columns (never written by the QKV epilogue) are zero-filled by TMA instead of read (0 * NaN garbage = NaN in P V)
+    if ((rc = make_map3(&mv, vt, c.operand_dtype, tokens, DHu, BH, (uint64_t)tokens_v * 2, DHu * tokens_v * 2, 64, dhp, 128))) return rc;
     // production kernel: warp-specialised pipeline (attention_ws.cuh); the sequential kernel of attention.cuh serves the
     // debug taps and FITV2_ATTN=v1 A/B runs
     static const bool use_v1 = [] { const char* e = getenv("FITV2_ATTN"); return e && !strcmp(e, "v1"); }();

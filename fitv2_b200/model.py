@@ -10,6 +10,7 @@ configurations and non-CUDA tensors raise.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional
 
 import torch
@@ -256,6 +257,8 @@ class FiT(nn.Module):
             self._workspace = torch.zeros(int(need), dtype=torch.uint8, device=self.device)
             _lib.check(lib.fitv2_set_workspace(self._handle, C.c_void_p(self._workspace.data_ptr()), self._workspace.numel()),
                        "fitv2_set_workspace")
+        if os.environ.get("FITV2_POISON_WORKSPACE") == "1":             # tests: every byte NaN, so a read of scratch memory that the
+            self._workspace.fill_(0xFF)                                 # current call did not write shows up in the result
         self._ws_shape = (rows, tokens)
 
     def _run(self, x: torch.Tensor, t, y, grid, mask, rows: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -7,6 +7,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 GOLDEN = os.path.join(ROOT, "tests", "golden")
+os.environ.setdefault("FITV2_POISON_WORKSPACE", "1")     # scratch memory starts as NaN whenever the (rows, tokens) layout changes
 
 
 def pytest_configure(config):

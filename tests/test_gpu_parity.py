@@ -373,10 +373,11 @@ def test_ragged_residual_tiling_matches_uniform(lib, monkeypatch):
     assert torch.equal(run(m1, *a), out)
 
 
-@pytest.mark.parametrize("R,hp,wp", [(40, 8, 8), (20, 10, 20), (12, 12, 24)])
+@pytest.mark.parametrize("R,hp,wp", [(40, 8, 8), (20, 10, 20), (12, 12, 24), (7, 1, 1), (130, 2, 3), (50, 3, 7)])
 def test_forward_many_rows_odd_tile_counts(lib, R, hp, wp):
     """Whole forward where every CTA of the attention kernel owns several work items and the number of 128-row query tiles
-    is odd (64 / 288 tokens) or the last tile is ragged (200 tokens)."""
+    is odd (64 / 288 tokens) or the last tile is ragged (200 tokens); 1 / 6 / 21 tokens: V^T rows padded to a multiple of 8
+    (the workspace is poisoned with NaN by conftest, so a read of the never-written pad columns would show)."""
     m, sd, cfg = build_model(1)
     a = inputs(R, hp, wp, seed=11)
     out = run(m, *a)
