@@ -17,7 +17,8 @@ torch.set_grad_enabled(False)
 torch.set_num_threads(os.cpu_count() or 1)
 KW = dict(learn_sigma=False, use_sit=True, use_swiglu=True, q_norm="layernorm", k_norm="layernorm", adaln_type="lora")
 WIDTHS = {"xl": dict(hidden_size=1152, num_heads=16, adaln_lora_dim=288), "3b": dict(hidden_size=2304, num_heads=24, adaln_lora_dim=576)}
-CASES = [("xl", 64, 16, 16, "none"), ("xl", 33, 16, 16, "pad"), ("xl", 64, 4, 4, "none"), ("xl", 7, 1, 1, "none"), ("xl", 50, 3, 7, "pad"),
+OPERAND = sys.argv[1] if len(sys.argv) > 1 else "bf16"
+CASES = [("xl", 2, 64, 64, "pad"), ("xl", 3, 40, 50, "mixed"), ("3b", 3, 32, 32, "pad"), ("xl", 64, 16, 16, "none"), ("xl", 33, 16, 16, "pad"), ("xl", 64, 4, 4, "none"), ("xl", 7, 1, 1, "none"), ("xl", 50, 3, 7, "pad"),
          ("xl", 5, 32, 32, "pad"), ("xl", 17, 12, 24, "mixed"), ("xl", 64, 10, 20, "none"), ("xl", 96, 8, 8, "mixed"), ("xl", 130, 2, 3, "none"),
          ("3b", 20, 8, 8, "pad"), ("3b", 6, 16, 16, "mixed"), ("3b", 30, 5, 5, "none")]
 models = {}
@@ -25,7 +26,7 @@ res = []
 for width, R, hp, wp, mk in CASES:
     if width not in models:
         torch.manual_seed(0)
-        m = FiT(**KW, depth=1, **WIDTHS[width]).randomize_zero_init_(1)
+        m = FiT(**KW, depth=1, operand_dtype=OPERAND, **WIDTHS[width]).randomize_zero_init_(1)
         sd = {k: v.detach().clone().float() for k, v in m.state_dict().items()}
         models[width] = (m.cuda().eval(), sd, O.FiTConfig(depth=1, **WIDTHS[width]))
     m, sd, cfg = models[width]
@@ -57,5 +58,5 @@ for width, R, hp, wp, mk in CASES:
 bad = [r for r in res if not (r["err"] < 1e-2 and r["deterministic"] and r["pad_zero"] and r["finite"])]
 print("FAILED" if bad else "all ok", len(res), "cases; worst err", max(r["err"] for r in res))
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-with open(os.path.join(ROOT, "gpurun_out", "shape_sweep.json"), "w") as f:
+with open(os.path.join(ROOT, "gpurun_out", f"shape_sweep_{OPERAND}.json"), "w") as f:
     json.dump(res, f, indent=1)
