@@ -384,3 +384,18 @@ def test_forward_many_rows_odd_tile_counts(lib, R, hp, wp):
     ref = O.forward(cfg, sd, *a)
     assert rel(out, ref) < V_TOL
     assert torch.equal(run(m, *a), out)
+
+
+def test_plain_c_client_of_the_abi(built_lib, tmp_path):
+    """The boundary is a C ABI: tools/cabi_client.c (gcc, no Python / torch / C++) creates a handle, binds weights, runs
+    fitv2_forward twice on NaN-poisoned scratch memory and fitv2_cfg_euler, and checks finiteness, exact-zero pad rows and
+    run-to-run identity itself (exit code)."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "cabi_client")
+    libdir = os.path.join(root, "fitv2_b200")
+    subprocess.run(["gcc", "-O2", "-I", os.path.join(root, "include"), "-I", "/usr/local/cuda/include", os.path.join(root, "tools", "cabi_client.c"),
+                    "-o", exe, "-L", libdir, "-lfitv2_b200", "-L", "/usr/local/cuda/lib64", "-lcudart", "-lm", f"-Wl,-rpath,{libdir}"], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "run-to-run identical 1" in r.stdout and "non-finite 0" in r.stdout
