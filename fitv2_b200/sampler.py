@@ -1,4 +1,5 @@
-"""CFG Euler/ODE sampler loop of ``sample_fitv2_ddp.py:273-314`` driven through the C ABI.
+"""CFG Euler/ODE sampler loop of ``sample_fitv2_ddp.py:273-314`` driven through the C ABI (both branches of
+``using_cfg``: with guidance the fused CFG + Euler kernel, without it the plain Euler update).
 
 One step = one ``fitv2_forward`` over 2n rows (the ``cat([z, z])`` of the script is done implicitly by
 the patch-embed kernel) + one fused ``fitv2_cfg_euler`` kernel (CFG combine over all 16 channels and
@@ -30,30 +31,43 @@ class EulerCFGSampler:
 
     def __init__(self, model: FiT, y: torch.Tensor, grid: torch.Tensor, mask: torch.Tensor, num_steps: int,
                  cfg_scale: float, use_cuda_graph: bool = False):
-        if cfg_scale <= 1.0:
-            raise NotImplementedError("the fused sampler implements the CFG branch (cfg_scale > 1) of the script")
         self.model, self.num_steps, self.cfg_scale = model, num_steps, float(cfg_scale)
+        self.using_cfg = cfg_scale > 1.0                                # sample_fitv2_ddp.py:242 (the script's default --cfg-scale is 1.0)
         dev = model.device
         n = y.shape[0]
         self.n = n
-        self.y2 = torch.cat([y.to(dev, torch.int64), torch.full((n,), model.num_classes, dtype=torch.int64, device=dev)], 0)
-        self.grid2 = torch.cat([grid, grid], 0).to(dev, torch.int64).contiguous()
-        self.mask2 = torch.cat([mask, mask], 0).to(dev, torch.float32).contiguous()
+        if self.using_cfg:
+            self.y2 = torch.cat([y.to(dev, torch.int64), torch.full((n,), model.num_classes, dtype=torch.int64, device=dev)], 0)
+            self.grid2 = torch.cat([grid, grid], 0).to(dev, torch.int64).contiguous()
+            self.mask2 = torch.cat([mask, mask], 0).to(dev, torch.float32).contiguous()
+        else:                                                           # :283-285, :300-301: the model sees the n rows as they are
+            self.y2 = y.to(dev, torch.int64).contiguous()
+            self.grid2 = grid.to(dev, torch.int64).contiguous()
+            self.mask2 = mask.to(dev, torch.float32).contiguous()
+        self.rows = self.y2.shape[0]
         sig = torch.linspace(0, 1, num_steps + 1)                       # CPU fp32, as the script (:287)
         self.sigmas = sig
         self.dsig = (sig[1:] - sig[:-1]).to(dev).contiguous()           # fp32 differences, per step
-        self.t_table = sig[:-1, None].expand(num_steps, 2 * n).to(dev).contiguous()
+        self.t_table = sig[:-1, None].expand(num_steps, self.rows).to(dev).contiguous()
+        self.step_scale = torch.stack([torch.ones(num_steps), sig[1:] - sig[:-1]], 1).to(dev).contiguous()   # (1, dsigma) per step
         self.use_cuda_graph = use_cuda_graph
         self._graph = None
-        self._t_cur = torch.zeros(2 * n, dtype=torch.float32, device=dev)
+        self._t_cur = torch.zeros(self.rows, dtype=torch.float32, device=dev)
+        self._sc_cur = torch.zeros(2, dtype=torch.float32, device=dev)
         self._ds_cur = torch.zeros(1, dtype=torch.float32, device=dev)
         self._v2 = None
         self._z = None
 
-    def _step(self, z: torch.Tensor, t_rows: torch.Tensor, dsig_dev: torch.Tensor):
+    def _step(self, z: torch.Tensor, t_rows: torch.Tensor, dsig_dev: torch.Tensor, scale_dev: Optional[torch.Tensor] = None):
         m = self.model
-        self._v2 = m._run(z, t_rows, self.y2, self.grid2, self.mask2, rows=2 * self.n, out=self._v2)
+        self._v2 = m._run(z, t_rows, self.y2, self.grid2, self.mask2, rows=self.rows, out=self._v2)
         st = torch.cuda.current_stream(m.device).cuda_stream
+        if not self.using_cfg:                                          # z = z + (sigma_next - sigma_current) * noise_pred  (:314), bit-exact
+            if scale_dev is None:
+                scale_dev = torch.stack([torch.ones_like(dsig_dev[0]), dsig_dev[0]])
+            _lib.check(_lib.load().fitv2_scaled_add(C.c_void_p(z.data_ptr()), C.c_void_p(z.data_ptr()), C.c_void_p(self._v2.data_ptr()),
+                                                    C.c_void_p(scale_dev.data_ptr()), z.numel(), C.c_void_p(st)), "fitv2_scaled_add")
+            return
         _lib.check(_lib.load().fitv2_cfg_euler(C.c_void_p(z.data_ptr()), C.c_void_p(self._v2.data_ptr()), self.cfg_scale, 0.0,
                                                C.c_void_p(dsig_dev.data_ptr()), self.n, z.shape[1], z.shape[2], C.c_void_p(st)),
                    "fitv2_cfg_euler")
@@ -67,7 +81,7 @@ class EulerCFGSampler:
         with torch.cuda.device(m.device):
             if not self.use_cuda_graph:
                 for i in range(steps):
-                    self._step(z, self.t_table[i], self.dsig[i:i + 1])
+                    self._step(z, self.t_table[i], self.dsig[i:i + 1], self.step_scale[i])
                 return z
             if self._graph is None:
                 self._z = torch.empty_like(z)
@@ -75,16 +89,17 @@ class EulerCFGSampler:
                 side = torch.cuda.Stream()
                 side.wait_stream(torch.cuda.current_stream())
                 with torch.cuda.stream(side):                           # warm-up outside capture (workspace, maps)
-                    self._t_cur.copy_(self.t_table[0]); self._ds_cur.zero_()
-                    self._step(self._z, self._t_cur, self._ds_cur)
+                    self._t_cur.copy_(self.t_table[0]); self._ds_cur.zero_(); self._sc_cur.copy_(torch.tensor([1.0, 0.0]))
+                    self._step(self._z, self._t_cur, self._ds_cur, self._sc_cur)
                 torch.cuda.current_stream().wait_stream(side)
                 self._graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(self._graph):
-                    self._step(self._z, self._t_cur, self._ds_cur)
+                    self._step(self._z, self._t_cur, self._ds_cur, self._sc_cur)
             self._z.copy_(z)
             for i in range(steps):
                 self._t_cur.copy_(self.t_table[i])
                 self._ds_cur.copy_(self.dsig[i:i + 1])
+                self._sc_cur.copy_(self.step_scale[i])
                 self._graph.replay()
             return self._z.clone()
 

@@ -399,3 +399,25 @@ def test_plain_c_client_of_the_abi(built_lib, tmp_path):
     r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "run-to-run identical 1" in r.stdout and "non-finite 0" in r.stdout
+
+
+def test_sampler_without_cfg(lib):
+    """cfg_scale = 1.0 (the script's default): no row duplication, z += dsigma * v (sample_fitv2_ddp.py:283-285,300-314)."""
+    m, sd, cfg = build_model(2)
+    n, hp, wp, steps = 3, 8, 8, 4
+    g = torch.Generator().manual_seed(21)
+    z0 = torch.randn(n, hp * wp, 16, generator=g)
+    y = torch.randint(0, 1000, (n,), generator=g)
+    grid, mask = make_grid(n, hp, wp), torch.ones(n, hp * wp)
+    sig = torch.linspace(0, 1, 251)
+    zr = z0.clone()
+    for i in range(steps):
+        v = O.forward(cfg, sd, zr, sig[i].expand(n), y, grid, mask)
+        zr = zr + (sig[i + 1] - sig[i]) * v
+    for graph in (False, True):
+        z = euler_cfg_sample(m, z0.cuda(), y.cuda(), grid.cuda(), mask.cuda(), None, 250, 1.0, use_cuda_graph=graph, first_steps=steps).cpu()
+        assert rel(z, zr) < 1e-4
+    # the update itself is bit-exact given the velocity
+    smp = EulerCFGSampler(m, y.cuda(), grid.cuda(), mask.cuda(), 250, 1.0)
+    z1 = smp.sample(z0.cuda(), first_steps=1).cpu()
+    assert torch.equal(z1, z0 + (sig[1] - sig[0]) * smp._v2.cpu())
