@@ -107,17 +107,18 @@ class ClockSampler:
                 self.proc.kill()
 
     def summary(self):
-        sm, mx, reasons = [], 0, set()
+        sm, mx, reasons, pw = [], 0, set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             try:
-                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+                sm.append(float(r[0])); mx = max(mx, float(r[1])); pw.append(float(r[2]))
                 for nme, v in zip(names, r[3:7]):
                     if v.lower().startswith("active"):
                         reasons.add(nme)
             except Exception:
                 pass
-        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=mx or None, reasons=sorted(reasons), samples=len(sm))
+        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=mx or None, reasons=sorted(reasons), samples=len(sm),
+                    power_w=statistics.median(pw) if pw else None)
 
 
 # --------------------------------------------------------------------------------------------------
