@@ -442,13 +442,26 @@ final_layer_kernel(const float* __restrict__ x, const float* __restrict__ fmod /
                     a = fmaf(v[i].z, ww.z, a); a = fmaf(v[i].w, ww.w, a);
                 }
             }
-            acc[o] = warp_sum(a);
+            acc[o] = a;
         }
-        if (lane < COUT) {
-            float r = 0.f;
+        // 16 warp reductions at once: a halving butterfly (8 + 4 + 2 + 1 + 1 = 16 shuffles instead of 16 x 5); afterwards
+        // lanes 2k and 2k+1 hold the total of output  o = bits (4,3,2,1) of the lane, most significant first
+        static_assert(COUT == 16, "the reduction butterfly is written for 16 outputs");
 #pragma unroll
-            for (int o = 0; o < COUT; ++o) if (lane == o) r = acc[o];
-            out[(size_t)m * COUT + lane] = (r + __ldg(b + lane)) * mask[m];
+        for (int step = 0; step < 4; ++step) {
+            const int off = 16 >> step, half = 8 >> step;             // lane bit `off` selects which half of the values a lane keeps
+            const bool up = (lane & off) != 0;
+#pragma unroll
+            for (int o = 0; o < half; ++o) {
+                const float send = up ? acc[o] : acc[o + half];
+                const float recv = __shfl_xor_sync(0xffffffffu, send, off);
+                acc[o] = (up ? acc[o + half] : acc[o]) + recv;
+            }
+        }
+        const float total = acc[0] + __shfl_xor_sync(0xffffffffu, acc[0], 1);
+        if ((lane & 1) == 0) {
+            const int o = lane >> 1;                                   // bits (4,3,2,1) -> output index
+            out[(size_t)m * COUT + o] = (total + __ldg(b + o)) * mask[m];
         }
     }
 }
