@@ -1,4 +1,5 @@
-// Attention variant with P kept in TENSOR MEMORY (experiment of round 1, selected with FITV2_ATTN=tm).
+// Attention variant with P kept in TENSOR MEMORY: the production kernel up to 256 tokens at head_dim 72 (FITV2_ATTN=ws / tm
+// overrides the choice; beyond 256 tokens attention_ws.cuh is faster, see profiles/README.md).
 //
 // Same math, operand layouts and roles as attention_ws.cuh.  Differences:
 //   * key tiles are consumed in 64-key SUB-tiles; every stream owns two 64-column S buffers in TMEM (ping-pong).
@@ -291,7 +292,9 @@ attention_tm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                 else if (mode == 1) soft32(std::integral_constant<int, 1>{});
                 else soft32(std::integral_constant<int, 2>{});
                 l_run += lsum;
+#ifdef FITV2_ATTN_TM_PREFETCH
                 have = j + 1 < sub_tiles;                               // S runs two sub-tiles ahead: the next one is normally complete;
+#endif
                 if (have) {                                             // its TMEM load flies while P is stored and handed over
                     mbar_wait(&s_full[x * 2 + (b ^ 1)], ((n_s + 1) >> 1) & 1);
                     tc_fence_after();

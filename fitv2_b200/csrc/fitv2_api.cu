@@ -404,7 +404,10 @@ int launch_attention(fitv2_handle* h, const void* q, const void* k, const void* 
     // production kernel: warp-specialised pipeline (attention_ws.cuh); the sequential kernel of attention.cuh serves the
     // debug taps and FITV2_ATTN=v1 A/B runs
     static const bool use_v1 = [] { const char* e = getenv("FITV2_ATTN"); return e && !strcmp(e, "v1"); }();
-    static const bool use_tm = [] { const char* e = getenv("FITV2_ATTN"); return e && !strcmp(e, "tm"); }();
+    // P-in-TMEM variant (attention_tm.cuh): faster up to 256 tokens (42.2 vs 46.2 us alone, 55.5 vs 60 us in-step at 256; 21.3 vs
+    // 23.4 at 128), slower beyond (512: 138 vs 127; 1024: 503 vs 405), head_dim 72 only.  FITV2_ATTN=tm / ws forces one of them.
+    static const int tm_mode = [] { const char* e = getenv("FITV2_ATTN"); return !e ? 0 : (!strcmp(e, "tm") ? 1 : (!strcmp(e, "ws") ? -1 : 0)); }();
+    const bool use_tm = tm_mode > 0 || (tm_mode == 0 && tokens <= 256);
     if (!use_v1 && !dbg_s && !dbg_o) {
         const int q_pairs = ((tokens + 127) / 128 + 1) / 2;
         const int items = q_pairs * c.num_heads * rows;
