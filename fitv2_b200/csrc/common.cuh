@@ -255,6 +255,12 @@ __device__ __forceinline__ float warp_sum(float v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
+// fp32 -> tf32 (10-bit mantissa, round to nearest); the low 13 bits of the result are zero
+__device__ __forceinline__ float tf32_round(float a) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(a));
+    return __uint_as_float(r);
+}
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 __device__ __forceinline__ float fast_exp2(float x) {          // MUFU.EX2, 2 ulp; exp2(-inf) = 0
     float y;

@@ -8,6 +8,7 @@
 #include "attention_ws.cuh"
 #include "attention_tm.cuh"
 #include "pointwise.cuh"
+#include "cond_tc.cuh"
 
 #include <cstdarg>
 #include <cstdio>
@@ -130,6 +131,22 @@ int make_map(CUtensorMap* map, const void* ptr, int operand_dtype, uint64_t rows
     return FITV2_OK;
 }
 
+// 2-D K-major fp32 (tf32 operand) map: box = 32 cols (128 bytes) x box_rows, 128B swizzle, zero fill out of bounds.
+int make_map_f32(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return fail(FITV2_E_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {ld * 4};
+    cuuint32_t box[2] = {32, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return fail(FITV2_E_CUDA, "cuTensorMapEncodeTiled(fp32) failed (%d) rows=%llu cols=%llu ld=%llu box_rows=%u ptr=%p", (int)r,
+                    (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows, ptr);
+    return FITV2_OK;
+}
+
 // 3-D map (d0 contiguous, d1, d2) with a (box0, box1, 1) box; swizzle_bytes = 128 / 64 / 32 must equal box0 * 2.
 int make_map3(CUtensorMap* map, const void* ptr, int operand_dtype, uint64_t d0, uint64_t d1, uint64_t d2,
               uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box0, uint32_t box1, int swizzle_bytes) {
@@ -171,7 +188,7 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct Layout {
     int rows = 0, tokens = 0, tokens_v = 0;
-    size_t x_res, h, ao, q, k, vt, hidden, te, t0, c, sc, lmid, gmod, mod, fmod, rope_cos, rope_sin, seg_uniform, cpart, sched_proj, sched_fc2, total;
+    size_t x_res, h, ao, q, k, vt, hidden, te, t0, c, sc, sc_split, lmid, lmid_split, gmod, mod, fmod, rope_cos, rope_sin, seg_uniform, cpart, sched_proj, sched_fc2, total;
 };
 
 }  // namespace
@@ -189,6 +206,10 @@ struct fitv2_handle {
     bool maps_valid = false;
     CUtensorMap map_h, map_ao, map_hidden;              // activations (A operands)
     CUtensorMap map_wqkv, map_wproj, map_wgu, map_wfc2; // stacked weights (B operands)
+    // conditioning on the tensor pipe (cond_tc.cuh): fp32 / tf32 maps of the split activations and of the adaLN weights
+    bool cond_tc = false;
+    int cond_bn_up = 0;
+    CUtensorMap map_sc_split, map_lmid_split, map_wglobal, map_wfinal, map_wlora_a, map_wlora_b;
     int bn_proj = 0, bn_fc2 = 0;
     int sched_stride_proj = 0, sched_stride_fc2 = 0;     // > 0: ragged tiling (BN-wide tiles + one narrower tail tile per row group)
     std::vector<int2> sched_host;
@@ -259,6 +280,10 @@ Layout make_layout(const fitv2_config& c, int rows, int tokens) {
     l.c = take((size_t)rows * D * 4);
     l.sc = take((size_t)rows * D * 4);
     l.lmid = take((size_t)rows * L * c.lora_dim * 4);
+    // hi / lo stacked tf32 operands of the tensor-pipe conditioning linears (cond_tc.cuh): 128 rows per 64 logical rows
+    const size_t split_rows = (size_t)((rows + kCondRows - 1) / kCondRows) * 128;
+    l.sc_split = take(split_rows * D * 4);
+    l.lmid_split = take(split_rows * L * c.lora_dim * 4);
     l.gmod = take((size_t)rows * 6 * D * 4);
     l.mod = take(L * (size_t)rows * 6 * D * 4);
     l.fmod = take((size_t)rows * 2 * D * 4);
@@ -545,7 +570,42 @@ int ensure_maps(fitv2_handle* h) {
     if ((rc = make_map(&h->map_wproj, h->w[FITV2_W_PROJ_W], c.operand_dtype, L * D, D, D, h->bn_proj / kGemmCluster))) return rc;
     if ((rc = make_map(&h->map_wgu, h->w[FITV2_W_GATEUP_W], c.operand_dtype, L * 2 * Hm, D, D, 256 / kGemmCluster))) return rc;
     if ((rc = make_map(&h->map_wfc2, h->w[FITV2_W_FC2_W], c.operand_dtype, L * D, Hm, Hm, h->bn_fc2 / kGemmCluster))) return rc;
+    // Conditioning linears on the tensor pipe when the shapes tile (every production config does); FITV2_COND=simt keeps the
+    // fp32-FMA kernels for A/B runs.  Other shapes use the SIMT kernels.
+    {
+        const uint64_t lora = c.lora_dim, split_rows = (uint64_t)((l.rows + kCondRows - 1) / kCondRows) * 128;
+        const char* e = getenv("FITV2_COND");
+        h->cond_tc = !(e && !strcmp(e, "simt")) && D % 32 == 0 && lora % 32 == 0 && (6 * D) % 48 == 0 && (2 * D) % 48 == 0 &&
+                     (L * lora) % 48 == 0;
+        if (h->cond_tc) {
+            h->cond_bn_up = (6 * D) % 128 == 0 ? 128 : 48;
+            if ((rc = make_map_f32(&h->map_sc_split, h->ws + l.sc_split, split_rows, D, D, 128))) return rc;
+            if ((rc = make_map_f32(&h->map_lmid_split, h->ws + l.lmid_split, split_rows, L * lora, L * lora, 128))) return rc;
+            if ((rc = make_map_f32(&h->map_wglobal, h->w[FITV2_W_GLOBAL_ADALN_W], 6 * D, D, D, 48))) return rc;
+            if ((rc = make_map_f32(&h->map_wfinal, h->w[FITV2_W_FINAL_ADALN_W], 2 * D, D, D, 48))) return rc;
+            if ((rc = make_map_f32(&h->map_wlora_a, h->w[FITV2_W_LORA_A_W], L * lora, D, D, 48))) return rc;
+            if ((rc = make_map_f32(&h->map_wlora_b, h->w[FITV2_W_LORA_B_W], L * 6 * D, lora, lora, h->cond_bn_up))) return rc;
+        }
+    }
     h->maps_valid = true;
+    return FITV2_OK;
+}
+
+template <int BN>
+int launch_cond_tc(fitv2_handle* h, const CUtensorMap& ma, const CUtensorMap& w0, const CUtensorMap& w1, const CUtensorMap& w2,
+                   const CondTc& p, cudaStream_t st) {
+    auto kern = cond_tc_kernel<BN>;
+    static bool configured = false;
+    if (!configured) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CondCfg<BN>::kSmemBytes));
+        configured = true;
+    }
+    const int m_tiles = (p.rows + kCondRows - 1) / kCondRows;
+    const int tiles = p.batches * m_tiles * p.nt_prefix[p.nseg];
+    const int grid = tiles < h->num_sms ? tiles : h->num_sms;
+    CUDA_TRY(launch_k(kern, dim3(grid), dim3(192), CondCfg<BN>::kSmemBytes, st, 1, ma, w0, w1, w2, p));
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
     return FITV2_OK;
 }
 
@@ -609,8 +669,32 @@ int forward_impl(fitv2_handle* h, const float* x, int x_rows, const float* t, co
     // c = W2 silu(t0) + b2 + E[y] ; sc = silu(c)
     p.A = t0; p.lda = D; p.act_silu_in = 1; p.W = (const float*)h->w[FITV2_W_T_MLP2_W]; p.bias = (const float*)h->w[FITV2_W_T_MLP2_B];
     p.emb = (const float*)h->w[FITV2_W_Y_TABLE]; p.labels = (const long long*)y; p.out = cc; p.out_silu = sc; p.N = D; p.K = D;
+    p.out_silu_split = h->cond_tc ? (float*)(ws + l.sc_split) : nullptr;   // hi / lo tf32 split of silu(c) for cond_tc.cuh
     if ((rc = launch_small_linear(h, p, 1, st))) return rc;
-    p.act_silu_in = 0; p.emb = nullptr; p.labels = nullptr; p.out_silu = nullptr;
+    p.act_silu_in = 0; p.emb = nullptr; p.labels = nullptr; p.out_silu = nullptr; p.out_silu_split = nullptr;
+    if (h->cond_tc) {
+        // tensor-pipe path (cond_tc.cuh): one launch for the three linears that read silu(c), one for the batched LoRA up
+        float* lmid_split = (float*)(ws + l.lmid_split);
+        CondTc q;
+        memset(&q, 0, sizeof(q));
+        q.nseg = 3; q.rows = rows; q.K = D; q.batches = 1;
+        q.nt_prefix[0] = 0; q.nt_prefix[1] = 6 * D / 48; q.nt_prefix[2] = q.nt_prefix[1] + 2 * D / 48; q.nt_prefix[3] = q.nt_prefix[2] + L * lora / 48;
+        q.bias[0] = (const float*)h->w[FITV2_W_GLOBAL_ADALN_B]; q.out[0] = gmod; q.ldo[0] = 6 * D;
+        q.bias[1] = (const float*)h->w[FITV2_W_FINAL_ADALN_B]; q.out[1] = fmod; q.ldo[1] = 2 * D;
+        q.bias[2] = (const float*)h->w[FITV2_W_LORA_A_B]; q.out[2] = lmid; q.ldo[2] = L * lora;
+        q.out_split[2] = lmid_split; q.ld_split[2] = L * lora;
+        if ((rc = launch_cond_tc<48>(h, h->map_sc_split, h->map_wglobal, h->map_wfinal, h->map_wlora_a, q, st))) return rc;
+        CondTc u;
+        memset(&u, 0, sizeof(u));
+        u.nseg = 1; u.rows = rows; u.K = lora; u.batches = L; u.a_batch_cols = lora;
+        u.nt_prefix[0] = 0; u.nt_prefix[1] = 6 * D / h->cond_bn_up;
+        u.w_batch_rows[0] = 6 * D;
+        u.bias[0] = (const float*)h->w[FITV2_W_LORA_B_B]; u.bias_batch_stride[0] = 6 * D;
+        u.add[0] = gmod; u.out[0] = mod; u.out_batch_stride[0] = (size_t)rows * 6 * D; u.ldo[0] = 6 * D;
+        if (h->cond_bn_up == 128) rc = launch_cond_tc<128>(h, h->map_lmid_split, h->map_wlora_b, h->map_wlora_b, h->map_wlora_b, u, st);
+        else rc = launch_cond_tc<48>(h, h->map_lmid_split, h->map_wlora_b, h->map_wlora_b, h->map_wlora_b, u, st);
+        if (rc) return rc;
+    } else {
     // global adaLN: gmod = Wg sc + bg
     p.A = sc; p.lda = D; p.W = (const float*)h->w[FITV2_W_GLOBAL_ADALN_W]; p.bias = (const float*)h->w[FITV2_W_GLOBAL_ADALN_B];
     p.out = gmod; p.ldo = 6 * D; p.N = 6 * D; p.K = D;
@@ -629,6 +713,7 @@ int forward_impl(fitv2_handle* h, const float* x, int x_rows, const float* t, co
     p.bias = (const float*)h->w[FITV2_W_LORA_B_B]; p.bias_batch_stride = 6 * D;
     p.add = gmod; p.out = mod; p.out_batch_stride = (size_t)rows * 6 * D; p.ldo = 6 * D; p.N = 6 * D; p.K = lora;
     if ((rc = launch_small_linear(h, p, L, st))) return rc;
+    }
     prof_end(h, st);
 
     // ---- patch embedding (modules.py:34-37); implicit cat([z, z]) when x_rows == rows / 2 ----

@@ -549,6 +549,7 @@ struct SmallLinear {
     const float* emb; const long long* labels;   // optional embedding-row add (label gather), ld = N
     float* out; size_t out_batch_stride; int ldo;
     float* out_silu;             // optional second output: silu(out) (same layout)
+    float* out_silu_split;       // optional: tf32 hi / lo split of silu(out), stacked [rows/64][128][N] (operand of cond_tc.cuh)
     int rows, N, K;
     int act_silu_in;             // apply SiLU to A on load
     int ksplit;                  // > 1: K is split over blockIdx.y; raw partial sums go to `partial`, finalize adds the rest
@@ -645,6 +646,11 @@ small_linear_kernel(SmallLinear p)
             if (p.emb) v += p.emb[(size_t)p.labels[r] * p.N + n];
             out[(size_t)r * p.ldo + n] = v;
             if (out_silu) out_silu[(size_t)r * p.ldo + n] = v / (1.f + expf(-v));
+            if (p.out_silu_split) {
+                const float sv = v / (1.f + expf(-v)), hi = tf32_round(sv);
+                float* d = p.out_silu_split + ((size_t)(r / 64) * 128 + (r % 64)) * p.N + n;
+                d[0] = hi; d[(size_t)64 * p.N] = sv - hi;
+            }
         }
     }
 }
@@ -667,6 +673,11 @@ __global__ void small_linear_finalize_kernel(SmallLinear p)
     if (p.emb) v += p.emb[(size_t)p.labels[r] * p.N + n];
     p.out[z * p.out_batch_stride + (size_t)r * p.ldo + n] = v;
     if (p.out_silu) p.out_silu[z * p.out_batch_stride + (size_t)r * p.ldo + n] = v / (1.f + expf(-v));
+    if (p.out_silu_split) {
+        const float sv = v / (1.f + expf(-v)), hi = tf32_round(sv);
+        float* d = p.out_silu_split + ((size_t)(r / 64) * 128 + (r % 64)) * p.N + n;
+        d[0] = hi; d[(size_t)64 * p.N] = sv - hi;
+    }
 }
 
 }  // namespace fitv2

@@ -215,6 +215,13 @@ class FiT(nn.Module):
         f32 = lambda p: p.detach().to(device=dev, dtype=torch.float32).contiguous()
         blocks = self.blocks
         stack32 = lambda get: torch.stack([get(b).detach().to(device=dev, dtype=torch.float32) for b in blocks]).contiguous()
+
+        def tf32(w):
+            # adaLN weights are tf32 operands of the tensor-pipe conditioning linears (csrc/cond_tc.cuh): round them to
+            # nearest once here (the tensor pipe itself would truncate the 13 low mantissa bits)
+            if os.environ.get("FITV2_COND") == "simt":
+                return w
+            return ((w.view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
         stack16 = lambda get: torch.stack([get(b).detach().to(device=dev, dtype=torch.float32).to(op) for b in blocks]).contiguous()
         Hm = self.mlp_hidden
 
@@ -230,11 +237,11 @@ class FiT(nn.Module):
             "T_MLP0_W": f32(self.t_embedder.mlp[0].weight), "T_MLP0_B": f32(self.t_embedder.mlp[0].bias),
             "T_MLP2_W": f32(self.t_embedder.mlp[2].weight), "T_MLP2_B": f32(self.t_embedder.mlp[2].bias),
             "Y_TABLE": f32(self.y_embedder.embedding_table.weight),
-            "GLOBAL_ADALN_W": f32(self.global_adaLN_modulation[1].weight),
+            "GLOBAL_ADALN_W": tf32(f32(self.global_adaLN_modulation[1].weight)),
             "GLOBAL_ADALN_B": f32(self.global_adaLN_modulation[1].bias),
-            "LORA_A_W": stack32(lambda b: b.adaLN_modulation[1].weight), "LORA_A_B": stack32(lambda b: b.adaLN_modulation[1].bias),
-            "LORA_B_W": stack32(lambda b: b.adaLN_modulation[2].weight), "LORA_B_B": stack32(lambda b: b.adaLN_modulation[2].bias),
-            "FINAL_ADALN_W": f32(self.final_layer.adaLN_modulation[1].weight),
+            "LORA_A_W": tf32(stack32(lambda b: b.adaLN_modulation[1].weight)), "LORA_A_B": stack32(lambda b: b.adaLN_modulation[1].bias),
+            "LORA_B_W": tf32(stack32(lambda b: b.adaLN_modulation[2].weight)), "LORA_B_B": stack32(lambda b: b.adaLN_modulation[2].bias),
+            "FINAL_ADALN_W": tf32(f32(self.final_layer.adaLN_modulation[1].weight)),
             "FINAL_ADALN_B": f32(self.final_layer.adaLN_modulation[1].bias),
             "FINAL_LINEAR_W": f32(self.final_layer.linear.weight), "FINAL_LINEAR_B": f32(self.final_layer.linear.bias),
             "QKV_W": stack16(lambda b: b.attn.qkv.weight), "QKV_B": stack32(lambda b: b.attn.qkv.bias),
