@@ -211,6 +211,7 @@ struct fitv2_handle {
     int cond_bn_up = 0;
     CUtensorMap map_sc_split, map_lmid_split, map_wglobal, map_wfinal, map_wlora_a, map_wlora_b;
     int bn_proj = 0, bn_fc2 = 0;
+    bool qkv3 = false;                                   // QKV GEMM uses the three-head 224-wide tile (head_dim 72)
     int sched_stride_proj = 0, sched_stride_fc2 = 0;     // > 0: ragged tiling (BN-wide tiles + one narrower tail tile per row group)
     std::vector<int2> sched_host;
     int num_sms = 148;
@@ -322,10 +323,11 @@ int launch_gemm_t(fitv2_handle* h, const CUtensorMap& ma, const CUtensorMap& mb,
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
         configured = true;
     }
-    if (N % BN != 0 && !(sched && EPI == EPI_RESID && (N % BN) % 32 == 0))
-        return fail(FITV2_E_INVALID, "GEMM N=%d is not a multiple of the tile width %d", N, BN);
+    constexpr int TN = Cfg::kTileN;
+    if (N % TN != 0 && !(sched && EPI == EPI_RESID && (N % BN) % 32 == 0))
+        return fail(FITV2_E_INVALID, "GEMM N=%d is not a multiple of the tile width %d", N, TN);
     const int m_tiles = (M + kGemmBM - 1) / kGemmBM;
-    const int groups = ((m_tiles + CL - 1) / CL) * ((N + BN - 1) / BN);
+    const int groups = ((m_tiles + CL - 1) / CL) * ((N + TN - 1) / TN);
     const int max_clusters = h->num_sms / CL;
     const int grid = (groups < max_clusters ? groups : max_clusters) * CL;
     CUDA_TRY(launch_k(kern, dim3(grid), dim3(Cfg::kThreads), Cfg::kSmemBytes, st, CL, ma, mb, M, N, K, b_row_off, ep, sched, sched_stride));
@@ -566,7 +568,13 @@ int ensure_maps(fitv2_handle* h) {
             h->sched_stride_proj = h->sched_stride_fc2 = stride;
         }
     }
-    if ((rc = make_map(&h->map_wqkv, h->w[FITV2_W_QKV_W], c.operand_dtype, L * 3 * D, D, D, 2 * c.head_dim / kGemmCluster))) return rc;
+    // head_dim 72: three heads per 224-wide tile when the 3 * heads head slots group by three (FITV2_QKV=2 keeps the two-head tile)
+    {
+        const char* e = getenv("FITV2_QKV");
+        h->qkv3 = c.head_dim == 72 && (3 * c.num_heads) % 3 == 0 && !(e && e[0] == '2');
+    }
+    if ((rc = make_map(&h->map_wqkv, h->w[FITV2_W_QKV_W], c.operand_dtype, L * 3 * D, D, D,
+                       (h->qkv3 ? 3 * c.head_dim + 8 : 2 * c.head_dim) / kGemmCluster))) return rc;
     if ((rc = make_map(&h->map_wproj, h->w[FITV2_W_PROJ_W], c.operand_dtype, L * D, D, D, h->bn_proj / kGemmCluster))) return rc;
     if ((rc = make_map(&h->map_wgu, h->w[FITV2_W_GATEUP_W], c.operand_dtype, L * 2 * Hm, D, D, 256 / kGemmCluster))) return rc;
     if ((rc = make_map(&h->map_wfc2, h->w[FITV2_W_FC2_W], c.operand_dtype, L * D, Hm, Hm, h->bn_fc2 / kGemmCluster))) return rc;
@@ -737,7 +745,8 @@ int forward_impl(fitv2_handle* h, const float* x, int x_rows, const float* t, co
         ep.tokens = tokens; ep.q = ws + l.q; ep.k = ws + l.k; ep.vt = ws + l.vt; ep.rope_cos = rcos; ep.rope_sin = rsin;
         ep.heads = H; ep.tokens_v = l.tokens_v;
         prof_begin(h, PC_QKV, st);
-        if (DH == 72) rc = launch_gemm_t<144, EPI_QKV, OT, 72>(h, h->map_h, h->map_wqkv, M, 3 * D, D, layer * 3 * D, ep, st);
+        if (DH == 72 && h->qkv3) rc = launch_gemm_t<224, EPI_QKV, OT, 72>(h, h->map_h, h->map_wqkv, M, 3 * D, D, layer * 3 * D, ep, st);
+        else if (DH == 72) rc = launch_gemm_t<144, EPI_QKV, OT, 72>(h, h->map_h, h->map_wqkv, M, 3 * D, D, layer * 3 * D, ep, st);
         else          rc = launch_gemm_t<192, EPI_QKV, OT, 96>(h, h->map_h, h->map_wqkv, M, 3 * D, D, layer * 3 * D, ep, st);
         if (rc) return rc;
         prof_end(h, st);

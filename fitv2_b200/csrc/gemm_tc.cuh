@@ -68,7 +68,12 @@ template <int BN, int EPI, int DH, int CL = 1> struct GemmCfg {
     // epilogue warps per TMEM lane quarter (each takes BN / kParts tile columns).  Four per quarter (16 epilogue warps)
     // only pay for the 256-wide residual tiles of the ragged-tiling experiments (proj 100 -> 79 us); at BN = 128 they
     // measured slightly slower than two (61.5 vs 57.3 us), so the production widths keep 8 epilogue warps.
-    static constexpr int kParts = (EPI == EPI_RESID && BN == 256) ? 4 : 2;
+    // QKV at head_dim 72: a 224-wide UMMA tile holds THREE heads (216 columns, one epilogue warp per quarter and head); the
+    // last 8 columns are the first 8 of the next tile, computed and dropped (tiles advance by kTileN = 216).  The 144-wide
+    // two-head tile is bound by shared-memory operand traffic (64 + 16384/BN bytes per tensor clock: 64 % tensor-pipe active).
+    static constexpr bool kQkv3 = EPI == EPI_QKV && BN == 3 * DH + 8;
+    static constexpr int kTileN = kQkv3 ? 3 * DH : BN;                  // output columns per tile
+    static constexpr int kParts = (EPI == EPI_RESID && BN == 256) ? 4 : (kQkv3 ? 3 : 2);
     static constexpr int kThreads = 64 + kParts * 128;
     static constexpr int kStageBytes = (kABytes + kBBytes) * kKSub;    // per CTA
     static constexpr int kTxBytes = kStageBytes * CL;                  // credited to the (leader's) full barrier per stage
@@ -103,7 +108,7 @@ template <int CPR> __device__ __forceinline__ void slab_task(int i, int lane, in
 // cluster, entries {row-tile group, n0 | width << 20}, terminated by a negative group: full BN-wide tiles first,
 // the narrower tail tiles fill the gaps of the last wave (fitv2_api.cu: build_schedule).
 struct TileWalk {
-    const int2* sched; int grp, num_groups, stride, n_tiles, bn;
+    const int2* sched; int grp, num_groups, stride, n_tiles, bn, tile_n;
     int2 ahead;                                                         // table mode: the entry after the current one (prefetched)
     __device__ __forceinline__ void start() { if (sched) ahead = __ldg(sched++); }
     __device__ __forceinline__ bool next(int& m_group, int& n0, int& bn_t) {
@@ -115,7 +120,7 @@ struct TileWalk {
             return true;
         }
         if (grp >= num_groups) return false;
-        m_group = grp / n_tiles; n0 = (grp % n_tiles) * bn; bn_t = bn;      // n fastest: a wave shares few A tiles
+        m_group = grp / n_tiles; n0 = (grp % n_tiles) * tile_n; bn_t = bn;  // n fastest: a wave shares few A tiles
         grp += stride;
         return true;
     }
@@ -144,7 +149,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int m_tiles = (M + kGemmBM - 1) / kGemmBM;
-    const int n_tiles = N / BN;
+    const int n_tiles = N / Cfg::kTileN;
     // work items are groups of CL vertically adjacent 128-row tiles; CTA `cta_rank` of the cluster owns row tile
     // group * CL + cta_rank (a phantom tile past the M tail computes on zero-filled rows and stores nothing)
     const int num_groups = ((m_tiles + CL - 1) / CL) * n_tiles;
@@ -152,7 +157,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     const uint32_t cta_rank = CL > 1 ? cluster_ctarank() : 0u;
     const bool leader = cta_rank == 0;
     const int group0 = blockIdx.x / CL, group_stride = gridDim.x / CL;
-    const TileWalk walk0 = {sched ? sched + (size_t)group0 * sched_stride : nullptr, group0, num_groups, group_stride, n_tiles, BN, make_int2(-1, 0)};
+    const TileWalk walk0 = {sched ? sched + (size_t)group0 * sched_stride : nullptr, group0, num_groups, group_stride, n_tiles, BN, Cfg::kTileN, make_int2(-1, 0)};
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tma_a);
@@ -268,7 +273,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         walk.start();
         int m_group, n0, bn_t;
         for (; walk.next(m_group, n0, bn_t); ++it) {
-            const int m_tile = m_group * CL + (int)cta_rank, n_tile = n0 / BN;
+            const int m_tile = m_group * CL + (int)cta_rank, n_tile = n0 / Cfg::kTileN;
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
             const uint32_t t_row = tmem_base + acc * Cfg::kAccStride + (uint32_t(quarter * 32) << 16);
@@ -414,13 +419,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                         }
                     }
                 }
-            } else {   // EPI_QKV: BN == 2 * DH, every tile holds two whole heads of the same kind (heads is even);
-                       // the two column halves are exactly the two heads.
-                static_assert(EPI != EPI_QKV || BN == 2 * DH, "QKV tile must be two heads wide");
+            } else {   // EPI_QKV: every tile holds kParts whole heads, one per epilogue warp of a lane quarter; q / k / v is
+                       // decided per head (a three-head tile may straddle the q|k or k|v boundary).
+                static_assert(EPI != EPI_QKV || BN == 2 * DH || Cfg::kQkv3, "QKV tile must be two or three heads wide");
                 static_assert(DH % 8 == 0, "head_dim must be a multiple of 8");
                 constexpr int CH = DH / 8;                            // 16-byte chunks per head row
                 constexpr int PITCH = Cfg::kEpiPitch;
-                const int ghead = n_tile * 2 + half;
+                const int ghead = n_tile * Cfg::kParts + half;
                 const int kind = ghead / ep.heads;                    // 0 = q, 1 = k, 2 = v   (modules.py:166-167)
                 const int head = ghead - kind * ep.heads;
                 const float* bias = ep.bias + n0 + half * DH;
