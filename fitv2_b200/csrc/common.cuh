@@ -158,6 +158,18 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap* m, uint64_t* bar,
         : "memory");
 }
 
+// TMA reduce-add of a 2-D shared-memory tile into global memory (element type from the tensor map; fp32 add performed in L2).
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, uint32_t src_smem, int c0, int c1) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+                 :: "l"(reinterpret_cast<uint64_t>(m)), "r"(src_smem), "r"(c0), "r"(c1) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+// wait until all but the N most recent bulk groups of this thread have finished READING their shared-memory source
+template <int N> __device__ __forceinline__ void tma_store_wait_read_n() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(N) : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" :: "r"(addr), "r"(v) : "memory"); }
+
 // --------------------------------------------------------------------------------------------
 // tcgen05: TMEM allocation, UMMA issue/commit, TMEM loads
 // --------------------------------------------------------------------------------------------

@@ -211,6 +211,9 @@ struct fitv2_handle {
     int cond_bn_up = 0;
     CUtensorMap map_sc_split, map_lmid_split, map_wglobal, map_wfinal, map_wlora_a, map_wlora_b;
     int bn_proj = 0, bn_fc2 = 0;
+    bool proj_t = false, fc2_t = false;                  // proj / fc2 run as transposed 256-token-wide tiles (EPI_RESID_T)
+    CUtensorMap map_wproj_t, map_wfc2_t;                 // the same weights with 128-row boxes (M operand of EPI_RESID_T)
+    CUtensorMap map_x;                                   // fp32 residual stream, 32-channel x 16-token boxes (TMA reduce-add target)
     bool qkv3 = false;                                   // QKV GEMM uses the three-head 224-wide tile (head_dim 72)
     int sched_stride_proj = 0, sched_stride_fc2 = 0;     // > 0: ragged tiling (BN-wide tiles + one narrower tail tile per row group)
     std::vector<int2> sched_host;
@@ -324,13 +327,23 @@ int launch_gemm_t(fitv2_handle* h, const CUtensorMap& ma, const CUtensorMap& mb,
         configured = true;
     }
     constexpr int TN = Cfg::kTileN;
+    if (EPI == EPI_RESID_T) {                         // N = token rows: the tail tile is zero-filled / clipped
+        const int m_tiles_t = (M + kGemmBM - 1) / kGemmBM;
+        const int groups_t = ((m_tiles_t + CL - 1) / CL) * ((N + TN - 1) / TN);
+        const int max_clusters_t = h->num_sms / CL;
+        const int grid_t = (groups_t < max_clusters_t ? groups_t : max_clusters_t) * CL;
+        CUDA_TRY(launch_k(kern, dim3(grid_t), dim3(Cfg::kThreads), Cfg::kSmemBytes, st, CL, ma, mb, h->map_x, M, N, K, b_row_off, ep, sched, sched_stride));
+        CUDA_TRY(cudaGetLastError());
+        h->launches++;
+        return FITV2_OK;
+    }
     if (N % TN != 0 && !(sched && EPI == EPI_RESID && (N % BN) % 32 == 0))
         return fail(FITV2_E_INVALID, "GEMM N=%d is not a multiple of the tile width %d", N, TN);
     const int m_tiles = (M + kGemmBM - 1) / kGemmBM;
     const int groups = ((m_tiles + CL - 1) / CL) * ((N + TN - 1) / TN);
     const int max_clusters = h->num_sms / CL;
     const int grid = (groups < max_clusters ? groups : max_clusters) * CL;
-    CUDA_TRY(launch_k(kern, dim3(grid), dim3(Cfg::kThreads), Cfg::kSmemBytes, st, CL, ma, mb, M, N, K, b_row_off, ep, sched, sched_stride));
+    CUDA_TRY(launch_k(kern, dim3(grid), dim3(Cfg::kThreads), Cfg::kSmemBytes, st, CL, ma, mb, h->map_x, M, N, K, b_row_off, ep, sched, sched_stride));
     CUDA_TRY(cudaGetLastError());
     h->launches++;
     return FITV2_OK;
@@ -578,6 +591,29 @@ int ensure_maps(fitv2_handle* h) {
     if ((rc = make_map(&h->map_wproj, h->w[FITV2_W_PROJ_W], c.operand_dtype, L * D, D, D, h->bn_proj / kGemmCluster))) return rc;
     if ((rc = make_map(&h->map_wgu, h->w[FITV2_W_GATEUP_W], c.operand_dtype, L * 2 * Hm, D, D, 256 / kGemmCluster))) return rc;
     if ((rc = make_map(&h->map_wfc2, h->w[FITV2_W_FC2_W], c.operand_dtype, L * D, Hm, Hm, h->bn_fc2 / kGemmCluster))) return rc;
+    {
+        // Transposed residual GEMM (EPI_RESID_T): 256-token-wide tiles + TMA reduce-add into x.  Measured at XL/2 (hidden 1152,
+        // five 256-channel groups, the last half empty): fc2 116 -> 110 us, proj 61 -> 63 us (proj is bound by the DRAM traffic of
+        // the residual either way), so only fc2 uses it, and only where the normal orientation has no 256-wide tile.
+        // FITV2_RESID_T=0 / 1 forces it off / on for both.
+        const char* e = getenv("FITV2_RESID_T");
+        const bool ragged = h->sched_stride_proj != 0;
+        h->fc2_t = !ragged && (e ? e[0] == '1' : h->bn_fc2 < 256);
+        h->proj_t = !ragged && e && e[0] == '1';
+        if ((rc = make_map(&h->map_wproj_t, h->w[FITV2_W_PROJ_W], c.operand_dtype, L * D, D, D, 128))) return rc;
+        {
+            EncodeTiledFn fn = get_encode_fn();
+            if (!fn) return fail(FITV2_E_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+            cuuint64_t dims[2] = {D, M};
+            cuuint64_t strides[1] = {D * 4};
+            cuuint32_t box[2] = {32, 16};
+            cuuint32_t estr[2] = {1, 1};
+            CUresult r = fn(&h->map_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, h->ws + l.x_res, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return fail(FITV2_E_CUDA, "cuTensorMapEncodeTiled(residual) failed (%d)", (int)r);
+        }
+        if ((rc = make_map(&h->map_wfc2_t, h->w[FITV2_W_FC2_W], c.operand_dtype, L * D, Hm, Hm, 128))) return rc;
+    }
     // Conditioning linears on the tensor pipe when the shapes tile (every production config does); FITV2_COND=simt keeps the
     // fp32-FMA kernels for A/B runs.  Other shapes use the SIMT kernels.
     {
@@ -757,8 +793,10 @@ int forward_impl(fitv2_handle* h, const float* x, int x_rows, const float* t, co
         ep.bias = (const float*)h->w[FITV2_W_PROJ_B] + (size_t)layer * D;
         ep.tokens = tokens; ep.x = x_res; ep.gate = modl + 2 * D; ep.gate_ld = 6 * D;
         prof_begin(h, PC_PROJ, st);
-        if ((rc = launch_gemm_bn<EPI_RESID, OT>(h, h->bn_proj, h->map_ao, h->map_wproj, M, D, D, layer * D, ep, st,
-                                               h->sched_stride_proj ? (const int2*)(ws + l.sched_proj) : nullptr, h->sched_stride_proj))) return rc;
+        if (h->proj_t) rc = launch_gemm_t<256, EPI_RESID_T, OT, 0>(h, h->map_wproj_t, h->map_ao, D, M, D, layer * D, ep, st);
+        else rc = launch_gemm_bn<EPI_RESID, OT>(h, h->bn_proj, h->map_ao, h->map_wproj, M, D, D, layer * D, ep, st,
+                                                h->sched_stride_proj ? (const int2*)(ws + l.sched_proj) : nullptr, h->sched_stride_proj);
+        if (rc) return rc;
         prof_end(h, st);
         // ---- SwiGLU branch (modules.py:273) ----
         prof_begin(h, PC_LNMOD, st);
@@ -774,8 +812,10 @@ int forward_impl(fitv2_handle* h, const float* x, int x_rows, const float* t, co
         ep.bias = (const float*)h->w[FITV2_W_FC2_B] + (size_t)layer * D;
         ep.tokens = tokens; ep.x = x_res; ep.gate = modl + 5 * D; ep.gate_ld = 6 * D;
         prof_begin(h, PC_FC2, st);
-        if ((rc = launch_gemm_bn<EPI_RESID, OT>(h, h->bn_fc2, h->map_hidden, h->map_wfc2, M, D, Hm, layer * D, ep, st,
-                                               h->sched_stride_fc2 ? (const int2*)(ws + l.sched_fc2) : nullptr, h->sched_stride_fc2))) return rc;
+        if (h->fc2_t) rc = launch_gemm_t<256, EPI_RESID_T, OT, 0>(h, h->map_wfc2_t, h->map_hidden, D, M, Hm, layer * D, ep, st);
+        else rc = launch_gemm_bn<EPI_RESID, OT>(h, h->bn_fc2, h->map_hidden, h->map_wfc2, M, D, Hm, layer * D, ep, st,
+                                                h->sched_stride_fc2 ? (const int2*)(ws + l.sched_fc2) : nullptr, h->sched_stride_fc2);
+        if (rc) return rc;
         prof_end(h, st);
     }
 

@@ -23,13 +23,20 @@
 //   EPI_RESID  x += gate[sample] * (acc + bias)                      (modules.py:205,272 and :273)
 //   EPI_SWIGLU hidden = silu(acc_gate + b_g) * (acc_up + b_x)        (timm SwiGLU; modules.py:251)
 //   EPI_PLAIN  out = acc + bias                                      (generic nn.Linear; tests)
+//   EPI_RESID_T  the same residual update computed TRANSPOSED: the weight rows are the M operand (128 output channels per
+//              CTA, 256 per pair) and 256 token rows the N operand, so the tile is 256 columns wide and the main loop is
+//              tensor-bound like gate/up instead of shared-memory bound (N = hidden_size only offers 128/144-wide tiles the
+//              other way round).  TMEM lane = channel, so bias and gate are per-thread scalars.  The SMs never read the
+//              residual: every warp stages gate * (acc + bias) for 16 token rows x 32 channels in shared memory and a TMA
+//              reduce-add (cp.reduce.async.bulk.tensor .add, fp32) applies it to x in L2.  (A register version that loaded and
+//              stored x itself was bound by the loads it could keep in flight: proj 102 us against 60.)
 #pragma once
 #include "common.cuh"
 #include "tc2sm.cuh"
 
 namespace fitv2 {
 
-enum { EPI_QKV = 0, EPI_RESID = 1, EPI_SWIGLU = 2, EPI_PLAIN = 3 };
+enum { EPI_QKV = 0, EPI_RESID = 1, EPI_SWIGLU = 2, EPI_PLAIN = 3, EPI_RESID_T = 4 };
 
 struct GemmEpi {
     const float* bias;        // [N] fp32 (layer slice)
@@ -109,6 +116,7 @@ template <int CPR> __device__ __forceinline__ void slab_task(int i, int lane, in
 // the narrower tail tiles fill the gaps of the last wave (fitv2_api.cu: build_schedule).
 struct TileWalk {
     const int2* sched; int grp, num_groups, stride, n_tiles, bn, tile_n;
+    int m_fast;                                                         // > 0: row-tile groups vary fastest (m_fast of them)
     int2 ahead;                                                         // table mode: the entry after the current one (prefetched)
     __device__ __forceinline__ void start() { if (sched) ahead = __ldg(sched++); }
     __device__ __forceinline__ bool next(int& m_group, int& n0, int& bn_t) {
@@ -120,7 +128,8 @@ struct TileWalk {
             return true;
         }
         if (grp >= num_groups) return false;
-        m_group = grp / n_tiles; n0 = (grp % n_tiles) * tile_n; bn_t = bn;  // n fastest: a wave shares few A tiles
+        if (m_fast) { m_group = grp % m_fast; n0 = (grp / m_fast) * tile_n; bn_t = bn; }   // a wave shares few B (token) tiles
+        else { m_group = grp / n_tiles; n0 = (grp % n_tiles) * tile_n; bn_t = bn; }       // n fastest: a wave shares few A tiles
         grp += stride;
         return true;
     }
@@ -129,6 +138,7 @@ struct TileWalk {
 template <int BN, int EPI, typename OT, int DH, int CL>
 __global__ void __launch_bounds__((GemmCfg<BN, EPI, DH, CL>::kThreads), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+               const __grid_constant__ CUtensorMap tma_x,   // EPI_RESID_T: fp32 residual stream (hidden_size, token rows), box 32 x 16
                int M, int N, int K, int b_row_offset, GemmEpi ep, const int2* __restrict__ sched, int sched_stride)
 {
     using Cfg = GemmCfg<BN, EPI, DH, CL>;
@@ -149,7 +159,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int m_tiles = (M + kGemmBM - 1) / kGemmBM;
-    const int n_tiles = N / Cfg::kTileN;
+    const int n_tiles = EPI == EPI_RESID_T ? (N + Cfg::kTileN - 1) / Cfg::kTileN : N / Cfg::kTileN;   // RESID_T: N = token rows, ragged tail
     // work items are groups of CL vertically adjacent 128-row tiles; CTA `cta_rank` of the cluster owns row tile
     // group * CL + cta_rank (a phantom tile past the M tail computes on zero-filled rows and stores nothing)
     const int num_groups = ((m_tiles + CL - 1) / CL) * n_tiles;
@@ -157,7 +167,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     const uint32_t cta_rank = CL > 1 ? cluster_ctarank() : 0u;
     const bool leader = cta_rank == 0;
     const int group0 = blockIdx.x / CL, group_stride = gridDim.x / CL;
-    const TileWalk walk0 = {sched ? sched + (size_t)group0 * sched_stride : nullptr, group0, num_groups, group_stride, n_tiles, BN, Cfg::kTileN, make_int2(-1, 0)};
+    const TileWalk walk0 = {sched ? sched + (size_t)group0 * sched_stride : nullptr, group0, num_groups, group_stride, n_tiles, BN, Cfg::kTileN,
+                            EPI == EPI_RESID_T ? (m_tiles + CL - 1) / CL : 0, make_int2(-1, 0)};
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tma_a);
@@ -197,7 +208,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 #pragma unroll
                     for (int j = 0; j < KSUB; ++j) {               // a K block past the end of K is zero-filled by TMA
                         const int kcol = (kb * KSUB + j) * kGemmBK;
-                        if constexpr (CL == 1) {
+                        if constexpr (EPI == EPI_RESID_T) {        // A = weight rows (layer offset), B = token rows
+                            static_assert(EPI != EPI_RESID_T || CL == 2, "transposed residual GEMM is written for CTA pairs");
+                            tma_load_2d_2sm(&tma_a, &full_bar[stage], sa + j * Cfg::kABytes, kcol, b_row_offset + m_tile * kGemmBM);
+                            tma_load_2d_2sm(&tma_b, &full_bar[stage], sb + j * Cfg::kBBytes, kcol, n0 + (int)cta_rank * (bn_t / CL));
+                        } else if constexpr (CL == 1) {
                             tma_load_2d(&tma_a, &full_bar[stage], sa + j * Cfg::kABytes, kcol, m_tile * kGemmBM);
                             tma_load_2d(&tma_b, &full_bar[stage], sb + j * Cfg::kBBytes, kcol, b_row_offset + n0);
                         } else {
@@ -354,6 +369,48 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     if (sl + NPF < NS) load_x(sl % NPF, sl + NPF);    // refill the ring slot (only tiles wider than 3 slabs)
                     }
                 }
+            } else if constexpr (EPI == EPI_RESID_T) {
+                // lane = output channel, columns = token rows.  M = channels (hidden_size), N = all token rows.
+                constexpr int COLS = BN / Cfg::kParts;                // token rows per warp
+                constexpr int CW = 16;                                // token rows per step (one tcgen05.ld.x16, one TMA box)
+                constexpr int NCH = COLS / CW;
+                static_assert(COLS % CW == 0 && Cfg::kEpiWarpBytes >= 2 * CW * 128, "transposed residual tile");
+                const int ch0 = m_tile * kGemmBM + quarter * 32;       // first channel of this warp (a 128-byte line of x)
+                const int ch = ch0 + lane;
+                const bool ch_ok = ch < M;
+                const int tok0 = n0 + half * COLS;
+                const float b = ch_ok ? __ldg(ep.bias + ch) : 0.f;
+                mbar_wait(&tfull_bar[acc], acc_phase);
+                tc_fence_after();
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) {
+                    uint32_t v[CW];
+                    tmem_ld16(t_row + half * COLS + c * CW, v);
+                    tmem_ld_wait();
+                    if (c == NCH - 1) release_acc(acc);
+                    const int t_first = tok0 + c * CW;
+                    const int s_a = t_first / ep.tokens;
+                    const bool same = (t_first + CW - 1) / ep.tokens == s_a;
+                    float g = 0.f;
+                    if (same && ch_ok) g = __ldg(ep.gate + (size_t)s_a * ep.gate_ld + ch);
+                    if (ch0 < M && t_first < N) {                       // warp-uniform; later steps of a tail tile are inactive too
+                        // two staging buffers per warp: the reduce issued two steps ago must have read its buffer
+                        if (lane == 0) tma_store_wait_read_n<1>();
+                        __syncwarp();
+                        const uint32_t buf = stg + (c & 1) * (CW * 128);
+#pragma unroll
+                        for (int j = 0; j < CW; ++j) {
+                            if (!same && ch_ok && t_first + j < N) g = __ldg(ep.gate + (size_t)((t_first + j) / ep.tokens) * ep.gate_ld + ch);
+                            sts32(buf + j * 128 + lane * 4, __float_as_uint(g * (__uint_as_float(v[j]) + b)));
+                        }
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        // rows past the last token and channels past hidden_size are clipped by the tensor map
+                        if (lane == 0) tma_reduce_add_2d(&tma_x, buf, ch0, t_first);
+                    }
+                }
+                if (lane == 0) tma_store_wait_read_n<0>();             // buffers are reused by the next tile
+                __syncwarp();
             } else if constexpr (EPI == EPI_SWIGLU) {
                 // tile columns: [0, BN/2) = gate rows of W, [BN/2, BN) = matching up rows (host packs W this way)
                 constexpr int HALF = BN / 2;                          // outputs per tile
@@ -519,6 +576,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         }
     }
 
+    if constexpr (EPI == EPI_RESID_T) {
+        if (warp >= 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // reduce-adds performed before exit
+    }
     tc_fence_before();
     if constexpr (CL > 1) cluster_sync(); else __syncthreads();   // the pair must be done with this CTA's smem / TMEM / barriers
     if (warp == 1) {

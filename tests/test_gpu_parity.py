@@ -391,6 +391,7 @@ def test_ragged_residual_tiling_matches_uniform(lib, monkeypatch):
     """The experimental 256-wide + tail-tile residual tiling with its host-built LPT schedule table (FITV2_RAGGED=1, see
     profiles/README.md) computes the same function as the production uniform tiling."""
     a = inputs(3, 10, 20)                                                    # 200 tokens: M tail inside a row-tile pair
+    monkeypatch.setenv("FITV2_RESID_T", "0")                                 # both sides in the normal orientation
     m0, _, _ = build_model(2)
     ref = run(m0, *a)
     monkeypatch.setenv("FITV2_RAGGED", "1")
@@ -398,6 +399,23 @@ def test_ragged_residual_tiling_matches_uniform(lib, monkeypatch):
     out = run(m1, *a)
     assert rel(out, ref) < 2e-5                                              # same operands; only the fp32 summation tiling differs
     assert torch.equal(run(m1, *a), out)
+
+
+@pytest.mark.parametrize("R,hp,wp", [(3, 10, 20), (5, 7, 9), (64, 16, 16)])
+def test_transposed_residual_gemm_matches_normal(lib, monkeypatch, R, hp, wp):
+    """EPI_RESID_T (weights as the M operand, 256-token-wide tiles, TMA reduce-add into the fp32 residual; the default for fc2
+    at hidden 1152) against the normal orientation, forced both ways: token tail tiles (600 / 315 rows), samples that change
+    inside a 16-token step (200 / 63 tokens per sample), and the headline shape."""
+    a = inputs(R, hp, wp, seed=13)
+    outs = []
+    for mode in ("0", "1"):
+        monkeypatch.setenv("FITV2_RESID_T", mode)
+        m, sd, cfg = build_model(2)
+        outs.append(run(m, *a))
+        assert torch.equal(run(m, *a), outs[-1])                             # one add per element: deterministic
+    assert rel(outs[1], outs[0]) < 2e-5                                      # same products; x + d rounded once more (reduce-add)
+    if R <= 5:
+        assert rel(outs[1], O.forward(cfg, sd, *a)) < V_TOL
 
 
 @pytest.mark.parametrize("R,hp,wp", [(40, 8, 8), (20, 10, 20), (12, 12, 24), (7, 1, 1), (130, 2, 3), (50, 3, 7)])
