@@ -179,6 +179,22 @@ cond_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const int acc = n_it & 1;
             const uint32_t acc_phase = (n_it >> 1) & 1;
             const uint32_t t_row = tmem_base + acc * Cfg::kAccStride + (uint32_t(quarter * 32) << 16);
+            // the `add` operand (global adaLN, L2-resident) does not depend on the accumulator: request the whole tile's share
+            // before waiting for the MMAs (the write-out loop below was bound by these loads: 8.7 us per tile)
+            constexpr int CPR = BN / 4;                                 // float4 chunks per row
+            constexpr int ITERS = kCondRows * CPR / 128;
+            static_assert(kCondRows * CPR % 128 == 0, "write-out mapping");
+            const int seg = it.seg;
+            const int n_seg = (p.nt_prefix[seg + 1] - p.nt_prefix[seg]) * BN;
+            const float* add = p.add[seg] ? p.add[seg] + it.n0 : nullptr;
+            float4 addv[ITERS];
+#pragma unroll
+            for (int i = 0; i < ITERS; ++i) {
+                const int idx = et + i * 128, r = idx / CPR, c = (idx - r * CPR) * 4;
+                const int rg = it.m_tile * kCondRows + r;
+                addv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (add && rg < p.rows) addv[i] = *reinterpret_cast<const float4*>(add + (size_t)rg * n_seg + c);
+            }
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             if (is_lo) {
@@ -214,21 +230,17 @@ cond_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
             named_bar_sync(2, 128);                                     // hi + lo sums staged
             // coalesced write-out of the 64 x BN tile
-            const int seg = it.seg;
             const float* bias = p.bias[seg] ? p.bias[seg] + (size_t)it.z * p.bias_batch_stride[seg] + it.n0 : nullptr;
-            const int n_seg = (p.nt_prefix[seg + 1] - p.nt_prefix[seg]) * BN;
-            const float* add = p.add[seg] ? p.add[seg] + it.n0 : nullptr;
             float* out = p.out[seg] + (size_t)it.z * p.out_batch_stride[seg] + it.n0;
             float* split = p.out_split[seg] ? p.out_split[seg] + (size_t)it.m_tile * 128 * p.ld_split[seg] + it.n0 : nullptr;
-            constexpr int CPR = BN / 4;                                 // float4 chunks per row
-#pragma unroll 4
-            for (int idx = et; idx < kCondRows * CPR; idx += 128) {
-                const int r = idx / CPR, c = (idx - r * CPR) * 4;
+#pragma unroll
+            for (int i = 0; i < ITERS; ++i) {
+                const int idx = et + i * 128, r = idx / CPR, c = (idx - r * CPR) * 4;
                 const int rg = it.m_tile * kCondRows + r;
                 if (rg >= p.rows) continue;
                 float4 v = *reinterpret_cast<const float4*>(stage_s + r * Cfg::kPitch + c);
                 if (bias) { const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c)); v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w; }
-                if (add) { const float4 a = *reinterpret_cast<const float4*>(add + (size_t)rg * n_seg + c); v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w; }
+                v.x += addv[i].x; v.y += addv[i].y; v.z += addv[i].z; v.w += addv[i].w;
                 *reinterpret_cast<float4*>(out + (size_t)rg * p.ldo[seg] + c) = v;
                 if (split) {
                     float4 hi = make_float4(tf32_round(v.x), tf32_round(v.y), tf32_round(v.z), tf32_round(v.w));

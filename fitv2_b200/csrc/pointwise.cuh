@@ -195,19 +195,22 @@ __global__ void cfg_combine_kernel(float* __restrict__ out, const float* __restr
 
 // ---------------------------------------------------------------------------------------------
 // Patch embedding  (fit/model/modules.py:34-37): x[m, :] = W (D x Cin) * xin[m % rows_in, :] + b
-// K = 16 -> bandwidth-bound (writes M*D fp32).  One block = 8 token rows; a thread owns 4 consecutive
-// output features and keeps their weight rows in registers.
+// K = 16 -> bandwidth-bound (writes M*D fp32).  One block = kPatchRows token rows; a thread owns 4 consecutive
+// output features and keeps their weight rows in registers (64 weight loads amortised over kPatchRows * 4 outputs; with 8
+// rows per block every block re-read the whole weight matrix for 32 outputs per thread: 59 us against 12 us of writes).
+// Launched with D / 4 threads (rounded up to a warp) so that one pass covers the row.
 // ---------------------------------------------------------------------------------------------
+constexpr int kPatchRows = 32;
 template <int CIN>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(576)
 patch_embed_kernel(const float* __restrict__ xin, const float* __restrict__ w, const float* __restrict__ b,
                    float* __restrict__ x, int M, int D, int rows_in_tokens /* tokens * rows_in */)
 {
     pdl_wait();
     pdl_launch_dependents();
-    __shared__ float sx[8][CIN];
-    const int m0 = blockIdx.x * 8;
-    for (int i = threadIdx.x; i < 8 * CIN; i += blockDim.x) {
+    __shared__ float sx[kPatchRows][CIN];
+    const int m0 = blockIdx.x * kPatchRows;
+    for (int i = threadIdx.x; i < kPatchRows * CIN; i += blockDim.x) {
         const int r = i / CIN, c = i % CIN;
         const int m = m0 + r;
         sx[r][c] = (m < M) ? xin[(size_t)(m % rows_in_tokens) * CIN + c] : 0.f;
@@ -223,8 +226,8 @@ patch_embed_kernel(const float* __restrict__ xin, const float* __restrict__ w, c
                 wr[j][c] = t.x; wr[j][c + 1] = t.y; wr[j][c + 2] = t.z; wr[j][c + 3] = t.w;
             }
         const float4 bb = __ldg(reinterpret_cast<const float4*>(b + d0));
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
+#pragma unroll 8
+        for (int r = 0; r < kPatchRows; ++r) {
             if (m0 + r >= M) break;
             float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -388,80 +391,111 @@ final_layer_kernel(const float* __restrict__ x, const float* __restrict__ fmod /
     pdl_wait();
     pdl_launch_dependents();
     extern __shared__ float sw[];                       // COUT * D
-    for (int i = threadIdx.x; i < COUT * D; i += blockDim.x) sw[i] = w[i];
+    {   // 73 KB of weights per block: 128-bit loads, several in flight per thread
+        const float4* w4 = reinterpret_cast<const float4*>(w);
+        float4* sw4 = reinterpret_cast<float4*>(sw);
+        const int n4 = COUT * D / 4;
+#pragma unroll 6
+        for (int i = threadIdx.x; i < n4; i += blockDim.x) sw4[i] = __ldg(w4 + i);
+    }
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int warps_per_block = blockDim.x >> 5;
     const int nvec = D >> 2;
-    for (int m = blockIdx.x * warps_per_block + (threadIdx.x >> 5); m < M; m += gridDim.x * warps_per_block) {
-        const float4* xr = reinterpret_cast<const float4*>(x + (size_t)m * D);
-        float4 v[NV];
-        float s = 0.f;
+    // Two rows per warp and iteration: every weight vector read from shared memory serves both rows (the kernel was bound by
+    // the 73 KB of shared-memory reads per row, 87 us for 75 MB of x), and the second row's loads overlap the first row's math.
+    constexpr int RW = 2;
+    const int stride = gridDim.x * warps_per_block;
+    for (int m0 = blockIdx.x * warps_per_block + (threadIdx.x >> 5); m0 < M; m0 += RW * stride) {
+        float4 v[RW][NV];
+        bool ok[RW];
 #pragma unroll
-        for (int i = 0; i < NV; ++i) {
-            const int j = lane + 32 * i;
-            v[i] = (j < nvec) ? xr[j] : make_float4(0.f, 0.f, 0.f, 0.f);
-            s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-        }
-        const float mean = warp_sum(s) / (float)D;
-        float q = 0.f;
+        for (int r = 0; r < RW; ++r) {
+            const int m = m0 + r * stride;
+            ok[r] = m < M;
+            const float4* xr = reinterpret_cast<const float4*>(x + (size_t)(ok[r] ? m : m0) * D);
 #pragma unroll
-        for (int i = 0; i < NV; ++i) {
-            const int j = lane + 32 * i;
-            if (j < nvec) {
-                const float a = v[i].x - mean, bq = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
-                q += (a * a + bq * bq) + (c * c + d * d);
+            for (int i = 0; i < NV; ++i) {
+                const int j = lane + 32 * i;
+                v[r][i] = (j < nvec) ? xr[j] : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
-        const float rstd = rsqrtf(warp_sum(q) / (float)D + 1e-6f);
-        const int sample = m / tokens;
-        const float4* sh = reinterpret_cast<const float4*>(fmod + (size_t)sample * 2 * D);
-        const float4* sc = reinterpret_cast<const float4*>(fmod + (size_t)sample * 2 * D + D);
 #pragma unroll
-        for (int i = 0; i < NV; ++i) {
-            const int j = lane + 32 * i;
-            if (j < nvec) {
-                const float4 a = __ldg(sh + j), g = __ldg(sc + j);
-                v[i].x = (v[i].x - mean) * rstd * (1.f + g.x) + a.x;
-                v[i].y = (v[i].y - mean) * rstd * (1.f + g.y) + a.y;
-                v[i].z = (v[i].z - mean) * rstd * (1.f + g.z) + a.z;
-                v[i].w = (v[i].w - mean) * rstd * (1.f + g.w) + a.w;
+        for (int r = 0; r < RW; ++r) {
+            const int m = ok[r] ? m0 + r * stride : m0;
+            float s = 0.f;
+#pragma unroll
+            for (int i = 0; i < NV; ++i) s += (v[r][i].x + v[r][i].y) + (v[r][i].z + v[r][i].w);
+            const float mean = warp_sum(s) / (float)D;
+            float q = 0.f;
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                const int j = lane + 32 * i;
+                if (j < nvec) {
+                    const float a = v[r][i].x - mean, bq = v[r][i].y - mean, c = v[r][i].z - mean, d = v[r][i].w - mean;
+                    q += (a * a + bq * bq) + (c * c + d * d);
+                }
+            }
+            const float rstd = rsqrtf(warp_sum(q) / (float)D + 1e-6f);
+            const int sample = m / tokens;
+            const float4* sh = reinterpret_cast<const float4*>(fmod + (size_t)sample * 2 * D);
+            const float4* sc = reinterpret_cast<const float4*>(fmod + (size_t)sample * 2 * D + D);
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                const int j = lane + 32 * i;
+                if (j < nvec) {
+                    const float4 a = __ldg(sh + j), g = __ldg(sc + j);
+                    v[r][i].x = (v[r][i].x - mean) * rstd * (1.f + g.x) + a.x;
+                    v[r][i].y = (v[r][i].y - mean) * rstd * (1.f + g.y) + a.y;
+                    v[r][i].z = (v[r][i].z - mean) * rstd * (1.f + g.z) + a.z;
+                    v[r][i].w = (v[r][i].w - mean) * rstd * (1.f + g.w) + a.w;
+                }
             }
         }
-        float acc[COUT];
+        float acc[RW][COUT];
 #pragma unroll
         for (int o = 0; o < COUT; ++o) {
             const float4* wr = reinterpret_cast<const float4*>(sw + (size_t)o * D);
-            float a = 0.f;
+            float a[RW];
+#pragma unroll
+            for (int r = 0; r < RW; ++r) a[r] = 0.f;
 #pragma unroll
             for (int i = 0; i < NV; ++i) {
                 const int j = lane + 32 * i;
                 if (j < nvec) {
                     const float4 ww = wr[j];
-                    a = fmaf(v[i].x, ww.x, a); a = fmaf(v[i].y, ww.y, a);
-                    a = fmaf(v[i].z, ww.z, a); a = fmaf(v[i].w, ww.w, a);
+#pragma unroll
+                    for (int r = 0; r < RW; ++r) {
+                        a[r] = fmaf(v[r][i].x, ww.x, a[r]); a[r] = fmaf(v[r][i].y, ww.y, a[r]);
+                        a[r] = fmaf(v[r][i].z, ww.z, a[r]); a[r] = fmaf(v[r][i].w, ww.w, a[r]);
+                    }
                 }
             }
-            acc[o] = a;
+#pragma unroll
+            for (int r = 0; r < RW; ++r) acc[r][o] = a[r];
         }
         // 16 warp reductions at once: a halving butterfly (8 + 4 + 2 + 1 + 1 = 16 shuffles instead of 16 x 5); afterwards
         // lanes 2k and 2k+1 hold the total of output  o = bits (4,3,2,1) of the lane, most significant first
         static_assert(COUT == 16, "the reduction butterfly is written for 16 outputs");
 #pragma unroll
-        for (int step = 0; step < 4; ++step) {
-            const int off = 16 >> step, half = 8 >> step;             // lane bit `off` selects which half of the values a lane keeps
-            const bool up = (lane & off) != 0;
+        for (int r = 0; r < RW; ++r) {
 #pragma unroll
-            for (int o = 0; o < half; ++o) {
-                const float send = up ? acc[o] : acc[o + half];
-                const float recv = __shfl_xor_sync(0xffffffffu, send, off);
-                acc[o] = (up ? acc[o + half] : acc[o]) + recv;
+            for (int step = 0; step < 4; ++step) {
+                const int off = 16 >> step, half = 8 >> step;         // lane bit `off` selects which half of the values a lane keeps
+                const bool up = (lane & off) != 0;
+#pragma unroll
+                for (int o = 0; o < half; ++o) {
+                    const float send = up ? acc[r][o] : acc[r][o + half];
+                    const float recv = __shfl_xor_sync(0xffffffffu, send, off);
+                    acc[r][o] = (up ? acc[r][o + half] : acc[r][o]) + recv;
+                }
             }
-        }
-        const float total = acc[0] + __shfl_xor_sync(0xffffffffu, acc[0], 1);
-        if ((lane & 1) == 0) {
-            const int o = lane >> 1;                                   // bits (4,3,2,1) -> output index
-            out[(size_t)m * COUT + o] = (total + __ldg(b + o)) * mask[m];
+            const float total = acc[r][0] + __shfl_xor_sync(0xffffffffu, acc[r][0], 1);
+            const int m = m0 + r * stride;
+            if (ok[r] && (lane & 1) == 0) {
+                const int o = lane >> 1;                               // bits (4,3,2,1) -> output index
+                out[(size_t)m * COUT + o] = (total + __ldg(b + o)) * mask[m];
+            }
         }
     }
 }

@@ -413,7 +413,8 @@ def test_transposed_residual_gemm_matches_normal(lib, monkeypatch, R, hp, wp):
         m, sd, cfg = build_model(2)
         outs.append(run(m, *a))
         assert torch.equal(run(m, *a), outs[-1])                             # one add per element: deterministic
-    assert rel(outs[1], outs[0]) < 2e-5                                      # same products; x + d rounded once more (reduce-add)
+    # same products; the reduce-add rounds x + d once more, and a 1-ulp change of x can flip a 16-bit rounding of LN(x)
+    assert rel(outs[1], outs[0]) < 5e-4
     if R <= 5:
         assert rel(outs[1], O.forward(cfg, sd, *a)) < V_TOL
 
