@@ -52,7 +52,12 @@ typedef struct fitv2_handle fitv2_handle;
 
 /* Weight slots.  fp32 slots hold the reference parameter unchanged; OP16 slots hold the parameter
  * converted to the handle's operand dtype.  Stacked slots are the per-block parameters concatenated
- * over blocks (leading dimension = depth).                                     reference parameter */
+ * over blocks (leading dimension = depth).
+ * The four adaLN matrices (GLOBAL_ADALN_W, LORA_A_W, LORA_B_W, FINAL_ADALN_W) are fp32 in memory but are
+ * consumed as TF32 operands by the tensor pipe (csrc/cond_tc.cuh) whenever the shapes tile (hidden_size
+ * and lora_dim multiples of 32, 6*hidden_size / 2*hidden_size / depth*lora_dim multiples of 48): bind
+ * them rounded to nearest TF32 (low 13 mantissa bits zero, as the Python packer does) - unrounded values
+ * are truncated by the hardware.  FITV2_COND=simt keeps the fp32 FMA kernels.     reference parameter */
 enum fitv2_weight {
     FITV2_W_X_EMBED_W = 0,     /* fp32 (D, 16)          x_embedder.proj.weight                        */
     FITV2_W_X_EMBED_B,         /* fp32 (D)              x_embedder.proj.bias                          */
