@@ -213,6 +213,8 @@ struct fitv2_handle {
     int bn_proj = 0, bn_fc2 = 0;
     bool proj_t = false, fc2_t = false;                  // proj / fc2 run as transposed 256-token-wide tiles (EPI_RESID_T)
     CUtensorMap map_wproj_t, map_wfc2_t;                 // the same weights with 128-row boxes (M operand of EPI_RESID_T)
+    CUtensorMap map_ao_t, map_hidden_t;                  // activations as the N operand of EPI_RESID_T: bn_resid_t / 2 token rows per box
+    int bn_resid_t = 256;                                // token rows per transposed tile (256 or 224, whichever needs fewer tensor clocks)
     CUtensorMap map_x;                                   // fp32 residual stream, 32-channel x 16-token boxes (TMA reduce-add target)
     bool qkv3 = false;                                   // QKV GEMM uses the three-head 224-wide tile (head_dim 72)
     int sched_stride_proj = 0, sched_stride_fc2 = 0;     // > 0: ragged tiling (BN-wide tiles + one narrower tail tile per row group)
@@ -613,6 +615,20 @@ int ensure_maps(fitv2_handle* h) {
             if (r != CUDA_SUCCESS) return fail(FITV2_E_CUDA, "cuTensorMapEncodeTiled(residual) failed (%d)", (int)r);
         }
         if ((rc = make_map(&h->map_wfc2_t, h->w[FITV2_W_FC2_W], c.operand_dtype, L * D, Hm, Hm, 128))) return rc;
+        {   // token-tile width: waves of (channel groups x token tiles) over the clusters times the cost of one K block
+            // (tensor pipe 2 * bn clocks, shared-memory pipe 256 + bn); 16 384 rows: 5 waves either way, 224 is 6 % cheaper
+            const long groups = ((long)((D + kGemmBM - 1) / kGemmBM) + kGemmCluster - 1) / kGemmCluster, clusters = h->num_sms / kGemmCluster;
+            long best = -1;
+            const int cand[2] = {256, 224};
+            for (int bn : cand) {
+                const long tiles = groups * (((long)M + bn - 1) / bn);
+                const long cost = ((tiles + clusters - 1) / clusters) * (2L * bn > 256L + bn ? 2L * bn : 256L + bn);
+                if (best < 0 || cost < best) { best = cost; h->bn_resid_t = bn; }
+            }
+            if (const char* e2 = getenv("FITV2_BN_RESID_T")) { const int v = atoi(e2); if (v == 256 || v == 224) h->bn_resid_t = v; }
+        }
+        if ((rc = make_map(&h->map_ao_t, h->ws + l.ao, c.operand_dtype, M, D, D, h->bn_resid_t / kGemmCluster))) return rc;
+        if ((rc = make_map(&h->map_hidden_t, h->ws + l.hidden, c.operand_dtype, M, Hm, Hm, h->bn_resid_t / kGemmCluster))) return rc;
     }
     // Conditioning linears on the tensor pipe when the shapes tile (every production config does); FITV2_COND=simt keeps the
     // fp32-FMA kernels for A/B runs.  Other shapes use the SIMT kernels.
@@ -801,7 +817,8 @@ int forward_impl(fitv2_handle* h, const float* x, int x_rows, const float* t, co
         ep.tokens = tokens; ep.x = x_res; ep.gate = modl + 2 * D; ep.gate_ld = 6 * D;
         prof_begin(h, PC_PROJ, st);
         x_kernels(true);
-        if (h->proj_t) rc = launch_gemm_t<256, EPI_RESID_T, OT, 0>(h, h->map_wproj_t, h->map_ao, D, M, D, layer * D, ep, st);
+        if (h->proj_t && h->bn_resid_t == 224) rc = launch_gemm_t<224, EPI_RESID_T, OT, 0>(h, h->map_wproj_t, h->map_ao_t, D, M, D, layer * D, ep, st);
+        else if (h->proj_t) rc = launch_gemm_t<256, EPI_RESID_T, OT, 0>(h, h->map_wproj_t, h->map_ao_t, D, M, D, layer * D, ep, st);
         else rc = launch_gemm_bn<EPI_RESID, OT>(h, h->bn_proj, h->map_ao, h->map_wproj, M, D, D, layer * D, ep, st,
                                                 h->sched_stride_proj ? (const int2*)(ws + l.sched_proj) : nullptr, h->sched_stride_proj);
         x_kernels(false);
@@ -824,7 +841,8 @@ int forward_impl(fitv2_handle* h, const float* x, int x_rows, const float* t, co
         ep.tokens = tokens; ep.x = x_res; ep.gate = modl + 5 * D; ep.gate_ld = 6 * D;
         prof_begin(h, PC_FC2, st);
         x_kernels(true);
-        if (h->fc2_t) rc = launch_gemm_t<256, EPI_RESID_T, OT, 0>(h, h->map_wfc2_t, h->map_hidden, D, M, Hm, layer * D, ep, st);
+        if (h->fc2_t && h->bn_resid_t == 224) rc = launch_gemm_t<224, EPI_RESID_T, OT, 0>(h, h->map_wfc2_t, h->map_hidden_t, D, M, Hm, layer * D, ep, st);
+        else if (h->fc2_t) rc = launch_gemm_t<256, EPI_RESID_T, OT, 0>(h, h->map_wfc2_t, h->map_hidden_t, D, M, Hm, layer * D, ep, st);
         else rc = launch_gemm_bn<EPI_RESID, OT>(h, h->bn_fc2, h->map_hidden, h->map_wfc2, M, D, Hm, layer * D, ep, st,
                                                 h->sched_stride_fc2 ? (const int2*)(ws + l.sched_fc2) : nullptr, h->sched_stride_fc2);
         x_kernels(false);
