@@ -94,6 +94,14 @@ def test_weight_packing_layout():
     assert P["LORA_A_W"].shape == (1, 288, D) and P["LORA_B_W"].shape == (1, 6 * D, 288) and P["ROPE_FREQS_H"].shape == (18,)
     m16 = FiT(**KW, **XL1, operand_dtype="fp16")
     assert m16.pack_weights(torch.device("cpu"))["FC2_W"].dtype == torch.float16
+    # the four adaLN matrices are tf32 operands of csrc/cond_tc.cuh: rounded to nearest, low 13 mantissa bits zero
+    for slot, ref in (("GLOBAL_ADALN_W", m.global_adaLN_modulation[1].weight), ("FINAL_ADALN_W", m.final_layer.adaLN_modulation[1].weight),
+                      ("LORA_A_W", m.blocks[0].adaLN_modulation[1].weight[None]), ("LORA_B_W", m.blocks[0].adaLN_modulation[2].weight[None])):
+        w = P[slot]
+        assert w.dtype == torch.float32 and w.shape == ref.shape
+        assert int((w.view(torch.int32) & 0x1FFF).abs().max()) == 0
+        assert float(((w - ref).abs() / ref.abs().clamp_min(1e-30)).max()) <= 2.0 ** -11
+    assert torch.equal(P["T_MLP2_W"], m.t_embedder.mlp[2].weight)            # everything else stays fp32-exact
 
 
 def test_library_exports_every_declared_symbol(built_lib):
