@@ -254,7 +254,7 @@ def run_ours(args):
         hout.copy_(dz, non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()                          # the host consumes the result every step
         hz.copy_(hout)
-    e2e_steps = max(3, min(args.steps, args.e2e_steps))
+    e2e_steps = max(3, min(args.steps, args.e2e_steps or args.steps))
     for i in range(2):
         e2e_step(i)
     barrier()
@@ -316,7 +316,7 @@ def main():
     ap.add_argument("--batch", type=int, default=32, help="samples per GPU (the script's --per-proc-batch-size)")
     ap.add_argument("--operand", default="bf16", choices=["bf16", "fp16"])
     ap.add_argument("--cuda-graph", action="store_true")
-    ap.add_argument("--e2e-steps", type=int, default=20)
+    ap.add_argument("--e2e-steps", type=int, default=0, help="timed steps of the end-to-end leg (0 = as many as --steps, the same power/thermal regime)")
     ap.add_argument("--cpu-budget", type=float, default=120.0, help="seconds of CPU work allowed for the CPU legs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -48,7 +48,7 @@ class FiT(nn.Module):
         unsupported = []
         if not use_sit: unsupported.append("use_sit=False (FiTv1 (B,C,N) layout)")
         if learn_sigma: unsupported.append("learn_sigma=True")
-        if not use_swiglu or use_swiglu_large: unsupported.append("use_swiglu must be True and use_swiglu_large False")
+        if not use_swiglu: unsupported.append("use_swiglu must be True")
         if adaln_type != "lora" or not adaln_lora_dim: unsupported.append("adaln_type must be 'lora' with adaln_lora_dim")
         if (rel_pos_embed or "").lower() != "rope": unsupported.append("rel_pos_embed must be 'rope'")
         if norm_type != "layernorm": unsupported.append("norm_type must be 'layernorm'")
@@ -76,7 +76,9 @@ class FiT(nn.Module):
         self.adaln_type, self.adaln_lora_dim = adaln_type, adaln_lora_dim
         self.online_rope, self.time_shifting, self.save_attention = online_rope, time_shifting, False
         self.head_dim = hidden_size // num_heads
-        self.mlp_hidden = (int(hidden_size * mlp_ratio) * 2) // 3          # modules.py:246,250
+        self.use_swiglu_large = bool(use_swiglu_large)
+        self.mlp_hidden = int(hidden_size * mlp_ratio) if use_swiglu_large else (int(hidden_size * mlp_ratio) * 2) // 3   # modules.py:246-251
+        if self.mlp_hidden % 128: raise NotImplementedError(f"fitv2_b200.FiT: SwiGLU hidden {self.mlp_hidden} must be a multiple of 128")
         self.operand_dtype = operand_dtype
         self.rope_args = dict(head_dim=self.head_dim, custom_freqs=custom_freqs, theta=rope_theta,
                               max_pe_len_h=max_pe_len_h, max_pe_len_w=max_pe_len_w, decouple=decouple,

@@ -68,6 +68,7 @@ class FiTConfig:
     time_shifting: int = 1
     max_cached_len: int = 256  # rope.py:126
     online_rope: bool = False  # fit_model.py:57,212-214: per-sample frequencies from `size`
+    use_swiglu_large: bool = False  # modules.py:248-249: SwiGLU hidden = int(hidden*mlp_ratio) instead of 2/3 of it
 
     @property
     def head_dim(self) -> int:
@@ -75,8 +76,9 @@ class FiTConfig:
 
     @property
     def mlp_hidden(self) -> int:
-        # modules.py:246,250 : (int(hidden*mlp_ratio) * 2) // 3
-        return (int(self.hidden_size * self.mlp_ratio) * 2) // 3
+        # modules.py:246-251 : (int(hidden*mlp_ratio) * 2) // 3, or the full int(hidden*mlp_ratio) with swiglu_large
+        full = int(self.hidden_size * self.mlp_ratio)
+        return full if self.use_swiglu_large else (full * 2) // 3
 
     @property
     def token_channels(self) -> int:

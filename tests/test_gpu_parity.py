@@ -262,6 +262,18 @@ def test_forward_other_widths_and_operands(lib, width, operand):
     assert rel(run(m, *a), O.forward(cfg, sd, *a)) < (2e-3 if operand == "fp16" else V_TOL)
 
 
+def test_forward_swiglu_large_golden(lib, golden_dir):
+    """use_swiglu_large=True (modules.py:248-249, SwiGLU hidden 4608) against the REAL reference's depth-1 forward."""
+    fx = torch.load(os.path.join(golden_dir, "swiglu_large_xl_d1.pt"))
+    m, sd, cfg = build_model(1, use_swiglu_large=True)
+    R = fx["x"].shape[0]
+    a = (fx["x"], fx["t"], fx["y"], make_grid(R, fx["hp"], fx["wp"]), torch.ones(R, fx["hp"] * fx["wp"]))
+    out = run(m, *a)
+    assert rel(out, fx["v_ref"]) < V_TOL and rel(out, O.forward(cfg, sd, *a)) < V_TOL
+    big = inputs(40, 16, 16, seed=9)                                         # several token tiles per cluster, K = 4608 main loop
+    assert rel(run(m, *big), O.forward(cfg, sd, *big)) < V_TOL
+
+
 def test_xl_config1_full_depth_and_sampler(lib, golden_dir):
     """BASELINE.json configs[0]: XL/2 depth 36, CFG Euler steps at batch 2 against the REAL reference's outputs."""
     fx = torch.load(os.path.join(golden_dir, "xl_config1.pt"))

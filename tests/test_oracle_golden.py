@@ -161,3 +161,21 @@ def test_online_rope_forward_golden(golden_dir):
             sh, sw = (s[:, 0], s[:, 1]) if dec else (torch.max(s[:, 0], s[:, 1]),) * 2
             assert torch.equal(fh, O.rope_1d_freqs_online(cf, 10000.0, 36, sh, 16).float())
             assert torch.equal(fw, O.rope_1d_freqs_online(cf, 10000.0, 36, sw, 16).float())
+
+
+def test_swiglu_large_golden(golden_dir):
+    """use_swiglu_large=True (modules.py:248-249: SwiGLU hidden int(D*mlp_ratio) = 4608): the oracle replays the REAL
+    reference's depth-1 forward (oracle/make_swiglu_large_golden.py); fitv2_b200.FiT draws the same weights."""
+    from fitv2_b200 import FiT, make_grid
+    fx = torch.load(os.path.join(golden_dir, "swiglu_large_xl_d1.pt"))
+    cfg = O.FiTConfig(depth=1, use_swiglu_large=True)
+    assert cfg.mlp_hidden == 4608 and O.FiTConfig(depth=1).mlp_hidden == 3072
+    torch.manual_seed(fx["init_seed"])
+    m = FiT(learn_sigma=False, use_sit=True, use_swiglu=True, use_swiglu_large=True, q_norm="layernorm", k_norm="layernorm",
+            adaln_type="lora", depth=1, hidden_size=1152, num_heads=16, adaln_lora_dim=288).randomize_zero_init_(fx["redraw_seed"])
+    sd = m.state_dict()
+    assert m.mlp_hidden == 4608 and sd["blocks.0.mlp.fc2.weight"].shape == (1152, 4608)
+    assert float(sd["blocks.0.mlp.fc1_g.weight"].double().abs().sum()) == pytest.approx(fx["fc1_g_abs_sum"], rel=1e-12)
+    R = fx["x"].shape[0]
+    out = O.forward(cfg, sd, fx["x"], fx["t"], fx["y"], make_grid(R, fx["hp"], fx["wp"]), torch.ones(R, fx["hp"] * fx["wp"]))
+    assert rel(out, fx["v_ref"]) < TOL
