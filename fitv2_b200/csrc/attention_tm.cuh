@@ -57,7 +57,7 @@ attention_tm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                     const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_kt,
                     const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_o,
                     const float* __restrict__ seg, const int* __restrict__ seg_uniform,
-                    int heads, int tokens, int num_items, float scale_log2e, float bound_log2e)
+                    int heads, int tokens, int num_items, float scale_log2e, float bound_log2e, int early)
 {
     using C = AttnTmCfg<DH>;
     extern __shared__ uint8_t smem_raw[];
@@ -239,6 +239,53 @@ attention_tm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
             }
         };
         fetch_meta(blockIdx.x);
+        uint32_t v[32];
+        // One 64-key sub-tile of the softmax: S(k) out of TMEM buffer n_s % 2, P(k) back into its first 32 columns, hand-over to
+        // the issuer.  Returns this thread's partial row sum.
+        auto do_sub = [&](int j, bool uniform, float my_seg) -> float {
+            const int kv0 = j * 64;
+            const int kv_valid = min(64, tokens - kv0);                 // may be <= 0 for the second half of a tail tile
+            const int mode = (uniform && kv_valid == 64) ? 0 : (uniform ? 1 : 2);
+            const uint32_t b = n_s & 1;
+            mbar_wait(&s_full[x * 2 + b], (n_s >> 1) & 1);
+            tc_fence_after();
+            tmem_ld32(t_x + b * 64 + half * 32, v);
+            tmem_ld_wait();
+            uint32_t packed[16];
+            float lsum = 0.f;
+            auto soft32 = [&](auto mode_c) {
+                constexpr int kMode = decltype(mode_c)::value;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    float p0 = fast_exp2(fmaf(__uint_as_float(v[2 * i]), scale_log2e, -bound_log2e));
+                    float p1 = fast_exp2(fmaf(__uint_as_float(v[2 * i + 1]), scale_log2e, -bound_log2e));
+                    if constexpr (kMode != 0) {
+                        const int col = half * 32 + 2 * i;
+                        bool ok0 = col < kv_valid, ok1 = col + 1 < kv_valid;
+                        if constexpr (kMode == 2) {
+                            ok0 = ok0 && seg_s[kv0 + col] == my_seg;
+                            ok1 = ok1 && seg_s[kv0 + col + 1] == my_seg;
+                        }
+                        p0 = ok0 ? p0 : 0.f;
+                        p1 = ok1 ? p1 : 0.f;
+                    }
+                    packed[i] = Op16<OT>::pack(p0, p1);
+                    lsum += p0 + p1;
+                }
+            };
+            if (mode == 0) soft32(std::integral_constant<int, 0>{});
+            else if (mode == 1) soft32(std::integral_constant<int, 1>{});
+            else soft32(std::integral_constant<int, 2>{});
+            tmem_st16(t_x + b * 64 + half * 32, packed);                // P(k) over the first 16 of this thread's own 32 S columns
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&p_full[x * 2 + b]);
+            ++n_s;
+            return lsum;
+        };
+        bool early_done = false;                                        // sub-tile 0 of this item was already processed ...
+        float l_early = 0.f;                                            // ... with this partial row sum
         for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
             const bool uniform = uni_nx != 0;
             const float my_seg = seg_nx;
@@ -252,59 +299,19 @@ attention_tm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                 for (int i = tid_wg; i < seg_pad; i += 256) seg_s[i] = i < tokens ? __ldg(segb + i) : 0.f;
                 named_bar_sync(1 + x, 256);
             }
-            float l_run = 0.f;
-            uint32_t v[32];
-            bool have = false;                                          // v already holds (a load in flight for) the next S sub-tile
-            for (int j = 0; j < sub_tiles; ++j, ++n_s) {
-                const int kv0 = j * 64;
-                const int kv_valid = min(64, tokens - kv0);             // may be <= 0 for the second half of a tail tile
-                const int mode = (uniform && kv_valid == 64) ? 0 : (uniform ? 1 : 2);
-                const uint32_t b = n_s & 1;
-                if (!have) {
-                    mbar_wait(&s_full[x * 2 + b], (n_s >> 1) & 1);
-                    tc_fence_after();
-                    tmem_ld32(t_x + b * 64 + half * 32, v);
+            float l_run = early_done ? l_early : 0.f;
+            for (int j = early_done ? 1 : 0; j < sub_tiles; ++j) l_run += do_sub(j, uniform, my_seg);
+            early_done = false;
+            // The last P V of the item has only just been issued: instead of waiting for it (17 % of the warp samples sat in
+            // the o_full wait below), the first sub-tile of the NEXT item -- its S was issued two sub-tiles ago -- is done now.
+            // The issuer's first P V of that item still waits for o_free, i.e. for the O read of the epilogue below.  Only when
+            // the next item needs no segment table (a staged table would be overwritten under the slower warps of this item).
+            {
+                const int nxt = item + gridDim.x;
+                if (early && nxt < num_items && uni_nx != 0) {
+                    const int bh_n = nxt / q_pairs;
+                    if (2 * (nxt - bh_n * q_pairs) + x < q_tiles) { l_early = do_sub(0, true, seg_nx); early_done = true; }
                 }
-                tmem_ld_wait();
-                uint32_t packed[16];
-                float lsum = 0.f;
-                auto soft32 = [&](auto mode_c) {
-                    constexpr int kMode = decltype(mode_c)::value;
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        float p0 = fast_exp2(fmaf(__uint_as_float(v[2 * i]), scale_log2e, -bound_log2e));
-                        float p1 = fast_exp2(fmaf(__uint_as_float(v[2 * i + 1]), scale_log2e, -bound_log2e));
-                        if constexpr (kMode != 0) {
-                            const int col = half * 32 + 2 * i;
-                            bool ok0 = col < kv_valid, ok1 = col + 1 < kv_valid;
-                            if constexpr (kMode == 2) {
-                                ok0 = ok0 && seg_s[kv0 + col] == my_seg;
-                                ok1 = ok1 && seg_s[kv0 + col + 1] == my_seg;
-                            }
-                            p0 = ok0 ? p0 : 0.f;
-                            p1 = ok1 ? p1 : 0.f;
-                        }
-                        packed[i] = Op16<OT>::pack(p0, p1);
-                        lsum += p0 + p1;
-                    }
-                };
-                if (mode == 0) soft32(std::integral_constant<int, 0>{});
-                else if (mode == 1) soft32(std::integral_constant<int, 1>{});
-                else soft32(std::integral_constant<int, 2>{});
-                l_run += lsum;
-#ifdef FITV2_ATTN_TM_PREFETCH
-                have = j + 1 < sub_tiles;                               // S runs two sub-tiles ahead: the next one is normally complete;
-#endif
-                if (have) {                                             // its TMEM load flies while P is stored and handed over
-                    mbar_wait(&s_full[x * 2 + (b ^ 1)], ((n_s + 1) >> 1) & 1);
-                    tc_fence_after();
-                    tmem_ld32(t_x + (b ^ 1) * 64 + half * 32, v);
-                }
-                tmem_st16(t_x + b * 64 + half * 32, packed);            // P(k) over the first 16 of this thread's own 32 S columns
-                tmem_st_wait();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&p_full[x * 2 + b]);
             }
 
             // ---- epilogue ----
