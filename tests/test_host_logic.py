@@ -166,3 +166,22 @@ def test_init_from_ckpt_rules(tmp_path):
     assert sorted(missing) == ["final_layer.linear.bias", "final_layer.linear.weight"] and unexpected == ["extra_buffer"]
     assert torch.equal(m3.final_layer.linear.weight, before)
     assert torch.equal(m3.x_embedder.proj.weight, sd["x_embedder.proj.weight"])
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours): one JSON line on the same metric / unit, with
+    `impl`, `cpu_baseline` and a zero-copy `e2e`, no GPU needed."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                          "--cpu-budget", "10"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "images/sec" and line["higher_is_better"] is True
+    assert line["metric"].startswith("images/sec FiTv2-XL/2 256^2 250-step ODE CFG 1.5")
+    assert line["value"] > 0 and line["n_gpus"] == 1 and line["vs_baseline"] is None and line["gpu_launches"] == 0
+    cb = line["cpu_baseline"]
+    assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["value"] == line["value"] and cb["sample"]
+    assert line["e2e"] == dict(value=line["value"], unit="images/sec", h2d_bytes_per_step=0, d2h_bytes_per_step=0)
