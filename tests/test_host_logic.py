@@ -185,3 +185,15 @@ def test_bench_reference_arm_contract():
     cb = line["cpu_baseline"]
     assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["value"] == line["value"] and cb["sample"]
     assert line["e2e"] == dict(value=line["value"], unit="images/sec", h2d_bytes_per_step=0, d2h_bytes_per_step=0)
+
+
+def test_missing_extension_fails_loudly():
+    """No CPU / PyTorch fallback: with the shared object absent the loader raises (it never routes around the CUDA path)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("from fitv2_b200 import _lib\n"
+            "try:\n    _lib.load()\nexcept _lib.FitV2Error as e:\n    print('LOUD', 'no CPU or PyTorch fallback' in str(e))\n")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd=root,
+                         env={**os.environ, "FITV2_B200_LIB": "/nonexistent/libfitv2_b200.so"})
+    assert out.returncode == 0 and out.stdout.strip().endswith("LOUD True"), out.stdout + out.stderr[-1000:]
