@@ -20,9 +20,49 @@ WEIGHT_SLOTS = [
     "FINAL_ADALN_W", "FINAL_ADALN_B", "FINAL_LINEAR_W", "FINAL_LINEAR_B",
     "QKV_W", "QKV_B", "PROJ_W", "PROJ_B", "GATEUP_W", "GATEUP_B", "FC2_W", "FC2_B",
     "ROPE_FREQS_H", "ROPE_FREQS_W",
+    "NORMAL_ADALN_W", "NORMAL_ADALN_B", "NORM1_W", "NORM2_W", "NORM_FINAL_W", "Q_NORM_W", "K_NORM_W",
 ]
 SLOT = {n: i for i, n in enumerate(WEIGHT_SLOTS)}
 OP16_SLOTS = {"QKV_W", "PROJ_W", "GATEUP_W", "FC2_W"}
+
+NORM_NONE, NORM_LAYERNORM, NORM_WLAYERNORM, NORM_RMSNORM = 0, 1, 2, 3       # FITV2_NORM_*
+ADALN_LORA, ADALN_NORMAL = 0, 1                                             # FITV2_ADALN_*
+
+
+def norm_code(name, weight: bool = False) -> int:
+    """fit/model/norms.py:35-50 (create_norm) names -> FITV2_NORM_*; ``weight`` is the ``qk_norm_weight`` promotion of
+    modules.py:141-144 ('layernorm' -> 'w_layernorm')."""
+    if name is None or name == "" or str(name).lower() == "none":
+        return NORM_NONE
+    name = str(name).lower()
+    if name == "layernorm":
+        return NORM_WLAYERNORM if weight else NORM_LAYERNORM
+    if name == "w_layernorm":
+        return NORM_WLAYERNORM
+    if name in ("rmsnorm", "w_rmsnorm"):
+        return NORM_RMSNORM
+    raise NotImplementedError(f"Unknown norm_type: '{name}'")
+
+
+# fitv2_set_option names <- FITV2_* environment variables (read when a handle is created, so tests / A/B tools can still use
+# the environment; the library itself never calls getenv)
+_ENV_OPTIONS = {
+    "FITV2_PDL": ("pdl", int), "FITV2_ATTN": ("attn", lambda v: {"tm": 1, "ws": 2, "general": 3, "v1": 3}.get(v, 0)),
+    "FITV2_ATTN_EARLY": ("attn_early", int), "FITV2_ATTN_POLY": ("attn_poly", int), "FITV2_LN_THREADS": ("ln_threads", int),
+    "FITV2_LN_WIDE_SINGLE": ("ln_wide_single", int), "FITV2_BN_RESID": ("bn_resid", int), "FITV2_QKV": ("qkv_heads", int),
+    "FITV2_RESID_T": ("resid_t", int), "FITV2_BN_RESID_T": ("bn_resid_t", int),
+    "FITV2_COND": ("cond", lambda v: 1 if v == "simt" else 0), "FITV2_L2_PERSIST_MB": ("l2_persist_mb", int),
+    "FITV2_FINAL_TC": ("final_tc", int), "FITV2_VERBOSE": ("verbose", int),
+}
+
+
+def apply_env_options(handle):
+    lib = load()
+    for env, (name, conv) in _ENV_OPTIONS.items():
+        v = os.environ.get(env)
+        if v is not None and v != "":
+            check(lib.fitv2_set_option(handle, name.encode(), int(conv(v))), f"fitv2_set_option({name})")
+
 
 PROFILE_CLASSES = ["conditioning", "ln_modulate", "qkv_gemm", "attention", "proj_gemm", "gateup_gemm", "fc2_gemm", "embed_final"]
 
@@ -36,7 +76,16 @@ class FitV2Config(C.Structure):
         ("mlp_hidden", C.c_int32), ("lora_dim", C.c_int32), ("token_channels", C.c_int32),
         ("num_embeddings", C.c_int32), ("operand_dtype", C.c_int32), ("time_shifting", C.c_float),
         ("rope_magnitude", C.c_float),
+        ("out_channels", C.c_int32), ("adaln_type", C.c_int32), ("block_norm", C.c_int32), ("q_norm", C.c_int32),
+        ("k_norm", C.c_int32), ("channels_first", C.c_int32),
     ]
+
+    def __init__(self, *a, **kw):
+        # FiTv2 defaults for the variant fields (so that positional 11-field constructions keep meaning FiTv2)
+        full = dict(out_channels=0, adaln_type=ADALN_LORA, block_norm=NORM_LAYERNORM, q_norm=NORM_LAYERNORM,
+                    k_norm=NORM_LAYERNORM, channels_first=0)
+        full.update(kw)
+        super().__init__(*a, **full)
 
 
 class FitV2Error(RuntimeError):
@@ -63,6 +112,9 @@ def load():
     lib.fitv2_destroy.argtypes = [vp]
     lib.fitv2_destroy.restype = None
     lib.fitv2_bind_weight.argtypes = [vp, i32, vp, i64]
+    lib.fitv2_set_option.argtypes = [vp, C.c_char_p, i64]
+    lib.fitv2_poll_error.argtypes = [vp]
+    lib.fitv2_rk_stage.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i64, vp]
     lib.fitv2_set_online_rope.argtypes = [vp, vp, vp, i32]
     lib.fitv2_workspace_bytes.argtypes = [vp, i32, i32]
     lib.fitv2_workspace_bytes.restype = i64
@@ -97,6 +149,7 @@ def check(rc: int, what: str = ""):
 EXPORTED_SYMBOLS = [
     "fitv2_last_error", "fitv2_version", "fitv2_create", "fitv2_destroy", "fitv2_bind_weight",
     "fitv2_set_online_rope", "fitv2_workspace_bytes", "fitv2_set_workspace", "fitv2_forward", "fitv2_cfg_combine", "fitv2_cfg_euler",
+    "fitv2_set_option", "fitv2_poll_error", "fitv2_rk_stage",
     "fitv2_sde_step", "fitv2_sde_drift", "fitv2_scaled_add", "fitv2_heun_combine", "fitv2_tweedie", "fitv2_unpatchify_scale", "fitv2_pack_uint8",
     "fitv2_debug_gemm", "fitv2_debug_attention", "fitv2_debug_tap", "fitv2_kernel_launches",
     "fitv2_profile_set", "fitv2_profile_read",

@@ -4,7 +4,7 @@
 #include "../../include/fitv2_b200.h"
 #include "common.cuh"
 #include "gemm_tc.cuh"
-#include "attention.cuh"
+#include "attention_general.cuh"
 #include "attention_ws.cuh"
 #include "attention_tm.cuh"
 #include "pointwise.cuh"
@@ -15,6 +15,7 @@
 #include <cstring>
 #include <cstdlib>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 using namespace fitv2;
@@ -24,20 +25,14 @@ namespace {
 // scratch for the split-K partial sums of the conditioning linears
 constexpr size_t kCondPartialBytes = 24u << 20;
 
-// per-GEMM tile schedule table (clusters x items int2), see build_schedule
-constexpr size_t kSchedBytes = 64u << 10;
-
 // Thread-block cluster size of the production GEMMs (weight-tile TMA multicast across the cluster).
 constexpr int kGemmCluster = 2;
 
 thread_local std::string g_last_error;
 
-// Programmatic dependent launch for every kernel of the chain (see pdl_wait() in common.cuh); FITV2_PDL=0 turns it off
-// for A/B measurements.
-bool pdl_enabled() {
-    static const bool on = [] { const char* e = getenv("FITV2_PDL"); return !(e && e[0] == '0'); }();
-    return on;
-}
+// Programmatic dependent launch for every kernel of the chain (see pdl_wait() in common.cuh).  Per handle (option "pdl");
+// the handle-less elementwise entry points always use it.
+thread_local bool g_pdl = true;
 
 // L2 residency window of the fp32 residual stream (set per forward): kernels launched while it is active carry an
 // access-policy window that marks `hit_ratio` of its lines persisting in L2 and everything else streaming, so that the
@@ -69,7 +64,7 @@ cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
         attr[n].val.clusterDim.x = cluster; attr[n].val.clusterDim.y = 1; attr[n].val.clusterDim.z = 1;
         ++n;
     }
-    if (pdl_enabled()) {
+    if (g_pdl) {
         attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[n].val.programmaticStreamSerializationAllowed = 1;
         ++n;
@@ -188,7 +183,7 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct Layout {
     int rows = 0, tokens = 0, tokens_v = 0;
-    size_t x_res, h, ao, q, k, vt, hidden, te, t0, c, sc, sc_split, lmid, lmid_split, gmod, mod, fmod, rope_cos, rope_sin, seg_uniform, cpart, sched_proj, sched_fc2, total;
+    size_t x_res, h, ao, q, k, vt, hidden, te, t0, c, sc, sc_split, lmid, lmid_split, gmod, mod, fmod, rope_cos, rope_sin, seg_uniform, cpart, xt, ot, wfin16, total;
 };
 
 }  // namespace
@@ -196,8 +191,35 @@ struct Layout {
 enum { PC_COND = 0, PC_LNMOD, PC_QKV, PC_ATTN, PC_PROJ, PC_GATEUP, PC_FC2, PC_MISC, PC_COUNT };
 struct ProfEvt { cudaEvent_t a, b; int cls; };
 
+// Per-handle tuning switches (fitv2_set_option).  They used to be FITV2_* environment variables latched in function-local
+// statics; now every handle carries its own copy and the Python layer forwards the environment at handle creation.
+struct Options {
+    int pdl = 1;                 // programmatic dependent launch on every kernel of the chain
+    int attn = 0;                // 0 auto, 1 attention_tm, 2 attention_ws, 3 attention_general (online max)
+    int attn_early = 1;          // attention_tm: softmax of the next item's first sub-tile ahead of the current epilogue
+    int attn_poly = -1;          // exp2 evaluated on the FMA pipe for this many of every 8 column pairs (-1 = kernel default)
+    int ln_threads = 64;         // threads per CTA of the LayerNorm + modulate kernel (one row per warp)
+    int ln_wide_single = 0;      // hidden 2304: one warp per row instead of a warp pair
+    int bn_resid = 0;            // tile width of the proj / fc2 GEMMs in the normal orientation (0 = cost model)
+    int qkv_heads = 3;           // heads per QKV tile at head_dim 72 (3 -> 224-wide tile, 2 -> 144)
+    int resid_t = -1;            // transposed residual GEMM + TMA reduce-add: -1 auto (fc2 only), 0 off, 1 proj and fc2
+    int bn_resid_t = 0;          // token rows per transposed tile (0 = cost model, 224, 256)
+    int cond = 0;                // conditioning linears: 0 tensor pipe (tf32) where the shapes tile, 1 fp32 FMA kernels
+    int l2_persist_mb = 0;       // persisting-L2 window on the fp32 residual stream (0 = off)
+    int final_tc = 1;            // final layer: 1 = LayerNorm+modulate kernel + skinny tcgen05 GEMM, 0 = fused fp32 SIMT kernel
+    int verbose = 0;
+};
+
+struct AttnMaps {                // TMA descriptors of one attention launch, cached per (pointers, rows, tokens)
+    const void *q = nullptr, *k = nullptr, *vt = nullptr, *out = nullptr;
+    int rows = 0, tokens = 0;
+    CUtensorMap mq, mqt, mk, mkt, mv, mo;
+};
+
 struct fitv2_handle {
     fitv2_config cfg;
+    Options opt;
+    int device = 0;
     const void* w[FITV2_W_COUNT];
     int64_t w_numel[FITV2_W_COUNT];
     uint8_t* ws = nullptr;
@@ -209,7 +231,7 @@ struct fitv2_handle {
     // conditioning on the tensor pipe (cond_tc.cuh): fp32 / tf32 maps of the split activations and of the adaLN weights
     bool cond_tc = false;
     int cond_bn_up = 0;
-    CUtensorMap map_sc_split, map_lmid_split, map_wglobal, map_wfinal, map_wlora_a, map_wlora_b;
+    CUtensorMap map_sc_split, map_lmid_split, map_wglobal, map_wfinal, map_wlora_a, map_wlora_b, map_wnormal;
     int bn_proj = 0, bn_fc2 = 0;
     bool proj_t = false, fc2_t = false;                  // proj / fc2 run as transposed 256-token-wide tiles (EPI_RESID_T)
     CUtensorMap map_wproj_t, map_wfc2_t;                 // the same weights with 128-row boxes (M operand of EPI_RESID_T)
@@ -217,14 +239,22 @@ struct fitv2_handle {
     int bn_resid_t = 256;                                // token rows per transposed tile (256 or 224, whichever needs fewer tensor clocks)
     CUtensorMap map_x;                                   // fp32 residual stream, 32-channel x 16-token boxes (TMA reduce-add target)
     bool qkv3 = false;                                   // QKV GEMM uses the three-head 224-wide tile (head_dim 72)
-    int sched_stride_proj = 0, sched_stride_fc2 = 0;     // > 0: ragged tiling (BN-wide tiles + one narrower tail tile per row group)
-    std::vector<int2> sched_host;
+    bool qkv_gen = false;                                // q / k norm other than affine-free LayerNorm: EPI_QKV_GEN + attention_general
+    bool final_tc = false;                               // final linear on the tensor pipe (16-bit copy of the weight in the workspace)
+    CUtensorMap map_hfinal, map_wfinal_lin;
+    AttnMaps attn_maps;
     int num_sms = 148;
     const float* online_fh = nullptr;                    // per-row RoPE frequencies (rows, head_dim/4), online_rope mode
     const float* online_fw = nullptr;
     int online_rows = 0;
     int64_t l2_persist_bytes = 0, l2_window_max = 0;     // persisting-L2 carve-out used for the residual stream (0 = off)
     int64_t launches = 0;
+    // kernels whose MaxDynamicSharedMemorySize attribute has been raised ON THIS HANDLE'S DEVICE (function attributes are per
+    // device; a process-wide latch skipped the call on a second GPU)
+    std::unordered_map<const void*, int> smem_configured;
+    // sticky device-side error word in pinned, mapped host memory (bit 0: class label outside the embedding table)
+    int* err_host = nullptr;
+    int* err_dev = nullptr;
     // optional per-kernel-class CUDA-event timing (fitv2_profile_*)
     uint32_t prof_mask = 0;
     std::vector<ProfEvt> prof_pool;
@@ -234,8 +264,13 @@ struct fitv2_handle {
 
 namespace {
 
+int out_channels(const fitv2_config& c) { return c.out_channels > 0 ? c.out_channels : c.token_channels; }
+bool norm_has_weight(int mode) { return mode == FITV2_NORM_WLAYERNORM || mode == FITV2_NORM_RMSNORM; }
+
+// Element count of a weight slot for this configuration; 0 = the slot is not used (and need not be bound).
 int64_t expected_numel(const fitv2_config& c, int slot) {
-    const int64_t D = c.hidden_size, L = c.depth, Hm = c.mlp_hidden, lora = c.lora_dim, C = c.token_channels;
+    const int64_t D = c.hidden_size, L = c.depth, Hm = c.mlp_hidden, lora = c.lora_dim, C = c.token_channels, Co = out_channels(c);
+    const bool lora_mode = c.adaln_type == FITV2_ADALN_LORA;
     switch (slot) {
         case FITV2_W_X_EMBED_W: return D * C;
         case FITV2_W_X_EMBED_B: return D;
@@ -244,16 +279,16 @@ int64_t expected_numel(const fitv2_config& c, int slot) {
         case FITV2_W_T_MLP2_W: return D * D;
         case FITV2_W_T_MLP2_B: return D;
         case FITV2_W_Y_TABLE: return (int64_t)c.num_embeddings * D;
-        case FITV2_W_GLOBAL_ADALN_W: return 6 * D * D;
-        case FITV2_W_GLOBAL_ADALN_B: return 6 * D;
-        case FITV2_W_LORA_A_W: return L * lora * D;
-        case FITV2_W_LORA_A_B: return L * lora;
-        case FITV2_W_LORA_B_W: return L * 6 * D * lora;
-        case FITV2_W_LORA_B_B: return L * 6 * D;
+        case FITV2_W_GLOBAL_ADALN_W: return lora_mode ? 6 * D * D : 0;
+        case FITV2_W_GLOBAL_ADALN_B: return lora_mode ? 6 * D : 0;
+        case FITV2_W_LORA_A_W: return lora_mode ? L * lora * D : 0;
+        case FITV2_W_LORA_A_B: return lora_mode ? L * lora : 0;
+        case FITV2_W_LORA_B_W: return lora_mode ? L * 6 * D * lora : 0;
+        case FITV2_W_LORA_B_B: return lora_mode ? L * 6 * D : 0;
         case FITV2_W_FINAL_ADALN_W: return 2 * D * D;
         case FITV2_W_FINAL_ADALN_B: return 2 * D;
-        case FITV2_W_FINAL_LINEAR_W: return C * D;
-        case FITV2_W_FINAL_LINEAR_B: return C;
+        case FITV2_W_FINAL_LINEAR_W: return Co * D;
+        case FITV2_W_FINAL_LINEAR_B: return Co;
         case FITV2_W_QKV_W: return L * 3 * D * D;
         case FITV2_W_QKV_B: return L * 3 * D;
         case FITV2_W_PROJ_W: return L * D * D;
@@ -264,6 +299,13 @@ int64_t expected_numel(const fitv2_config& c, int slot) {
         case FITV2_W_FC2_B: return L * D;
         case FITV2_W_ROPE_FREQS_H: return c.head_dim / 4;
         case FITV2_W_ROPE_FREQS_W: return c.head_dim / 4;
+        case FITV2_W_NORMAL_ADALN_W: return lora_mode ? 0 : L * 6 * D * D;
+        case FITV2_W_NORMAL_ADALN_B: return lora_mode ? 0 : L * 6 * D;
+        case FITV2_W_NORM1_W: return norm_has_weight(c.block_norm) ? L * D : 0;
+        case FITV2_W_NORM2_W: return norm_has_weight(c.block_norm) ? L * D : 0;
+        case FITV2_W_NORM_FINAL_W: return norm_has_weight(c.block_norm) ? D : 0;
+        case FITV2_W_Q_NORM_W: return norm_has_weight(c.q_norm) ? L * c.head_dim : 0;
+        case FITV2_W_K_NORM_W: return norm_has_weight(c.k_norm) ? L * c.head_dim : 0;
     }
     return -1;
 }
@@ -272,6 +314,7 @@ Layout make_layout(const fitv2_config& c, int rows, int tokens) {
     Layout l;
     l.rows = rows; l.tokens = tokens; l.tokens_v = (tokens + 7) / 8 * 8;
     const size_t M = (size_t)rows * tokens, D = c.hidden_size, Hm = c.mlp_hidden, L = c.depth;
+    const size_t lora = c.adaln_type == FITV2_ADALN_LORA ? c.lora_dim : 0;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 1024); return o; };
     l.x_res = take(M * D * 4);
@@ -285,11 +328,11 @@ Layout make_layout(const fitv2_config& c, int rows, int tokens) {
     l.t0 = take((size_t)rows * D * 4);
     l.c = take((size_t)rows * D * 4);
     l.sc = take((size_t)rows * D * 4);
-    l.lmid = take((size_t)rows * L * c.lora_dim * 4);
+    l.lmid = take((size_t)rows * L * lora * 4);
     // hi / lo stacked tf32 operands of the tensor-pipe conditioning linears (cond_tc.cuh): 128 rows per 64 logical rows
     const size_t split_rows = (size_t)((rows + kCondRows - 1) / kCondRows) * 128;
     l.sc_split = take(split_rows * D * 4);
-    l.lmid_split = take(split_rows * L * c.lora_dim * 4);
+    l.lmid_split = take(split_rows * L * lora * 4);
     l.gmod = take((size_t)rows * 6 * D * 4);
     l.mod = take(L * (size_t)rows * 6 * D * 4);
     l.fmod = take((size_t)rows * 2 * D * 4);
@@ -297,8 +340,10 @@ Layout make_layout(const fitv2_config& c, int rows, int tokens) {
     l.rope_sin = take(M * (c.head_dim / 2) * 4);
     l.seg_uniform = take((size_t)rows * 4);
     l.cpart = take(kCondPartialBytes);
-    l.sched_proj = take(kSchedBytes);
-    l.sched_fc2 = take(kSchedBytes);
+    // channels-first callers (use_sit = False: (B, C, N) tensors): token-major copies of the input / output
+    l.xt = take(c.channels_first ? M * c.token_channels * 4 : 0);
+    l.ot = take(c.channels_first ? M * out_channels(c) * 4 : 0);
+    l.wfin16 = take((size_t)out_channels(c) * D * 2);                   // fp16 copy of final_layer.linear.weight (tensor-pipe final layer)
     l.total = off;
     return l;
 }
@@ -318,34 +363,33 @@ inline void prof_end(fitv2_handle* h, cudaStream_t st) {
     h->prof_open = -1;
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device function attribute: remember per handle (= per device) what was set.
+template <typename K>
+int ensure_smem(fitv2_handle* h, K kern, int bytes) {
+    int& have = h->smem_configured[reinterpret_cast<const void*>(kern)];
+    if (have < bytes) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        have = bytes;
+    }
+    return FITV2_OK;
+}
+
 template <int BN, int EPI, typename OT, int DH, int CL = kGemmCluster>
 int launch_gemm_t(fitv2_handle* h, const CUtensorMap& ma, const CUtensorMap& mb, int M, int N, int K, int b_row_off,
-                  const GemmEpi& ep, cudaStream_t st, const int2* sched = nullptr, int sched_stride = 0) {
+                  const GemmEpi& ep, cudaStream_t st) {
     using Cfg = GemmCfg<BN, EPI, DH, CL>;
     auto kern = gemm_tc_kernel<BN, EPI, OT, DH, CL>;
-    static bool configured = false;
-    if (!configured) {
-        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-        configured = true;
-    }
+    int rc = ensure_smem(h, kern, Cfg::kSmemBytes);
+    if (rc) return rc;
     constexpr int TN = Cfg::kTileN;
-    if (EPI == EPI_RESID_T) {                         // N = token rows: the tail tile is zero-filled / clipped
-        const int m_tiles_t = (M + kGemmBM - 1) / kGemmBM;
-        const int groups_t = ((m_tiles_t + CL - 1) / CL) * ((N + TN - 1) / TN);
-        const int max_clusters_t = h->num_sms / CL;
-        const int grid_t = (groups_t < max_clusters_t ? groups_t : max_clusters_t) * CL;
-        CUDA_TRY(launch_k(kern, dim3(grid_t), dim3(Cfg::kThreads), Cfg::kSmemBytes, st, CL, ma, mb, h->map_x, M, N, K, b_row_off, ep, sched, sched_stride));
-        CUDA_TRY(cudaGetLastError());
-        h->launches++;
-        return FITV2_OK;
-    }
-    if (N % TN != 0 && !(sched && EPI == EPI_RESID && (N % BN) % 32 == 0))
+    // EPI_RESID_T: N = token rows, the tail tile is zero-filled / clipped; every other epilogue needs whole tiles
+    if (EPI != EPI_RESID_T && N % TN != 0)
         return fail(FITV2_E_INVALID, "GEMM N=%d is not a multiple of the tile width %d", N, TN);
     const int m_tiles = (M + kGemmBM - 1) / kGemmBM;
     const int groups = ((m_tiles + CL - 1) / CL) * ((N + TN - 1) / TN);
     const int max_clusters = h->num_sms / CL;
     const int grid = (groups < max_clusters ? groups : max_clusters) * CL;
-    CUDA_TRY(launch_k(kern, dim3(grid), dim3(Cfg::kThreads), Cfg::kSmemBytes, st, CL, ma, mb, h->map_x, M, N, K, b_row_off, ep, sched, sched_stride));
+    CUDA_TRY(launch_k(kern, dim3(grid), dim3(Cfg::kThreads), Cfg::kSmemBytes, st, CL, ma, mb, h->map_x, M, N, K, b_row_off, ep));
     CUDA_TRY(cudaGetLastError());
     h->launches++;
     return FITV2_OK;
@@ -353,57 +397,21 @@ int launch_gemm_t(fitv2_handle* h, const CUtensorMap& ma, const CUtensorMap& mb,
 
 template <int EPI, typename OT, int CL = kGemmCluster>
 int launch_gemm_bn(fitv2_handle* h, int bn, const CUtensorMap& ma, const CUtensorMap& mb, int M, int N, int K,
-                   int b_row_off, const GemmEpi& ep, cudaStream_t st, const int2* sched = nullptr, int sched_stride = 0) {
+                   int b_row_off, const GemmEpi& ep, cudaStream_t st) {
     switch (bn) {
-        case 128: return launch_gemm_t<128, EPI, OT, 0, CL>(h, ma, mb, M, N, K, b_row_off, ep, st, sched, sched_stride);
-        case 144: return launch_gemm_t<144, EPI, OT, 0, CL>(h, ma, mb, M, N, K, b_row_off, ep, st, sched, sched_stride);
-        case 192: return launch_gemm_t<192, EPI, OT, 0, CL>(h, ma, mb, M, N, K, b_row_off, ep, st, sched, sched_stride);
-        case 256: return launch_gemm_t<256, EPI, OT, 0, CL>(h, ma, mb, M, N, K, b_row_off, ep, st, sched, sched_stride);
+        case 128: return launch_gemm_t<128, EPI, OT, 0, CL>(h, ma, mb, M, N, K, b_row_off, ep, st);
+        case 144: return launch_gemm_t<144, EPI, OT, 0, CL>(h, ma, mb, M, N, K, b_row_off, ep, st);
+        case 192: return launch_gemm_t<192, EPI, OT, 0, CL>(h, ma, mb, M, N, K, b_row_off, ep, st);
+        case 256: return launch_gemm_t<256, EPI, OT, 0, CL>(h, ma, mb, M, N, K, b_row_off, ep, st);
     }
     return fail(FITV2_E_INVALID, "unsupported GEMM tile width %d", bn);
 }
 
-// Cost of one 64-deep K block of a (128 rows per CTA) x bn tile in SM clocks: the tensor pipe needs 2*bn, the shared
-// memory pipe (TMA writes + UMMA operand reads share 128 B/clk) needs (16384 + 64*bn) * 2 / 128 = 256 + bn: tiles
-// narrower than 256 columns are shared-memory bound (measured: 72 % tensor-pipe ceiling at bn = 144).
-long tile_cost(int bn) { return (2L * bn > 256L + bn ? 2L * bn : 256L + bn) + 24; }
-
-// LPT schedule of (row-tile group, column tile) items over `clusters` persistent clusters: full bn-wide tiles in
-// n-fastest order first, then one narrower tail tile per row group.  Returns the makespan in tile_cost units and,
-// when `out` is given, the per-cluster item lists (stride entries each, terminated by {-1, 0}).
-long build_schedule(int M, int N, int bn, int clusters, std::vector<int2>* out, int* stride_out) {
-    const int m_tiles = (M + kGemmBM - 1) / kGemmBM;
-    const int m_groups = (m_tiles + kGemmCluster - 1) / kGemmCluster;
-    const int n_full = N / bn, tail = N % bn;
-    std::vector<long> load(clusters, 0);
-    std::vector<std::vector<int2>> items(clusters);
-    auto place = [&](int mg, int n0, int width) {
-        int best = 0;
-        for (int c = 1; c < clusters; ++c) if (load[c] < load[best]) best = c;
-        load[best] += tile_cost(width);
-        items[best].push_back(make_int2(mg, n0 | (width << 20)));
-    };
-    for (int mg = 0; mg < m_groups; ++mg)
-        for (int n = 0; n < n_full; ++n) place(mg, n * bn, bn);
-    if (tail)
-        for (int mg = 0; mg < m_groups; ++mg) place(mg, n_full * bn, tail);
-    long makespan = 0;
-    size_t longest = 0;
-    for (int c = 0; c < clusters; ++c) { if (load[c] > makespan) makespan = load[c]; if (items[c].size() > longest) longest = items[c].size(); }
-    if (out) {
-        const int stride = (int)longest + 2;                            // terminator + one readable entry for the lookahead
-        out->assign((size_t)clusters * stride, make_int2(-1, 0));
-        for (int c = 0; c < clusters; ++c)
-            for (size_t i = 0; i < items[c].size(); ++i) (*out)[(size_t)c * stride + i] = items[c][i];
-        *stride_out = stride;
-    }
-    return makespan;
-}
-
 // Tile width for the N = hidden_size projections among the uniform widths that divide N: minimise (waves x per-tile cost).
-// Measured (profiles/README.md): these two GEMMs are bound by their fp32 read-modify-write residual epilogue, not by the
-// main loop, so the wider, better-scheduling ragged 256 + tail tiling (build_schedule; FITV2_RAGGED=1) is SLOWER for them
-// (proj 66 -> 100 us, fc2 111 -> 121 us) although it lifts the shared-memory ceiling of the main loop from 72 % to 100 %.
+// Cost of one 64-deep K block of a (128 rows per CTA) x bn tile in SM clocks: the tensor pipe needs 2*bn, the shared memory
+// pipe (TMA writes + UMMA operand reads share 128 B/clk) needs (16384 + 64*bn) * 2 / 128 = 256 + bn, so tiles narrower than
+// 256 columns are shared-memory bound (measured: 72 % tensor-pipe ceiling at bn = 144).  A ragged 256 + tail tiling was
+// measured slower for these two GEMMs (they are bound by the residual epilogue, profiles/README.md) and has been removed.
 int pick_bn(int M, int N, int num_sms, bool prefer_aligned) {
     const int cands[4] = {256, 192, 144, 128};
     int best = 0; long best_cost = 0;
@@ -425,107 +433,121 @@ int launch_attention(fitv2_handle* h, const void* q, const void* k, const void* 
                      float* dbg_s = nullptr, float* dbg_o = nullptr) {
     const fitv2_config& c = h->cfg;
     const float scale_log2e = (1.0f / sqrtf((float)c.head_dim)) * 1.4426950408889634f;
-    // logit bound from the affine-free QK-LayerNorm (see attention.cuh): |q.k|/sqrt(dh) <= mag^2 * sqrt(dh); 2% margin.
+    // logit bound from the affine-free QK-LayerNorm (attention_ws.cuh): |q.k|/sqrt(dh) <= mag^2 * sqrt(dh); 2% margin.
     // fp16 operands: shift by 8 binades so that P stays in the normal fp16 range (cancels in O / l).
     const float bound_log2e = c.rope_magnitude * c.rope_magnitude * sqrtf((float)c.head_dim) * 1.02f * 1.4426950408889634f -
                               (c.operand_dtype == FITV2_OPERAND_FP16 ? 8.0f : 0.0f);
-    const int num_items = ((tokens + 127) / 128) * c.num_heads * rows;          // (query tile, head, sample) work items
-    const int grid = num_items < 2 * h->num_sms ? num_items : 2 * h->num_sms;     // persistent: two CTAs per SM
-    // TMA maps over Q / K (dh, tokens, rows*heads) and V^T (tokens_v, dh, rows*heads); out-of-bounds = zero fill
-    const uint64_t DHu = c.head_dim, BH = (uint64_t)rows * c.num_heads;
-    const int dhp = (c.head_dim + 15) / 16 * 16, tail = dhp - 64;
-    CUtensorMap mq, mqt, mk, mkt, mv;
-    int rc;
-    if ((rc = make_map3(&mq, q, c.operand_dtype, DHu, tokens, BH, DHu * 2, (uint64_t)tokens * DHu * 2, 64, 128, 128))) return rc;
-    if ((rc = make_map3(&mqt, q, c.operand_dtype, DHu, tokens, BH, DHu * 2, (uint64_t)tokens * DHu * 2, tail, 128, tail * 2))) return rc;
-    if ((rc = make_map3(&mk, k, c.operand_dtype, DHu, tokens, BH, DHu * 2, (uint64_t)tokens * DHu * 2, 64, 128, 128))) return rc;
-    if ((rc = make_map3(&mkt, k, c.operand_dtype, DHu, tokens, BH, DHu * 2, (uint64_t)tokens * DHu * 2, tail, 128, tail * 2))) return rc;
-    // V^T rows are tokens_v (a multiple of 8) long in memory, but only `tokens` keys exist: the map ends at `tokens`, so the pad
-    // columns (never written by the QKV epilogue) are zero-filled by TMA instead of read (0 * NaN garbage = NaN in P V)
-    if ((rc = make_map3(&mv, vt, c.operand_dtype, tokens, DHu, BH, (uint64_t)tokens_v * 2, DHu * tokens_v * 2, 64, dhp, 128))) return rc;
-    // production kernel: warp-specialised pipeline (attention_ws.cuh); the sequential kernel of attention.cuh serves the
-    // debug taps and FITV2_ATTN=v1 A/B runs
-    static const bool use_v1 = [] { const char* e = getenv("FITV2_ATTN"); return e && !strcmp(e, "v1"); }();
-    // P-in-TMEM variant (attention_tm.cuh): faster up to 256 tokens (42.2 vs 46.2 us alone, 55.5 vs 60 us in-step at 256; 21.3 vs
-    // 23.4 at 128), slower beyond (512: 138 vs 127; 1024: 503 vs 405), head_dim 72 only.  FITV2_ATTN=tm / ws forces one of them.
-    static const int tm_mode = [] { const char* e = getenv("FITV2_ATTN"); return !e ? 0 : (!strcmp(e, "tm") ? 1 : (!strcmp(e, "ws") ? -1 : 0)); }();
-    const bool use_tm = tm_mode > 0 || (tm_mode == 0 && tokens <= 256);
-    if (!use_v1 && !dbg_s && !dbg_o) {
-        const int q_pairs = ((tokens + 127) / 128 + 1) / 2;
-        const int items = q_pairs * c.num_heads * rows;
-        const int g = items < h->num_sms ? items : h->num_sms;
-        CUtensorMap mo;
-        if ((rc = make_map_attn_out(&mo, out, c.operand_dtype, DHu, c.num_heads, tokens, rows))) return rc;
-        if (use_tm && c.head_dim == 72) {                          // experiment: P kept in tensor memory (attention_tm.cuh)
-            using A = AttnTmCfg<72>;
-            auto kern = attention_tm_kernel<OT, 72>;
-            const int smem = A::smem_bytes(tokens);
-            if (smem > kSmemBudget) return fail(FITV2_E_INVALID, "tokens %d: attention shared memory %d exceeds %d", tokens, smem, kSmemBudget);
-            static int configured = 0;
-            if (configured < smem) { CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); configured = smem; }
-            // softmax of the next work item's first sub-tile ahead of the epilogue of the current one: 43.9 -> 40.8 us alone,
-            // 57.7 -> 53.2 us in-step at 256 tokens (A/B on one box); FITV2_ATTN_EARLY=0 restores the plain order
-            static const int early = [] { const char* e = getenv("FITV2_ATTN_EARLY"); return (e && e[0] == '0') ? 0 : 1; }();
-            CUDA_TRY(launch_k(kern, dim3(g), dim3(A::kThreads), smem, st, 1, mq, mqt, mk, mkt, mv, mo, seg, seg_uniform,
-                              c.num_heads, tokens, items, scale_log2e, bound_log2e, early));
-        } else if (c.head_dim == 72) {
-            using A = AttnWsCfg<72>;
-            auto kern = attention_ws_kernel<OT, 72>;
-            const int smem = A::smem_bytes(tokens);
-            if (smem > kSmemBudget) return fail(FITV2_E_INVALID, "tokens %d: attention shared memory %d exceeds %d", tokens, smem, kSmemBudget);
-            static int configured = 0;
-            if (configured < smem) { CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); configured = smem; }
-            CUDA_TRY(launch_k(kern, dim3(g), dim3(A::kThreads), smem, st, 1, mq, mqt, mk, mkt, mv, mo, seg, seg_uniform,
-                              c.num_heads, tokens, items, scale_log2e, bound_log2e));
+    // TMA maps over Q / K (dh, tokens, rows*heads), V^T (tokens_v, dh, rows*heads) and the output; out-of-bounds = zero fill.
+    // Encoded once per (buffers, rows, tokens): a forward launches this `depth` times with the same workspace buffers.
+    AttnMaps& am = h->attn_maps;
+    if (am.q != q || am.k != k || am.vt != vt || am.out != out || am.rows != rows || am.tokens != tokens) {
+        const uint64_t DHu = c.head_dim, BH = (uint64_t)rows * c.num_heads;
+        const int dhp = (c.head_dim + 15) / 16 * 16, tail = dhp - 64;
+        int rc;
+        am.q = nullptr;
+        if ((rc = make_map3(&am.mq, q, c.operand_dtype, DHu, tokens, BH, DHu * 2, (uint64_t)tokens * DHu * 2, 64, 128, 128))) return rc;
+        if ((rc = make_map3(&am.mqt, q, c.operand_dtype, DHu, tokens, BH, DHu * 2, (uint64_t)tokens * DHu * 2, tail, 128, tail * 2))) return rc;
+        if ((rc = make_map3(&am.mk, k, c.operand_dtype, DHu, tokens, BH, DHu * 2, (uint64_t)tokens * DHu * 2, 64, 128, 128))) return rc;
+        if ((rc = make_map3(&am.mkt, k, c.operand_dtype, DHu, tokens, BH, DHu * 2, (uint64_t)tokens * DHu * 2, tail, 128, tail * 2))) return rc;
+        // V^T rows are tokens_v (a multiple of 8) long in memory, but only `tokens` keys exist: the map ends at `tokens`, so the pad
+        // columns (never written by the QKV epilogue) are zero-filled by TMA instead of read (0 * NaN garbage = NaN in P V)
+        if ((rc = make_map3(&am.mv, vt, c.operand_dtype, tokens, DHu, BH, (uint64_t)tokens_v * 2, DHu * tokens_v * 2, 64, dhp, 128))) return rc;
+        if ((rc = make_map_attn_out(&am.mo, out, c.operand_dtype, DHu, c.num_heads, tokens, rows))) return rc;
+        am.q = q; am.k = k; am.vt = vt; am.out = out; am.rows = rows; am.tokens = tokens;
+    }
+    // Kernel choice.  Affine-free QK-LayerNorm (the FiTv2 family): bound-based softmax, P in tensor memory up to 256 tokens at
+    // head_dim 72 (attention_tm.cuh), the shared-memory-P pipeline beyond (attention_ws.cuh).  Any other q / k norm has
+    // unbounded logits: online-max kernel (attention_general.cuh), which also serves the debug taps.
+    const bool bounded = c.q_norm == FITV2_NORM_LAYERNORM && c.k_norm == FITV2_NORM_LAYERNORM;
+    int mode = h->opt.attn;
+    if (!bounded || dbg_s || dbg_o) mode = 3;
+    if (mode == 0) mode = (tokens <= 256 && c.head_dim == 72) ? 1 : 2;
+    if (mode == 1 && c.head_dim != 72) mode = 2;
+    if (mode == 3) {
+        const int num_items = ((tokens + 127) / 128) * c.num_heads * rows;      // (query tile, head, sample) work items
+        const int grid = num_items < h->num_sms ? num_items : h->num_sms;
+        int rc;
+        if (c.head_dim == 72) {
+            auto kern = attention_general_kernel<OT, 72>;
+            if ((rc = ensure_smem(h, kern, AttnGenCfg<72>::kSmemBytes))) return rc;
+            CUDA_TRY(launch_k(kern, grid, dim3(AttnGenCfg<72>::kThreads), AttnGenCfg<72>::kSmemBytes, st, 1, am.mq, am.mqt, am.mk, am.mkt, am.mv,
+                              seg, seg_uniform, (OT*)out, c.num_heads, tokens, num_items, scale_log2e, dbg_s, dbg_o));
         } else {
-            using A = AttnWsCfg<96>;
-            auto kern = attention_ws_kernel<OT, 96>;
-            const int smem = A::smem_bytes(tokens);
-            if (smem > kSmemBudget) return fail(FITV2_E_INVALID, "tokens %d: attention shared memory %d exceeds %d", tokens, smem, kSmemBudget);
-            static int configured = 0;
-            if (configured < smem) { CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); configured = smem; }
-            CUDA_TRY(launch_k(kern, dim3(g), dim3(A::kThreads), smem, st, 1, mq, mqt, mk, mkt, mv, mo, seg, seg_uniform,
-                              c.num_heads, tokens, items, scale_log2e, bound_log2e));
+            auto kern = attention_general_kernel<OT, 96>;
+            if ((rc = ensure_smem(h, kern, AttnGenCfg<96>::kSmemBytes))) return rc;
+            CUDA_TRY(launch_k(kern, grid, dim3(AttnGenCfg<96>::kThreads), AttnGenCfg<96>::kSmemBytes, st, 1, am.mq, am.mqt, am.mk, am.mkt, am.mv,
+                              seg, seg_uniform, (OT*)out, c.num_heads, tokens, num_items, scale_log2e, dbg_s, dbg_o));
         }
+        CUDA_TRY(cudaGetLastError());
         h->launches++;
         return FITV2_OK;
     }
-    if (c.head_dim == 72) {
-        auto kern = attention_kernel<OT, 72>;
-        static bool configured = false;
-        if (!configured) { CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<72>::kSmemBytes)); configured = true; }
-        CUDA_TRY(launch_k(kern, grid, dim3(AttnCfg<72>::kThreads), AttnCfg<72>::kSmemBytes, st, 1, mq, mqt, mk, mkt, mv, seg, seg_uniform, (OT*)out,
-                                                        c.num_heads, tokens, num_items, scale_log2e, bound_log2e, dbg_s, dbg_o));
-    } else if (c.head_dim == 96) {
-        auto kern = attention_kernel<OT, 96>;
-        static bool configured = false;
-        if (!configured) { CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<96>::kSmemBytes)); configured = true; }
-        CUDA_TRY(launch_k(kern, grid, dim3(AttnCfg<96>::kThreads), AttnCfg<96>::kSmemBytes, st, 1, mq, mqt, mk, mkt, mv, seg, seg_uniform, (OT*)out,
-                                                        c.num_heads, tokens, num_items, scale_log2e, bound_log2e, dbg_s, dbg_o));
+    const int q_pairs = ((tokens + 127) / 128 + 1) / 2;
+    const int items = q_pairs * c.num_heads * rows;
+    const int g = items < h->num_sms ? items : h->num_sms;
+    int rc;
+    if (mode == 1) {
+        using A = AttnTmCfg<72>;
+        auto kern = attention_tm_kernel<OT, 72>;
+        const int smem = A::smem_bytes(tokens);
+        if (smem > kSmemBudget) return fail(FITV2_E_INVALID, "tokens %d: attention shared memory %d exceeds %d", tokens, smem, kSmemBudget);
+        if ((rc = ensure_smem(h, kern, smem))) return rc;
+        // softmax of the next work item's first sub-tile ahead of the epilogue of the current one: 43.9 -> 40.8 us alone,
+        // 57.7 -> 53.2 us in-step at 256 tokens (A/B on one box); option attn_early = 0 restores the plain order
+        CUDA_TRY(launch_k(kern, dim3(g), dim3(A::kThreads), smem, st, 1, am.mq, am.mqt, am.mk, am.mkt, am.mv, am.mo, seg, seg_uniform,
+                          c.num_heads, tokens, items, scale_log2e, bound_log2e, h->opt.attn_early));
+    } else if (c.head_dim == 72) {
+        using A = AttnWsCfg<72>;
+        auto kern = attention_ws_kernel<OT, 72>;
+        const int smem = A::smem_bytes(tokens);
+        if (smem > kSmemBudget) return fail(FITV2_E_INVALID, "tokens %d: attention shared memory %d exceeds %d", tokens, smem, kSmemBudget);
+        if ((rc = ensure_smem(h, kern, smem))) return rc;
+        CUDA_TRY(launch_k(kern, dim3(g), dim3(A::kThreads), smem, st, 1, am.mq, am.mqt, am.mk, am.mkt, am.mv, am.mo, seg, seg_uniform,
+                          c.num_heads, tokens, items, scale_log2e, bound_log2e));
     } else {
-        return fail(FITV2_E_INVALID, "head_dim %d not supported (72 or 96)", c.head_dim);
+        using A = AttnWsCfg<96>;
+        auto kern = attention_ws_kernel<OT, 96>;
+        const int smem = A::smem_bytes(tokens);
+        if (smem > kSmemBudget) return fail(FITV2_E_INVALID, "tokens %d: attention shared memory %d exceeds %d", tokens, smem, kSmemBudget);
+        if ((rc = ensure_smem(h, kern, smem))) return rc;
+        CUDA_TRY(launch_k(kern, dim3(g), dim3(A::kThreads), smem, st, 1, am.mq, am.mqt, am.mk, am.mkt, am.mv, am.mo, seg, seg_uniform,
+                          c.num_heads, tokens, items, scale_log2e, bound_log2e));
     }
     CUDA_TRY(cudaGetLastError());
     h->launches++;
     return FITV2_OK;
 }
 
+// LayerNorm / RMSNorm (+ weight) + adaLN modulate -> 16-bit operand.  norm_mode: FITV2_NORM_* of the block norms.
 template <typename OT>
 int launch_ln_modulate(fitv2_handle* h, const float* x, const float* shift, const float* scale, int mod_ld, void* out,
-                       int M, int D, int tokens, cudaStream_t st) {
+                       int M, int D, int tokens, cudaStream_t st, int norm_mode = FITV2_NORM_LAYERNORM, const float* norm_w = nullptr) {
     const int nv = (D / 4 + 31) / 32;
     // two rows per CTA: measured 25.8 us per launch against 26.2 (4 rows) and 28.0 (8 rows) - shorter tail, finer CTA refill
-    static const int ln_threads = [] { const char* e = getenv("FITV2_LN_THREADS"); const int v = e ? atoi(e) : 64; return (v == 32 || v == 64 || v == 128 || v == 256) ? v : 64; }();
+    const int lt = h->opt.ln_threads;
+    const int ln_threads = (lt == 32 || lt == 64 || lt == 128 || lt == 256) ? lt : 64;
     const int blocks = (M * 32 + ln_threads - 1) / ln_threads;
-    if (nv <= 1) CUDA_TRY(launch_k(ln_modulate_kernel<OT, 1>, dim3(blocks), dim3(ln_threads), 0, st, 1, x, shift, scale, mod_ld, (OT*)out, M, D, tokens));
-    else if (nv <= 3) CUDA_TRY(launch_k(ln_modulate_kernel<OT, 3>, dim3(blocks), dim3(ln_threads), 0, st, 1, x, shift, scale, mod_ld, (OT*)out, M, D, tokens));
-    else if (nv <= 9) CUDA_TRY(launch_k(ln_modulate_kernel<OT, 9>, dim3(blocks), dim3(ln_threads), 0, st, 1, x, shift, scale, mod_ld, (OT*)out, M, D, tokens));
-    else if (nv <= 18) {                                             // wide rows: one row per warp pair (4 rows per CTA)
-        static const bool single = [] { const char* e = getenv("FITV2_LN_WIDE_SINGLE"); return e && e[0] == '1'; }();
-        if (single) CUDA_TRY(launch_k(ln_modulate_kernel<OT, 18>, dim3(blocks), dim3(ln_threads), 0, st, 1, x, shift, scale, mod_ld, (OT*)out, M, D, tokens));
+    if (nv > 18) return fail(FITV2_E_INVALID, "hidden_size %d too large for the LayerNorm kernel", D);
+    if (norm_mode != FITV2_NORM_LAYERNORM) {
+        if (norm_mode == FITV2_NORM_NONE) return fail(FITV2_E_INVALID, "block norm 'none' is not supported");
+        if (!norm_w) return fail(FITV2_E_UNBOUND, "block norm weight is not bound");
+#define FITV2_LN_W(NV_)                                                                                                                           \
+        do {                                                                                                                                      \
+            if (norm_mode == FITV2_NORM_WLAYERNORM)                                                                                               \
+                CUDA_TRY(launch_k(ln_modulate_kernel<OT, NV_, 1>, dim3(blocks), dim3(ln_threads), 0, st, 1, x, shift, scale, mod_ld, (OT*)out, M, D, tokens, norm_w)); \
+            else                                                                                                                                  \
+                CUDA_TRY(launch_k(ln_modulate_kernel<OT, NV_, 2>, dim3(blocks), dim3(ln_threads), 0, st, 1, x, shift, scale, mod_ld, (OT*)out, M, D, tokens, norm_w)); \
+        } while (0)
+        if (nv <= 9) FITV2_LN_W(9); else FITV2_LN_W(18);
+#undef FITV2_LN_W
+    }
+    else if (nv <= 1) CUDA_TRY(launch_k(ln_modulate_kernel<OT, 1>, dim3(blocks), dim3(ln_threads), 0, st, 1, x, shift, scale, mod_ld, (OT*)out, M, D, tokens, norm_w));
+    else if (nv <= 3) CUDA_TRY(launch_k(ln_modulate_kernel<OT, 3>, dim3(blocks), dim3(ln_threads), 0, st, 1, x, shift, scale, mod_ld, (OT*)out, M, D, tokens, norm_w));
+    else if (nv <= 9) CUDA_TRY(launch_k(ln_modulate_kernel<OT, 9>, dim3(blocks), dim3(ln_threads), 0, st, 1, x, shift, scale, mod_ld, (OT*)out, M, D, tokens, norm_w));
+    else {                                                           // wide rows: one row per warp pair (4 rows per CTA)
+        if (h->opt.ln_wide_single) CUDA_TRY(launch_k(ln_modulate_kernel<OT, 18>, dim3(blocks), dim3(ln_threads), 0, st, 1, x, shift, scale, mod_ld, (OT*)out, M, D, tokens, norm_w));
         else CUDA_TRY(launch_k(ln_modulate_pair_kernel<OT, 9>, dim3((M + 3) / 4), dim3(256), 0, st, 1, x, shift, scale, mod_ld, (OT*)out, M, D, tokens));
     }
-    else return fail(FITV2_E_INVALID, "hidden_size %d too large for the LayerNorm kernel", D);
     CUDA_TRY(cudaGetLastError());
     h->launches++;
     return FITV2_OK;
@@ -559,9 +581,11 @@ int launch_small_linear(fitv2_handle* h, SmallLinear p, int batches, cudaStream_
 int ensure_maps(fitv2_handle* h) {
     if (h->maps_valid) return FITV2_OK;
     const fitv2_config& c = h->cfg;
+    const Options& o = h->opt;
     const Layout& l = h->lay;
     const uint64_t M = (uint64_t)l.rows * l.tokens, D = c.hidden_size, Hm = c.mlp_hidden, L = c.depth;
     int rc;
+    h->attn_maps = AttnMaps();
     if ((rc = make_map(&h->map_h, h->ws + l.h, c.operand_dtype, M, D, D, 128))) return rc;
     if ((rc = make_map(&h->map_ao, h->ws + l.ao, c.operand_dtype, M, D, D, 128))) return rc;
     if ((rc = make_map(&h->map_hidden, h->ws + l.hidden, c.operand_dtype, M, Hm, Hm, 128))) return rc;
@@ -569,28 +593,13 @@ int ensure_maps(fitv2_handle* h) {
     // fc2 (K = mlp_hidden) has the longer main loop: pure wave / tile-size cost.
     h->bn_proj = pick_bn((int)M, (int)D, h->num_sms, /*prefer_aligned=*/true);
     h->bn_fc2 = pick_bn((int)M, (int)D, h->num_sms, /*prefer_aligned=*/false);
-    if (const char* e = getenv("FITV2_BN_RESID")) {             // tuning experiments only
-        const int v = atoi(e);
-        if ((v == 128 || v == 144 || v == 192 || v == 256) && D % v == 0) h->bn_proj = h->bn_fc2 = v;
-    }
+    if ((o.bn_resid == 128 || o.bn_resid == 144 || o.bn_resid == 192 || o.bn_resid == 256) && D % o.bn_resid == 0)
+        h->bn_proj = h->bn_fc2 = o.bn_resid;                        // tuning experiments only
     if (!h->bn_proj || !h->bn_fc2) return fail(FITV2_E_INVALID, "hidden_size %d has no supported tile width (multiple of 128/144/192/256)", (int)D);
-    h->sched_stride_proj = h->sched_stride_fc2 = 0;
-    if (const char* e = getenv("FITV2_RAGGED")) {               // tuning experiments only: 256-wide tiles + tail tile, LPT schedule
-        if (atoi(e) == 1 && D % 256 != 0 && (D % 256) % 32 == 0 && D > 256) {
-            int stride = 0;
-            build_schedule((int)M, (int)D, 256, h->num_sms / kGemmCluster, &h->sched_host, &stride);
-            if (h->sched_host.size() * sizeof(int2) > kSchedBytes) return fail(FITV2_E_WORKSPACE, "tile schedule does not fit its workspace slot");
-            CUDA_TRY(cudaMemcpy(h->ws + l.sched_proj, h->sched_host.data(), h->sched_host.size() * sizeof(int2), cudaMemcpyHostToDevice));
-            CUDA_TRY(cudaMemcpy(h->ws + l.sched_fc2, h->sched_host.data(), h->sched_host.size() * sizeof(int2), cudaMemcpyHostToDevice));
-            h->bn_proj = h->bn_fc2 = 256;
-            h->sched_stride_proj = h->sched_stride_fc2 = stride;
-        }
-    }
-    // head_dim 72: three heads per 224-wide tile when the 3 * heads head slots group by three (FITV2_QKV=2 keeps the two-head tile)
-    {
-        const char* e = getenv("FITV2_QKV");
-        h->qkv3 = c.head_dim == 72 && (3 * c.num_heads) % 3 == 0 && !(e && e[0] == '2');
-    }
+    // q / k norm other than the affine-free LayerNorm of the FiTv2 configs: generic epilogue (two-head tile) + online-max attention
+    h->qkv_gen = !(c.q_norm == FITV2_NORM_LAYERNORM && c.k_norm == FITV2_NORM_LAYERNORM);
+    // head_dim 72: three heads per 224-wide tile (option qkv_heads = 2 keeps the two-head 144-wide tile)
+    h->qkv3 = c.head_dim == 72 && o.qkv_heads != 2 && !h->qkv_gen;
     if ((rc = make_map(&h->map_wqkv, h->w[FITV2_W_QKV_W], c.operand_dtype, L * 3 * D, D, D,
                        (h->qkv3 ? 3 * c.head_dim + 8 : 2 * c.head_dim) / kGemmCluster))) return rc;
     if ((rc = make_map(&h->map_wproj, h->w[FITV2_W_PROJ_W], c.operand_dtype, L * D, D, D, h->bn_proj / kGemmCluster))) return rc;
@@ -600,11 +609,9 @@ int ensure_maps(fitv2_handle* h) {
         // Transposed residual GEMM (EPI_RESID_T): 256-token-wide tiles + TMA reduce-add into x.  Measured at XL/2 (hidden 1152,
         // five 256-channel groups, the last half empty): fc2 116 -> 110 us, proj 61 -> 63 us (proj is bound by the DRAM traffic of
         // the residual either way), so only fc2 uses it, and only where the normal orientation has no 256-wide tile.
-        // FITV2_RESID_T=0 / 1 forces it off / on for both.
-        const char* e = getenv("FITV2_RESID_T");
-        const bool ragged = h->sched_stride_proj != 0;
-        h->fc2_t = !ragged && (e ? e[0] == '1' : h->bn_fc2 < 256);
-        h->proj_t = !ragged && e && e[0] == '1';
+        // Option resid_t = 0 / 1 forces it off / on for both.
+        h->fc2_t = o.resid_t < 0 ? h->bn_fc2 < 256 : o.resid_t == 1;
+        h->proj_t = o.resid_t == 1;
         if ((rc = make_map(&h->map_wproj_t, h->w[FITV2_W_PROJ_W], c.operand_dtype, L * D, D, D, 128))) return rc;
         {
             EncodeTiledFn fn = get_encode_fn();
@@ -628,27 +635,40 @@ int ensure_maps(fitv2_handle* h) {
                 const long cost = ((tiles + clusters - 1) / clusters) * (2L * bn > 256L + bn ? 2L * bn : 256L + bn);
                 if (best < 0 || cost < best) { best = cost; h->bn_resid_t = bn; }
             }
-            if (const char* e2 = getenv("FITV2_BN_RESID_T")) { const int v = atoi(e2); if (v == 256 || v == 224) h->bn_resid_t = v; }
+            if (o.bn_resid_t == 256 || o.bn_resid_t == 224) h->bn_resid_t = o.bn_resid_t;
         }
         if ((rc = make_map(&h->map_ao_t, h->ws + l.ao, c.operand_dtype, M, D, D, h->bn_resid_t / kGemmCluster))) return rc;
         if ((rc = make_map(&h->map_hidden_t, h->ws + l.hidden, c.operand_dtype, M, Hm, Hm, h->bn_resid_t / kGemmCluster))) return rc;
     }
-    // Conditioning linears on the tensor pipe when the shapes tile (every production config does); FITV2_COND=simt keeps the
+    // Conditioning linears on the tensor pipe when the shapes tile (every production config does); option cond = 1 keeps the
     // fp32-FMA kernels for A/B runs.  Other shapes use the SIMT kernels.
     {
-        const uint64_t lora = c.lora_dim, split_rows = (uint64_t)((l.rows + kCondRows - 1) / kCondRows) * 128;
-        const char* e = getenv("FITV2_COND");
-        h->cond_tc = !(e && !strcmp(e, "simt")) && D % 32 == 0 && lora % 32 == 0 && (6 * D) % 48 == 0 && (2 * D) % 48 == 0 &&
-                     (L * lora) % 48 == 0;
+        const bool lora_mode = c.adaln_type == FITV2_ADALN_LORA;
+        const uint64_t lora = lora_mode ? c.lora_dim : 0, split_rows = (uint64_t)((l.rows + kCondRows - 1) / kCondRows) * 128;
+        h->cond_tc = o.cond == 0 && D % 32 == 0 && (6 * D) % 48 == 0 && (2 * D) % 48 == 0 &&
+                     (!lora_mode || (lora % 32 == 0 && (L * lora) % 48 == 0));
         if (h->cond_tc) {
             h->cond_bn_up = (6 * D) % 128 == 0 ? 128 : 48;
             if ((rc = make_map_f32(&h->map_sc_split, h->ws + l.sc_split, split_rows, D, D, 128))) return rc;
-            if ((rc = make_map_f32(&h->map_lmid_split, h->ws + l.lmid_split, split_rows, L * lora, L * lora, 128))) return rc;
-            if ((rc = make_map_f32(&h->map_wglobal, h->w[FITV2_W_GLOBAL_ADALN_W], 6 * D, D, D, 48))) return rc;
             if ((rc = make_map_f32(&h->map_wfinal, h->w[FITV2_W_FINAL_ADALN_W], 2 * D, D, D, 48))) return rc;
-            if ((rc = make_map_f32(&h->map_wlora_a, h->w[FITV2_W_LORA_A_W], L * lora, D, D, 48))) return rc;
-            if ((rc = make_map_f32(&h->map_wlora_b, h->w[FITV2_W_LORA_B_W], L * 6 * D, lora, lora, h->cond_bn_up))) return rc;
+            if (lora_mode) {
+                if ((rc = make_map_f32(&h->map_lmid_split, h->ws + l.lmid_split, split_rows, L * lora, L * lora, 128))) return rc;
+                if ((rc = make_map_f32(&h->map_wglobal, h->w[FITV2_W_GLOBAL_ADALN_W], 6 * D, D, D, 48))) return rc;
+                if ((rc = make_map_f32(&h->map_wlora_a, h->w[FITV2_W_LORA_A_W], L * lora, D, D, 48))) return rc;
+                if ((rc = make_map_f32(&h->map_wlora_b, h->w[FITV2_W_LORA_B_W], L * 6 * D, lora, lora, h->cond_bn_up))) return rc;
+            } else {
+                if ((rc = make_map_f32(&h->map_wnormal, h->w[FITV2_W_NORMAL_ADALN_W], L * 6 * D, D, D, h->cond_bn_up))) return rc;
+            }
         }
+    }
+    // Final layer on the tensor pipe: LayerNorm + modulate kernel -> fp16 operand, skinny tcgen05 GEMM (N = 16 / 32) with the
+    // fp16 copy of final_layer.linear.weight; fp16 (10-bit mantissa) rather than the handle's operand type because this
+    // product IS the output.  Option final_tc = 0 keeps the fused fp32 SIMT kernel.
+    h->final_tc = o.final_tc != 0;
+    if (h->final_tc) {
+        const uint64_t Co = out_channels(c);
+        if ((rc = make_map(&h->map_hfinal, h->ws + l.h, FITV2_OPERAND_FP16, M, D, D, 128))) return rc;
+        if ((rc = make_map(&h->map_wfinal_lin, h->ws + l.wfin16, FITV2_OPERAND_FP16, Co, D, D, (uint32_t)(Co / kGemmCluster)))) return rc;
     }
     h->maps_valid = true;
     return FITV2_OK;
@@ -658,11 +678,8 @@ template <int BN>
 int launch_cond_tc(fitv2_handle* h, const CUtensorMap& ma, const CUtensorMap& w0, const CUtensorMap& w1, const CUtensorMap& w2,
                    const CondTc& p, cudaStream_t st) {
     auto kern = cond_tc_kernel<BN>;
-    static bool configured = false;
-    if (!configured) {
-        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CondCfg<BN>::kSmemBytes));
-        configured = true;
-    }
+    int rc = ensure_smem(h, kern, CondCfg<BN>::kSmemBytes);
+    if (rc) return rc;
     const int m_tiles = (p.rows + kCondRows - 1) / kCondRows;
     const int tiles = p.batches * m_tiles * p.nt_prefix[p.nseg];
     const int grid = tiles < h->num_sms ? tiles : h->num_sms;
@@ -673,11 +690,14 @@ int launch_cond_tc(fitv2_handle* h, const CUtensorMap& ma, const CUtensorMap& w0
 }
 
 template <typename OT>
-int forward_impl(fitv2_handle* h, const float* x, int x_rows, const float* t, const int64_t* y, const int64_t* grid,
-                 const float* mask, float* out, int rows, int tokens, cudaStream_t st) {
+int forward_impl(fitv2_handle* h, const float* x_in, int x_rows, const float* t, const int64_t* y, const int64_t* grid,
+                 const float* mask, float* out_user, int rows, int tokens, cudaStream_t st) {
     const fitv2_config& c = h->cfg;
     const Layout& l = h->lay;
-    const int D = c.hidden_size, L = c.depth, Hm = c.mlp_hidden, lora = c.lora_dim, H = c.num_heads, DH = c.head_dim;
+    const int D = c.hidden_size, L = c.depth, Hm = c.mlp_hidden, H = c.num_heads, DH = c.head_dim;
+    const bool lora_mode = c.adaln_type == FITV2_ADALN_LORA;
+    const int lora = lora_mode ? c.lora_dim : 0;
+    const int Cin = c.token_channels, Cout = out_channels(c);
     const int M = rows * tokens;
     uint8_t* ws = h->ws;
     float* x_res = (float*)(ws + l.x_res);
@@ -693,7 +713,8 @@ int forward_impl(fitv2_handle* h, const float* x, int x_rows, const float* t, co
     float* rsin = (float*)(ws + l.rope_sin);
     int* segu = (int*)(ws + l.seg_uniform);
     int rc;
-    struct WindowGuard { ~WindowGuard() { g_l2_window = L2Window(); } } window_guard;
+    g_pdl = h->opt.pdl != 0;
+    struct WindowGuard { ~WindowGuard() { g_l2_window = L2Window(); g_pdl = true; } } window_guard;
     // the window is attached only to the kernels that read or write the residual (LayerNorm, proj, fc2); everything else
     // launches without an access policy
     L2Window x_window;
@@ -705,6 +726,18 @@ int forward_impl(fitv2_handle* h, const float* x, int x_rows, const float* t, co
         x_window.hit_ratio = r < 1.f ? r : 1.f;
     }
     auto x_kernels = [&](bool on) { g_l2_window = on ? x_window : L2Window(); };
+
+    // ---- use_sit = False callers hand in (rows, C, tokens): token-major copy first (fit_model.py:204) ----
+    const float* x = x_in;
+    float* out = out_user;
+    if (c.channels_first) {
+        float* xt = (float*)(ws + l.xt);
+        const size_t n = (size_t)x_rows * tokens * Cin;
+        CUDA_TRY(launch_k(transpose_inner_kernel, dim3((unsigned)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184)), dim3(256), 0, st, 1, x_in, xt, x_rows, Cin, tokens));
+        h->launches++;
+        x = xt;
+        out = (float*)(ws + l.ot);
+    }
 
     // ---- per-call tables: segment-uniformity flags, RoPE cos/sin (rope.py:308-333) ----
     prof_begin(h, PC_COND, st);
@@ -718,11 +751,10 @@ int forward_impl(fitv2_handle* h, const float* x, int x_rows, const float* t, co
             CUDA_TRY(launch_k(rope_table_kernel, dim3(blocks), dim3(256), 0, st, 1, (const long long*)grid, h->online_fh, h->online_fw, DH / 4,
                               1.0f, rcos, rsin, rows, tokens, DH / 2));
         else
-        CUDA_TRY(launch_k(rope_table_kernel, dim3(blocks), dim3(256), 0, st, 1, (const long long*)grid, (const float*)h->w[FITV2_W_ROPE_FREQS_H],
-                                                   (const float*)h->w[FITV2_W_ROPE_FREQS_W], 0, c.rope_magnitude, rcos, rsin,
-                                                   rows, tokens, DH / 2));
+            CUDA_TRY(launch_k(rope_table_kernel, dim3(blocks), dim3(256), 0, st, 1, (const long long*)grid, (const float*)h->w[FITV2_W_ROPE_FREQS_H],
+                              (const float*)h->w[FITV2_W_ROPE_FREQS_W], 0, c.rope_magnitude, rcos, rsin, rows, tokens, DH / 2));
     }
-    // ---- conditioning (fit_model.py:202-209,218-219; modules.py:52-76,101-106,259-264,287-293) ----
+    // ---- conditioning (fit_model.py:202-209,218-219; modules.py:52-76,101-106,254-264,287-293) ----
     CUDA_TRY(launch_k(timestep_features_kernel, dim3((rows * 128 + 255) / 256), dim3(256), 0, st, 1, t, c.time_shifting, te, rows));
     CUDA_TRY(cudaGetLastError());
     h->launches += 3;
@@ -735,11 +767,12 @@ int forward_impl(fitv2_handle* h, const float* x, int x_rows, const float* t, co
     if ((rc = launch_small_linear(h, p, 1, st))) return rc;
     // c = W2 silu(t0) + b2 + E[y] ; sc = silu(c)
     p.A = t0; p.lda = D; p.act_silu_in = 1; p.W = (const float*)h->w[FITV2_W_T_MLP2_W]; p.bias = (const float*)h->w[FITV2_W_T_MLP2_B];
-    p.emb = (const float*)h->w[FITV2_W_Y_TABLE]; p.labels = (const long long*)y; p.out = cc; p.out_silu = sc; p.N = D; p.K = D;
+    p.emb = (const float*)h->w[FITV2_W_Y_TABLE]; p.labels = (const long long*)y; p.num_emb = c.num_embeddings; p.err = h->err_dev;
+    p.out = cc; p.out_silu = sc; p.N = D; p.K = D;
     p.out_silu_split = h->cond_tc ? (float*)(ws + l.sc_split) : nullptr;   // hi / lo tf32 split of silu(c) for cond_tc.cuh
     if ((rc = launch_small_linear(h, p, 1, st))) return rc;
-    p.act_silu_in = 0; p.emb = nullptr; p.labels = nullptr; p.out_silu = nullptr; p.out_silu_split = nullptr;
-    if (h->cond_tc) {
+    p.act_silu_in = 0; p.emb = nullptr; p.labels = nullptr; p.out_silu = nullptr; p.out_silu_split = nullptr; p.err = nullptr;
+    if (h->cond_tc && lora_mode) {
         // tensor-pipe path (cond_tc.cuh): one launch for the three linears that read silu(c), one for the batched LoRA up
         float* lmid_split = (float*)(ws + l.lmid_split);
         CondTc q;
@@ -761,30 +794,56 @@ int forward_impl(fitv2_handle* h, const float* x, int x_rows, const float* t, co
         if (h->cond_bn_up == 128) rc = launch_cond_tc<128>(h, h->map_lmid_split, h->map_wlora_b, h->map_wlora_b, h->map_wlora_b, u, st);
         else rc = launch_cond_tc<48>(h, h->map_lmid_split, h->map_wlora_b, h->map_wlora_b, h->map_wlora_b, u, st);
         if (rc) return rc;
+    } else if (h->cond_tc) {
+        // adaln_type 'normal' (modules.py:254-258): final adaLN, then every block's Linear(D -> 6D) on silu(c) as one batched launch
+        CondTc q;
+        memset(&q, 0, sizeof(q));
+        q.nseg = 1; q.rows = rows; q.K = D; q.batches = 1;
+        q.nt_prefix[0] = 0; q.nt_prefix[1] = 2 * D / 48;
+        q.bias[0] = (const float*)h->w[FITV2_W_FINAL_ADALN_B]; q.out[0] = fmod; q.ldo[0] = 2 * D;
+        if ((rc = launch_cond_tc<48>(h, h->map_sc_split, h->map_wfinal, h->map_wfinal, h->map_wfinal, q, st))) return rc;
+        CondTc u;
+        memset(&u, 0, sizeof(u));
+        u.nseg = 1; u.rows = rows; u.K = D; u.batches = L; u.a_batch_cols = 0;
+        u.nt_prefix[0] = 0; u.nt_prefix[1] = 6 * D / h->cond_bn_up;
+        u.w_batch_rows[0] = 6 * D;
+        u.bias[0] = (const float*)h->w[FITV2_W_NORMAL_ADALN_B]; u.bias_batch_stride[0] = 6 * D;
+        u.out[0] = mod; u.out_batch_stride[0] = (size_t)rows * 6 * D; u.ldo[0] = 6 * D;
+        if (h->cond_bn_up == 128) rc = launch_cond_tc<128>(h, h->map_sc_split, h->map_wnormal, h->map_wnormal, h->map_wnormal, u, st);
+        else rc = launch_cond_tc<48>(h, h->map_sc_split, h->map_wnormal, h->map_wnormal, h->map_wnormal, u, st);
+        if (rc) return rc;
     } else {
-    // global adaLN: gmod = Wg sc + bg
-    p.A = sc; p.lda = D; p.W = (const float*)h->w[FITV2_W_GLOBAL_ADALN_W]; p.bias = (const float*)h->w[FITV2_W_GLOBAL_ADALN_B];
-    p.out = gmod; p.ldo = 6 * D; p.N = 6 * D; p.K = D;
-    if ((rc = launch_small_linear(h, p, 1, st))) return rc;
-    // final adaLN: fmod = Wf sc + bf   (shift | scale)
-    p.W = (const float*)h->w[FITV2_W_FINAL_ADALN_W]; p.bias = (const float*)h->w[FITV2_W_FINAL_ADALN_B];
-    p.out = fmod; p.ldo = 2 * D; p.N = 2 * D;
-    if ((rc = launch_small_linear(h, p, 1, st))) return rc;
-    // LoRA down for all blocks at once: lmid = Wa_all sc + ba_all
-    p.W = (const float*)h->w[FITV2_W_LORA_A_W]; p.bias = (const float*)h->w[FITV2_W_LORA_A_B];
-    p.out = lmid; p.ldo = L * lora; p.N = L * lora;
-    if ((rc = launch_small_linear(h, p, 1, st))) return rc;
-    // LoRA up, batched over blocks: mod[l] = Wb[l] lmid[:, l] + bb[l] + gmod
-    p.A = lmid; p.a_batch_stride = lora; p.lda = L * lora;
-    p.W = (const float*)h->w[FITV2_W_LORA_B_W]; p.w_batch_stride = (size_t)6 * D * lora;
-    p.bias = (const float*)h->w[FITV2_W_LORA_B_B]; p.bias_batch_stride = 6 * D;
-    p.add = gmod; p.out = mod; p.out_batch_stride = (size_t)rows * 6 * D; p.ldo = 6 * D; p.N = 6 * D; p.K = lora;
-    if ((rc = launch_small_linear(h, p, L, st))) return rc;
+        // final adaLN: fmod = Wf sc + bf   (shift | scale)
+        p.A = sc; p.lda = D; p.K = D;
+        p.W = (const float*)h->w[FITV2_W_FINAL_ADALN_W]; p.bias = (const float*)h->w[FITV2_W_FINAL_ADALN_B];
+        p.out = fmod; p.ldo = 2 * D; p.N = 2 * D;
+        if ((rc = launch_small_linear(h, p, 1, st))) return rc;
+        if (lora_mode) {
+            // global adaLN: gmod = Wg sc + bg
+            p.W = (const float*)h->w[FITV2_W_GLOBAL_ADALN_W]; p.bias = (const float*)h->w[FITV2_W_GLOBAL_ADALN_B];
+            p.out = gmod; p.ldo = 6 * D; p.N = 6 * D;
+            if ((rc = launch_small_linear(h, p, 1, st))) return rc;
+            // LoRA down for all blocks at once: lmid = Wa_all sc + ba_all
+            p.W = (const float*)h->w[FITV2_W_LORA_A_W]; p.bias = (const float*)h->w[FITV2_W_LORA_A_B];
+            p.out = lmid; p.ldo = L * lora; p.N = L * lora;
+            if ((rc = launch_small_linear(h, p, 1, st))) return rc;
+            // LoRA up, batched over blocks: mod[l] = Wb[l] lmid[:, l] + bb[l] + gmod
+            p.A = lmid; p.a_batch_stride = lora; p.lda = L * lora;
+            p.W = (const float*)h->w[FITV2_W_LORA_B_W]; p.w_batch_stride = (size_t)6 * D * lora;
+            p.bias = (const float*)h->w[FITV2_W_LORA_B_B]; p.bias_batch_stride = 6 * D;
+            p.add = gmod; p.out = mod; p.out_batch_stride = (size_t)rows * 6 * D; p.ldo = 6 * D; p.N = 6 * D; p.K = lora;
+            if ((rc = launch_small_linear(h, p, L, st))) return rc;
+        } else {
+            // adaln_type 'normal': mod[l] = W[l] sc + b[l], batched over blocks
+            p.W = (const float*)h->w[FITV2_W_NORMAL_ADALN_W]; p.w_batch_stride = (size_t)6 * D * D;
+            p.bias = (const float*)h->w[FITV2_W_NORMAL_ADALN_B]; p.bias_batch_stride = 6 * D;
+            p.out = mod; p.out_batch_stride = (size_t)rows * 6 * D; p.ldo = 6 * D; p.N = 6 * D;
+            if ((rc = launch_small_linear(h, p, L, st))) return rc;
+        }
     }
     prof_end(h, st);
 
     // ---- patch embedding (modules.py:34-37); implicit cat([z, z]) when x_rows == rows / 2 ----
-    if (c.token_channels != 16) return fail(FITV2_E_INVALID, "token_channels %d not supported (16)", c.token_channels);
     prof_begin(h, PC_MISC, st);
     const int pe_threads = D / 4 >= 576 ? 576 : ((D / 4 + 31) / 32) * 32;   // more features than threads: the kernel loops
     CUDA_TRY(launch_k(patch_embed_kernel<16>, dim3((M + kPatchRows - 1) / kPatchRows), dim3(pe_threads), 0, st, 1, x, (const float*)h->w[FITV2_W_X_EMBED_W], (const float*)h->w[FITV2_W_X_EMBED_B],
@@ -793,13 +852,15 @@ int forward_impl(fitv2_handle* h, const float* x, int x_rows, const float* t, co
     h->launches++;
     prof_end(h, st);
 
+    const bool norm_w = norm_has_weight(c.block_norm);
     GemmEpi ep;
     for (int layer = 0; layer < L; ++layer) {
         const float* modl = mod + (size_t)layer * rows * 6 * D;
         // ---- attention branch (modules.py:272) ----
         prof_begin(h, PC_LNMOD, st);
         x_kernels(true);
-        if ((rc = launch_ln_modulate<OT>(h, x_res, modl, modl + D, 6 * D, ws + l.h, M, D, tokens, st))) return rc;
+        if ((rc = launch_ln_modulate<OT>(h, x_res, modl, modl + D, 6 * D, ws + l.h, M, D, tokens, st, c.block_norm,
+                                         norm_w ? (const float*)h->w[FITV2_W_NORM1_W] + (size_t)layer * D : nullptr))) return rc;
         x_kernels(false);
         prof_end(h, st);
         memset(&ep, 0, sizeof(ep));
@@ -807,7 +868,14 @@ int forward_impl(fitv2_handle* h, const float* x, int x_rows, const float* t, co
         ep.tokens = tokens; ep.q = ws + l.q; ep.k = ws + l.k; ep.vt = ws + l.vt; ep.rope_cos = rcos; ep.rope_sin = rsin;
         ep.heads = H; ep.tokens_v = l.tokens_v;
         prof_begin(h, PC_QKV, st);
-        if (DH == 72 && h->qkv3) rc = launch_gemm_t<224, EPI_QKV, OT, 72>(h, h->map_h, h->map_wqkv, M, 3 * D, D, layer * 3 * D, ep, st);
+        if (h->qkv_gen) {
+            ep.q_norm = c.q_norm; ep.k_norm = c.k_norm;
+            ep.q_norm_w = norm_has_weight(c.q_norm) ? (const float*)h->w[FITV2_W_Q_NORM_W] + (size_t)layer * DH : nullptr;
+            ep.k_norm_w = norm_has_weight(c.k_norm) ? (const float*)h->w[FITV2_W_K_NORM_W] + (size_t)layer * DH : nullptr;
+            if (DH == 72) rc = launch_gemm_t<144, EPI_QKV_GEN, OT, 72>(h, h->map_h, h->map_wqkv, M, 3 * D, D, layer * 3 * D, ep, st);
+            else          rc = launch_gemm_t<192, EPI_QKV_GEN, OT, 96>(h, h->map_h, h->map_wqkv, M, 3 * D, D, layer * 3 * D, ep, st);
+        }
+        else if (DH == 72 && h->qkv3) rc = launch_gemm_t<224, EPI_QKV, OT, 72>(h, h->map_h, h->map_wqkv, M, 3 * D, D, layer * 3 * D, ep, st);
         else if (DH == 72) rc = launch_gemm_t<144, EPI_QKV, OT, 72>(h, h->map_h, h->map_wqkv, M, 3 * D, D, layer * 3 * D, ep, st);
         else          rc = launch_gemm_t<192, EPI_QKV, OT, 96>(h, h->map_h, h->map_wqkv, M, 3 * D, D, layer * 3 * D, ep, st);
         if (rc) return rc;
@@ -822,15 +890,15 @@ int forward_impl(fitv2_handle* h, const float* x, int x_rows, const float* t, co
         x_kernels(true);
         if (h->proj_t && h->bn_resid_t == 224) rc = launch_gemm_t<224, EPI_RESID_T, OT, 0>(h, h->map_wproj_t, h->map_ao_t, D, M, D, layer * D, ep, st);
         else if (h->proj_t) rc = launch_gemm_t<256, EPI_RESID_T, OT, 0>(h, h->map_wproj_t, h->map_ao_t, D, M, D, layer * D, ep, st);
-        else rc = launch_gemm_bn<EPI_RESID, OT>(h, h->bn_proj, h->map_ao, h->map_wproj, M, D, D, layer * D, ep, st,
-                                                h->sched_stride_proj ? (const int2*)(ws + l.sched_proj) : nullptr, h->sched_stride_proj);
+        else rc = launch_gemm_bn<EPI_RESID, OT>(h, h->bn_proj, h->map_ao, h->map_wproj, M, D, D, layer * D, ep, st);
         x_kernels(false);
         if (rc) return rc;
         prof_end(h, st);
         // ---- SwiGLU branch (modules.py:273) ----
         prof_begin(h, PC_LNMOD, st);
         x_kernels(true);
-        if ((rc = launch_ln_modulate<OT>(h, x_res, modl + 3 * D, modl + 4 * D, 6 * D, ws + l.h, M, D, tokens, st))) return rc;
+        if ((rc = launch_ln_modulate<OT>(h, x_res, modl + 3 * D, modl + 4 * D, 6 * D, ws + l.h, M, D, tokens, st, c.block_norm,
+                                         norm_w ? (const float*)h->w[FITV2_W_NORM2_W] + (size_t)layer * D : nullptr))) return rc;
         x_kernels(false);
         prof_end(h, st);
         memset(&ep, 0, sizeof(ep));
@@ -846,8 +914,7 @@ int forward_impl(fitv2_handle* h, const float* x, int x_rows, const float* t, co
         x_kernels(true);
         if (h->fc2_t && h->bn_resid_t == 224) rc = launch_gemm_t<224, EPI_RESID_T, OT, 0>(h, h->map_wfc2_t, h->map_hidden_t, D, M, Hm, layer * D, ep, st);
         else if (h->fc2_t) rc = launch_gemm_t<256, EPI_RESID_T, OT, 0>(h, h->map_wfc2_t, h->map_hidden_t, D, M, Hm, layer * D, ep, st);
-        else rc = launch_gemm_bn<EPI_RESID, OT>(h, h->bn_fc2, h->map_hidden, h->map_wfc2, M, D, Hm, layer * D, ep, st,
-                                                h->sched_stride_fc2 ? (const int2*)(ws + l.sched_fc2) : nullptr, h->sched_stride_fc2);
+        else rc = launch_gemm_bn<EPI_RESID, OT>(h, h->bn_fc2, h->map_hidden, h->map_wfc2, M, D, Hm, layer * D, ep, st);
         x_kernels(false);
         if (rc) return rc;
         prof_end(h, st);
@@ -855,24 +922,44 @@ int forward_impl(fitv2_handle* h, const float* x, int x_rows, const float* t, co
 
     // ---- final layer + output mask (modules.py:292-296, fit_model.py:230) ----
     prof_begin(h, PC_MISC, st);
-    {
+    const float* nfw = norm_w ? (const float*)h->w[FITV2_W_NORM_FINAL_W] : nullptr;
+    if (h->final_tc) {
+        // LN + modulate -> fp16 operand (the block kernel), then out = (h W^T + b) * mask as a skinny tcgen05 GEMM
+        const size_t nw = (size_t)Cout * D;
+        CUDA_TRY(launch_k(f32_to_f16_kernel, dim3((unsigned)((nw + 255) / 256)), dim3(256), 0, st, 1, (const float*)h->w[FITV2_W_FINAL_LINEAR_W],
+                          (__half*)(ws + l.wfin16), nw));
+        h->launches++;
+        if ((rc = launch_ln_modulate<__half>(h, x_res, fmod, fmod + D, 2 * D, ws + l.h, M, D, tokens, st, c.block_norm, nfw))) return rc;
+        memset(&ep, 0, sizeof(ep));
+        ep.bias = (const float*)h->w[FITV2_W_FINAL_LINEAR_B];
+        ep.tokens = tokens; ep.out32 = out; ep.ld_out = Cout; ep.row_scale = mask;
+        if (Cout == 16) rc = launch_gemm_t<16, EPI_PLAIN, __half, 0>(h, h->map_hfinal, h->map_wfinal_lin, M, Cout, D, 0, ep, st);
+        else            rc = launch_gemm_t<32, EPI_PLAIN, __half, 0>(h, h->map_hfinal, h->map_wfinal_lin, M, Cout, D, 0, ep, st);
+        if (rc) return rc;
+    } else {
         const int nv = (D / 4 + 31) / 32;
         const size_t smem = (size_t)16 * D * 4;
         const int blocks = h->num_sms * 2;             // measured: 85 us with two waves of blocks against 97 us with one block per SM
-        if (nv <= 9) {
-            auto kern = final_layer_kernel<9, 16>;
-            static bool configured = false;
-            if (!configured) { CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 1152 * 4)); configured = true; }
-            CUDA_TRY(launch_k(kern, dim3(blocks), dim3(256), smem, st, 1, x_res, fmod, (const float*)h->w[FITV2_W_FINAL_LINEAR_W], (const float*)h->w[FITV2_W_FINAL_LINEAR_B],
-                                            mask, out, M, D, tokens));
-        } else {
-            auto kern = final_layer_kernel<18, 16>;
-            static bool configured = false;
-            if (!configured) { CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 2304 * 4)); configured = true; }
-            CUDA_TRY(launch_k(kern, dim3(blocks), dim3(256), smem, st, 1, x_res, fmod, (const float*)h->w[FITV2_W_FINAL_LINEAR_W], (const float*)h->w[FITV2_W_FINAL_LINEAR_B],
-                                            mask, out, M, D, tokens));
+        const int rms = c.block_norm == FITV2_NORM_RMSNORM;
+        for (int col0 = 0; col0 < Cout; col0 += 16) {  // learn_sigma: two launches of 16 output channels each
+            if (nv <= 9) {
+                auto kern = final_layer_kernel<9, 16>;
+                if ((rc = ensure_smem(h, kern, 16 * 1152 * 4))) return rc;
+                CUDA_TRY(launch_k(kern, dim3(blocks), dim3(256), smem, st, 1, x_res, fmod, (const float*)h->w[FITV2_W_FINAL_LINEAR_W], (const float*)h->w[FITV2_W_FINAL_LINEAR_B],
+                                  mask, out, M, D, tokens, nfw, rms, Cout, col0));
+            } else {
+                auto kern = final_layer_kernel<18, 16>;
+                if ((rc = ensure_smem(h, kern, 16 * 2304 * 4))) return rc;
+                CUDA_TRY(launch_k(kern, dim3(blocks), dim3(256), smem, st, 1, x_res, fmod, (const float*)h->w[FITV2_W_FINAL_LINEAR_W], (const float*)h->w[FITV2_W_FINAL_LINEAR_B],
+                                  mask, out, M, D, tokens, nfw, rms, Cout, col0));
+            }
+            CUDA_TRY(cudaGetLastError());
+            h->launches++;
         }
-        CUDA_TRY(cudaGetLastError());
+    }
+    if (c.channels_first) {                            // (rows, tokens, C_out) -> (rows, C_out, tokens)  (fit_model.py:231)
+        const size_t n = (size_t)M * Cout;
+        CUDA_TRY(launch_k(transpose_inner_kernel, dim3((unsigned)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184)), dim3(256), 0, st, 1, (const float*)out, out_user, rows, tokens, Cout));
         h->launches++;
     }
     prof_end(h, st);
@@ -900,7 +987,13 @@ int fitv2_create(const fitv2_config* cfg, fitv2_handle** out) {
     if (c.mlp_hidden % 128) return fail(FITV2_E_INVALID, "mlp_hidden %d must be a multiple of 128", c.mlp_hidden);
     if (c.hidden_size > 2304 || c.hidden_size % 16) return fail(FITV2_E_INVALID, "hidden_size %d must be a multiple of 16 and <= 2304", c.hidden_size);
     if (c.token_channels != 16) return fail(FITV2_E_INVALID, "token_channels %d not supported (p*p*C_in = 16)", c.token_channels);
-    if (c.lora_dim % 4) return fail(FITV2_E_INVALID, "lora_dim %d must be a multiple of 4", c.lora_dim);
+    if (c.out_channels != 0 && c.out_channels != 16 && c.out_channels != 32)
+        return fail(FITV2_E_INVALID, "out_channels %d not supported (16, or 32 with learn_sigma)", c.out_channels);
+    if (c.adaln_type != FITV2_ADALN_LORA && c.adaln_type != FITV2_ADALN_NORMAL) return fail(FITV2_E_INVALID, "adaln_type %d unknown", c.adaln_type);
+    if (c.adaln_type == FITV2_ADALN_LORA && (c.lora_dim <= 0 || c.lora_dim % 4)) return fail(FITV2_E_INVALID, "lora_dim %d must be a positive multiple of 4", c.lora_dim);
+    if (c.block_norm < FITV2_NORM_LAYERNORM || c.block_norm > FITV2_NORM_RMSNORM) return fail(FITV2_E_INVALID, "block_norm %d unknown (layernorm / w_layernorm / rmsnorm)", c.block_norm);
+    if (c.q_norm < FITV2_NORM_NONE || c.q_norm > FITV2_NORM_RMSNORM || c.k_norm < FITV2_NORM_NONE || c.k_norm > FITV2_NORM_RMSNORM)
+        return fail(FITV2_E_INVALID, "q_norm %d / k_norm %d unknown", c.q_norm, c.k_norm);
     if (c.operand_dtype != FITV2_OPERAND_BF16 && c.operand_dtype != FITV2_OPERAND_FP16)
         return fail(FITV2_E_INVALID, "operand_dtype %d unknown", c.operand_dtype);
     int dev = 0, major = 0, sms = 0;
@@ -910,25 +1003,18 @@ int fitv2_create(const fitv2_config* cfg, fitv2_handle** out) {
     if (major != 10) return fail(FITV2_E_INVALID, "device compute capability %d.x: this library contains sm_100a code only", major);
     fitv2_handle* h = new fitv2_handle();
     h->cfg = c;
+    h->device = dev;
     memset(h->w, 0, sizeof(h->w));
     memset(h->w_numel, 0, sizeof(h->w_numel));
     h->num_sms = sms;
-    {   // persisting L2 for the fp32 residual stream: FITV2_L2_PERSIST_MB (default 0 = off)
-        int max_persist = 0, max_window = 0;
-        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
-        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
-        const char* e = getenv("FITV2_L2_PERSIST_MB");
-        long want = e ? atol(e) : 0;
-        if (want > 0 && max_persist > 0) {
-            long bytes = want << 20;
-            if (bytes > max_persist) bytes = max_persist;
-            if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)bytes) == cudaSuccess) {
-                h->l2_persist_bytes = bytes;
-                h->l2_window_max = max_window;
-            }
-        }
-        if (getenv("FITV2_VERBOSE")) fprintf(stderr, "[fitv2] L2 persist max %d MB, window max %d MB, using %lld MB\n", max_persist >> 20, max_window >> 20, (long long)(h->l2_persist_bytes >> 20));
+    // sticky error word, written by kernels through the mapped device alias, read by the host without synchronising
+    if (cudaHostAlloc(&h->err_host, sizeof(int), cudaHostAllocMapped) != cudaSuccess || cudaHostGetDevicePointer(&h->err_dev, h->err_host, 0) != cudaSuccess) {
+        cudaGetLastError();
+        if (h->err_host) cudaFreeHost(h->err_host);
+        delete h;
+        return fail(FITV2_E_CUDA, "cannot allocate the pinned error word");
     }
+    *h->err_host = 0;
     *out = h;
     return FITV2_OK;
 }
@@ -936,12 +1022,57 @@ int fitv2_create(const fitv2_config* cfg, fitv2_handle** out) {
 void fitv2_destroy(fitv2_handle* h) {
     if (!h) return;
     for (auto& e : h->prof_pool) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    if (h->err_host) cudaFreeHost(h->err_host);
     delete h;
+}
+
+int fitv2_set_option(fitv2_handle* h, const char* name, int64_t value) {
+    if (!h || !name) return fail(FITV2_E_INVALID, "null argument");
+    Options& o = h->opt;
+    const int v = (int)value;
+    struct { const char* n; int* p; } tab[] = {
+        {"pdl", &o.pdl}, {"attn", &o.attn}, {"attn_early", &o.attn_early}, {"attn_poly", &o.attn_poly}, {"ln_threads", &o.ln_threads},
+        {"ln_wide_single", &o.ln_wide_single}, {"bn_resid", &o.bn_resid}, {"qkv_heads", &o.qkv_heads}, {"resid_t", &o.resid_t},
+        {"bn_resid_t", &o.bn_resid_t}, {"cond", &o.cond}, {"l2_persist_mb", &o.l2_persist_mb}, {"final_tc", &o.final_tc}, {"verbose", &o.verbose}};
+    for (auto& e : tab) {
+        if (strcmp(e.n, name)) continue;
+        *e.p = v;
+        h->maps_valid = false;                                         // kernel selection / tile widths are derived in ensure_maps
+        if (e.p == &o.l2_persist_mb) {                                 // persisting L2 for the fp32 residual stream (default off)
+            int max_persist = 0, max_window = 0;
+            cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, h->device);
+            cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, h->device);
+            h->l2_persist_bytes = 0;
+            if (v > 0 && max_persist > 0) {
+                long bytes = (long)v << 20;
+                if (bytes > max_persist) bytes = max_persist;
+                if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)bytes) == cudaSuccess) {
+                    h->l2_persist_bytes = bytes;
+                    h->l2_window_max = max_window;
+                }
+            }
+            if (o.verbose) fprintf(stderr, "[fitv2] L2 persist max %d MB, window max %d MB, using %lld MB\n", max_persist >> 20, max_window >> 20, (long long)(h->l2_persist_bytes >> 20));
+        }
+        return FITV2_OK;
+    }
+    return fail(FITV2_E_INVALID, "unknown option '%s'", name);
+}
+
+int fitv2_poll_error(fitv2_handle* h) {
+    if (!h) return fail(FITV2_E_INVALID, "null handle");
+    const int e = *(volatile int*)h->err_host;
+    if (e) {
+        *(volatile int*)h->err_host = 0;
+        return fail(FITV2_E_INVALID, "device-side check failed (flags 0x%x): a class label was outside [0, %d) (the reference raises an "
+                                     "index error; row 0 of the table was used instead)", e, h->cfg.num_embeddings);
+    }
+    return FITV2_OK;
 }
 
 int fitv2_bind_weight(fitv2_handle* h, int slot, const void* dev_ptr, int64_t numel) {
     if (!h || slot < 0 || slot >= FITV2_W_COUNT || !dev_ptr) return fail(FITV2_E_INVALID, "bad bind_weight argument (slot %d)", slot);
     const int64_t want = expected_numel(h->cfg, slot);
+    if (want == 0) return fail(FITV2_E_INVALID, "weight slot %d is not used by this configuration", slot);
     if (numel != want) return fail(FITV2_E_INVALID, "weight slot %d: got %lld elements, expected %lld", slot, (long long)numel, (long long)want);
     if (reinterpret_cast<uintptr_t>(dev_ptr) % 16) return fail(FITV2_E_INVALID, "weight slot %d pointer is not 16-byte aligned", slot);
     h->w[slot] = dev_ptr;
@@ -981,9 +1112,14 @@ int fitv2_forward(fitv2_handle* h, const float* x, int x_rows, const float* t, c
     if (rows <= 0 || tokens <= 0) return fail(FITV2_E_INVALID, "rows %d / tokens %d must be positive", rows, tokens);
     if (x_rows != rows && !(rows % 2 == 0 && x_rows == rows / 2))
         return fail(FITV2_E_INVALID, "x_rows %d must equal rows %d or rows/2", x_rows, rows);
+    int dev = -1;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev != h->device) return fail(FITV2_E_INVALID, "handle was created on device %d, the current device is %d", h->device, dev);
     for (int s = 0; s < FITV2_W_COUNT; ++s)
-        if (!h->w[s]) return fail(FITV2_E_UNBOUND, "weight slot %d is not bound", s);
+        if (!h->w[s] && expected_numel(h->cfg, s) > 0) return fail(FITV2_E_UNBOUND, "weight slot %d is not bound", s);
     if (!h->ws) return fail(FITV2_E_UNBOUND, "workspace is not set");
+    int rc = fitv2_poll_error(h);                                      // an earlier launch saw an out-of-range label
+    if (rc) return rc;
     if (h->lay.rows != rows || h->lay.tokens != tokens) {
         Layout l = make_layout(h->cfg, rows, tokens);
         if ((int64_t)l.total > h->ws_bytes)
@@ -991,7 +1127,7 @@ int fitv2_forward(fitv2_handle* h, const float* x, int x_rows, const float* t, c
         h->lay = l;
         h->maps_valid = false;
     }
-    int rc = ensure_maps(h);
+    rc = ensure_maps(h);
     if (rc) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (h->cfg.operand_dtype == FITV2_OPERAND_FP16)
@@ -1060,6 +1196,14 @@ int fitv2_heun_combine(float* out, const float* xhat, const float* k1, const flo
 int fitv2_tweedie(float* out, const float* x, const float* v, const float* coef_dev, int64_t n, void* stream) {
     if (!out || !x || !v || !coef_dev || n <= 0) return fail(FITV2_E_INVALID, "bad tweedie argument");
     CUDA_TRY(launch_k(tweedie_kernel, dim3(elementwise_grid(n * 4)), dim3(256), 0, static_cast<cudaStream_t>(stream), 1, out, x, v, coef_dev, (size_t)n));
+    return FITV2_OK;
+}
+
+int fitv2_rk_stage(float* out, const float* y, const float* k1, const float* k2, const float* k3, const float* k4,
+                   const float* s_dev, int mode, int64_t n, void* stream) {
+    if (!out || !y || !k1 || !s_dev || n <= 0 || mode < 0 || mode > 5) return fail(FITV2_E_INVALID, "bad rk_stage argument");
+    if ((mode >= 1 && !k2) || ((mode == 2 || mode >= 4) && !k3) || (mode == 5 && !k4)) return fail(FITV2_E_INVALID, "rk_stage mode %d misses a slope", mode);
+    CUDA_TRY(launch_k(rk_stage_kernel, dim3(elementwise_grid(n * 4)), dim3(256), 0, static_cast<cudaStream_t>(stream), 1, out, y, k1, k2, k3, k4, s_dev, mode, (size_t)n));
     return FITV2_OK;
 }
 

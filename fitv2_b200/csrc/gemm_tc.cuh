@@ -36,7 +36,11 @@
 
 namespace fitv2 {
 
-enum { EPI_QKV = 0, EPI_RESID = 1, EPI_SWIGLU = 2, EPI_PLAIN = 3, EPI_RESID_T = 4 };
+enum { EPI_QKV = 0, EPI_RESID = 1, EPI_SWIGLU = 2, EPI_PLAIN = 3, EPI_RESID_T = 4, EPI_QKV_GEN = 5 };
+// EPI_QKV_GEN: the QKV epilogue with a run-time q / k norm (none, LayerNorm with or without weight, RMSNorm with weight:
+// fit/model/norms.py:35-50) for the configurations outside the FiTv2 default (affine-free LayerNorm, EPI_QKV).
+__host__ __device__ constexpr bool epi_is_qkv(int epi) { return epi == EPI_QKV || epi == EPI_QKV_GEN; }
+enum { QKNORM_NONE = 0, QKNORM_LN = 1, QKNORM_WLN = 2, QKNORM_RMS = 3 };
 
 struct GemmEpi {
     const float* bias;        // [N] fp32 (layer slice)
@@ -57,6 +61,12 @@ struct GemmEpi {
     const float* rope_sin;    // [DH/2, M]
     int heads;
     int tokens_v;
+    // EPI_QKV_GEN
+    int q_norm, k_norm;       // QKNORM_*
+    const float* q_norm_w;    // [DH] (layer slice) or null
+    const float* k_norm_w;
+    // EPI_PLAIN
+    const float* row_scale;   // [M] or null: out = (acc + bias) * row_scale[m]  (final layer: fit_model.py:230)
 };
 
 constexpr int kGemmBM = 128;          // rows per CTA
@@ -78,7 +88,7 @@ template <int BN, int EPI, int DH, int CL = 1> struct GemmCfg {
     // QKV at head_dim 72: a 224-wide UMMA tile holds THREE heads (216 columns, one epilogue warp per quarter and head); the
     // last 8 columns are the first 8 of the next tile, computed and dropped (tiles advance by kTileN = 216).  The 144-wide
     // two-head tile is bound by shared-memory operand traffic (64 + 16384/BN bytes per tensor clock: 64 % tensor-pipe active).
-    static constexpr bool kQkv3 = EPI == EPI_QKV && BN == 3 * DH + 8;
+    static constexpr bool kQkv3 = epi_is_qkv(EPI) && BN == 3 * DH + 8;
     static constexpr int kTileN = kQkv3 ? 3 * DH : BN;                  // output columns per tile
     static constexpr int kParts = (EPI == EPI_RESID && BN == 256) ? 4 : (kQkv3 ? 3 : 2);
     static constexpr int kThreads = 64 + kParts * 128;
@@ -87,7 +97,7 @@ template <int BN, int EPI, int DH, int CL = 1> struct GemmCfg {
     static constexpr int kBarrierBytes = 1024;
     // epilogue staging: per warp 32 rows; QKV rows hold one head (16-bit) with a bank-conflict-free pitch,
     // the other epilogues use 128-byte XOR-swizzled rows.
-    static constexpr int kEpiPitch = EPI == EPI_QKV ? ((DH * 2 / 4) % 8 == 4 ? DH * 2 : DH * 2 + 16) : 128;
+    static constexpr int kEpiPitch = epi_is_qkv(EPI) ? ((DH * 2 / 4) % 8 == 4 ? DH * 2 : DH * 2 + 16) : 128;
     static constexpr int kEpiWarpBytes = 32 * kEpiPitch;
     static constexpr int kEpiBytes = (EPI == EPI_PLAIN ? 0 : 4 * kParts * kEpiWarpBytes);
     static constexpr int kStagesRaw = (kSmemBudget - kBarrierBytes - 1024 - kEpiBytes) / kStageBytes;
@@ -97,7 +107,7 @@ template <int BN, int EPI, int DH, int CL = 1> struct GemmCfg {
     static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N constraint for M=128/256");
     static_assert(kBBytes % 1024 == 0, "B stage must keep 1024B alignment for SWIZZLE_128B");
     static_assert(kStages >= 3, "pipeline too shallow");
-    static_assert(EPI != EPI_QKV || DH * 64 <= kEpiWarpBytes, "V^T staging does not fit");
+    static_assert(!epi_is_qkv(EPI) || DH * 64 <= kEpiWarpBytes, "V^T staging does not fit");
 };
 
 // ---- warp-private staging slab: 32 rows x 128 bytes, 16-byte chunk c of row r lives at chunk (c ^ (r & 7)) ----
@@ -110,26 +120,16 @@ template <int CPR> __device__ __forceinline__ void slab_task(int i, int lane, in
     c = task % CPR;
 }
 
-// Work items of one cluster.  Uniform tiling (sched == nullptr): item i of cluster c is tile c + i * clusters in
-// n-fastest order.  Ragged tiling (EPI_RESID with N not a multiple of BN): the host builds an LPT schedule per
-// cluster, entries {row-tile group, n0 | width << 20}, terminated by a negative group: full BN-wide tiles first,
-// the narrower tail tiles fill the gaps of the last wave (fitv2_api.cu: build_schedule).
+// Work items of one cluster: item i of cluster c is tile c + i * clusters, n fastest (a wave shares few A tiles), or -- for the
+// transposed residual GEMM -- row-tile groups fastest (a wave shares few token tiles).
 struct TileWalk {
-    const int2* sched; int grp, num_groups, stride, n_tiles, bn, tile_n;
+    int grp, num_groups, stride, n_tiles, bn, tile_n;
     int m_fast;                                                         // > 0: row-tile groups vary fastest (m_fast of them)
-    int2 ahead;                                                         // table mode: the entry after the current one (prefetched)
-    __device__ __forceinline__ void start() { if (sched) ahead = __ldg(sched++); }
+    __device__ __forceinline__ void start() {}
     __device__ __forceinline__ bool next(int& m_group, int& n0, int& bn_t) {
-        if (sched) {
-            const int2 w = ahead;
-            if (w.x < 0) return false;
-            ahead = __ldg(sched++);                                     // the terminator is always followed by readable entries
-            m_group = w.x; n0 = w.y & 0xFFFFF; bn_t = w.y >> 20;
-            return true;
-        }
         if (grp >= num_groups) return false;
-        if (m_fast) { m_group = grp % m_fast; n0 = (grp / m_fast) * tile_n; bn_t = bn; }   // a wave shares few B (token) tiles
-        else { m_group = grp / n_tiles; n0 = (grp % n_tiles) * tile_n; bn_t = bn; }       // n fastest: a wave shares few A tiles
+        if (m_fast) { m_group = grp % m_fast; n0 = (grp / m_fast) * tile_n; bn_t = bn; }
+        else { m_group = grp / n_tiles; n0 = (grp % n_tiles) * tile_n; bn_t = bn; }
         grp += stride;
         return true;
     }
@@ -139,7 +139,7 @@ template <int BN, int EPI, typename OT, int DH, int CL>
 __global__ void __launch_bounds__((GemmCfg<BN, EPI, DH, CL>::kThreads), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                const __grid_constant__ CUtensorMap tma_x,   // EPI_RESID_T: fp32 residual stream (hidden_size, token rows), box 32 x 16
-               int M, int N, int K, int b_row_offset, GemmEpi ep, const int2* __restrict__ sched, int sched_stride)
+               int M, int N, int K, int b_row_offset, GemmEpi ep)
 {
     using Cfg = GemmCfg<BN, EPI, DH, CL>;
     constexpr int STAGES = Cfg::kStages;
@@ -167,8 +167,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     const uint32_t cta_rank = CL > 1 ? cluster_ctarank() : 0u;
     const bool leader = cta_rank == 0;
     const int group0 = blockIdx.x / CL, group_stride = gridDim.x / CL;
-    const TileWalk walk0 = {sched ? sched + (size_t)group0 * sched_stride : nullptr, group0, num_groups, group_stride, n_tiles, BN, Cfg::kTileN,
-                            EPI == EPI_RESID_T ? (m_tiles + CL - 1) / CL : 0, make_int2(-1, 0)};
+    const TileWalk walk0 = {group0, num_groups, group_stride, n_tiles, BN, Cfg::kTileN, EPI == EPI_RESID_T ? (m_tiles + CL - 1) / CL : 0};
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tma_a);
@@ -463,8 +462,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     if (c == NG - 1) release_acc(acc);
                     if (row_ok) {
                         float o[8];
+                        const float rs = ep.row_scale ? __ldg(ep.row_scale + m) : 1.0f;
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) o[j] = __uint_as_float(v[j]) + __ldg(bias + c * 8 + j);
+                        for (int j = 0; j < 8; ++j) o[j] = (__uint_as_float(v[j]) + __ldg(bias + c * 8 + j)) * rs;
                         if (ep.out16 != nullptr) {
                             OT* orow = reinterpret_cast<OT*>(ep.out16) + (size_t)m * ep.ld_out + n0 + half * HALF + c * 8;
                             *reinterpret_cast<uint4*>(orow) = make_uint4(Op16<OT>::pack(o[0], o[1]), Op16<OT>::pack(o[2], o[3]),
@@ -478,7 +478,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 }
             } else {   // EPI_QKV: every tile holds kParts whole heads, one per epilogue warp of a lane quarter; q / k / v is
                        // decided per head (a three-head tile may straddle the q|k or k|v boundary).
-                static_assert(EPI != EPI_QKV || BN == 2 * DH || Cfg::kQkv3, "QKV tile must be two or three heads wide");
+                static_assert(!epi_is_qkv(EPI) || BN == 2 * DH || Cfg::kQkv3, "QKV tile must be two or three heads wide");
                 static_assert(DH % 8 == 0, "head_dim must be a multiple of 8");
                 constexpr int CH = DH / 8;                            // 16-byte chunks per head row
                 constexpr int PITCH = Cfg::kEpiPitch;
@@ -501,17 +501,44 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 }
                 if (kind < 2) {
                     // LayerNorm over the head (no affine, eps 1e-6, biased variance): norms.py:41-42
-                    float s4[4] = {0.f, 0.f, 0.f, 0.f};               // 4 independent chains instead of one 72-long one
+                    float mean = 0.f, rstd = 1.f;
+                    const int nmode = EPI == EPI_QKV ? QKNORM_LN : (kind == 0 ? ep.q_norm : ep.k_norm);
+                    if (nmode == QKNORM_LN || nmode == QKNORM_WLN) {
+                        float s4[4] = {0.f, 0.f, 0.f, 0.f};           // 4 independent chains instead of one 72-long one
 #pragma unroll
-                    for (int j = 0; j < DH; j += 4) { s4[0] += v[j]; s4[1] += v[j + 1]; s4[2] += v[j + 2]; s4[3] += v[j + 3]; }
-                    const float mean = ((s4[0] + s4[1]) + (s4[2] + s4[3])) * (1.0f / DH);
-                    float q4[4] = {0.f, 0.f, 0.f, 0.f};
+                        for (int j = 0; j < DH; j += 4) { s4[0] += v[j]; s4[1] += v[j + 1]; s4[2] += v[j + 2]; s4[3] += v[j + 3]; }
+                        mean = ((s4[0] + s4[1]) + (s4[2] + s4[3])) * (1.0f / DH);
+                        float q4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                    for (int j = 0; j < DH; j += 4) {
-                        const float d0 = v[j] - mean, d1 = v[j + 1] - mean, d2 = v[j + 2] - mean, d3 = v[j + 3] - mean;
-                        q4[0] = fmaf(d0, d0, q4[0]); q4[1] = fmaf(d1, d1, q4[1]); q4[2] = fmaf(d2, d2, q4[2]); q4[3] = fmaf(d3, d3, q4[3]);
+                        for (int j = 0; j < DH; j += 4) {
+                            const float d0 = v[j] - mean, d1 = v[j + 1] - mean, d2 = v[j + 2] - mean, d3 = v[j + 3] - mean;
+                            q4[0] = fmaf(d0, d0, q4[0]); q4[1] = fmaf(d1, d1, q4[1]); q4[2] = fmaf(d2, d2, q4[2]); q4[3] = fmaf(d3, d3, q4[3]);
+                        }
+                        rstd = rsqrtf(((q4[0] + q4[1]) + (q4[2] + q4[3])) * (1.0f / DH) + 1e-6f);
+                    } else if (nmode == QKNORM_RMS) {                  // norms.py:72-77: x * rsqrt(mean(x^2) + eps) * weight
+                        float q4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                        for (int j = 0; j < DH; j += 4) {
+                            q4[0] = fmaf(v[j], v[j], q4[0]); q4[1] = fmaf(v[j + 1], v[j + 1], q4[1]);
+                            q4[2] = fmaf(v[j + 2], v[j + 2], q4[2]); q4[3] = fmaf(v[j + 3], v[j + 3], q4[3]);
+                        }
+                        rstd = rsqrtf(((q4[0] + q4[1]) + (q4[2] + q4[3])) * (1.0f / DH) + 1e-6f);
                     }
-                    const float rstd = rsqrtf(((q4[0] + q4[1]) + (q4[2] + q4[3])) * (1.0f / DH) + 1e-6f);
+                    if constexpr (EPI == EPI_QKV_GEN) {
+                        const float* nw = kind == 0 ? ep.q_norm_w : ep.k_norm_w;
+                        if (nmode != QKNORM_NONE) {
+#pragma unroll
+                            for (int j = 0; j < DH; ++j) v[j] = (v[j] - mean) * rstd;
+                            mean = 0.f; rstd = 1.f;
+                        }
+                        if ((nmode == QKNORM_WLN || nmode == QKNORM_RMS) && nw != nullptr) {
+#pragma unroll
+                            for (int j = 0; j < DH; j += 4) {
+                                const float4 w4 = __ldg(reinterpret_cast<const float4*>(nw + j));
+                                v[j] *= w4.x; v[j + 1] *= w4.y; v[j + 2] *= w4.z; v[j + 3] *= w4.w;
+                            }
+                        }
+                    }
                     const float* cs = ep.rope_cos + (row_ok ? m : 0);        // pair-major tables: coalesced across lanes
                     const float* sn = ep.rope_sin + (row_ok ? m : 0);
 #pragma unroll

@@ -172,6 +172,57 @@ __global__ void pack_uint8_kernel(const float* __restrict__ img, unsigned char* 
     }
 }
 
+// Fixed-grid Runge-Kutta stages of torchdiffeq.odeint (the reference's sample_ode route, integrators.py:109-116; torchdiffeq
+// itself is an un-vendored dependency: the expressions below restate its rk_common.py / fixed_grid.py step functions).
+// Every operation is a separately rounded fp32 operation in PyTorch's evaluation order.  s[0] = dt (0-dim tensor in the
+// reference), s[1..3] = the Python-float coefficients rounded to fp32.
+//   mode 0: out = y + (dt * k1) * s1                                 (rk2 / rk3 / rk4 second-stage argument:  y0 + dt * k1 * a21)
+//   mode 1: out = y + dt * (k1 * s1 + k2 * s2)                       (rk3 third-stage argument; rk2 final update)
+//   mode 2: out = y + dt * (k1 * s1 + k2 * s2 + k3 * s3)             (rk3 final update)
+//   mode 3: out = y + dt * (k2 - k1 * s1)                            (rk4 3/8-rule third-stage argument)
+//   mode 4: out = y + dt * (k1 - k2 + k3)                            (rk4 fourth-stage argument)
+//   mode 5: out = y + (k1 + 3 * (k2 + k3) + k4) * dt * 0.125         (rk4 3/8-rule final update)
+__global__ void rk_stage_kernel(float* __restrict__ out, const float* __restrict__ y, const float* __restrict__ k1,
+                                const float* __restrict__ k2, const float* __restrict__ k3, const float* __restrict__ k4,
+                                const float* __restrict__ s, int mode, size_t n)
+{
+    pdl_wait();
+    pdl_launch_dependents();
+    const float dt = s[0], s1 = s[1], s2 = s[2], s3 = s[3];
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float d;
+        switch (mode) {
+            case 0: d = __fmul_rn(__fmul_rn(dt, k1[i]), s1); break;
+            case 1: d = __fmul_rn(dt, __fadd_rn(__fmul_rn(k1[i], s1), __fmul_rn(k2[i], s2))); break;
+            case 2: d = __fmul_rn(dt, __fadd_rn(__fadd_rn(__fmul_rn(k1[i], s1), __fmul_rn(k2[i], s2)), __fmul_rn(k3[i], s3))); break;
+            case 3: d = __fmul_rn(dt, __fsub_rn(k2[i], __fmul_rn(k1[i], s1))); break;
+            case 4: d = __fmul_rn(dt, __fadd_rn(__fsub_rn(k1[i], k2[i]), k3[i])); break;
+            default: d = __fmul_rn(__fmul_rn(__fadd_rn(__fadd_rn(k1[i], __fmul_rn(3.0f, __fadd_rn(k2[i], k3[i]))), k4[i]), dt), 0.125f); break;
+        }
+        out[i] = __fadd_rn(y[i], d);
+    }
+}
+
+// (rows, A, B) -> (rows, B, A): the 'B C N' <-> 'B N C' rearranges of the use_sit = False layout (fit_model.py:204,231).
+__global__ void transpose_inner_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int A, int B)
+{
+    pdl_wait();
+    pdl_launch_dependents();
+    const size_t total = (size_t)rows * A * B;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int a = (int)(i % A), b = (int)((i / A) % B);
+        const size_t r = i / ((size_t)A * B);
+        out[i] = in[(r * A + a) * B + b];
+    }
+}
+
+__global__ void f32_to_f16_kernel(const float* __restrict__ in, __half* __restrict__ out, size_t n)
+{
+    pdl_wait();
+    pdl_launch_dependents();
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = __float2half_rn(in[i]);
+}
+
 // forward_with_cfg channel-limited guidance (fit_model.py:253-275): channels [0, c_cfg) of BOTH halves become
 // uncond + s_b * (cond - uncond); channels >= c_cfg pass through.  out: (2B, tokens, C) in place.
 // scale_per_sample may be null (then `scale` is used for every sample).
@@ -247,10 +298,12 @@ patch_embed_kernel(const float* __restrict__ xin, const float* __restrict__ w, c
 //   h = LN(x) * (1 + scale[sample]) + shift[sample]      (norms.py:41-42, fit/model/utils.py:6-7, modules.py:272-273)
 // One warp per token row, the row lives in registers (NV float4 per lane), two-pass fp32 statistics.
 // ---------------------------------------------------------------------------------------------
-template <typename OT, int NV>
+// MODE 0: affine-free LayerNorm (the FiTv2 configs); 1: LayerNorm * weight ('w_layernorm', norms.py:35-38);
+// 2: RMSNorm * weight ('rmsnorm', norms.py:53-77).  The weight vector (D floats, cache-resident) is fetched in the output loop.
+template <typename OT, int NV, int MODE = 0>
 __global__ void __launch_bounds__(256)
 ln_modulate_kernel(const float* __restrict__ x, const float* __restrict__ shift, const float* __restrict__ scale,
-                   int mod_ld, OT* __restrict__ h, int M, int D, int tokens)
+                   int mod_ld, OT* __restrict__ h, int M, int D, int tokens, const float* __restrict__ norm_w)
 {
     pdl_wait();
     pdl_launch_dependents();
@@ -281,10 +334,13 @@ ln_modulate_kernel(const float* __restrict__ x, const float* __restrict__ shift,
             g[i] = (j < nvec) ? __ldg(sc + j) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
     }
-    float s = 0.f;
+    float mean = 0.f;
+    if constexpr (MODE != 2) {
+        float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < NV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-    const float mean = warp_sum(s) / (float)D;
+        for (int i = 0; i < NV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        mean = warp_sum(s) / (float)D;
+    }
     float q = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
@@ -296,15 +352,18 @@ ln_modulate_kernel(const float* __restrict__ x, const float* __restrict__ shift,
     }
     const float rstd = rsqrtf(warp_sum(q) / (float)D + 1e-6f);
     uint2* hr = reinterpret_cast<uint2*>(h + (size_t)m * D);
+    const float4* nw = reinterpret_cast<const float4*>(norm_w);
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
         const int j = lane + 32 * i;
         if (j < nvec) {
             if constexpr (!kEarlyMod) { a[i] = __ldg(sh + j); g[i] = __ldg(sc + j); }
-            const float o0 = (v[i].x - mean) * rstd * (1.f + g[i].x) + a[i].x;
-            const float o1 = (v[i].y - mean) * rstd * (1.f + g[i].y) + a[i].y;
-            const float o2 = (v[i].z - mean) * rstd * (1.f + g[i].z) + a[i].z;
-            const float o3 = (v[i].w - mean) * rstd * (1.f + g[i].w) + a[i].w;
+            float n0 = (v[i].x - mean) * rstd, n1 = (v[i].y - mean) * rstd, n2 = (v[i].z - mean) * rstd, n3 = (v[i].w - mean) * rstd;
+            if constexpr (MODE != 0) { const float4 w4 = __ldg(nw + j); n0 *= w4.x; n1 *= w4.y; n2 *= w4.z; n3 *= w4.w; }
+            const float o0 = n0 * (1.f + g[i].x) + a[i].x;
+            const float o1 = n1 * (1.f + g[i].y) + a[i].y;
+            const float o2 = n2 * (1.f + g[i].z) + a[i].z;
+            const float o3 = n3 * (1.f + g[i].w) + a[i].w;
             hr[j] = make_uint2(Op16<OT>::pack(o0, o1), Op16<OT>::pack(o2, o3));
         }
     }
@@ -386,10 +445,14 @@ template <int NV, int COUT>
 __global__ void __launch_bounds__(256)
 final_layer_kernel(const float* __restrict__ x, const float* __restrict__ fmod /* (samples, 2D): shift | scale */,
                    const float* __restrict__ w, const float* __restrict__ b, const float* __restrict__ mask,
-                   float* __restrict__ out, int M, int D, int tokens)
+                   float* __restrict__ out, int M, int D, int tokens,
+                   const float* __restrict__ norm_w /* null, or (D) weight of norm_final */, int rms /* 1: RMSNorm instead of LayerNorm */,
+                   int out_ld /* output channels per token (16, or 32 with learn_sigma) */, int out_col0 /* first channel of this launch */)
 {
     pdl_wait();
     pdl_launch_dependents();
+    w += (size_t)out_col0 * D;
+    b += out_col0;
     extern __shared__ float sw[];                       // COUT * D
     {   // 73 KB of weights per block: 128-bit loads, several in flight per thread
         const float4* w4 = reinterpret_cast<const float4*>(w);
@@ -426,7 +489,7 @@ final_layer_kernel(const float* __restrict__ x, const float* __restrict__ fmod /
             float s = 0.f;
 #pragma unroll
             for (int i = 0; i < NV; ++i) s += (v[r][i].x + v[r][i].y) + (v[r][i].z + v[r][i].w);
-            const float mean = warp_sum(s) / (float)D;
+            const float mean = rms ? 0.f : warp_sum(s) / (float)D;
             float q = 0.f;
 #pragma unroll
             for (int i = 0; i < NV; ++i) {
@@ -445,10 +508,12 @@ final_layer_kernel(const float* __restrict__ x, const float* __restrict__ fmod /
                 const int j = lane + 32 * i;
                 if (j < nvec) {
                     const float4 a = __ldg(sh + j), g = __ldg(sc + j);
-                    v[r][i].x = (v[r][i].x - mean) * rstd * (1.f + g.x) + a.x;
-                    v[r][i].y = (v[r][i].y - mean) * rstd * (1.f + g.y) + a.y;
-                    v[r][i].z = (v[r][i].z - mean) * rstd * (1.f + g.z) + a.z;
-                    v[r][i].w = (v[r][i].w - mean) * rstd * (1.f + g.w) + a.w;
+                    float4 nw = make_float4(1.f, 1.f, 1.f, 1.f);
+                    if (norm_w) nw = __ldg(reinterpret_cast<const float4*>(norm_w) + j);
+                    v[r][i].x = (v[r][i].x - mean) * rstd * nw.x * (1.f + g.x) + a.x;
+                    v[r][i].y = (v[r][i].y - mean) * rstd * nw.y * (1.f + g.y) + a.y;
+                    v[r][i].z = (v[r][i].z - mean) * rstd * nw.z * (1.f + g.z) + a.z;
+                    v[r][i].w = (v[r][i].w - mean) * rstd * nw.w * (1.f + g.w) + a.w;
                 }
             }
         }
@@ -494,7 +559,7 @@ final_layer_kernel(const float* __restrict__ x, const float* __restrict__ fmod /
             const int m = m0 + r * stride;
             if (ok[r] && (lane & 1) == 0) {
                 const int o = lane >> 1;                               // bits (4,3,2,1) -> output index
-                out[(size_t)m * COUT + o] = (total + __ldg(b + o)) * mask[m];
+                out[(size_t)m * out_ld + out_col0 + o] = (total + __ldg(b + o)) * mask[m];
             }
         }
     }
@@ -581,6 +646,7 @@ struct SmallLinear {
     const float* bias; size_t bias_batch_stride;
     const float* add;            // (rows, N) or null, shared by all batches
     const float* emb; const long long* labels;   // optional embedding-row add (label gather), ld = N
+    int num_emb; int* err;       // rows of the table; labels outside [0, num_emb) set bit 0 of *err and read row 0 (the reference raises)
     float* out; size_t out_batch_stride; int ldo;
     float* out_silu;             // optional second output: silu(out) (same layout)
     float* out_silu_split;       // optional: tf32 hi / lo split of silu(out), stacked [rows/64][128][N] (operand of cond_tc.cuh)
@@ -677,7 +743,11 @@ small_linear_kernel(SmallLinear p)
             float v = acc[i][j];
             if (bias) v += bias[n];
             if (p.add) v += p.add[(size_t)r * p.N + n];
-            if (p.emb) v += p.emb[(size_t)p.labels[r] * p.N + n];
+            if (p.emb) {
+                long long lab = p.labels[r];
+                if (lab < 0 || lab >= p.num_emb) { if (p.err) atomicOr(p.err, 1); lab = 0; }
+                v += p.emb[(size_t)lab * p.N + n];
+            }
             out[(size_t)r * p.ldo + n] = v;
             if (out_silu) out_silu[(size_t)r * p.ldo + n] = v / (1.f + expf(-v));
             if (p.out_silu_split) {
@@ -704,7 +774,11 @@ __global__ void small_linear_finalize_kernel(SmallLinear p)
     for (int s = 0; s < p.ksplit; ++s) v += part[(size_t)s * total];
     if (p.bias) v += p.bias[z * p.bias_batch_stride + n];
     if (p.add) v += p.add[(size_t)r * p.N + n];
-    if (p.emb) v += p.emb[(size_t)p.labels[r] * p.N + n];
+    if (p.emb) {
+        long long lab = p.labels[r];
+        if (lab < 0 || lab >= p.num_emb) { if (p.err) atomicOr(p.err, 1); lab = 0; }
+        v += p.emb[(size_t)lab * p.N + n];
+    }
     p.out[z * p.out_batch_stride + (size_t)r * p.ldo + n] = v;
     if (p.out_silu) p.out_silu[z * p.out_batch_stride + (size_t)r * p.ldo + n] = v / (1.f + expf(-v));
     if (p.out_silu_split) {

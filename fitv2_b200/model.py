@@ -11,6 +11,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import weakref
 from typing import Optional
 
 import torch
@@ -22,6 +23,40 @@ from .rope import rope_frequencies, online_rope_frequencies, _ONLINE_RULES
 
 class _Holder(nn.Module):
     """Parameter container (never called)."""
+
+
+class _NormWeight(nn.Module):
+    """``norm.weight`` of a weighted LayerNorm / RMSNorm (fit/model/norms.py:35-50): ones, never called."""
+
+    def __init__(self, dim: int):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(dim))
+
+
+# ------------------------------------------------------------------------------------------------
+# torch.library registration: the forward is a registered operator (with a fake / meta kernel), so torch.jit.trace,
+# fvcore's FlopCountAnalysis (sample_fitv2_ddp.py:197-213) and torch.export see a node with a data dependence from x to the
+# output instead of an opaque ctypes call writing into torch.empty.  The module instance is passed by registry id.
+# ------------------------------------------------------------------------------------------------
+_MODELS: "weakref.WeakValueDictionary[int, FiT]" = weakref.WeakValueDictionary()
+
+
+@torch.library.custom_op("fitv2_b200::forward", mutates_args=(), device_types="cuda")
+def _forward_op(x: torch.Tensor, t: torch.Tensor, y: torch.Tensor, grid: torch.Tensor, mask: torch.Tensor, model_id: int,
+                rows: int) -> torch.Tensor:
+    model = _MODELS.get(model_id)
+    if model is None:
+        raise _lib.FitV2Error(f"fitv2_b200::forward: model {model_id} is gone")
+    return model._run(x, t, y, grid, mask, rows)
+
+
+@_forward_op.register_fake
+def _(x, t, y, grid, mask, model_id, rows):
+    model = _MODELS.get(model_id)
+    co = model.out_token_channels if model is not None else x.shape[-1]
+    if model is not None and not model.use_sit:
+        return x.new_empty((rows, co, x.shape[2]), dtype=torch.float32)
+    return x.new_empty((rows, x.shape[1], co), dtype=torch.float32)
 
 
 def _seq(*mods):
@@ -46,19 +81,25 @@ class FiT(nn.Module):
         super().__init__()
         # ---- reject what the kernels do not implement (no silent fallback) ----
         unsupported = []
-        if not use_sit: unsupported.append("use_sit=False (FiTv1 (B,C,N) layout)")
-        if learn_sigma: unsupported.append("learn_sigma=True")
-        if not use_swiglu: unsupported.append("use_swiglu must be True")
-        if adaln_type != "lora" or not adaln_lora_dim: unsupported.append("adaln_type must be 'lora' with adaln_lora_dim")
+        assert not (learn_sigma and use_sit)                                # fit_model.py:68
+        if not use_swiglu: unsupported.append("use_swiglu must be True (the GELU Mlp is not built)")
+        if adaln_type not in ("lora", "normal"): unsupported.append("adaln_type must be 'lora' or 'normal'")
+        if adaln_type == "lora" and not adaln_lora_dim: unsupported.append("adaln_type='lora' needs adaln_lora_dim")
         if (rel_pos_embed or "").lower() != "rope": unsupported.append("rel_pos_embed must be 'rope'")
-        if norm_type != "layernorm": unsupported.append("norm_type must be 'layernorm'")
-        if q_norm != "layernorm" or k_norm != "layernorm" or qk_norm_weight: unsupported.append("q_norm/k_norm must be 'layernorm' without weight")
+        try:
+            self.block_norm = _lib.norm_code(norm_type)
+            self.q_norm_code = _lib.norm_code(q_norm, qk_norm_weight)
+            self.k_norm_code = _lib.norm_code(k_norm, qk_norm_weight)
+        except NotImplementedError as e:
+            unsupported.append(str(e))
+            self.block_norm = self.q_norm_code = self.k_norm_code = _lib.NORM_LAYERNORM
+        if self.block_norm == _lib.NORM_NONE: unsupported.append("norm_type must be 'layernorm', 'w_layernorm' or 'rmsnorm'")
         if not (qkv_bias and ffn_bias and adaln_bias): unsupported.append("qkv_bias/ffn_bias/adaln_bias must be True")
         if online_rope and (custom_freqs.lower() not in _ONLINE_RULES or not isinstance(ori_max_pe_len, int)):
             unsupported.append("online_rope=True needs custom_freqs in ('linear', 'ntk-aware', 'ntk-by-parts') and ori_max_pe_len "
                                "(the reference's online mode has no 'normal' branch and never sets the yarn / ntk-aware-pro magnitudes)")
         if add_rel_pe_to_v: unsupported.append("add_rel_pe_to_v=True")
-        if use_checkpoint: unsupported.append("use_checkpoint=True (inference only)")
+        # use_checkpoint (activation checkpointing, fit_model.py:222-226) changes nothing in a no-grad forward: accepted, unused
         if finetune is not None or pretrain_ckpt is not None: unsupported.append("pretrain_ckpt/finetune (load weights with load_state_dict)")
         if save_attention: unsupported.append("save_attention=True")
         if patch_size ** 2 * in_channels != 16: unsupported.append("patch_size**2 * in_channels must be 16")
@@ -71,7 +112,7 @@ class FiT(nn.Module):
         self.learn_sigma, self.use_sit, self.use_checkpoint = learn_sigma, use_sit, use_checkpoint
         self.mlp_ratio, self.class_dropout_prob, self.num_classes = mlp_ratio, class_dropout_prob, num_classes
         self.in_channels = in_channels
-        self.out_channels = in_channels
+        self.out_channels = in_channels * 2 if learn_sigma else in_channels   # fit_model.py:78
         self.patch_size, self.num_heads = patch_size, num_heads
         self.adaln_type, self.adaln_lora_dim = adaln_type, adaln_lora_dim
         self.online_rope, self.time_shifting, self.save_attention = online_rope, time_shifting, False
@@ -88,32 +129,46 @@ class FiT(nn.Module):
         rope_frequencies(**self.rope_args)                                  # validate early
         self._online_key, self._online_freqs = None, None
 
-        # ---- parameters: same names / shapes / creation order as the reference (fit_model.py:84-112) ----
+        # ---- parameters: same names / shapes / creation order as the reference (fit_model.py:84-112, modules.py:239-264) ----
         D, C = hidden_size, in_channels * patch_size ** 2
+        wn = lambda code, dim: _NormWeight(dim) if code in (_lib.NORM_WLAYERNORM, _lib.NORM_RMSNORM) else _Holder()
         self.x_embedder = _Holder(); self.x_embedder.proj = nn.Linear(C, D)
         self.t_embedder = _Holder(); self.t_embedder.mlp = _seq(nn.Linear(256, D), nn.SiLU(), nn.Linear(D, D))
         self.y_embedder = _Holder()
         self.y_embedder.embedding_table = nn.Embedding(num_classes + (class_dropout_prob > 0), D)
-        self.global_adaLN_modulation = _seq(nn.SiLU(), nn.Linear(D, 6 * D))
+        self.global_adaLN_modulation = _seq(nn.SiLU(), nn.Linear(D, 6 * D)) if adaln_type == "lora" else None
         blocks = []
         for _ in range(depth):
             blk = _Holder()
-            blk.attn = _Holder(); blk.attn.qkv = nn.Linear(D, 3 * D); blk.attn.proj = nn.Linear(D, D)
+            blk.norm1, blk.norm2 = wn(self.block_norm, D), wn(self.block_norm, D)
+            blk.attn = _Holder(); blk.attn.qkv = nn.Linear(D, 3 * D)
+            blk.attn.q_norm, blk.attn.k_norm = wn(self.q_norm_code, self.head_dim), wn(self.k_norm_code, self.head_dim)
+            blk.attn.proj = nn.Linear(D, D)
             blk.mlp = _Holder()
             blk.mlp.fc1_g = nn.Linear(D, self.mlp_hidden); blk.mlp.fc1_x = nn.Linear(D, self.mlp_hidden)
             blk.mlp.fc2 = nn.Linear(self.mlp_hidden, D)
-            blk.adaLN_modulation = _seq(nn.SiLU(), nn.Linear(D, adaln_lora_dim), nn.Linear(adaln_lora_dim, 6 * D))
+            if adaln_type == "lora":
+                blk.adaLN_modulation = _seq(nn.SiLU(), nn.Linear(D, adaln_lora_dim), nn.Linear(adaln_lora_dim, 6 * D))
+            else:
+                blk.adaLN_modulation = _seq(nn.SiLU(), nn.Linear(D, 6 * D))
             blocks.append(blk)
         self.blocks = nn.ModuleList(blocks)
         self.final_layer = _Holder()
-        self.final_layer.linear = nn.Linear(D, C)
+        self.final_layer.norm_final = wn(self.block_norm, D)
+        self.final_layer.linear = nn.Linear(D, patch_size * patch_size * self.out_channels)
         self.final_layer.adaLN_modulation = _seq(nn.SiLU(), nn.Linear(D, 2 * D))
         self.initialize_weights()
 
         self._handle = None
+        self._handle_device = None
         self._packed = None
         self._workspace = None
         self._ws_shape = None
+        _MODELS[id(self)] = self
+
+    @property
+    def out_token_channels(self) -> int:
+        return self.patch_size * self.patch_size * self.out_channels
 
     # ------------------------------------------------------------------------------------------
     # weights
@@ -135,7 +190,10 @@ class FiT(nn.Module):
         for blk in self.blocks:
             nn.init.constant_(blk.adaLN_modulation[-1].weight, 0)
             nn.init.constant_(blk.adaLN_modulation[-1].bias, 0)
-        for lin in (self.global_adaLN_modulation[-1], self.final_layer.adaLN_modulation[-1], self.final_layer.linear):
+        if self.global_adaLN_modulation is not None:                        # fit_model.py:146-148 (adaln_type 'lora' only)
+            nn.init.constant_(self.global_adaLN_modulation[-1].weight, 0)
+            nn.init.constant_(self.global_adaLN_modulation[-1].bias, 0)
+        for lin in (self.final_layer.adaLN_modulation[-1], self.final_layer.linear):
             nn.init.constant_(lin.weight, 0)
             nn.init.constant_(lin.bias, 0)
 
@@ -161,7 +219,13 @@ class FiT(nn.Module):
         self._packed = None
         self._workspace = None
         self._ws_shape = None
+        self._online_key = None
         return out
+
+    def _drop_handle(self):
+        if getattr(self, "_handle", None) is not None:
+            _lib.load().fitv2_destroy(self._handle)
+        self._handle, self._handle_device, self._packed, self._workspace, self._ws_shape = None, None, None, None, None
 
     @property
     def dtype(self) -> torch.dtype:
@@ -188,16 +252,23 @@ class FiT(nn.Module):
         dev = self._require_cuda()
         lib = _lib.load()
         fh, fw, mag = rope_frequencies(**self.rope_args)
+        if self._handle is not None and self._handle_device != dev:         # .to('cuda:1'): a handle belongs to one device
+            self._drop_handle()
         with torch.cuda.device(dev):
             if self._handle is None:
                 cfg = _lib.FitV2Config(self.hidden_size, self.depth, self.num_heads, self.head_dim, self.mlp_hidden,
-                                       self.adaln_lora_dim, self.in_channels * self.patch_size ** 2,
+                                       self.adaln_lora_dim or 0, self.in_channels * self.patch_size ** 2,
                                        self.y_embedder.embedding_table.weight.shape[0],
                                        _lib.OPERAND_FP16 if self.operand_dtype == "fp16" else _lib.OPERAND_BF16,
-                                       float(self.time_shifting), float(mag))
+                                       float(self.time_shifting), float(mag),
+                                       out_channels=self.out_token_channels,
+                                       adaln_type=_lib.ADALN_LORA if self.adaln_type == "lora" else _lib.ADALN_NORMAL,
+                                       block_norm=self.block_norm, q_norm=self.q_norm_code, k_norm=self.k_norm_code,
+                                       channels_first=0 if self.use_sit else 1)
                 h = C.c_void_p()
                 _lib.check(lib.fitv2_create(C.byref(cfg), C.byref(h)), "fitv2_create")
-                self._handle = h
+                self._handle, self._handle_device = h, dev
+                _lib.apply_env_options(h)                                   # FITV2_* tuning switches -> fitv2_set_option
             op = torch.float16 if self.operand_dtype == "fp16" else torch.bfloat16
             P = self.pack_weights(dev)
             for name, tns in P.items():
@@ -206,6 +277,17 @@ class FiT(nn.Module):
                 _lib.check(lib.fitv2_bind_weight(self._handle, _lib.SLOT[name], C.c_void_p(tns.data_ptr()), tns.numel()),
                            f"fitv2_bind_weight({name})")
             self._packed = P
+
+    def set_option(self, name: str, value: int):
+        """Per-handle tuning switch (include/fitv2_b200.h: fitv2_set_option)."""
+        self._ensure_packed()
+        _lib.check(_lib.load().fitv2_set_option(self._handle, name.encode(), int(value)), f"fitv2_set_option({name})")
+
+    def check_device_errors(self):
+        """Raise if a kernel of an earlier call saw an out-of-range class label (the reference raises an IndexError /
+        device assert there).  Non-blocking; meaningful after a synchronisation."""
+        if self._handle is not None:
+            _lib.check(_lib.load().fitv2_poll_error(self._handle), "fitv2_poll_error")
 
     @torch.no_grad()
     def pack_weights(self, dev) -> dict:
@@ -239,10 +321,6 @@ class FiT(nn.Module):
             "T_MLP0_W": f32(self.t_embedder.mlp[0].weight), "T_MLP0_B": f32(self.t_embedder.mlp[0].bias),
             "T_MLP2_W": f32(self.t_embedder.mlp[2].weight), "T_MLP2_B": f32(self.t_embedder.mlp[2].bias),
             "Y_TABLE": f32(self.y_embedder.embedding_table.weight),
-            "GLOBAL_ADALN_W": tf32(f32(self.global_adaLN_modulation[1].weight)),
-            "GLOBAL_ADALN_B": f32(self.global_adaLN_modulation[1].bias),
-            "LORA_A_W": tf32(stack32(lambda b: b.adaLN_modulation[1].weight)), "LORA_A_B": stack32(lambda b: b.adaLN_modulation[1].bias),
-            "LORA_B_W": tf32(stack32(lambda b: b.adaLN_modulation[2].weight)), "LORA_B_B": stack32(lambda b: b.adaLN_modulation[2].bias),
             "FINAL_ADALN_W": tf32(f32(self.final_layer.adaLN_modulation[1].weight)),
             "FINAL_ADALN_B": f32(self.final_layer.adaLN_modulation[1].bias),
             "FINAL_LINEAR_W": f32(self.final_layer.linear.weight), "FINAL_LINEAR_B": f32(self.final_layer.linear.bias),
@@ -253,6 +331,23 @@ class FiT(nn.Module):
             "FC2_W": stack16(lambda b: b.mlp.fc2.weight), "FC2_B": stack32(lambda b: b.mlp.fc2.bias),
             "ROPE_FREQS_H": fh.to(dev).contiguous(), "ROPE_FREQS_W": fw.to(dev).contiguous(),
         }
+        if self.adaln_type == "lora":
+            P.update({
+                "GLOBAL_ADALN_W": tf32(f32(self.global_adaLN_modulation[1].weight)),
+                "GLOBAL_ADALN_B": f32(self.global_adaLN_modulation[1].bias),
+                "LORA_A_W": tf32(stack32(lambda b: b.adaLN_modulation[1].weight)), "LORA_A_B": stack32(lambda b: b.adaLN_modulation[1].bias),
+                "LORA_B_W": tf32(stack32(lambda b: b.adaLN_modulation[2].weight)), "LORA_B_B": stack32(lambda b: b.adaLN_modulation[2].bias),
+            })
+        else:                                                               # modules.py:254-258: one Linear(D -> 6D) per block
+            P.update({"NORMAL_ADALN_W": tf32(stack32(lambda b: b.adaLN_modulation[1].weight)),
+                      "NORMAL_ADALN_B": stack32(lambda b: b.adaLN_modulation[1].bias)})
+        if self.block_norm != _lib.NORM_LAYERNORM:
+            P.update({"NORM1_W": stack32(lambda b: b.norm1.weight), "NORM2_W": stack32(lambda b: b.norm2.weight),
+                      "NORM_FINAL_W": f32(self.final_layer.norm_final.weight)})
+        if self.q_norm_code in (_lib.NORM_WLAYERNORM, _lib.NORM_RMSNORM):
+            P["Q_NORM_W"] = stack32(lambda b: b.attn.q_norm.weight)
+        if self.k_norm_code in (_lib.NORM_WLAYERNORM, _lib.NORM_RMSNORM):
+            P["K_NORM_W"] = stack32(lambda b: b.attn.k_norm.weight)
         return P
 
     def _ensure_workspace(self, rows: int, tokens: int):
@@ -271,23 +366,29 @@ class FiT(nn.Module):
         self._ws_shape = (rows, tokens)
 
     def _run(self, x: torch.Tensor, t, y, grid, mask, rows: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """x (x_rows, N, C) fp32 contiguous with x_rows == rows or rows // 2 (implicit CFG duplication)."""
+        """x fp32 contiguous, (x_rows, N, C) (use_sit) or (x_rows, C, N), with x_rows == rows or rows // 2 (implicit CFG
+        duplication).  Returns (rows, N, C_out) / (rows, C_out, N)."""
         self._ensure_packed()
         dev = self.device
         for name, tns in (("x", x), ("t", t), ("y", y), ("grid", grid), ("mask", mask)):
             if tns.device != dev:
                 raise _lib.FitV2Error(f"{name} is on {tns.device}, the model on {dev}")
-        x_rows, tokens, ch = x.shape
+        if self.use_sit:
+            x_rows, tokens, ch = x.shape
+        else:
+            x_rows, ch, tokens = x.shape
         assert x.dtype == torch.float32 and x.is_contiguous()
         t = t.to(torch.float32).contiguous()
         y = y.to(torch.int64).contiguous()
         grid = grid.to(torch.int64).contiguous()
         mask = mask.to(torch.float32).contiguous()
-        if t.shape != (rows,) or y.shape != (rows,) or grid.shape != (rows, 2, tokens) or mask.shape != (rows, tokens):
-            raise ValueError(f"shape mismatch: rows={rows} tokens={tokens} t{tuple(t.shape)} y{tuple(y.shape)} "
+        if ch != self.in_channels * self.patch_size ** 2 or t.shape != (rows,) or y.shape != (rows,) or grid.shape != (rows, 2, tokens) \
+                or mask.shape != (rows, tokens):
+            raise ValueError(f"shape mismatch: rows={rows} tokens={tokens} x{tuple(x.shape)} t{tuple(t.shape)} y{tuple(y.shape)} "
                              f"grid{tuple(grid.shape)} mask{tuple(mask.shape)}")
+        co = self.out_token_channels
         if out is None:
-            out = torch.empty((rows, tokens, ch), dtype=torch.float32, device=dev)
+            out = torch.empty((rows, tokens, co) if self.use_sit else (rows, co, tokens), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
             self._ensure_workspace(rows, tokens)
             st = torch.cuda.current_stream(dev).cuda_stream
@@ -301,8 +402,9 @@ class FiT(nn.Module):
     # reference-facing API
     # ------------------------------------------------------------------------------------------
     def _set_online_rope(self, size, rows: int):
-        """online_rope (fit_model.py:212-214): per-sample frequencies from ``size`` (B,1,2), recomputed only when the
-        caller hands in a different tensor (a sampling loop passes the same one every step)."""
+        """online_rope (fit_model.py:212-214): per-sample frequencies from ``size`` (B,1,2).  The cache is keyed on the VALUES
+        of ``size`` (a fresh tensor per batch usually reuses the freed allocation of the previous one, so a storage key would
+        hand a new batch the old frequencies); a sampling loop should bind once through ``EulerCFGSampler(size=...)``."""
         if not self.online_rope:
             return
         if size is None:
@@ -310,11 +412,11 @@ class FiT(nn.Module):
         if size.reshape(-1, 2).shape[0] != rows:
             raise ValueError(f"size has {size.reshape(-1, 2).shape[0]} rows, the batch {rows}")
         self._ensure_packed()
-        key = (size.data_ptr(), size._version, tuple(size.shape), str(size.device))
+        key = tuple(size.reshape(-1).tolist())
         if key != self._online_key:
             a = self.rope_args
             fh, fw = online_rope_frequencies(a["head_dim"], a["custom_freqs"], a["theta"], a["decouple"], a["ori_max_pe_len"], size)
-            self._online_freqs = (fh.to(self.device), fw.to(self.device))
+            self._online_freqs = (fh.to(self.device), fw.to(self.device))  # kept alive until replaced: the forward reads them
             self._online_key = key
         fh, fw = self._online_freqs
         _lib.check(_lib.load().fitv2_set_online_rope(self._handle, C.c_void_p(fh.data_ptr()), C.c_void_p(fw.data_ptr()), rows),
@@ -322,11 +424,15 @@ class FiT(nn.Module):
 
     @torch.no_grad()
     def forward(self, x, t, y, grid, mask, size=None):
-        """fit_model.py:189-233.  x (B,N,p*p*C), t (B,), y (B,), grid (B,2,N), mask (B,N); ``size`` (B,1,2) is read only
-        with online_rope=True.  Returns the velocity (B,N,p*p*C) in x.dtype."""
+        """fit_model.py:189-233.  x (B,N,p*p*C) (use_sit) or (B,p*p*C,N), t (B,), y (B,), grid (B,2,N), mask (B,N); ``size``
+        (B,1,2) is read only with online_rope=True.  Returns the model output (B,N,p*p*C_out) / (B,p*p*C_out,N) in x.dtype.
+        Dispatched as the registered operator ``fitv2_b200::forward`` (traceable, see the top of this file)."""
         xf = x.to(torch.float32).contiguous()
-        self._set_online_rope(size, x.shape[0])
-        out = self._run(xf, t, y, grid, mask, rows=x.shape[0])
+        if xf.is_cuda:
+            self._set_online_rope(size, x.shape[0])
+            out = torch.ops.fitv2_b200.forward(xf, t, y, grid, mask, id(self), x.shape[0])
+        else:
+            out = self._run(xf, t, y, grid, mask, rows=x.shape[0])          # raises: no CPU path
         return out if x.dtype == torch.float32 else out.to(x.dtype)
 
     @torch.no_grad()
@@ -345,10 +451,13 @@ class FiT(nn.Module):
             per = ((cfg_scale - 1) * step + 1)[:half].contiguous()
             scale_ptr = C.c_void_p(per.data_ptr())
         lib = _lib.load()
+        # (2B, N, C): guided channels are the first c_cfg of every token; (2B, C, N) (use_sit = False): the first c_cfg * N
+        # elements of every sample -- the same kernel with one "token" of C * N channels
+        tokens, chans, cc = (out.shape[1], out.shape[2], c_cfg) if self.use_sit else (1, out.shape[1] * out.shape[2], c_cfg * out.shape[2])
         with torch.cuda.device(self.device):
             st = torch.cuda.current_stream(self.device).cuda_stream
-            _lib.check(lib.fitv2_cfg_combine(C.c_void_p(out.data_ptr()), scale_ptr, scale, half, out.shape[1], out.shape[2],
-                                             c_cfg, C.c_void_p(st)), "fitv2_cfg_combine")
+            _lib.check(lib.fitv2_cfg_combine(C.c_void_p(out.data_ptr()), scale_ptr, scale, half, tokens, chans,
+                                             cc, C.c_void_p(st)), "fitv2_cfg_combine")
         return out if x.dtype == torch.float32 else out.to(x.dtype)
 
     def unpatchify(self, x, hw, scaling_factor: float = 1.0):
@@ -359,6 +468,8 @@ class FiT(nn.Module):
         h, w = hw
         p = self.patch_size
         B = x.shape[0]
+        if not self.use_sit:                                                # fit_model.py:184-186: 'b (c p1 p2) (h w)' input
+            x = x.transpose(1, 2)
         if x.is_cuda and x.dtype == torch.float32:
             x = x.contiguous()
             ch = x.shape[2] // (p * p)
@@ -422,3 +533,17 @@ class FiT(nn.Module):
                 self._handle = None
         except Exception:
             pass
+
+    def __deepcopy__(self, memo):
+        # the C handle / workspace are per instance: a copy gets its own lazily
+        import copy
+        cls = self.__class__
+        new = cls.__new__(cls)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            if k in ("_handle", "_handle_device", "_packed", "_workspace", "_ws_shape", "_online_key", "_online_freqs"):
+                setattr(new, k, None)
+            else:
+                setattr(new, k, copy.deepcopy(v, memo))
+        _MODELS[id(new)] = new
+        return new

@@ -30,12 +30,24 @@ class EulerCFGSampler:
     """Holds the static per-batch tensors (labels, grid, mask, sigma schedule) of one sampling job."""
 
     def __init__(self, model: FiT, y: torch.Tensor, grid: torch.Tensor, mask: torch.Tensor, num_steps: int,
-                 cfg_scale: float, use_cuda_graph: bool = False):
+                 cfg_scale: float, use_cuda_graph: bool = False, size: Optional[torch.Tensor] = None):
         self.model, self.num_steps, self.cfg_scale = model, num_steps, float(cfg_scale)
         self.using_cfg = cfg_scale > 1.0                                # sample_fitv2_ddp.py:242 (the script's default --cfg-scale is 1.0)
         dev = model.device
         n = y.shape[0]
         self.n = n
+        if not model.use_sit:
+            raise NotImplementedError("the Euler / CFG loop of sample_fitv2_ddp.py integrates a velocity model (use_sit=True)")
+        if self.using_cfg and model.y_embedder.embedding_table.weight.shape[0] <= model.num_classes:
+            raise ValueError("cfg_scale > 1 needs the null-class row of the label table (class_dropout_prob > 0, "
+                             "sample_fitv2_ddp.py:277)")
+        if model.online_rope and size is None:
+            raise ValueError("online_rope=True: pass `size` (n, 1, 2) = (h, w) patches per sample (sample_fitv2_ddp.py:269-271)")
+        # online_rope: the per-sample frequencies depend on `size` only, so they are bound ONCE here (duplicated for the CFG
+        # rows like every other model input, sample_fitv2_ddp.py:278-282) instead of inside the step loop
+        self.size2 = None
+        if size is not None:
+            self.size2 = (torch.cat([size, size], 0) if self.using_cfg else size).to(torch.int64)
         if self.using_cfg:
             self.y2 = torch.cat([y.to(dev, torch.int64), torch.full((n,), model.num_classes, dtype=torch.int64, device=dev)], 0)
             self.grid2 = torch.cat([grid, grid], 0).to(dev, torch.int64).contiguous()
@@ -57,6 +69,8 @@ class EulerCFGSampler:
         self._ds_cur = torch.zeros(1, dtype=torch.float32, device=dev)
         self._v2 = None
         self._z = None
+        if model.online_rope:
+            model._set_online_rope(self.size2, self.rows)
 
     def _step(self, z: torch.Tensor, t_rows: torch.Tensor, dsig_dev: torch.Tensor, scale_dev: Optional[torch.Tensor] = None):
         m = self.model
@@ -78,6 +92,8 @@ class EulerCFGSampler:
         m = self.model
         z = z.to(m.device, torch.float32).contiguous().clone()
         steps = self.num_steps if first_steps is None else first_steps
+        if m.online_rope:                                               # another caller may have bound other frequencies since
+            m._set_online_rope(self.size2, self.rows)
         with torch.cuda.device(m.device):
             if not self.use_cuda_graph:
                 for i in range(steps):
@@ -97,18 +113,23 @@ class EulerCFGSampler:
                     self._step(self._z, self._t_cur, self._ds_cur, self._sc_cur)
             self._z.copy_(z)
             for i in range(steps):
-                self._t_cur.copy_(self.t_table[i])
-                self._ds_cur.copy_(self.dsig[i:i + 1])
-                self._sc_cur.copy_(self.step_scale[i])
-                self._graph.replay()
+                self.replay_step(i)
             return self._z.clone()
+
+    def replay_step(self, i: int):
+        """One step of the captured graph (after ``sample`` has captured it): copies the step's scalars into the graph's
+        device buffers and replays."""
+        self._t_cur.copy_(self.t_table[i])
+        self._ds_cur.copy_(self.dsig[i:i + 1])
+        self._sc_cur.copy_(self.step_scale[i])
+        self._graph.replay()
 
 
 @torch.no_grad()
 def euler_cfg_sample(model: FiT, z, y, grid, mask, size=None, num_steps: int = 250, cfg_scale: float = 1.5,
                      use_cuda_graph: bool = False, first_steps: Optional[int] = None) -> torch.Tensor:
     """Functional form of the script's loop: z (n,N,C), y (n,), grid (n,2,N), mask (n,N)."""
-    return EulerCFGSampler(model, y, grid, mask, num_steps, cfg_scale, use_cuda_graph).sample(z, first_steps)
+    return EulerCFGSampler(model, y, grid, mask, num_steps, cfg_scale, use_cuda_graph, size=size).sample(z, first_steps)
 
 
 def pack_images_uint8(samples: torch.Tensor) -> torch.Tensor:

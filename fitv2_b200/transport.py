@@ -16,9 +16,15 @@ network evaluation between the velocity and the score term (the reference calls 
 transport.py:256-258).  The per-step scalars (score variance, diffusion coefficient, step sizes) are computed once
 on the host in fp32 with the reference's expression order and kept in a device table.
 
-Not built: adaptive ``dopri5`` (data-dependent number of network evaluations; ``torchdiffeq`` is an un-vendored
-dependency of the reference) and the likelihood ODE — both raise ``NotImplementedError``.  Paths / predictions
-other than Linear / velocity raise at ``create_transport``.
+ODE route: every FIXED-GRID solver of ``torchdiffeq.odeint`` that the reference's ``--ode-sampling-method`` string can name
+— ``euler``, ``midpoint``, ``heun2``, ``heun3``, ``rk4`` (torchdiffeq's rk4 is the 3/8-rule variant) — with one fused update
+kernel per stage (``fitv2_scaled_add`` / ``fitv2_rk_stage``).  ``torchdiffeq`` is an un-vendored dependency of the reference:
+its published ``fixed_grid.py`` / ``rk_common.py`` step functions are restated, expression order included.
+
+Not built: the ADAPTIVE solvers (``dopri5`` — the reference's ODE default —, ``dopri8``, ``bosh3``, ``adaptive_heun``, ...):
+their number of network evaluations depends on a per-step error norm read back on the host, so the step is not a fixed
+launch sequence; and the likelihood ODE (autograd through the network).  Both raise ``NotImplementedError`` naming the
+fixed-grid alternatives.  Paths / predictions other than Linear / velocity raise at ``create_transport``.
 """
 from __future__ import annotations
 
@@ -30,6 +36,7 @@ import torch as th
 
 from . import _lib
 
+_ODE_FIXED = ("euler", "midpoint", "heun2", "heun3", "rk4")
 _DIFFUSION_FORMS = ("constant", "SBDM", "sigma", "linear", "decreasing", "increasing-decreasing")
 
 
@@ -201,15 +208,17 @@ class Sampler:
     # ------------------------------------------------------------------ ODE
     def sample_ode(self, *, sampling_method="dopri5", num_steps=50, atol=1e-6, rtol=1e-3, reverse=False
                    ) -> Callable[..., List[th.Tensor]]:
-        """transport.py:358-401 with the fixed-grid methods of ``torchdiffeq.odeint`` ("euler", "midpoint") on
-        ``linspace(t0, t1, num_steps)`` (integrators.py:95-116); returns the solution at every grid point."""
-        if sampling_method not in ("euler", "midpoint"):
-            raise NotImplementedError(f"ODE method {sampling_method!r}: only the fixed-grid 'euler' and 'midpoint' solvers are built "
-                                      "(adaptive solvers have a data-dependent number of network evaluations)")
+        """transport.py:358-401 with the fixed-grid methods of ``torchdiffeq.odeint`` on ``linspace(t0, t1, num_steps)``
+        (integrators.py:95-116); returns the solution at every grid point.  ``atol`` / ``rtol`` are accepted for signature
+        compatibility (fixed-grid solvers ignore them, as in torchdiffeq)."""
+        if sampling_method not in _ODE_FIXED:
+            raise NotImplementedError(f"ODE method {sampling_method!r}: the fixed-grid solvers {_ODE_FIXED} are built; adaptive solvers "
+                                      "(dopri5, ...) have a data-dependent number of network evaluations and are out of scope")
         tr = self.transport
         t0, t1 = tr.check_interval(tr.train_eps, tr.sample_eps, sde=False, eval=True, reverse=reverse, last_step_size=0.0)
         ts = th.linspace(t0, t1, num_steps)
         lib = _lib.load()
+        third, two_thirds = 1.0 / 3.0, 2.0 / 3.0                                 # rk_common.py: _one_third, _two_thirds
 
         def _sample(x: th.Tensor, model: Callable, **model_kwargs) -> List[th.Tensor]:
             y = _check_state(x, "x").clone()
@@ -224,19 +233,40 @@ class Sampler:
 
             with th.cuda.device(dev), th.no_grad():
                 st = _stream(dev)
+
+                def stage(out, k1, k2, k3, k4, dt, mode, s1=0.0, s2=0.0, s3=0.0):
+                    sc = th.stack([_f32(dt), _f32(s1), _f32(s2), _f32(s3)]).to(dev)
+                    _lib.check(lib.fitv2_rk_stage(_p(out), _p(y), _p(k1), _p(k2), _p(k3), _p(k4), _p(sc), mode, n, st), "fitv2_rk_stage")
+                    return out
+
                 for i in range(num_steps - 1):
                     ta, tb = ts[i], ts[i + 1]
                     dt = tb - ta
                     if sampling_method == "euler":
                         s = th.stack([_f32(1.0), dt]).to(dev)
                         _lib.check(lib.fitv2_scaled_add(_p(y), _p(y), _p(f(ta, y)), _p(s), n, st), "fitv2_scaled_add")
-                    else:
+                    elif sampling_method == "midpoint":
                         half = 0.5 * dt
                         y_mid = th.empty_like(y)
                         s1 = th.stack([_f32(1.0), half]).to(dev)
                         _lib.check(lib.fitv2_scaled_add(_p(y_mid), _p(y), _p(f(ta, y)), _p(s1), n, st), "fitv2_scaled_add")
                         s2 = th.stack([_f32(1.0), dt]).to(dev)
                         _lib.check(lib.fitv2_scaled_add(_p(y), _p(y), _p(f(ta + half, y_mid)), _p(s2), n, st), "fitv2_scaled_add")
+                    elif sampling_method == "heun2":                             # tableau [[0,0,0],[1,1,0],[0,1/2,1/2]] (rk2_step_func)
+                        k1 = f(ta, y)
+                        k2 = f(ta + dt * 1.0, stage(th.empty_like(y), k1, None, None, None, dt, 0, 1.0))
+                        stage(y, k1, k2, None, None, dt, 1, 0.5, 0.5)
+                    elif sampling_method == "heun3":                             # tableau c = (0, 1/3, 2/3), b = (1/4, 0, 3/4) (rk3_step_func)
+                        k1 = f(ta, y)
+                        k2 = f(ta + dt * third, stage(th.empty_like(y), k1, None, None, None, dt, 0, third))
+                        k3 = f(ta + dt * two_thirds, stage(th.empty_like(y), k1, k2, None, None, dt, 1, 0.0, two_thirds))
+                        stage(y, k1, k2, k3, None, dt, 2, 0.25, 0.0, 0.75)
+                    else:                                                        # rk4: torchdiffeq's 3/8 rule (rk4_alt_step_func)
+                        k1 = f(ta, y)
+                        k2 = f(ta + dt * third, stage(th.empty_like(y), k1, None, None, None, dt, 0, third))
+                        k3 = f(ta + dt * two_thirds, stage(th.empty_like(y), k1, k2, None, None, dt, 3, third))
+                        k4 = f(tb, stage(th.empty_like(y), k1, k2, k3, None, dt, 4))
+                        stage(y, k1, k2, k3, k4, dt, 5)
                     ys.append(y.clone())
             return ys
 

@@ -11,7 +11,9 @@
  *     or frees device memory; the workspace is caller-provided via fitv2_set_workspace);
  *   - all work is enqueued on the `stream` argument (a cudaStream_t passed as void*), nothing
  *     synchronises; the calls are CUDA-graph capturable;
- *   - a handle is not thread-safe; use one handle per stream/thread.
+ *   - a handle is not thread-safe; use one handle per stream/thread.  A handle belongs to the CUDA device that was current
+ *     in fitv2_create (kernel attributes, TMA descriptors and the workspace live there); calls under another current
+ *     device fail with FITV2_E_INVALID.
  */
 #ifndef FITV2_B200_H_
 #define FITV2_B200_H_
@@ -32,8 +34,18 @@ extern "C" {
 #define FITV2_OPERAND_BF16    0   /* 16-bit GEMM / attention operand type: bfloat16 (default) */
 #define FITV2_OPERAND_FP16    1   /* float16 (same tensor-core rate, 3 more mantissa bits)   */
 
-/* Model geometry: the constructor contract of fit.model.fit_model.FiT (fit_model.py:25-65) for the
- * FiTv2 family (use_sit, SwiGLU, adaLN-LoRA, layernorm q/k norm, rope). */
+/* Normalisation kinds of fit/model/norms.py:35-50 (create_norm): block norms (norm1 / norm2 / norm_final, `norm_type`) accept
+ * LAYERNORM / WLAYERNORM / RMSNORM; the per-head q / k norms (`q_norm`, `k_norm`, `qk_norm_weight`) also NONE. */
+#define FITV2_NORM_NONE        0  /* nn.Identity                                                   */
+#define FITV2_NORM_LAYERNORM   1  /* nn.LayerNorm(elementwise_affine=False, eps 1e-6): FiTv2 default */
+#define FITV2_NORM_WLAYERNORM  2  /* nn.LayerNorm(bias=False): weight only                          */
+#define FITV2_NORM_RMSNORM     3  /* RMSNorm with weight (norms.py:53-77)                           */
+
+#define FITV2_ADALN_LORA       0  /* global adaLN + per-block LoRA (modules.py:259-264): FiTv2      */
+#define FITV2_ADALN_NORMAL     1  /* per-block Linear(D -> 6D), no global term (modules.py:254-258): FiTv1 / DiT */
+
+/* Model geometry: the constructor contract of fit.model.fit_model.FiT (fit_model.py:25-65).  Zero-initialised trailing
+ * fields select the FiTv2 family except for the three norm fields, which must be set (FITV2_NORM_LAYERNORM for FiTv2). */
 typedef struct fitv2_config {
     int32_t hidden_size;      /* D      : 1152 (XL/2), 2304 (3B/2)                  */
     int32_t depth;            /* L      : 36, 40                                    */
@@ -46,6 +58,12 @@ typedef struct fitv2_config {
     int32_t operand_dtype;    /* FITV2_OPERAND_*                                    */
     float   time_shifting;    /* fit_model.py:202 ; 1.0 for the released configs    */
     float   rope_magnitude;   /* cos/sin magnitude (yarn mscale / ntk-pro proportion), 1.0 otherwise */
+    int32_t out_channels;     /* p*p*C_out : 0 = token_channels; 32 with learn_sigma (fit_model.py:78) */
+    int32_t adaln_type;       /* FITV2_ADALN_*                                      */
+    int32_t block_norm;       /* FITV2_NORM_* of norm1 / norm2 / norm_final         */
+    int32_t q_norm;           /* FITV2_NORM_* of the per-head q norm (modules.py:146) */
+    int32_t k_norm;           /* FITV2_NORM_* of the per-head k norm (modules.py:147) */
+    int32_t channels_first;   /* 1: use_sit = False callers, x (B, C, N) -> out (B, C_out, N) (fit_model.py:204,231) */
 } fitv2_config;
 
 typedef struct fitv2_handle fitv2_handle;
@@ -66,7 +84,7 @@ enum fitv2_weight {
     FITV2_W_T_MLP2_W,          /* fp32 (D, D)           t_embedder.mlp.2.weight                       */
     FITV2_W_T_MLP2_B,          /* fp32 (D)                                                           */
     FITV2_W_Y_TABLE,           /* fp32 (num_embeddings, D)  y_embedder.embedding_table.weight         */
-    FITV2_W_GLOBAL_ADALN_W,    /* fp32 (6D, D)          global_adaLN_modulation.1.weight              */
+    FITV2_W_GLOBAL_ADALN_W,    /* fp32 (6D, D)          global_adaLN_modulation.1.weight   (this and the LORA_* slots: adaln_type 'lora' only) */
     FITV2_W_GLOBAL_ADALN_B,    /* fp32 (6D)                                                          */
     FITV2_W_LORA_A_W,          /* fp32 (L*lora, D)      blocks.i.adaLN_modulation.1.weight, stacked   */
     FITV2_W_LORA_A_B,          /* fp32 (L*lora)                                                      */
@@ -74,8 +92,8 @@ enum fitv2_weight {
     FITV2_W_LORA_B_B,          /* fp32 (L, 6D)                                                       */
     FITV2_W_FINAL_ADALN_W,     /* fp32 (2D, D)          final_layer.adaLN_modulation.1.weight         */
     FITV2_W_FINAL_ADALN_B,     /* fp32 (2D)                                                          */
-    FITV2_W_FINAL_LINEAR_W,    /* fp32 (16, D)          final_layer.linear.weight                     */
-    FITV2_W_FINAL_LINEAR_B,    /* fp32 (16)                                                          */
+    FITV2_W_FINAL_LINEAR_W,    /* fp32 (C_out, D)       final_layer.linear.weight  (C_out = 16, or 32 with learn_sigma) */
+    FITV2_W_FINAL_LINEAR_B,    /* fp32 (C_out)                                                       */
     FITV2_W_QKV_W,             /* OP16 (L, 3D, D)       blocks.i.attn.qkv.weight                      */
     FITV2_W_QKV_B,             /* fp32 (L, 3D)                                                       */
     FITV2_W_PROJ_W,            /* OP16 (L, D, D)        blocks.i.attn.proj.weight                     */
@@ -87,6 +105,14 @@ enum fitv2_weight {
     FITV2_W_FC2_B,             /* fp32 (L, D)                                                        */
     FITV2_W_ROPE_FREQS_H,      /* fp32 (head_dim/4)     VisionRotaryEmbedding.freqs_h (rope.py:162)   */
     FITV2_W_ROPE_FREQS_W,      /* fp32 (head_dim/4)     VisionRotaryEmbedding.freqs_w                 */
+    /* slots of the non-default variants; a slot the configuration does not use need not (and cannot) be bound */
+    FITV2_W_NORMAL_ADALN_W,    /* fp32 (L, 6D, D)       blocks.i.adaLN_modulation.1.weight, adaln_type 'normal' (tf32-rounded like the other adaLN matrices) */
+    FITV2_W_NORMAL_ADALN_B,    /* fp32 (L, 6D)                                                       */
+    FITV2_W_NORM1_W,           /* fp32 (L, D)           blocks.i.norm1.weight   (w_layernorm / rmsnorm) */
+    FITV2_W_NORM2_W,           /* fp32 (L, D)           blocks.i.norm2.weight                           */
+    FITV2_W_NORM_FINAL_W,      /* fp32 (D)              final_layer.norm_final.weight                   */
+    FITV2_W_Q_NORM_W,          /* fp32 (L, head_dim)    blocks.i.attn.q_norm.weight                     */
+    FITV2_W_K_NORM_W,          /* fp32 (L, head_dim)    blocks.i.attn.k_norm.weight                     */
     FITV2_W_COUNT
 };
 
@@ -96,6 +122,19 @@ const char* fitv2_version(void);
 /* Replaces FiT.__init__ (fit/model/fit_model.py:25-115) for the geometry part. */
 int fitv2_create(const fitv2_config* cfg, fitv2_handle** out);
 void fitv2_destroy(fitv2_handle* h);
+
+/* Per-handle tuning switches (they replace the FITV2_* environment variables of earlier versions; the Python layer forwards
+ * the environment when it creates a handle).  Names: "pdl" (1), "attn" (0 auto / 1 P-in-TMEM / 2 shared-memory-P / 3 online-max),
+ * "attn_early" (1), "attn_poly" (-1 = kernel default), "ln_threads" (64), "ln_wide_single" (0), "bn_resid" (0 = cost model),
+ * "qkv_heads" (3), "resid_t" (-1 auto), "bn_resid_t" (0 = cost model), "cond" (0 tensor pipe / 1 fp32 FMA), "l2_persist_mb" (0),
+ * "final_tc" (1), "verbose" (0).  Unknown names fail. */
+int fitv2_set_option(fitv2_handle* h, const char* name, int64_t value);
+
+/* Device-side checks report through a sticky word in pinned host memory instead of trapping: returns FITV2_E_INVALID (and
+ * clears the word) when a kernel launched through this handle saw a class label outside [0, num_embeddings) - the reference
+ * raises an index error there (modules.py:101-106).  Non-blocking: meaningful after the stream has been synchronised;
+ * fitv2_forward also calls it on entry. */
+int fitv2_poll_error(fitv2_handle* h);
 
 /* Replaces load_state_dict / init_from_ckpt binding (fit/utils/eval_utils.py:12-71): records the device
  * pointer of one packed weight.  `numel` is checked against the slot's expected element count. */
@@ -110,14 +149,15 @@ int fitv2_set_online_rope(fitv2_handle* h, const float* freqs_h_rows, const floa
 int64_t fitv2_workspace_bytes(const fitv2_handle* h, int rows, int tokens);
 int fitv2_set_workspace(fitv2_handle* h, void* dev_ptr, int64_t bytes);
 
-/* Replaces FiT.forward (fit/model/fit_model.py:189-233), use_sit layout.
+/* Replaces FiT.forward (fit/model/fit_model.py:189-233).  Layouts below are the use_sit ones; with cfg.channels_first
+ * x is (x_rows, C, tokens) and out (rows, C_out, tokens).
  *   x      fp32 (x_rows, tokens, C)  latent tokens; x_rows == rows, or rows/2 when the caller wants the
  *                                    CFG duplication cat([z, z]) of sample_fitv2_ddp.py:299 done implicitly
  *   t      fp32 (rows)               timesteps in [0, 1]
  *   y      int64 (rows)              class labels (num_classes = null class)
  *   grid   int64 (rows, 2, tokens)   [:,0] = w index, [:,1] = h index
  *   mask   fp32 (rows, tokens)       segment ids (0 = padding)
- *   out    fp32 (rows, tokens, C)    velocity; rows with mask 0 are exactly 0
+ *   out    fp32 (rows, tokens, C_out) velocity (or eps | sigma with learn_sigma); rows with mask 0 are exactly 0
  */
 int fitv2_forward(fitv2_handle* h, const float* x, int x_rows, const float* t, const int64_t* y,
                   const int64_t* grid, const float* mask, float* out, int rows, int tokens, void* stream);
@@ -155,6 +195,14 @@ int fitv2_heun_combine(float* out, const float* xhat, const float* k1, const flo
 /* "Tweedie" last step (transport.py:281-286): out = x/[6] + [7]*score(v, x, t). */
 int fitv2_tweedie(float* out, const float* x, const float* v, const float* coef_dev, int64_t n, void* stream);
 
+/* Fixed-grid Runge-Kutta stages of the reference's ODE route (Sampler.sample_ode -> torchdiffeq.odeint, integrators.py:109-116;
+ * torchdiffeq is an un-vendored dependency, its fixed_grid.py / rk_common.py step functions are restated).  s_dev: 4 device
+ * floats {dt, s1, s2, s3}; every operation is a separately rounded fp32 operation in PyTorch's evaluation order.
+ *   mode 0: out = y + (dt*k1)*s1          mode 1: out = y + dt*(k1*s1 + k2*s2)      mode 2: out = y + dt*(k1*s1 + k2*s2 + k3*s3)
+ *   mode 3: out = y + dt*(k2 - k1*s1)     mode 4: out = y + dt*(k1 - k2 + k3)       mode 5: out = y + (k1 + 3*(k2+k3) + k4)*dt*0.125 */
+int fitv2_rk_stage(float* out, const float* y, const float* k1, const float* k2, const float* k3, const float* k4,
+                   const float* s_dev, int mode, int64_t n, void* stream);
+
 /* ---- after the trajectory (sample_fitv2_ddp.py:319-324) ----
  * Replaces FiT.unpatchify (fit_model.py:171-187, use_sit layout) fused with the latent scaling `samples / vae.config.scaling_factor`:
  *   z (batch, hp*wp, channels*patch*patch) fp32 -> out (batch, channels, hp*patch, wp*patch) fp32, out = unpatchify(z) / scaling_factor
@@ -168,7 +216,8 @@ int fitv2_pack_uint8(const float* img, unsigned char* out, int batch, int channe
 int fitv2_debug_gemm(fitv2_handle* h, int epilogue /*3 = plain*/, const void* a, const void* w, const float* bias,
                      float* out32, int M, int N, int K, int bn, void* stream);
 /* dbg_s (128x128 fp32) / dbg_o (128 x head_dim_padded fp32), both nullable: raw S = Q K^T and P V tiles of
- * CTA (0,0,0), first key tile. */
+ * CTA (0,0,0), first key tile (served by the online-max kernel, attention_general.cuh).  The kernel follows the handle's
+ * q_norm / k_norm and the "attn" option like the forward does. */
 int fitv2_debug_attention(fitv2_handle* h, const void* q, const void* k, const void* vt, const float* mask,
                           void* out, int rows, int tokens, float* dbg_s, float* dbg_o, void* stream);
 int fitv2_debug_tap(fitv2_handle* h, int what, void* dst, int64_t bytes, void* stream);

@@ -69,6 +69,14 @@ class FiTConfig:
     max_cached_len: int = 256  # rope.py:126
     online_rope: bool = False  # fit_model.py:57,212-214: per-sample frequencies from `size`
     use_swiglu_large: bool = False  # modules.py:248-249: SwiGLU hidden = int(hidden*mlp_ratio) instead of 2/3 of it
+    # FiTv1-style variants (configs/fit/config_fit_xl.yaml:20-36) and the other norm kinds of norms.py:35-50
+    learn_sigma: bool = False       # fit_model.py:78: out_channels = 2 * in_channels
+    use_sit: bool = True            # fit_model.py:204,231: False = (B, C, N) tensors in and out
+    adaln_type: str = "lora"        # 'lora' (modules.py:259-264) or 'normal' (modules.py:254-258, no global adaLN)
+    norm_type: str = "layernorm"    # block norms: 'layernorm' (no affine) | 'w_layernorm' | 'rmsnorm'
+    q_norm: Optional[str] = "layernorm"
+    k_norm: Optional[str] = "layernorm"
+    qk_norm_weight: bool = False    # modules.py:141-144: promotes 'layernorm' to 'w_layernorm'
 
     @property
     def head_dim(self) -> int:
@@ -83,6 +91,20 @@ class FiTConfig:
     @property
     def token_channels(self) -> int:
         return self.in_channels * self.patch_size ** 2
+
+    @property
+    def out_token_channels(self) -> int:
+        return self.token_channels * (2 if self.learn_sigma else 1)
+
+    def norm_kind(self, which: str) -> Optional[str]:
+        """Resolved create_norm name of 'block' / 'q' / 'k' (modules.py:141-147)."""
+        if which == "block":
+            return self.norm_type.lower()
+        n = self.q_norm if which == "q" else self.k_norm
+        if n is None or n == "" or n.lower() == "none":
+            return None
+        n = n.lower()
+        return "w_layernorm" if (n == "layernorm" and self.qk_norm_weight) else n
 
 
 XL2 = dict(hidden_size=1152, depth=36, num_heads=16, adaln_lora_dim=288)   # configs/fitv2/config_fitv2_xl.yaml:26-47
@@ -263,10 +285,21 @@ class _SwiGLU(nn.Module):
         self.fc2 = nn.Linear(h, d)
 
 
-class _Attn(nn.Module):
-    def __init__(self, d):
+class _Norm(nn.Module):
+    """create_norm (norms.py:35-50): a ``weight`` of ones for 'w_layernorm' / 'rmsnorm', nothing otherwise."""
+    def __init__(self, kind: Optional[str], dim: int):
         super().__init__()
+        if kind in ("w_layernorm", "rmsnorm", "w_rmsnorm"):
+            self.weight = nn.Parameter(torch.ones(dim))
+
+
+class _Attn(nn.Module):
+    def __init__(self, cfg: "FiTConfig"):
+        super().__init__()
+        d = cfg.hidden_size
         self.qkv = nn.Linear(d, 3 * d)      # modules.py:140
+        self.q_norm = _Norm(cfg.norm_kind("q"), cfg.head_dim)   # modules.py:146-147
+        self.k_norm = _Norm(cfg.norm_kind("k"), cfg.head_dim)
         self.proj = nn.Linear(d, d)         # modules.py:151
 
 
@@ -274,17 +307,23 @@ class _Block(nn.Module):
     def __init__(self, cfg: FiTConfig):
         super().__init__()
         d = cfg.hidden_size
-        self.attn = _Attn(d)                                    # modules.py:237-242
+        self.norm1 = _Norm(cfg.norm_kind("block"), d)           # modules.py:239-240
+        self.norm2 = _Norm(cfg.norm_kind("block"), d)
+        self.attn = _Attn(cfg)                                  # modules.py:242-247
         self.mlp = _SwiGLU(d, cfg.mlp_hidden)                   # modules.py:250
-        self.adaLN_modulation = nn.Sequential(                  # modules.py:259-264
-            nn.SiLU(), nn.Linear(d, cfg.adaln_lora_dim), nn.Linear(cfg.adaln_lora_dim, 6 * d))
+        if cfg.adaln_type == "lora":
+            self.adaLN_modulation = nn.Sequential(              # modules.py:259-264
+                nn.SiLU(), nn.Linear(d, cfg.adaln_lora_dim), nn.Linear(cfg.adaln_lora_dim, 6 * d))
+        else:
+            self.adaLN_modulation = nn.Sequential(nn.SiLU(), nn.Linear(d, 6 * d))   # modules.py:254-258
 
 
 class _Final(nn.Module):
     def __init__(self, cfg: FiTConfig):
         super().__init__()
         d = cfg.hidden_size
-        self.linear = nn.Linear(d, cfg.token_channels)          # modules.py:283
+        self.norm_final = _Norm(cfg.norm_kind("block"), d)      # modules.py:282
+        self.linear = nn.Linear(d, cfg.out_token_channels)      # modules.py:283
         self.adaLN_modulation = nn.Sequential(nn.SiLU(), nn.Linear(d, 2 * d))  # modules.py:287-290
 
 
@@ -311,7 +350,10 @@ class _Skeleton(nn.Module):
         self.x_embedder = _X()
         self.t_embedder = _T()
         self.y_embedder = _Y()
-        self.global_adaLN_modulation = nn.Sequential(nn.SiLU(), nn.Linear(d, 6 * d))
+        if cfg.adaln_type == "lora":                                        # fit_model.py:97-103
+            self.global_adaLN_modulation = nn.Sequential(nn.SiLU(), nn.Linear(d, 6 * d))
+        else:
+            self.global_adaLN_modulation = None
         self.blocks = nn.ModuleList([_Block(cfg) for _ in range(cfg.depth)])
         self.final_layer = _Final(cfg)
 
@@ -338,8 +380,9 @@ def reference_init_state_dict(cfg: FiTConfig, seed: int = 0) -> Dict[str, torch.
     for blk in m.blocks:
         nn.init.constant_(blk.adaLN_modulation[-1].weight, 0)
         nn.init.constant_(blk.adaLN_modulation[-1].bias, 0)
-    nn.init.constant_(m.global_adaLN_modulation[-1].weight, 0)
-    nn.init.constant_(m.global_adaLN_modulation[-1].bias, 0)
+    if m.global_adaLN_modulation is not None:
+        nn.init.constant_(m.global_adaLN_modulation[-1].weight, 0)
+        nn.init.constant_(m.global_adaLN_modulation[-1].bias, 0)
     nn.init.constant_(m.final_layer.adaLN_modulation[-1].weight, 0)
     nn.init.constant_(m.final_layer.adaLN_modulation[-1].bias, 0)
     nn.init.constant_(m.final_layer.linear.weight, 0)
@@ -398,16 +441,33 @@ def conditioning(cfg: FiTConfig, sd, t: torch.Tensor, y: torch.Tensor) -> torch.
     return te + sd["y_embedder.embedding_table.weight"][y]
 
 
-def block_modulation(cfg: FiTConfig, sd, c: torch.Tensor, i: int, global_adaln: torch.Tensor) -> torch.Tensor:
-    """modules.py:259-264,271 -> (B, 6D)."""
+def block_modulation(cfg: FiTConfig, sd, c: torch.Tensor, i: int, global_adaln) -> torch.Tensor:
+    """modules.py:254-264,271 -> (B, 6D)."""
     s = F.silu(c)
     p = f"blocks.{i}.adaLN_modulation"
+    if cfg.adaln_type == "normal":
+        return _linear(s, sd, p + ".1") + global_adaln
     return _linear(_linear(s, sd, p + ".1"), sd, p + ".2") + global_adaln
 
 
 def layer_norm(x: torch.Tensor) -> torch.Tensor:
     """norms.py:41-42: nn.LayerNorm(dim, eps=1e-6, elementwise_affine=False)."""
     return F.layer_norm(x, (x.shape[-1],), eps=1e-6)
+
+
+def apply_norm(kind: Optional[str], x: torch.Tensor, sd, name: str) -> torch.Tensor:
+    """create_norm(kind, dim)(x) (norms.py:35-50, 53-77); ``name`` is the module path that owns ``weight``."""
+    if kind is None:
+        return x
+    if kind == "layernorm":
+        return layer_norm(x)
+    if kind == "w_layernorm":                                            # nn.LayerNorm(dim, eps, bias=False)
+        return F.layer_norm(x, (x.shape[-1],), weight=sd[name + ".weight"], eps=1e-6)
+    if kind in ("rmsnorm", "w_rmsnorm"):                                 # norms.py:72-77
+        xf = x.float()
+        out = (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-6)).type_as(x)
+        return out * sd[name + ".weight"]
+    raise NotImplementedError(kind)
 
 
 def modulate(x, shift, scale):
@@ -421,7 +481,8 @@ def attention(cfg: FiTConfig, sd, i: int, x, mask, cos, sin, quant=None, taps=No
     H, dh = cfg.num_heads, cfg.head_dim
     qkv = _linear(x, sd, f"blocks.{i}.attn.qkv", quant).reshape(B, N, 3, H, dh).permute(2, 0, 3, 1, 4)
     q, k, v = qkv.unbind(0)
-    q, k = layer_norm(q), layer_norm(k)                                  # :168
+    q = apply_norm(cfg.norm_kind("q"), q, sd, f"blocks.{i}.attn.q_norm")  # :168
+    k = apply_norm(cfg.norm_kind("k"), k, sd, f"blocks.{i}.attn.k_norm")
     q = q * cos + rotate_half(q) * sin                                   # :173
     k = k * cos + rotate_half(k) * sin                                   # :174
     if taps is not None:
@@ -453,27 +514,34 @@ def forward(cfg: FiTConfig, sd, x, t, y, grid, mask, size=None, quant: Optional[
     x = x.float()
     maskf = mask.to(x.dtype) if mask.dtype != torch.bool else mask
     c = conditioning(cfg, sd, t.to(x.dtype), y)
+    if not cfg.use_sit:
+        x = x.transpose(1, 2)                                            # :204 'B C N -> B N C'
+    bn = cfg.norm_kind("block")
     h = _linear(x, sd, "x_embedder.proj")                                # :206
     if cfg.online_rope:
         cos, sin = rope_cos_sin_online(cfg, grid, size)                  # :212-214
     else:
         cos, sin = rope_cos_sin(cfg, grid)                               # :216
     cos, sin = cos.unsqueeze(1), sin.unsqueeze(1)
-    g_adaln = _linear(F.silu(c), sd, "global_adaLN_modulation.1")        # :218-219
+    g_adaln = _linear(F.silu(c), sd, "global_adaLN_modulation.1") if cfg.adaln_type == "lora" else 0.0   # :218-221
     if taps is not None:
-        taps["c"], taps["global_adaln"], taps["x0"] = c.clone(), g_adaln.clone(), h.clone()
+        taps["c"], taps["x0"] = c.clone(), h.clone()
+        if cfg.adaln_type == "lora":
+            taps["global_adaln"] = g_adaln.clone()
     for i in range(cfg.depth):
         sh1, sc1, g1, sh2, sc2, g2 = block_modulation(cfg, sd, c, i, g_adaln).chunk(6, dim=1)
-        a = attention(cfg, sd, i, modulate(layer_norm(h), sh1, sc1), maskf, cos, sin, quant,
+        a = attention(cfg, sd, i, modulate(apply_norm(bn, h, sd, f"blocks.{i}.norm1"), sh1, sc1), maskf, cos, sin, quant,
                       taps if (taps is not None and i == 0) else None)
         h = h + g1.unsqueeze(1) * a                                      # modules.py:272
-        m = swiglu(cfg, sd, i, modulate(layer_norm(h), sh2, sc2), quant)
+        m = swiglu(cfg, sd, i, modulate(apply_norm(bn, h, sd, f"blocks.{i}.norm2"), sh2, sc2), quant)
         h = h + g2.unsqueeze(1) * m                                      # modules.py:273
         if taps is not None and i == 0:
             taps["x1"] = h.clone()
     shift, scale = _linear(F.silu(c), sd, "final_layer.adaLN_modulation.1").chunk(2, dim=1)
-    out = _linear(modulate(layer_norm(h), shift, scale), sd, "final_layer.linear")  # modules.py:292-296
-    return out * maskf[..., None]                                        # fit_model.py:230
+    out = _linear(modulate(apply_norm(bn, h, sd, "final_layer.norm_final"), shift, scale), sd, "final_layer.linear")  # modules.py:292-296
+    out = out * maskf[..., None]                                         # fit_model.py:230
+    return out if cfg.use_sit else out.transpose(1, 2)                   # :231-232 'B N C -> B C N'
+
 
 
 def forward_with_cfg(cfg: FiTConfig, sd, x, t, y, grid, mask, size, cfg_scale, scale_pow=0.0, quant=None):
@@ -482,7 +550,10 @@ def forward_with_cfg(cfg: FiTConfig, sd, x, t, y, grid, mask, size, cfg_scale, s
     combined = torch.cat([half, half], dim=0)
     out = forward(cfg, sd, combined, t, y, grid, mask, size, quant)
     c_cfg = 3 * cfg.patch_size * cfg.patch_size
-    eps, rest = out[:, :, :c_cfg], out[:, :, c_cfg:]
+    if cfg.use_sit:
+        eps, rest = out[:, :, :c_cfg], out[:, :, c_cfg:]
+    else:
+        eps, rest = out[:, :c_cfg], out[:, c_cfg:]                       # :256-257
     cond, uncond = torch.split(eps, len(eps) // 2, dim=0)
     if scale_pow == 0.0:
         real = cfg_scale
@@ -491,7 +562,7 @@ def forward_with_cfg(cfg: FiTConfig, sd, x, t, y, grid, mask, size, cfg_scale, s
         real = ((cfg_scale - 1) * step + 1)[: len(x) // 2].view(-1, 1, 1)
     half_eps = uncond + real * (cond - uncond)
     eps = torch.cat([half_eps, half_eps], dim=0)
-    return torch.cat([eps, rest], dim=2)
+    return torch.cat([eps, rest], dim=2 if cfg.use_sit else 1)
 
 
 def unpatchify(cfg: FiTConfig, x: torch.Tensor, hw) -> torch.Tensor:
@@ -545,3 +616,16 @@ def flops_per_forward_row(cfg: FiTConfig, n_tokens: int) -> float:
     mac = N * (L * (4 * D * D + 3 * D * Hm + 2 * N * D) + 32 * D) \
         + L * (D * lora + 6 * D * lora) + 256 * D + D * D + 6 * D * D + 2 * D * D
     return 2.0 * mac
+
+
+def perturb_norm_weights(sd: Dict[str, torch.Tensor], seed: int = 2, std: float = 0.2) -> Dict[str, torch.Tensor]:
+    """Synthetic weights for the weighted norms (they are initialised to ones, which would hide a missing multiply):
+    every ``*norm*.weight`` vector becomes 1 + std * N(0,1) from a dedicated CPU generator, in state_dict order."""
+    g = torch.Generator().manual_seed(seed)
+    out = {}
+    for k, v in sd.items():
+        if k.endswith(".weight") and v.dim() == 1 and "norm" in k.rsplit(".", 2)[-2]:
+            out[k] = 1.0 + std * torch.randn(v.shape, generator=g, dtype=torch.float32)
+        else:
+            out[k] = v
+    return out

@@ -19,9 +19,14 @@ Reference lines restated (paths relative to the reference repo):
 ``torchdiffeq`` (requirements.txt, unpinned, NOT vendored and not installed here) supplies ``odeint``; for the
 fixed-grid methods its published algorithm is  y_{i+1} = y_i + (t_{i+1} - t_i) * f(t_i, y_i)  ("euler") and
 y_{i+1} = y_i + dt * f(t_i + dt/2, y_i + dt/2 * f(t_i, y_i))  ("midpoint"), evaluated on exactly the grid passed in
-(no ``step_size`` option is given by the reference).  Those two are restated here; parity of the ODE integrator
-itself is therefore anchored on the reference's call site only ("parity unpinned" for that one function), while
-everything on the SDE route is pinned against the reference's own code.
+(no ``step_size`` option is given by the reference).  The other fixed-grid solvers the method string can name are restated
+from ``torchdiffeq/_impl/rk_common.py`` (rk2_step_func / rk3_step_func / rk4_alt_step_func) and ``fixed_grid.py``:
+  "heun2":  k2 = f(t + dt*1, y + dt*k1*1);                      y' = y + dt*(k1*1/2 + k2*1/2)
+  "heun3":  k2 = f(t + dt/3, y + dt*k1*(1/3)); k3 = f(t + 2dt/3, y + dt*(k1*0 + k2*(2/3)));  y' = y + dt*(k1/4 + k2*0 + k3*3/4)
+  "rk4":    the 3/8 rule: k2 = f(t + dt/3, y + dt*k1/3); k3 = f(t + 2dt/3, y + dt*(k2 - k1/3)); k4 = f(t1, y + dt*(k1 - k2 + k3));
+            y' = y + (k1 + 3*(k2 + k3) + k4)*dt*0.125
+Parity of the ODE integrator itself is therefore anchored on the reference's call site only ("parity unpinned" for
+torchdiffeq.odeint), while everything on the SDE route is pinned against the reference's own code.
 """
 from __future__ import annotations
 
@@ -190,6 +195,22 @@ def sample_ode(model: Callable, x: th.Tensor, *, sampling_method="euler", num_st
             half_dt = 0.5 * dt
             y_mid = y + f(ta, y) * half_dt
             y = y + dt * f(ta + half_dt, y_mid)
+        elif sampling_method == "heun2":
+            k1 = f(ta, y)
+            k2 = f(ta + dt * 1.0, y + dt * k1 * 1.0)
+            y = y + dt * (k1 * (1 / 2) + k2 * (1 / 2))
+        elif sampling_method == "heun3":
+            k1 = f(ta, y)
+            k2 = f(ta + dt * (1 / 3), y + dt * k1 * (1 / 3))
+            k3 = f(ta + dt * (2 / 3), y + dt * (k1 * 0.0 + k2 * (2 / 3)))
+            y = y + dt * (k1 * (1 / 4) + k2 * 0.0 + k3 * (3 / 4))
+        elif sampling_method == "rk4":
+            one_third, two_thirds = 1 / 3, 2 / 3
+            k1 = f(ta, y)
+            k2 = f(ta + dt * one_third, y + dt * k1 * one_third)
+            k3 = f(ta + dt * two_thirds, y + dt * (k2 - k1 * one_third))
+            k4 = f(tb, y + dt * (k1 - k2 + k3))
+            y = y + (k1 + 3 * (k2 + k3) + k4) * dt * 0.125
         else:
             raise NotImplementedError(f"fixed-grid ODE method {sampling_method!r} not restated (adaptive dopri5 has data-dependent NFE)")
         ys.append(y)

@@ -37,12 +37,183 @@ def test_constructor_contract_and_rejections():
             use_swiglu_large=False, use_checkpoint=False, qk_norm_weight=False, rel_pos_embed="rope", abs_pos_embed=None,
             custom_freqs="normal", online_rope=False)     # every key of configs/fitv2/config_fitv2_xl.yaml:26-47 + injected keys
     assert m.in_channels == 4 and m.dtype == torch.float32 and m.mlp_hidden == 3072 and m.head_dim == 72
-    for bad in (dict(use_sit=False), dict(adaln_type="normal"), dict(online_rope=True), dict(q_norm=None), dict(learn_sigma=True),
-                dict(use_swiglu=False), dict(num_heads=18), dict(operand_dtype="fp8"), dict(add_rel_pe_to_v=True)):
+    for bad in (dict(adaln_type="swiglu"), dict(online_rope=True), dict(q_norm="batchnorm"), dict(norm_type="none"),
+                dict(use_swiglu=False), dict(num_heads=18), dict(operand_dtype="fp8"), dict(add_rel_pe_to_v=True),
+                dict(rel_pos_embed=None), dict(qkv_bias=False)):
         with pytest.raises(NotImplementedError):
             FiT(**{**KW, **XL1, **bad})
+    with pytest.raises(AssertionError):                    # fit_model.py:68: assert not (learn_sigma and use_sit)
+        FiT(**{**KW, **XL1, "learn_sigma": True})
     with pytest.raises(FitV2Error):                        # no CPU fallback
         m(torch.zeros(1, 16, 16), torch.zeros(1), torch.zeros(1, dtype=torch.long), torch.zeros(1, 2, 16, dtype=torch.long), torch.ones(1, 16))
+
+
+# The literal `params:` blocks of the reference's model configs (configs/fitv2/config_fitv2_{xl,3B,hr_xl}.yaml and
+# configs/fit/config_fit_xl.yaml, `network_config.params`), as text: instantiate_from_config (fit/utils/utils.py:76-93) calls
+# `FiT(**params)` after sample_fitv2_ddp.py:75-99 has injected the resolution-dependent RoPE keys.
+_YAML_PARAMS = {
+    "config_fitv2_xl": """
+      context_size: 256
+      patch_size: 2
+      in_channels: 4
+      hidden_size: 1152
+      depth: 36
+      num_heads: 16
+      mlp_ratio: 4.0
+      class_dropout_prob: 0.1
+      num_classes: 1000
+      learn_sigma: false
+      use_sit: true
+      use_swiglu: true
+      use_swiglu_large: false
+      use_checkpoint: false
+      q_norm: layernorm
+      k_norm: layernorm
+      qk_norm_weight: false
+      rel_pos_embed: rope
+      abs_pos_embed: null
+      adaln_type: lora
+      adaln_lora_dim: 288
+    """,
+    "config_fitv2_3B": """
+      context_size: 256
+      patch_size: 2
+      in_channels: 4
+      hidden_size: 2304
+      depth: 40
+      num_heads: 24
+      mlp_ratio: 4.0
+      class_dropout_prob: 0.1
+      num_classes: 1000
+      learn_sigma: false
+      use_sit: true
+      use_swiglu: true
+      use_swiglu_large: false
+      q_norm: layernorm
+      k_norm: layernorm
+      qk_norm_weight: false
+      rel_pos_embed: rope
+      abs_pos_embed: null
+      adaln_type: lora
+      adaln_lora_dim: 576
+    """,
+    "config_fitv2_hr_xl": """
+      context_size: 1024
+      patch_size: 2
+      in_channels: 4
+      hidden_size: 1152
+      depth: 36
+      num_heads: 16
+      mlp_ratio: 4.0
+      class_dropout_prob: 0.1
+      num_classes: 1000
+      learn_sigma: false
+      use_sit: true
+      use_swiglu: true
+      use_swiglu_large: false
+      use_checkpoint: true
+      q_norm: layernorm
+      k_norm: layernorm
+      qk_norm_weight: false
+      rel_pos_embed: rope
+      custom_freqs: ntk-aware
+      decouple: true
+      ori_max_pe_len: 16
+      online_rope: true
+      abs_pos_embed: null
+      adaln_type: lora
+      adaln_lora_dim: 288
+    """,
+    "config_fit_xl": """
+      context_size: 256
+      patch_size: 2
+      in_channels: 4
+      hidden_size: 1152
+      depth: 28
+      num_heads: 16
+      mlp_ratio: 4.0
+      class_dropout_prob: 0.1
+      num_classes: 1000
+      learn_sigma: true
+      use_swiglu: true
+      use_swiglu_large: true
+      rel_pos_embed: rope
+    """,
+}
+
+
+def _parse_params(text):
+    """Flat `key: scalar` YAML (omegaconf is not installed): ints, floats, booleans, null, strings."""
+    out = {}
+    for line in text.strip().splitlines():
+        k, v = [p.strip() for p in line.split(":", 1)]
+        if v in ("true", "false"): out[k] = v == "true"
+        elif v in ("null", "~"): out[k] = None
+        elif re.fullmatch(r"-?\d+", v): out[k] = int(v)
+        elif re.fullmatch(r"-?\d+\.\d*", v): out[k] = float(v)
+        else: out[k] = v
+    return out
+
+
+def test_yaml_params_match_the_reference_configs():
+    """The embedded text is the reference's own (checked where /root/reference exists, i.e. in the build container)."""
+    ref = "/root/reference/configs"
+    if not os.path.isdir(ref):
+        pytest.skip("reference checkout not present")
+    for name, text in _YAML_PARAMS.items():
+        sub = "fit" if name == "config_fit_xl" else "fitv2"
+        with open(os.path.join(ref, sub, name + ".yaml")) as f:
+            src = f.read()
+        block = src.split("network_config:")[1].split("params:")[1]
+        got = {}
+        for line in block.splitlines()[1:]:
+            if not line.strip() or line.strip().startswith("#"):
+                continue
+            if len(line) - len(line.lstrip()) < 6:            # dedent: end of the params block
+                break
+            got.update(_parse_params(line.split("#")[0]))
+        assert got == _parse_params(text), name
+
+
+@pytest.mark.parametrize("name", sorted(_YAML_PARAMS))
+def test_constructor_from_the_reference_yaml(name):
+    """`FiT(**params)` exactly as instantiate_from_config builds it, with the keys sample_fitv2_ddp.py:75-99 injects for a
+    160x320 ntk-aware decoupled run (the hr_xl config carries use_checkpoint: true, which inference accepts as a no-op)."""
+    params = _parse_params(_YAML_PARAMS[name])
+    params["depth"] = 1                                                       # CPU test: one block is enough for the contract
+    injected = dict(custom_freqs="ntk-aware", max_pe_len_h=10, max_pe_len_w=20, decouple=True, ori_max_pe_len=16, online_rope=False)
+    if name == "config_fit_xl":                                               # the FiTv1 scripts do not touch the RoPE keys
+        injected = {}
+    m = FiT(**{**params, **injected})
+    assert not m.online_rope
+    full = _parse_params(_YAML_PARAMS[name])
+    assert m.hidden_size == full["hidden_size"] and m.num_heads == full["num_heads"] and m.in_channels == 4
+    assert m.learn_sigma == full["learn_sigma"] and m.use_sit == full.get("use_sit", False)
+    assert m.out_channels == (8 if full["learn_sigma"] else 4)
+    cfg = O.FiTConfig(hidden_size=full["hidden_size"], depth=1, num_heads=full["num_heads"], adaln_lora_dim=full.get("adaln_lora_dim") or 0,
+                      learn_sigma=full["learn_sigma"], use_sit=full.get("use_sit", False), adaln_type=full.get("adaln_type", "normal"),
+                      q_norm=full.get("q_norm"), k_norm=full.get("k_norm"), use_swiglu_large=full["use_swiglu_large"])
+    assert list(m.state_dict().keys()) == list(O.reference_init_state_dict(cfg, 0).keys())
+
+
+def test_variant_state_dict_keys_and_init_parity():
+    """FiTv1 layout (adaLN 'normal', learn_sigma, no q/k norm) and the weighted norm kinds: parameter names, shapes and the
+    init under a seed equal the oracle's (which make_variant_goldens.py pins bit-equal to the real reference classes)."""
+    for kw, okw in ((dict(learn_sigma=True, use_sit=False, use_swiglu=True, use_swiglu_large=True),
+                     dict(learn_sigma=True, use_sit=False, adaln_type="normal", q_norm=None, k_norm=None, use_swiglu_large=True, adaln_lora_dim=0)),
+                    (dict(**KW, adaln_lora_dim=288, norm_type="rmsnorm", qk_norm_weight=True),
+                     dict(adaln_lora_dim=288, norm_type="rmsnorm", qk_norm_weight=True))):
+        torch.manual_seed(0)
+        m = FiT(hidden_size=1152, depth=1, num_heads=16, **kw)
+        ref = O.reference_init_state_dict(O.FiTConfig(hidden_size=1152, depth=1, num_heads=16, **okw), 0)
+        sd = m.state_dict()
+        assert list(sd.keys()) == list(ref.keys())
+        assert all(torch.equal(sd[k], ref[k]) for k in ref)
+        P = m.pack_weights(torch.device("cpu"))
+        if not m.use_sit:
+            assert "GLOBAL_ADALN_W" not in P and P["NORMAL_ADALN_W"].shape == (1, 6 * 1152, 1152) and P["FINAL_LINEAR_W"].shape == (32, 1152)
+        else:
+            assert P["NORM1_W"].shape == (1, 1152) and P["Q_NORM_W"].shape == (1, 72) and P["K_NORM_W"].shape == (1, 72)
 
 
 def test_state_dict_keys_and_init_parity():
@@ -74,7 +245,7 @@ def test_weight_packing_layout():
     torch.manual_seed(0)
     m = FiT(**KW, **XL1).randomize_zero_init_(1)
     P = m.pack_weights(torch.device("cpu"))
-    assert set(P) == set(_lib.WEIGHT_SLOTS)
+    assert set(P) == set(_lib.WEIGHT_SLOTS[:27])           # the FiTv2 family binds the first 27 slots; the rest belong to the variants
     D, Hm = 1152, 3072
     assert P["QKV_W"].shape == (1, 3 * D, D) and P["QKV_W"].dtype == torch.bfloat16
     assert P["GATEUP_W"].shape == (1, 2 * Hm, D) and P["GATEUP_B"].shape == (1, 2 * Hm)

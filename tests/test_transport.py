@@ -53,6 +53,26 @@ def test_oracle_ode_fixed_grid(kat):
         T.sample_ode(T.toy_velocity_model, o["init"], sampling_method="dopri5")
 
 
+def test_oracle_rk_tableaus_have_their_published_order():
+    """torchdiffeq is not installed, so the heun2 / heun3 / rk4 restatements cannot be pinned against it; what CAN be checked
+    is the defining property of each Butcher tableau: the global error of y' = f(t, y) on a fixed grid falls as dt^order
+    (euler 1, midpoint / heun2 2, heun3 3, rk4 4).  fp64 so that rounding does not mask the rate."""
+    x0 = th.linspace(-1.0, 1.0, 32, dtype=th.float64).reshape(2, 4, 4)
+    model = lambda x, t, **kw: T.toy_velocity_model(x, t.to(x.dtype))
+    fine = T.sample_ode(model, x0, sampling_method="rk4", num_steps=2049)[-1]
+    for method, order in (("euler", 1), ("midpoint", 2), ("heun2", 2), ("heun3", 3), ("rk4", 4)):
+        errs = []
+        for n in (9, 17, 33):
+            ts_back = th.get_default_dtype()
+            th.set_default_dtype(th.float64)                                 # linspace / ones inside the oracle
+            try:
+                errs.append(float((T.sample_ode(model, x0, sampling_method=method, num_steps=n)[-1] - fine).abs().max()))
+            finally:
+                th.set_default_dtype(ts_back)
+        r1, r2 = errs[0] / errs[1], errs[1] / errs[2]
+        assert 2 ** order * 0.7 < r1 < 2 ** order * 1.45 and 2 ** order * 0.7 < r2 < 2 ** order * 1.45, (method, errs)
+
+
 # ------------------------------------------------------------------------------------------------ CPU: host logic of the product
 def test_create_transport_and_intervals():
     tr = create_transport(path_type="Linear", prediction="velocity", loss_weight=None, train_eps=None, sample_eps=None, snr_type="lognorm")
@@ -125,6 +145,10 @@ def test_ode_kernels_bit_exact(kat, built_lib):
     for m in ("euler", "midpoint"):
         ys = s.sample_ode(sampling_method=m, num_steps=o["num_steps"])(o["init"].cuda(), _gpu_toy)
         assert len(ys) == o["num_steps"] and th.equal(ys[-1].cpu(), o[f"{m}_final"])
+    for m in ("heun2", "heun3", "rk4"):                                       # fitv2_rk_stage: every stage bit-equal to the restated expressions
+        ys = s.sample_ode(sampling_method=m, num_steps=o["num_steps"])(o["init"].cuda(), _gpu_toy)
+        ref = T.sample_ode(T.toy_velocity_model, o["init"], sampling_method=m, num_steps=o["num_steps"])
+        assert len(ys) == o["num_steps"] and all(th.equal(a.cpu(), b) for a, b in zip(ys, ref)), m
     yr = s.sample_ode(sampling_method="euler", num_steps=5, reverse=True)(o["init"].cuda(), _gpu_toy)
     assert th.equal(yr[-1].cpu(), T.sample_ode(T.toy_velocity_model, o["init"], sampling_method="euler", num_steps=5, reverse=True)[-1])
 

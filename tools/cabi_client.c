@@ -34,7 +34,8 @@ static int upload(fitv2_handle* h, int slot, int64_t n, int is16) {
 
 int main(void) {
     const int D = 1152, L = 1, H = 16, DH = 72, HM = 3072, LORA = 288, C = 16, NE = 1001, R = 4, N = 64;
-    fitv2_config cfg = {D, L, H, DH, HM, LORA, C, NE, FITV2_OPERAND_BF16, 1.0f, 1.0f};
+    fitv2_config cfg = {D, L, H, DH, HM, LORA, C, NE, FITV2_OPERAND_BF16, 1.0f, 1.0f,
+                        /*out_channels*/ 0, FITV2_ADALN_LORA, FITV2_NORM_LAYERNORM, FITV2_NORM_LAYERNORM, FITV2_NORM_LAYERNORM, /*channels_first*/ 0};
     fitv2_handle* h = NULL;
     CK(fitv2_create(&cfg, &h));
     const int64_t numel[FITV2_W_COUNT] = {
@@ -43,6 +44,7 @@ int main(void) {
         (int64_t)L * 3 * D * D, L * 3 * D, (int64_t)L * D * D, L * D, (int64_t)L * 2 * HM * D, L * 2 * HM, (int64_t)L * D * HM, L * D,
         DH / 4, DH / 4};
     for (int s = 0; s < FITV2_W_COUNT; ++s) {
+        if (numel[s] == 0) continue;                          /* slots of the model variants: unused by this configuration */
         const int is16 = s == FITV2_W_QKV_W || s == FITV2_W_PROJ_W || s == FITV2_W_GATEUP_W || s == FITV2_W_FC2_W;
         if (upload(h, s, numel[s], is16)) return 1;
     }

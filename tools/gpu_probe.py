@@ -109,6 +109,7 @@ def _handle(operand="bf16"):
     cfg = _lib.FitV2Config(1152, 1, 16, 72, 3072, 288, 16, 1001, 1 if operand == "fp16" else 0, 1.0, 1.0)
     h = C.c_void_p()
     _lib.check(lib.fitv2_create(C.byref(cfg), C.byref(h)))
+    _lib.apply_env_options(h)
     ws = torch.zeros(1 << 20, dtype=torch.uint8, device="cuda")
     _lib.check(lib.fitv2_set_workspace(h, _p(ws), ws.numel()))
     return lib, h, ws
