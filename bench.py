@@ -205,8 +205,14 @@ def run_ours(args):
     z = z_host.to(dev).contiguous()
     lib = _lib.load()
 
+    if args.cuda_graph:
+        smp.capture(z)                                    # the timed loop replays the captured step (scalars copied per step)
+
     def step(i):
-        smp._step(z, smp.t_table[i % NUM_SAMPLING_STEPS], smp.dsig[(i % NUM_SAMPLING_STEPS):(i % NUM_SAMPLING_STEPS) + 1])
+        if args.cuda_graph:
+            smp.replay_step(i % NUM_SAMPLING_STEPS)
+        else:
+            smp._step(z, smp.t_table[i % NUM_SAMPLING_STEPS], smp.dsig[(i % NUM_SAMPLING_STEPS):(i % NUM_SAMPLING_STEPS) + 1])
 
     def barrier():
         if world > 1:
@@ -216,7 +222,8 @@ def run_ours(args):
     # ---------------- device-resident timing (`value`) ----------------
     for i in range(args.warmup):
         step(i)
-    model.profile(["gateup_gemm"])                        # dominant kernel, event-timed during the timed region
+    if not args.cuda_graph:
+        model.profile(["gateup_gemm"])                    # dominant kernel, event-timed during the timed region (eager launches only)
     l0 = model.kernel_launches()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -228,8 +235,12 @@ def run_ours(args):
         barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1), dev)
     launches = model.kernel_launches() - l0 + args.steps      # + one cfg_euler kernel per step
-    prof = model.profile_read()
-    model.profile(None)
+    if args.cuda_graph:                                       # replayed launches are not counted by the handle: the captured step's count
+        launches = args.steps * (smp.launches_per_step + 1)
+        prof = {"gateup_gemm": (0.0, 0)}
+    else:
+        prof = model.profile_read()
+        model.profile(None)
     ms_step = ms_total / args.steps
     img_s = n * world / (NUM_SAMPLING_STEPS * ms_step / 1e3)
 
@@ -298,6 +309,10 @@ def run_ours(args):
         clocks=clocks.summary(),
         gathered_latents=list(gathered.shape),
     )
+    # the step runs power-capped: time ~ energy / cap, so J/step is the quantity a kernel change has to lower
+    pw = line["clocks"].get("power_w")
+    line["energy_j_per_step"] = (pw * ms_step / 1e3) if pw else None
+    line["energy_j_per_image"] = (pw * ms_step / 1e3 * NUM_SAMPLING_STEPS / n) if pw else None
     if world == 1 and not args.no_cpu_baseline:
         r = cpu_reference_run(args.workload, steps=3, warmup=1, n_samples=1, budget_s=args.cpu_budget)
         line["cpu_baseline"] = dict(value=r["images_per_sec"], unit="images/sec", cores=r["cores"], kind="port",

@@ -74,7 +74,9 @@ class EulerCFGSampler:
 
     def _step(self, z: torch.Tensor, t_rows: torch.Tensor, dsig_dev: torch.Tensor, scale_dev: Optional[torch.Tensor] = None):
         m = self.model
+        l0 = m.kernel_launches()
         self._v2 = m._run(z, t_rows, self.y2, self.grid2, self.mask2, rows=self.rows, out=self._v2)
+        self.launches_per_step = m.kernel_launches() - l0
         st = torch.cuda.current_stream(m.device).cuda_stream
         if not self.using_cfg:                                          # z = z + (sigma_next - sigma_current) * noise_pred  (:314), bit-exact
             if scale_dev is None:
@@ -99,22 +101,31 @@ class EulerCFGSampler:
                 for i in range(steps):
                     self._step(z, self.t_table[i], self.dsig[i:i + 1], self.step_scale[i])
                 return z
-            if self._graph is None:
-                self._z = torch.empty_like(z)
-                self._z.copy_(z)
-                side = torch.cuda.Stream()
-                side.wait_stream(torch.cuda.current_stream())
-                with torch.cuda.stream(side):                           # warm-up outside capture (workspace, maps)
-                    self._t_cur.copy_(self.t_table[0]); self._ds_cur.zero_(); self._sc_cur.copy_(torch.tensor([1.0, 0.0]))
-                    self._step(self._z, self._t_cur, self._ds_cur, self._sc_cur)
-                torch.cuda.current_stream().wait_stream(side)
-                self._graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(self._graph):
-                    self._step(self._z, self._t_cur, self._ds_cur, self._sc_cur)
+            self.capture(z)
             self._z.copy_(z)
             for i in range(steps):
                 self.replay_step(i)
             return self._z.clone()
+
+    @torch.no_grad()
+    def capture(self, z: torch.Tensor):
+        """Capture one step (forward + update, 260-odd launches) into a CUDA graph operating on an internal latent buffer
+        ``self._z`` shaped like ``z``; idempotent."""
+        if self._graph is not None:
+            return
+        m = self.model
+        with torch.cuda.device(m.device):
+            self._z = torch.empty_like(z, dtype=torch.float32, device=m.device)
+            self._z.copy_(z)
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):                               # warm-up outside capture (workspace, maps)
+                self._t_cur.copy_(self.t_table[0]); self._ds_cur.zero_(); self._sc_cur.copy_(torch.tensor([1.0, 0.0]))
+                self._step(self._z, self._t_cur, self._ds_cur, self._sc_cur)
+            torch.cuda.current_stream().wait_stream(side)
+            self._graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph):
+                self._step(self._z, self._t_cur, self._ds_cur, self._sc_cur)
 
     def replay_step(self, i: int):
         """One step of the captured graph (after ``sample`` has captured it): copies the step's scalars into the graph's
