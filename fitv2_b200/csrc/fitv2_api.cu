@@ -197,7 +197,7 @@ struct Options {
     int pdl = 1;                 // programmatic dependent launch on every kernel of the chain
     int attn = 0;                // 0 auto, 1 attention_tm, 2 attention_ws, 3 attention_general (online max)
     int attn_early = 1;          // attention_tm: softmax of the next item's first sub-tile ahead of the current epilogue
-    int attn_poly = -1;          // exp2 evaluated on the FMA pipe for this many of every 8 column pairs (-1 = kernel default)
+    int attn_stagger = 0;        // clocks by which the second query-tile stream of the attention kernels starts late
     int ln_threads = 64;         // threads per CTA of the LayerNorm + modulate kernel (one row per warp)
     int ln_wide_single = 0;      // hidden 2304: one warp per row instead of a warp pair
     int bn_resid = 0;            // tile width of the proj / fc2 GEMMs in the normal orientation (0 = cost model)
@@ -495,7 +495,7 @@ int launch_attention(fitv2_handle* h, const void* q, const void* k, const void* 
         // softmax of the next work item's first sub-tile ahead of the epilogue of the current one: 43.9 -> 40.8 us alone,
         // 57.7 -> 53.2 us in-step at 256 tokens (A/B on one box); option attn_early = 0 restores the plain order
         CUDA_TRY(launch_k(kern, dim3(g), dim3(A::kThreads), smem, st, 1, am.mq, am.mqt, am.mk, am.mkt, am.mv, am.mo, seg, seg_uniform,
-                          c.num_heads, tokens, items, scale_log2e, bound_log2e, h->opt.attn_early));
+                          c.num_heads, tokens, items, scale_log2e, bound_log2e, h->opt.attn_early, h->opt.attn_stagger));
     } else if (c.head_dim == 72) {
         using A = AttnWsCfg<72>;
         auto kern = attention_ws_kernel<OT, 72>;
@@ -503,7 +503,7 @@ int launch_attention(fitv2_handle* h, const void* q, const void* k, const void* 
         if (smem > kSmemBudget) return fail(FITV2_E_INVALID, "tokens %d: attention shared memory %d exceeds %d", tokens, smem, kSmemBudget);
         if ((rc = ensure_smem(h, kern, smem))) return rc;
         CUDA_TRY(launch_k(kern, dim3(g), dim3(A::kThreads), smem, st, 1, am.mq, am.mqt, am.mk, am.mkt, am.mv, am.mo, seg, seg_uniform,
-                          c.num_heads, tokens, items, scale_log2e, bound_log2e));
+                          c.num_heads, tokens, items, scale_log2e, bound_log2e, h->opt.attn_stagger));
     } else {
         using A = AttnWsCfg<96>;
         auto kern = attention_ws_kernel<OT, 96>;
@@ -511,7 +511,7 @@ int launch_attention(fitv2_handle* h, const void* q, const void* k, const void* 
         if (smem > kSmemBudget) return fail(FITV2_E_INVALID, "tokens %d: attention shared memory %d exceeds %d", tokens, smem, kSmemBudget);
         if ((rc = ensure_smem(h, kern, smem))) return rc;
         CUDA_TRY(launch_k(kern, dim3(g), dim3(A::kThreads), smem, st, 1, am.mq, am.mqt, am.mk, am.mkt, am.mv, am.mo, seg, seg_uniform,
-                          c.num_heads, tokens, items, scale_log2e, bound_log2e));
+                          c.num_heads, tokens, items, scale_log2e, bound_log2e, h->opt.attn_stagger));
     }
     CUDA_TRY(cudaGetLastError());
     h->launches++;
@@ -1031,7 +1031,7 @@ int fitv2_set_option(fitv2_handle* h, const char* name, int64_t value) {
     Options& o = h->opt;
     const int v = (int)value;
     struct { const char* n; int* p; } tab[] = {
-        {"pdl", &o.pdl}, {"attn", &o.attn}, {"attn_early", &o.attn_early}, {"attn_poly", &o.attn_poly}, {"ln_threads", &o.ln_threads},
+        {"pdl", &o.pdl}, {"attn", &o.attn}, {"attn_early", &o.attn_early}, {"attn_stagger", &o.attn_stagger}, {"ln_threads", &o.ln_threads},
         {"ln_wide_single", &o.ln_wide_single}, {"bn_resid", &o.bn_resid}, {"qkv_heads", &o.qkv_heads}, {"resid_t", &o.resid_t},
         {"bn_resid_t", &o.bn_resid_t}, {"cond", &o.cond}, {"l2_persist_mb", &o.l2_persist_mb}, {"final_tc", &o.final_tc}, {"verbose", &o.verbose}};
     for (auto& e : tab) {

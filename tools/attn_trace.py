@@ -16,6 +16,8 @@ cfg = _lib.FitV2Config(H * dh, 1, H, dh, 3072, 288, 16, 1001, 0, 1.0, 1.0)
 h = C.c_void_p()
 _lib.check(lib.fitv2_create(C.byref(cfg), C.byref(h)))
 _lib.apply_env_options(h)
+if os.environ.get('ATTN_STAGGER'):
+    _lib.check(lib.fitv2_set_option(h, b'attn_stagger', int(os.environ['ATTN_STAGGER'])))
 ws = torch.zeros(1 << 20, dtype=torch.uint8, device="cuda")
 _lib.check(lib.fitv2_set_workspace(h, C.c_void_p(ws.data_ptr()), ws.numel()))
 g = torch.Generator().manual_seed(0)
@@ -42,7 +44,7 @@ for role in range(20):
 ev.sort()
 t0 = ev[0][0]
 names = {0: "TMA", 1: "MMAa", 2: "MMAb"}
-roles = set(sys.argv[2].split(",")) if len(sys.argv) > 2 else None
+roles = set(sys.argv[2].split(",")) if len(sys.argv) > 2 and sys.argv[2] else None
 limit = int(sys.argv[3]) if len(sys.argv) > 3 else 260
 shown = 0
 for t, role, tag in ev:
