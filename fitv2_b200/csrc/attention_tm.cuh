@@ -57,7 +57,7 @@ attention_tm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                     const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_kt,
                     const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_o,
                     const float* __restrict__ seg, const int* __restrict__ seg_uniform,
-                    int heads, int tokens, int num_items, float scale_log2e, float bound_log2e, int early, int stagger)
+                    int heads, int tokens, int num_items, float scale_log2e, float bound_log2e, int early)
 {
     using C = AttnTmCfg<DH>;
     extern __shared__ uint8_t smem_raw[];
@@ -257,13 +257,8 @@ attention_tm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                 constexpr int kMode = decltype(mode_c)::value;
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-#ifdef FITV2_ATTN_DBG_NOFMA
-                    float p0 = attn_exp2(__uint_as_float(v[2 * i]), i);
-                    float p1 = attn_exp2(__uint_as_float(v[2 * i + 1]), i);
-#else
-                    float p0 = attn_exp2(fmaf(__uint_as_float(v[2 * i]), scale_log2e, -bound_log2e), i);
-                    float p1 = attn_exp2(fmaf(__uint_as_float(v[2 * i + 1]), scale_log2e, -bound_log2e), i);
-#endif
+                    float p0 = fast_exp2(fmaf(__uint_as_float(v[2 * i]), scale_log2e, -bound_log2e));
+                    float p1 = fast_exp2(fmaf(__uint_as_float(v[2 * i + 1]), scale_log2e, -bound_log2e));
                     if constexpr (kMode != 0) {
                         const int col = half * 32 + 2 * i;
                         bool ok0 = col < kv_valid, ok1 = col + 1 < kv_valid;
@@ -275,9 +270,7 @@ attention_tm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                         p1 = ok1 ? p1 : 0.f;
                     }
                     packed[i] = Op16<OT>::pack(p0, p1);
-#ifndef FITV2_ATTN_DBG_NOSUM
                     lsum += p0 + p1;
-#endif
                 }
             };
             if (mode == 0) soft32(std::integral_constant<int, 0>{});
@@ -291,10 +284,6 @@ attention_tm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
             ++n_s;
             return lsum;
         };
-        if (x == 1 && stagger > 0) {                                    // start stream b late: see attention_ws.cuh
-            const long long t_start = clock64();
-            while (clock64() - t_start < (long long)stagger) { }
-        }
         bool early_done = false;                                        // sub-tile 0 of this item was already processed ...
         float l_early = 0.f;                                            // ... with this partial row sum
         for (int item = blockIdx.x; item < num_items; item += gridDim.x) {

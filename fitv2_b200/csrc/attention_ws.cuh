@@ -13,12 +13,12 @@
 //                 the previous one out of TMEM (s_free), i.e. it overlaps the exponentials; P_x V_t is issued when
 //                 P_x(t) has been written (p_full).  One issuer per stream, so a stream never waits for the other
 //                 (a single issuer walking both streams in a fixed order cost 58 us, a polling one 63 us).
-//   warps 3-18    softmax: all 16 warps work on one 128 x 128 tile at a time (four threads per query row, 32 key
-//                 columns each: four warps per scheduler keep the MUFU pipe full, 128 x 128 exp2 = 1024 clk/SM at
-//                 16 lanes/clk) and ALTERNATE between the streams, a(0) b(0) a(1) b(1) ...: the tensor-core work of
-//                 one stream runs under the exponentials of the other.  (Measured alternatives: one 8-warp group
-//                 per stream runs the two groups in lockstep - MUFU idle during every barrier round trip, 45.8 us;
-//                 making them take turns leaves 2 warps per scheduler, too few to fill the MUFU - same 45.8 us.)
+//   warps 3-18    softmax: one 8-warp group per stream (two threads per query row, 64 key columns each).  Measured
+//                 alternatives (profiles/README.md): all 16 warps on one tile alternating between the streams (52.9 us at 256
+//                 tokens against 45.8: every barrier round trip becomes serial); exp2 on the FMA pipe for a fraction of the
+//                 elements, dropping the scale FMA / the row-sum adds, starting stream b late, a CTA-pair variant with P and a
+//                 double-buffered S in TMEM (round 2, all slower or equal: the XU pipe sits at 59-67 % and the rest of the
+//                 time is the chain of MIO round trips -- barrier test, TMEM load, TMEM / shared store, arrive -- per tile).
 //                 The normalised output tile leaves through shared memory and ONE TMA store per tile
 //                 (row-per-thread global stores cost ~2000 clk per tile).
 //
@@ -83,30 +83,13 @@ __device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
     asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(nthreads) : "memory");
 }
 
-// exp2 on the FMA pipe (Cody-Waite range reduction + degree-3 minimax polynomial, max relative error 8.8e-5 -- far below the
-// 16-bit rounding of P): the MUFU evaluates 16 exp2 per clock and SM while the FMA pipe has 128 lanes, so handing a fraction
-// of the exponentials of every row to the FMA pipe shortens the softmax, which is MUFU-bound (the FlashAttention-4 trick).
-// x must lie in [-126, 126]: here x = s * c - bound in [-2 * bound, 0].
-__device__ __forceinline__ float exp2_poly3(float x) {
-    const float r = __fadd_rd(x, 12582912.0f);                  // 2^23 + 2^22 + floor(x): the integer sits in the low mantissa bits
-    const float f = x - (r - 12582912.0f);                      // fractional part in [0, 1)
-    const float p = fmaf(fmaf(fmaf(0.077119089663028717041015625f, f, 0.227564394474029541015625f), f, 0.695146143436431884765625f), f, 1.0f);
-    return __int_as_float(__float_as_int(p) + (__float_as_int(r) << 23));   // 2^f * 2^floor(x): add floor(x) to the exponent field
-}
-// FITV2_ATTN_POLY of every 8 column pairs of a row go through the polynomial, the rest through MUFU.EX2 (j = pair index, a
-// compile-time constant after unrolling).
-#ifndef FITV2_ATTN_POLY
-#define FITV2_ATTN_POLY 0
-#endif
-__device__ __forceinline__ float attn_exp2(float x, int j) { return ((j & 7) < FITV2_ATTN_POLY) ? exp2_poly3(x) : fast_exp2(x); }
-
 template <typename OT, int DH>
 __global__ void __launch_bounds__(608, 1)
 attention_ws_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_qt,
                     const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_kt,
                     const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_o,
                     const float* __restrict__ seg, const int* __restrict__ seg_uniform,
-                    int heads, int tokens, int num_items, float scale_log2e, float bound_log2e, int stagger)
+                    int heads, int tokens, int num_items, float scale_log2e, float bound_log2e)
 {
     using C = AttnWsCfg<DH>;
     extern __shared__ uint8_t smem_raw[];
@@ -162,14 +145,9 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
             mbar_wait(&k_empty[ks], kph ^ 1);
             if (elect_one()) {
                 uint8_t* dst = smem + C::kOffK + ks * C::kQKTile;
-#ifdef FITV2_ATTN_DBG_NOTAIL
-                mbar_arrive_expect_tx(&k_full[ks], C::kQMain);
-                tma_load_3d(&map_k, &k_full[ks], dst, 0, t * 128, bh);
-#else
                 mbar_arrive_expect_tx(&k_full[ks], C::kQKBytes);
                 tma_load_3d(&map_k, &k_full[ks], dst, 0, t * 128, bh);
                 tma_load_3d(&map_kt, &k_full[ks], dst + C::kQMain, 64, t * 128, bh);
-#endif
             }
             __syncwarp();
             ATTN_TRACE(0, 110 + t);
@@ -195,14 +173,9 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                 if (n_q[x] > 0) mbar_wait(&q_empty[x], (n_q[x] - 1) & 1);
                 if (elect_one()) {
                     uint8_t* dst = smem + C::kOffQ + x * C::kQKTile;
-#ifdef FITV2_ATTN_DBG_NOTAIL
-                    mbar_arrive_expect_tx(&q_full[x], C::kQMain);
-                    tma_load_3d(&map_q, &q_full[x], dst, 0, (2 * qp + x) * 128, bh);
-#else
                     mbar_arrive_expect_tx(&q_full[x], C::kQKBytes);
                     tma_load_3d(&map_q, &q_full[x], dst, 0, (2 * qp + x) * 128, bh);
                     tma_load_3d(&map_qt, &q_full[x], dst + C::kQMain, 64, (2 * qp + x) * 128, bh);
-#endif
                 }
                 __syncwarp();
                 ATTN_TRACE(0, 100 + x);
@@ -323,15 +296,6 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
             }
         };
         fetch_meta(blockIdx.x);
-        // The two streams execute the same sequence (wait, TMEM load, exponentials, P store, fence, arrive) and, started together,
-        // stay in lockstep: both sit in the latency part of the sequence at the same time and the MUFU idles (timeline of
-        // profiles/r2_attn_trace_1024.txt: ~2050 clk of exponentials + ~1400 clk of latencies per key tile).  An offset between
-        // them is neutrally stable (the stream that is alone on the MUFU runs at twice the rate), so stream b is simply started
-        // `stagger` clocks late: its latencies then fall under stream a's exponentials and vice versa.
-        if (x == 1 && stagger > 0) {
-            const long long t_start = clock64();
-            while (clock64() - t_start < (long long)stagger) { }
-        }
         for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
             const bool uniform = uni_nx != 0;
             const float my_seg = seg_nx;
@@ -372,18 +336,8 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                         constexpr int kMode = decltype(mode_c)::value;
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
-#ifdef FITV2_ATTN_DBG_NOEXP
-                            float p0 = fmaf(__uint_as_float(v[2 * j]), scale_log2e, -bound_log2e);
-                            float p1 = fmaf(__uint_as_float(v[2 * j + 1]), scale_log2e, -bound_log2e);
-#else
-#ifdef FITV2_ATTN_DBG_NOFMA
-                            float p0 = attn_exp2(__uint_as_float(v[2 * j]), j);
-                            float p1 = attn_exp2(__uint_as_float(v[2 * j + 1]), j);
-#else
-                            float p0 = attn_exp2(fmaf(__uint_as_float(v[2 * j]), scale_log2e, -bound_log2e), j);
-                            float p1 = attn_exp2(fmaf(__uint_as_float(v[2 * j + 1]), scale_log2e, -bound_log2e), j);
-#endif
-#endif
+                            float p0 = fast_exp2(fmaf(__uint_as_float(v[2 * j]), scale_log2e, -bound_log2e));
+                            float p1 = fast_exp2(fmaf(__uint_as_float(v[2 * j + 1]), scale_log2e, -bound_log2e));
                             if constexpr (kMode != 0) {
                                 const int col = half * 64 + c * 32 + 2 * j;
                                 bool ok0 = col < kv_valid, ok1 = col + 1 < kv_valid;
@@ -395,9 +349,7 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                                 p1 = ok1 ? p1 : 0.f;
                             }
                             packed[c * 16 + j] = Op16<OT>::pack(p0, p1);
-#ifndef FITV2_ATTN_DBG_NOSUM
                             lsum += p0 + p1;
-#endif
                         }
                     };
                     if (mode == 0) soft32(std::integral_constant<int, 0>{});
@@ -457,9 +409,7 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
             }
             fence_proxy_async_smem();
             named_bar_sync(1 + x, 256);
-#ifndef FITV2_ATTN_DBG_NOSTORE
             if (tid_wg == 0) tma_store_4d(&map_o, smem_px, 0, head, qt * 128, sample);   // rows >= tokens are clipped
-#endif
             store_pending = true;
             ATTN_TRACE(warp, 530);
         }

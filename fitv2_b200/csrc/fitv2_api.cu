@@ -7,7 +7,6 @@
 #include "attention_general.cuh"
 #include "attention_ws.cuh"
 #include "attention_tm.cuh"
-#include "attention_p2.cuh"
 #include "pointwise.cuh"
 #include "cond_tc.cuh"
 
@@ -196,9 +195,8 @@ struct ProfEvt { cudaEvent_t a, b; int cls; };
 // statics; now every handle carries its own copy and the Python layer forwards the environment at handle creation.
 struct Options {
     int pdl = 1;                 // programmatic dependent launch on every kernel of the chain
-    int attn = 0;                // 0 auto, 1 attention_tm, 2 attention_ws, 3 attention_general (online max), 4 attention_p2 (CTA pairs)
+    int attn = 0;                // 0 auto, 1 attention_tm, 2 attention_ws, 3 attention_general (online max)
     int attn_early = 1;          // attention_tm: softmax of the next item's first sub-tile ahead of the current epilogue
-    int attn_stagger = 0;        // clocks by which the second query-tile stream of the attention kernels starts late
     int ln_threads = 64;         // threads per CTA of the LayerNorm + modulate kernel (one row per warp)
     int ln_wide_single = 0;      // hidden 2304: one warp per row instead of a warp pair
     int bn_resid = 0;            // tile width of the proj / fc2 GEMMs in the normal orientation (0 = cost model)
@@ -215,7 +213,6 @@ struct AttnMaps {                // TMA descriptors of one attention launch, cac
     const void *q = nullptr, *k = nullptr, *vt = nullptr, *out = nullptr;
     int rows = 0, tokens = 0;
     CUtensorMap mq, mqt, mk, mkt, mv, mo;
-    CUtensorMap mk64, mkt64, mvh;   // CTA-pair kernel (attention_p2.cuh): 64-key boxes of K, (64 keys x head_dim_padded / 2 rows) boxes of V^T
 };
 
 struct fitv2_handle {
@@ -455,9 +452,6 @@ int launch_attention(fitv2_handle* h, const void* q, const void* k, const void* 
         // columns (never written by the QKV epilogue) are zero-filled by TMA instead of read (0 * NaN garbage = NaN in P V)
         if ((rc = make_map3(&am.mv, vt, c.operand_dtype, tokens, DHu, BH, (uint64_t)tokens_v * 2, DHu * tokens_v * 2, 64, dhp, 128))) return rc;
         if ((rc = make_map_attn_out(&am.mo, out, c.operand_dtype, DHu, c.num_heads, tokens, rows))) return rc;
-        if ((rc = make_map3(&am.mk64, k, c.operand_dtype, DHu, tokens, BH, DHu * 2, (uint64_t)tokens * DHu * 2, 64, 64, 128))) return rc;
-        if ((rc = make_map3(&am.mkt64, k, c.operand_dtype, DHu, tokens, BH, DHu * 2, (uint64_t)tokens * DHu * 2, tail, 64, tail * 2))) return rc;
-        if ((rc = make_map3(&am.mvh, vt, c.operand_dtype, tokens, DHu, BH, (uint64_t)tokens_v * 2, DHu * tokens_v * 2, 64, dhp / 2, 128))) return rc;
         am.q = q; am.k = k; am.vt = vt; am.out = out; am.rows = rows; am.tokens = tokens;
     }
     // Kernel choice.  Affine-free QK-LayerNorm (the FiTv2 family): bound-based softmax, P in tensor memory up to 256 tokens at
@@ -491,27 +485,7 @@ int launch_attention(fitv2_handle* h, const void* q, const void* k, const void* 
     const int items = q_pairs * c.num_heads * rows;
     const int g = items < h->num_sms ? items : h->num_sms;
     int rc;
-    if (mode == 4) {
-        // CTA pairs (attention_p2.cuh): one cluster of two CTAs per (sample, head, pair of query tiles)
-        const int clusters = items < h->num_sms / 2 ? items : h->num_sms / 2;
-        if (c.head_dim == 72) {
-            using A = AttnP2Cfg<72>;
-            auto kern = attention_p2_kernel<OT, 72>;
-            const int smem = A::smem_bytes(tokens);
-            if (smem > kSmemBudget) return fail(FITV2_E_INVALID, "tokens %d: attention shared memory %d exceeds %d", tokens, smem, kSmemBudget);
-            if ((rc = ensure_smem(h, kern, smem))) return rc;
-            CUDA_TRY(launch_k(kern, dim3(2 * clusters), dim3(A::kThreads), smem, st, 2, am.mq, am.mqt, am.mk64, am.mkt64, am.mvh, am.mo, seg, seg_uniform,
-                              c.num_heads, tokens, items, scale_log2e, bound_log2e));
-        } else {
-            using A = AttnP2Cfg<96>;
-            auto kern = attention_p2_kernel<OT, 96>;
-            const int smem = A::smem_bytes(tokens);
-            if (smem > kSmemBudget) return fail(FITV2_E_INVALID, "tokens %d: attention shared memory %d exceeds %d", tokens, smem, kSmemBudget);
-            if ((rc = ensure_smem(h, kern, smem))) return rc;
-            CUDA_TRY(launch_k(kern, dim3(2 * clusters), dim3(A::kThreads), smem, st, 2, am.mq, am.mqt, am.mk64, am.mkt64, am.mvh, am.mo, seg, seg_uniform,
-                              c.num_heads, tokens, items, scale_log2e, bound_log2e));
-        }
-    } else if (mode == 1) {
+    if (mode == 1) {
         using A = AttnTmCfg<72>;
         auto kern = attention_tm_kernel<OT, 72>;
         const int smem = A::smem_bytes(tokens);
@@ -520,7 +494,7 @@ int launch_attention(fitv2_handle* h, const void* q, const void* k, const void* 
         // softmax of the next work item's first sub-tile ahead of the epilogue of the current one: 43.9 -> 40.8 us alone,
         // 57.7 -> 53.2 us in-step at 256 tokens (A/B on one box); option attn_early = 0 restores the plain order
         CUDA_TRY(launch_k(kern, dim3(g), dim3(A::kThreads), smem, st, 1, am.mq, am.mqt, am.mk, am.mkt, am.mv, am.mo, seg, seg_uniform,
-                          c.num_heads, tokens, items, scale_log2e, bound_log2e, h->opt.attn_early, h->opt.attn_stagger));
+                          c.num_heads, tokens, items, scale_log2e, bound_log2e, h->opt.attn_early));
     } else if (c.head_dim == 72) {
         using A = AttnWsCfg<72>;
         auto kern = attention_ws_kernel<OT, 72>;
@@ -528,7 +502,7 @@ int launch_attention(fitv2_handle* h, const void* q, const void* k, const void* 
         if (smem > kSmemBudget) return fail(FITV2_E_INVALID, "tokens %d: attention shared memory %d exceeds %d", tokens, smem, kSmemBudget);
         if ((rc = ensure_smem(h, kern, smem))) return rc;
         CUDA_TRY(launch_k(kern, dim3(g), dim3(A::kThreads), smem, st, 1, am.mq, am.mqt, am.mk, am.mkt, am.mv, am.mo, seg, seg_uniform,
-                          c.num_heads, tokens, items, scale_log2e, bound_log2e, h->opt.attn_stagger));
+                          c.num_heads, tokens, items, scale_log2e, bound_log2e));
     } else {
         using A = AttnWsCfg<96>;
         auto kern = attention_ws_kernel<OT, 96>;
@@ -536,7 +510,7 @@ int launch_attention(fitv2_handle* h, const void* q, const void* k, const void* 
         if (smem > kSmemBudget) return fail(FITV2_E_INVALID, "tokens %d: attention shared memory %d exceeds %d", tokens, smem, kSmemBudget);
         if ((rc = ensure_smem(h, kern, smem))) return rc;
         CUDA_TRY(launch_k(kern, dim3(g), dim3(A::kThreads), smem, st, 1, am.mq, am.mqt, am.mk, am.mkt, am.mv, am.mo, seg, seg_uniform,
-                          c.num_heads, tokens, items, scale_log2e, bound_log2e, h->opt.attn_stagger));
+                          c.num_heads, tokens, items, scale_log2e, bound_log2e));
     }
     CUDA_TRY(cudaGetLastError());
     h->launches++;
@@ -1056,7 +1030,7 @@ int fitv2_set_option(fitv2_handle* h, const char* name, int64_t value) {
     Options& o = h->opt;
     const int v = (int)value;
     struct { const char* n; int* p; } tab[] = {
-        {"pdl", &o.pdl}, {"attn", &o.attn}, {"attn_early", &o.attn_early}, {"attn_stagger", &o.attn_stagger}, {"ln_threads", &o.ln_threads},
+        {"pdl", &o.pdl}, {"attn", &o.attn}, {"attn_early", &o.attn_early}, {"ln_threads", &o.ln_threads},
         {"ln_wide_single", &o.ln_wide_single}, {"bn_resid", &o.bn_resid}, {"qkv_heads", &o.qkv_heads}, {"resid_t", &o.resid_t},
         {"bn_resid_t", &o.bn_resid_t}, {"cond", &o.cond}, {"l2_persist_mb", &o.l2_persist_mb}, {"final_tc", &o.final_tc}, {"verbose", &o.verbose}};
     for (auto& e : tab) {

@@ -125,7 +125,7 @@ void fitv2_destroy(fitv2_handle* h);
 
 /* Per-handle tuning switches (they replace the FITV2_* environment variables of earlier versions; the Python layer forwards
  * the environment when it creates a handle).  Names: "pdl" (1), "attn" (0 auto / 1 P-in-TMEM / 2 shared-memory-P / 3 online-max),
- * "attn_early" (1), "attn_stagger" (clocks the second query-tile stream starts late), "ln_threads" (64), "ln_wide_single" (0), "bn_resid" (0 = cost model),
+ * "attn_early" (1), "ln_threads" (64), "ln_wide_single" (0), "bn_resid" (0 = cost model),
  * "qkv_heads" (3), "resid_t" (-1 auto), "bn_resid_t" (0 = cost model), "cond" (0 tensor pipe / 1 fp32 FMA), "l2_persist_mb" (0),
  * "final_tc" (1), "verbose" (0).  Unknown names fail. */
 int fitv2_set_option(fitv2_handle* h, const char* name, int64_t value);

@@ -13,8 +13,7 @@ from fitv2_b200 import _lib
 specs = [a for a in sys.argv[1:] if "," in a] or ["64,256,72", "64,1024,72", "64,256,96"]
 lib = _lib.load()
 p = lambda t: C.c_void_p(t.data_ptr())
-staggers = [int(v) for v in os.environ.get("ATTN_STAGGERS", "-1").split(",")]      # sweep of the attn_stagger option (-1 = leave the default)
-for spec, stagger in [(s_, g_) for s_ in specs for g_ in staggers]:
+for spec in specs:
     parts = [int(v) for v in spec.split(",")]
     R, T, dh = parts[:3]
     reps = parts[3] if len(parts) > 3 else 30
@@ -23,8 +22,6 @@ for spec, stagger in [(s_, g_) for s_ in specs for g_ in staggers]:
     h = C.c_void_p()
     _lib.check(lib.fitv2_create(C.byref(cfg), C.byref(h)))
     _lib.apply_env_options(h)
-    if stagger >= 0:
-        _lib.check(lib.fitv2_set_option(h, b"attn_stagger", stagger))
     ws = torch.zeros(1 << 20, dtype=torch.uint8, device="cuda")
     _lib.check(lib.fitv2_set_workspace(h, p(ws), ws.numel()))
     g = torch.Generator(device="cuda").manual_seed(0)
@@ -56,6 +53,6 @@ for spec, stagger in [(s_, g_) for s_ in specs for g_ in staggers]:
     ref = torch.nn.functional.scaled_dot_product_attention(qf, kf, vf, attn_mask=(am == am.transpose(-2, -1)))
     ref = ref.transpose(1, 2).reshape(1, T, H * dh) * (mask[:1] != 0)[..., None]
     err = float((out[:1].float() - ref).abs().max() / ref.abs().max())
-    print(f"attention R={R} T={T} dh={dh} lib={os.path.basename(_lib.LIB_PATH)} attn={os.environ.get('FITV2_ATTN', 'auto')} stagger={stagger}: "
+    print(f"attention R={R} T={T} dh={dh} lib={os.path.basename(_lib.LIB_PATH)} attn={os.environ.get('FITV2_ATTN', 'auto')}: "
           f"{us:.1f} us/launch  {fl / us / 1e6:.0f} TFLOP/s  max-rel-err {err:.2e}", flush=True)
     lib.fitv2_destroy(h)

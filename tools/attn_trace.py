@@ -16,8 +16,6 @@ cfg = _lib.FitV2Config(H * dh, 1, H, dh, 3072, 288, 16, 1001, 0, 1.0, 1.0)
 h = C.c_void_p()
 _lib.check(lib.fitv2_create(C.byref(cfg), C.byref(h)))
 _lib.apply_env_options(h)
-if os.environ.get('ATTN_STAGGER'):
-    _lib.check(lib.fitv2_set_option(h, b'attn_stagger', int(os.environ['ATTN_STAGGER'])))
 ws = torch.zeros(1 << 20, dtype=torch.uint8, device="cuda")
 _lib.check(lib.fitv2_set_workspace(h, C.c_void_p(ws.data_ptr()), ws.numel()))
 g = torch.Generator().manual_seed(0)
