@@ -132,6 +132,7 @@ def load():
     lib.fitv2_debug_gemm.argtypes = [vp, i32, vp, vp, vp, vp, i32, i32, i32, i32, vp]
     lib.fitv2_debug_attention.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp]
     lib.fitv2_debug_tap.argtypes = [vp, i32, vp, i64, vp]
+    lib.fitv2_debug_layout.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), i32]
     lib.fitv2_kernel_launches.argtypes = [vp]
     lib.fitv2_kernel_launches.restype = i64
     lib.fitv2_profile_set.argtypes = [vp, C.c_uint32]
@@ -151,6 +152,6 @@ EXPORTED_SYMBOLS = [
     "fitv2_set_online_rope", "fitv2_workspace_bytes", "fitv2_set_workspace", "fitv2_forward", "fitv2_cfg_combine", "fitv2_cfg_euler",
     "fitv2_set_option", "fitv2_poll_error", "fitv2_rk_stage",
     "fitv2_sde_step", "fitv2_sde_drift", "fitv2_scaled_add", "fitv2_heun_combine", "fitv2_tweedie", "fitv2_unpatchify_scale", "fitv2_pack_uint8",
-    "fitv2_debug_gemm", "fitv2_debug_attention", "fitv2_debug_tap", "fitv2_kernel_launches",
+    "fitv2_debug_gemm", "fitv2_debug_attention", "fitv2_debug_tap", "fitv2_debug_layout", "fitv2_kernel_launches",
     "fitv2_profile_set", "fitv2_profile_read",
 ]

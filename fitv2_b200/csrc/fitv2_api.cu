@@ -183,6 +183,8 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct Layout {
     int rows = 0, tokens = 0, tokens_v = 0;
+    int n_spans = 0;                                   // (offset, bytes) of every buffer, in allocation order (fitv2_debug_layout)
+    size_t span_off[40], span_bytes[40];
     size_t x_res, h, ao, q, k, vt, hidden, te, t0, c, sc, sc_split, lmid, lmid_split, gmod, mod, fmod, rope_cos, rope_sin, seg_uniform, cpart, xt, ot, wfin16, total;
 };
 
@@ -205,6 +207,7 @@ struct Options {
     int bn_resid_t = 0;          // token rows per transposed tile (0 = cost model, 224, 256)
     int cond = 0;                // conditioning linears: 0 tensor pipe (tf32) where the shapes tile, 1 fp32 FMA kernels
     int l2_persist_mb = 0;       // persisting-L2 window on the fp32 residual stream (0 = off)
+    int ws_guard = 0;            // bytes of guard padding behind every workspace buffer (bounds test)
     int final_tc = 1;            // final layer: 1 = LayerNorm+modulate kernel + skinny tcgen05 GEMM, 0 = fused fp32 SIMT kernel
     int verbose = 0;
 };
@@ -309,13 +312,20 @@ int64_t expected_numel(const fitv2_config& c, int slot) {
     return -1;
 }
 
-Layout make_layout(const fitv2_config& c, int rows, int tokens) {
+Layout make_layout(const fitv2_config& c, int rows, int tokens, size_t guard = 0) {
     Layout l;
     l.rows = rows; l.tokens = tokens; l.tokens_v = (tokens + 7) / 8 * 8;
     const size_t M = (size_t)rows * tokens, D = c.hidden_size, Hm = c.mlp_hidden, L = c.depth;
     const size_t lora = c.adaln_type == FITV2_ADALN_LORA ? c.lora_dim : 0;
     size_t off = 0;
-    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 1024); return o; };
+    // `guard` bytes of untouched padding behind every buffer (option "ws_guard"): the bounds test fills the workspace with a
+    // canary, runs a forward and checks that the padding still holds it
+    auto take = [&](size_t bytes) {
+        size_t o = off;
+        if (l.n_spans < 40) { l.span_off[l.n_spans] = o; l.span_bytes[l.n_spans] = bytes; ++l.n_spans; }
+        off = align_up(off + bytes + guard, 1024);
+        return o;
+    };
     l.x_res = take(M * D * 4);
     l.h = take(M * D * 2);
     l.ao = take(M * D * 2);
@@ -1032,11 +1042,12 @@ int fitv2_set_option(fitv2_handle* h, const char* name, int64_t value) {
     struct { const char* n; int* p; } tab[] = {
         {"pdl", &o.pdl}, {"attn", &o.attn}, {"attn_early", &o.attn_early}, {"ln_threads", &o.ln_threads},
         {"ln_wide_single", &o.ln_wide_single}, {"bn_resid", &o.bn_resid}, {"qkv_heads", &o.qkv_heads}, {"resid_t", &o.resid_t},
-        {"bn_resid_t", &o.bn_resid_t}, {"cond", &o.cond}, {"l2_persist_mb", &o.l2_persist_mb}, {"final_tc", &o.final_tc}, {"verbose", &o.verbose}};
+        {"bn_resid_t", &o.bn_resid_t}, {"cond", &o.cond}, {"l2_persist_mb", &o.l2_persist_mb}, {"final_tc", &o.final_tc}, {"ws_guard", &o.ws_guard}, {"verbose", &o.verbose}};
     for (auto& e : tab) {
         if (strcmp(e.n, name)) continue;
         *e.p = v;
-        h->maps_valid = false;                                         // kernel selection / tile widths are derived in ensure_maps
+        h->maps_valid = false;
+        if (e.p == &o.ws_guard) h->lay = Layout();                    // buffer offsets change: re-derive at the next forward                                         // kernel selection / tile widths are derived in ensure_maps
         if (e.p == &o.l2_persist_mb) {                                 // persisting L2 for the fp32 residual stream (default off)
             int max_persist = 0, max_window = 0;
             cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, h->device);
@@ -1092,7 +1103,7 @@ int fitv2_set_online_rope(fitv2_handle* h, const float* freqs_h_rows, const floa
 
 int64_t fitv2_workspace_bytes(const fitv2_handle* h, int rows, int tokens) {
     if (!h || rows <= 0 || tokens <= 0) return fail(FITV2_E_INVALID, "bad workspace query");
-    return (int64_t)make_layout(h->cfg, rows, tokens).total;
+    return (int64_t)make_layout(h->cfg, rows, tokens, (size_t)h->opt.ws_guard).total;
 }
 
 int fitv2_set_workspace(fitv2_handle* h, void* dev_ptr, int64_t bytes) {
@@ -1120,7 +1131,7 @@ int fitv2_forward(fitv2_handle* h, const float* x, int x_rows, const float* t, c
     int rc = fitv2_poll_error(h);                                      // an earlier launch saw an out-of-range label
     if (rc) return rc;
     if (h->lay.rows != rows || h->lay.tokens != tokens) {
-        Layout l = make_layout(h->cfg, rows, tokens);
+        Layout l = make_layout(h->cfg, rows, tokens, (size_t)h->opt.ws_guard);
         if ((int64_t)l.total > h->ws_bytes)
             return fail(FITV2_E_WORKSPACE, "workspace has %lld bytes, (rows=%d, tokens=%d) needs %lld", (long long)h->ws_bytes, rows, tokens, (long long)l.total);
         h->lay = l;
@@ -1301,6 +1312,14 @@ int fitv2_debug_attn_trace(unsigned long long* host_trace, unsigned int* host_n,
     return FITV2_OK;
 }
 #endif
+
+int fitv2_debug_layout(const fitv2_handle* h, int64_t* offsets, int64_t* sizes, int max_entries) {
+    if (!h || !offsets || !sizes || max_entries <= 0) return fail(FITV2_E_INVALID, "bad debug_layout argument");
+    if (!h->lay.rows) return fail(FITV2_E_UNBOUND, "no forward has run yet");
+    const int n = h->lay.n_spans < max_entries ? h->lay.n_spans : max_entries;
+    for (int i = 0; i < n; ++i) { offsets[i] = (int64_t)h->lay.span_off[i]; sizes[i] = (int64_t)h->lay.span_bytes[i]; }
+    return n;
+}
 
 int64_t fitv2_kernel_launches(const fitv2_handle* h) { return h ? h->launches : 0; }
 

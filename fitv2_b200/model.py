@@ -282,6 +282,16 @@ class FiT(nn.Module):
         """Per-handle tuning switch (include/fitv2_b200.h: fitv2_set_option)."""
         self._ensure_packed()
         _lib.check(_lib.load().fitv2_set_option(self._handle, name.encode(), int(value)), f"fitv2_set_option({name})")
+        if name == "ws_guard":
+            self._ws_shape = None                                           # the workspace is re-sized at the next call
+
+    def workspace_layout(self):
+        """[(offset, bytes)] of the buffers the last forward used inside ``self._workspace`` (fitv2_debug_layout)."""
+        off, size = (C.c_int64 * 40)(), (C.c_int64 * 40)()
+        n = _lib.load().fitv2_debug_layout(self._handle, off, size, 40)
+        if n < 0:
+            _lib.check(n, "fitv2_debug_layout")
+        return [(int(off[i]), int(size[i])) for i in range(n)]
 
     def check_device_errors(self):
         """Raise if a kernel of an earlier call saw an out-of-range class label (the reference raises an IndexError /
@@ -358,7 +368,9 @@ class FiT(nn.Module):
         if need <= 0:
             _lib.check(int(need), "fitv2_workspace_bytes")
         if self._workspace is None or self._workspace.numel() < need:
-            self._workspace = torch.zeros(int(need), dtype=torch.uint8, device=self.device)
+            # FITV2_POISON_WORKSPACE=empty leaves the scratch memory unwritten (compute-sanitizer initcheck runs)
+            alloc = torch.empty if os.environ.get("FITV2_POISON_WORKSPACE") == "empty" else torch.zeros
+            self._workspace = alloc(int(need), dtype=torch.uint8, device=self.device)
             _lib.check(lib.fitv2_set_workspace(self._handle, C.c_void_p(self._workspace.data_ptr()), self._workspace.numel()),
                        "fitv2_set_workspace")
         if os.environ.get("FITV2_POISON_WORKSPACE") == "1":             # tests: every byte NaN, so a read of scratch memory that the

@@ -127,7 +127,7 @@ void fitv2_destroy(fitv2_handle* h);
  * the environment when it creates a handle).  Names: "pdl" (1), "attn" (0 auto / 1 P-in-TMEM / 2 shared-memory-P / 3 online-max),
  * "attn_early" (1), "ln_threads" (64), "ln_wide_single" (0), "bn_resid" (0 = cost model),
  * "qkv_heads" (3), "resid_t" (-1 auto), "bn_resid_t" (0 = cost model), "cond" (0 tensor pipe / 1 fp32 FMA), "l2_persist_mb" (0),
- * "final_tc" (1), "verbose" (0).  Unknown names fail. */
+ * "final_tc" (1), "ws_guard" (0), "verbose" (0).  Unknown names fail. */
 int fitv2_set_option(fitv2_handle* h, const char* name, int64_t value);
 
 /* Device-side checks report through a sticky word in pinned host memory instead of trapping: returns FITV2_E_INVALID (and
@@ -221,6 +221,10 @@ int fitv2_debug_gemm(fitv2_handle* h, int epilogue /*3 = plain*/, const void* a,
 int fitv2_debug_attention(fitv2_handle* h, const void* q, const void* k, const void* vt, const float* mask,
                           void* out, int rows, int tokens, float* dbg_s, float* dbg_o, void* stream);
 int fitv2_debug_tap(fitv2_handle* h, int what, void* dst, int64_t bytes, void* stream);
+/* (offset, bytes) of every buffer the last forward carved out of the workspace, in allocation order; returns the count.  With
+ * option "ws_guard" = G every buffer is followed by at least G bytes that no kernel may touch: the bounds test (compute-sanitizer is
+ * not available on the target pool) fills the workspace with a canary, runs a forward and checks the padding. */
+int fitv2_debug_layout(const fitv2_handle* h, int64_t* offsets, int64_t* sizes, int max_entries);
 int64_t fitv2_kernel_launches(const fitv2_handle* h);   /* launches enqueued by this handle so far */
 
 /* Per-kernel-class device timing with CUDA events on the launching stream (measurement support for bench.py).

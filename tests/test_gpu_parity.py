@@ -765,3 +765,33 @@ def test_options_are_per_handle(lib, monkeypatch):
     assert rel(run(m0, *a), ref) < V_TOL
     with pytest.raises(_lib.FitV2Error, match="unknown option"):
         m0.set_option("bogus", 1)
+
+
+@pytest.mark.parametrize("width,depth,R,hp,wp,extra", [(XL, 2, 5, 10, 20, {}), (XL, 1, 3, 7, 9, {}), (B3, 1, 3, 10, 20, {}), (XL, 1, 2, 32, 32, {}),
+                                                       (XL, 1, 66, 3, 5, {}), (XL, 1, 4, 16, 16, dict(q_norm=None, k_norm=None))])
+def test_workspace_bounds_canary(lib, width, depth, R, hp, wp, extra):
+    """compute-sanitizer is closed on this GPU pool (profiles/r2_sanitizer_unavailable.txt), so out-of-bounds writes are hunted
+    with guard bands: every workspace buffer is followed by 4 KB of padding, the whole workspace (and a frame around the output
+    tensor) is filled with a canary, and after the forward every byte of padding must still hold it -- for ragged shapes that
+    exercise the M / key / V^T tails, the 1024-token path, 3B width, > 64 rows, and the online-max attention."""
+    torch.manual_seed(0)
+    m = FiT(**{**KW, **width, **extra}, depth=depth).randomize_zero_init_(1).cuda().eval()
+    a = [v.cuda() for v in inputs(R, hp, wp, seed=23)]
+    m.set_option("ws_guard", 4096)
+    ref = m(*a).cpu()                                                        # sizes the workspace
+    ws = m._workspace
+    ws.fill_(0xA5)
+    N = hp * wp
+    frame = torch.full((R * N * 16 + 2048,), float("nan"), device="cuda")    # output in the middle of a NaN frame
+    out = frame[1024:1024 + R * N * 16].view(R, N, 16)
+    m._run(a[0].float().contiguous(), *a[1:], rows=R, out=out)
+    torch.cuda.synchronize()
+    assert torch.equal(out.cpu(), ref)
+    assert bool(torch.isnan(frame[:1024]).all()) and bool(torch.isnan(frame[-1024:]).all())
+    spans = m.workspace_layout()
+    assert len(spans) >= 20
+    host = ws.cpu()
+    for i, (off, size) in enumerate(spans):
+        end = spans[i + 1][0] if i + 1 < len(spans) else off + size + 4096
+        pad = host[off + size:end]
+        assert pad.numel() >= 4096 and bool((pad == 0xA5).all()), f"buffer {i} (offset {off}, {size} bytes): padding overwritten"
