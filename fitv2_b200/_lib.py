@@ -115,6 +115,8 @@ def load():
     lib.fitv2_set_option.argtypes = [vp, C.c_char_p, i64]
     lib.fitv2_poll_error.argtypes = [vp]
     lib.fitv2_rk_stage.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i64, vp]
+    lib.fitv2_lincomb.argtypes = [vp, vp, C.POINTER(vp), vp, i32, i64, vp]
+    lib.fitv2_scaled_rms.argtypes = [vp, vp, vp, vp, f32, f32, i64, vp]
     lib.fitv2_set_online_rope.argtypes = [vp, vp, vp, i32]
     lib.fitv2_workspace_bytes.argtypes = [vp, i32, i32]
     lib.fitv2_workspace_bytes.restype = i64
@@ -150,7 +152,7 @@ def check(rc: int, what: str = ""):
 EXPORTED_SYMBOLS = [
     "fitv2_last_error", "fitv2_version", "fitv2_create", "fitv2_destroy", "fitv2_bind_weight",
     "fitv2_set_online_rope", "fitv2_workspace_bytes", "fitv2_set_workspace", "fitv2_forward", "fitv2_cfg_combine", "fitv2_cfg_euler",
-    "fitv2_set_option", "fitv2_poll_error", "fitv2_rk_stage",
+    "fitv2_set_option", "fitv2_poll_error", "fitv2_rk_stage", "fitv2_lincomb", "fitv2_scaled_rms",
     "fitv2_sde_step", "fitv2_sde_drift", "fitv2_scaled_add", "fitv2_heun_combine", "fitv2_tweedie", "fitv2_unpatchify_scale", "fitv2_pack_uint8",
     "fitv2_debug_gemm", "fitv2_debug_attention", "fitv2_debug_tap", "fitv2_debug_layout", "fitv2_kernel_launches",
     "fitv2_profile_set", "fitv2_profile_read",

@@ -1217,6 +1217,23 @@ int fitv2_rk_stage(float* out, const float* y, const float* k1, const float* k2,
     return FITV2_OK;
 }
 
+int fitv2_lincomb(float* out, const float* y, const float* const* k, const float* c_dev, int nk, int64_t n, void* stream) {
+    if (!out || !y || !c_dev || nk < 0 || nk > 7 || (nk > 0 && !k) || n <= 0) return fail(FITV2_E_INVALID, "bad lincomb argument");
+    LinComb ks;
+    for (int i = 0; i < 7; ++i) {
+        ks.k[i] = i < nk ? k[i] : y;
+        if (!ks.k[i]) return fail(FITV2_E_INVALID, "lincomb: slope %d is null", i);
+    }
+    CUDA_TRY(launch_k(lincomb_kernel, dim3(elementwise_grid(n * 4)), dim3(256), 0, static_cast<cudaStream_t>(stream), 1, out, y, ks, c_dev, nk, (size_t)n));
+    return FITV2_OK;
+}
+
+int fitv2_scaled_rms(float* out_dev, const float* a, const float* b, const float* s, float atol, float rtol, int64_t n, void* stream) {
+    if (!out_dev || !a || n <= 0) return fail(FITV2_E_INVALID, "bad scaled_rms argument");
+    CUDA_TRY(launch_k(scaled_rms_kernel, dim3(1), dim3(1024), 0, static_cast<cudaStream_t>(stream), 1, out_dev, a, b, s, atol, rtol, (size_t)n));
+    return FITV2_OK;
+}
+
 int fitv2_unpatchify_scale(const float* z, float* out, float scaling_factor, int batch, int hp, int wp, int channels, int patch, void* stream) {
     if (!z || !out || batch <= 0 || hp <= 0 || wp <= 0 || channels <= 0 || patch <= 0 || scaling_factor == 0.0f)
         return fail(FITV2_E_INVALID, "bad unpatchify_scale argument");

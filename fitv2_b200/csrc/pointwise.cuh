@@ -203,6 +203,54 @@ __global__ void rk_stage_kernel(float* __restrict__ out, const float* __restrict
     }
 }
 
+// Adaptive Dormand-Prince 5(4) ("dopri5", the reference's default --ode-sampling-method through torchdiffeq.odeint): the two
+// device-side pieces of a step.
+//   lincomb:     out = c[0] * y + sum_{i < nk} c[1 + i] * k_i        (stage arguments, the 5th-order solution, the error estimate,
+//                                                                     the dense-output polynomial and its evaluation)
+//   scaled_rms:  out[0] = sqrt(mean(((a - b) / (atol + rtol * |s|))^2))   (b, s nullable: plain RMS norm, torchdiffeq's default `norm`)
+// One block, fixed summation order (deterministic); the state is at most a few 10^5 elements and the solver synchronises on
+// this scalar anyway to accept / reject the step.
+struct LinComb { const float* k[7]; };
+__global__ void lincomb_kernel(float* __restrict__ out, const float* __restrict__ y, LinComb ks, const float* __restrict__ c, int nk, size_t n)
+{
+    pdl_wait();
+    pdl_launch_dependents();
+    float cc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) cc[i] = i <= nk ? c[i] : 0.f;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float acc = __fmul_rn(cc[0], y[i]);
+#pragma unroll
+        for (int j = 0; j < 7; ++j)
+            if (j < nk) acc = __fadd_rn(acc, __fmul_rn(cc[1 + j], ks.k[j][i]));
+        out[i] = acc;
+    }
+}
+
+__global__ void __launch_bounds__(1024)
+scaled_rms_kernel(float* __restrict__ out, const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ s,
+                  float atol, float rtol, size_t n)
+{
+    pdl_wait();
+    pdl_launch_dependents();
+    __shared__ double red[32];
+    double acc = 0.0;
+    for (size_t i = threadIdx.x; i < n; i += blockDim.x) {
+        float v = b ? __fsub_rn(a[i], b[i]) : a[i];
+        if (s) v = __fdiv_rn(v, __fadd_rn(atol, __fmul_rn(rtol, fabsf(s[i]))));
+        acc += (double)v * (double)v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+        out[0] = (float)sqrt(t / (double)n);
+    }
+}
+
 // (rows, A, B) -> (rows, B, A): the 'B C N' <-> 'B N C' rearranges of the use_sit = False layout (fit_model.py:204,231).
 __global__ void transpose_inner_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int A, int B)
 {

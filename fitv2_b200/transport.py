@@ -16,15 +16,18 @@ network evaluation between the velocity and the score term (the reference calls 
 transport.py:256-258).  The per-step scalars (score variance, diffusion coefficient, step sizes) are computed once
 on the host in fp32 with the reference's expression order and kept in a device table.
 
-ODE route: every FIXED-GRID solver of ``torchdiffeq.odeint`` that the reference's ``--ode-sampling-method`` string can name
-— ``euler``, ``midpoint``, ``heun2``, ``heun3``, ``rk4`` (torchdiffeq's rk4 is the 3/8-rule variant) — with one fused update
-kernel per stage (``fitv2_scaled_add`` / ``fitv2_rk_stage``).  ``torchdiffeq`` is an un-vendored dependency of the reference:
-its published ``fixed_grid.py`` / ``rk_common.py`` step functions are restated, expression order included.
+ODE route: the fixed-grid solvers of ``torchdiffeq.odeint`` that the reference's ``--ode-sampling-method`` string can name —
+``euler``, ``midpoint``, ``heun2``, ``heun3``, ``rk4`` (torchdiffeq's rk4 is the 3/8-rule variant) — with one fused update
+kernel per stage (``fitv2_scaled_add`` / ``fitv2_rk_stage``), and the reference's DEFAULT, the adaptive ``dopri5``
+(Dormand-Prince 5(4) with torchdiffeq's step-size controller and 4th-order dense output): stage arguments, solution, error
+estimate and interpolation are ``fitv2_lincomb`` launches, the error / state norms ``fitv2_scaled_rms`` reductions, and the
+accept / reject decision is taken on the host from three scalars per step (the number of network evaluations is data dependent
+by construction).  ``torchdiffeq`` is an un-vendored dependency of the reference: its published ``fixed_grid.py`` /
+``rk_common.py`` / ``dopri5.py`` / ``misc.py`` / ``interp.py`` are restated ("parity unpinned" for the integrator itself).
 
-Not built: the ADAPTIVE solvers (``dopri5`` — the reference's ODE default —, ``dopri8``, ``bosh3``, ``adaptive_heun``, ...):
-their number of network evaluations depends on a per-step error norm read back on the host, so the step is not a fixed
-launch sequence; and the likelihood ODE (autograd through the network).  Both raise ``NotImplementedError`` naming the
-fixed-grid alternatives.  Paths / predictions other than Linear / velocity raise at ``create_transport``.
+Not built: the other adaptive solvers (``dopri8``, ``bosh3``, ``fehlberg2``, ``adaptive_heun``), the Adams multistep family and
+the likelihood ODE (autograd through the network); they raise ``NotImplementedError`` naming what exists.  Paths / predictions
+other than Linear / velocity raise at ``create_transport``.
 """
 from __future__ import annotations
 
@@ -37,6 +40,14 @@ import torch as th
 from . import _lib
 
 _ODE_FIXED = ("euler", "midpoint", "heun2", "heun3", "rk4")
+# Dormand-Prince-Shampine tableau and dense-output mid-point weights (torchdiffeq/_impl/dopri5.py)
+_DP_ALPHA = (1 / 5, 3 / 10, 4 / 5, 8 / 9, 1.0, 1.0)
+_DP_BETA = ((1 / 5,), (3 / 40, 9 / 40), (44 / 45, -56 / 15, 32 / 9), (19372 / 6561, -25360 / 2187, 64448 / 6561, -212 / 729),
+            (9017 / 3168, -355 / 33, 46732 / 5247, 49 / 176, -5103 / 18656), (35 / 384, 0, 500 / 1113, 125 / 192, -2187 / 6784, 11 / 84))
+_DP_C_ERROR = (35 / 384 - 1951 / 21600, 0, 500 / 1113 - 22642 / 50085, 125 / 192 - 451 / 720, -2187 / 6784 - -12231 / 42400,
+               11 / 84 - 649 / 6300, -1.0 / 60.0)
+_DP_C_MID = (6025192743 / 30085553152 / 2, 0, 51252292925 / 65400821598 / 2, -2691868925 / 45128329728 / 2,
+             187940372067 / 1594534317056 / 2, -1776094331 / 19743644256 / 2, 11237099 / 235043384 / 2)
 _DIFFUSION_FORMS = ("constant", "SBDM", "sigma", "linear", "decreasing", "increasing-decreasing")
 
 
@@ -117,11 +128,93 @@ def _check_state(x: th.Tensor, what: str) -> th.Tensor:
     return x.contiguous()
 
 
+def _dopri5(f: Callable, y0: th.Tensor, ts: th.Tensor, rtol: float, atol: float, stats: dict) -> List[th.Tensor]:
+    """torchdiffeq's adaptive dopri5 (RKAdaptiveStepsizeODESolver: _before_integrate, _advance, _adaptive_step, _runge_kutta_step;
+    misc._select_initial_step / _compute_error_ratio / _optimal_step_size with safety 0.9, ifactor 10, dfactor 0.2, RMS norm;
+    interp._interp_fit / _interp_evaluate) on device tensors: the solution at every time of ``ts``.  The step size and the times live
+    on the host in fp32 like torchdiffeq's 0-dim tensors; per step the device reports three norms."""
+    lib = _lib.load()
+    dev, n = y0.device, y0.numel()
+    st = _stream(dev)
+    sign = 1.0 if float(ts[-1]) >= float(ts[0]) else -1.0                    # decreasing grids: integrate -f(-t, y) forwards
+    tt = ts * sign
+    nfe = 0
+
+    def func(t: th.Tensor, state: th.Tensor) -> th.Tensor:
+        nonlocal nfe
+        nfe += 1
+        out = f(t * sign, state)
+        return out if sign > 0 else -out
+
+    def lincomb(base: th.Tensor, cy, ks, cs, out: Optional[th.Tensor] = None) -> th.Tensor:
+        out = th.empty_like(base) if out is None else out
+        c = th.stack([_f32(cy)] + [_f32(v) for v in cs]).to(dev)
+        ptrs = (C.c_void_p * max(len(ks), 1))(*[k.data_ptr() for k in ks])
+        _lib.check(lib.fitv2_lincomb(_p(out), _p(base), ptrs, _p(c), len(ks), n, st), "fitv2_lincomb")
+        return out
+
+    norms = th.empty(3, dtype=th.float32, device=dev)
+
+    def rms(slot: int, a, b=None, s=None, at=0.0, rt=0.0):
+        _lib.check(lib.fitv2_scaled_rms(C.c_void_p(norms.data_ptr() + 4 * slot), _p(a), _p(b), _p(s), at, rt, n, st), "fitv2_scaled_rms")
+
+    t0 = tt[0]
+    f0 = func(t0, y0)
+    # ---- _select_initial_step (order 4) ----
+    rms(0, y0, None, y0, atol, rtol); rms(1, f0, None, y0, atol, rtol)
+    d0, d1 = [th.tensor(v) for v in norms[:2].tolist()]
+    h0 = th.tensor(1e-6) if (d0 < 1e-5 or d1 < 1e-5) else 0.01 * d0 / d1
+    f1 = func(t0 + h0, lincomb(y0, 1.0, [f0], [h0]))
+    rms(2, f1, f0, y0, atol, rtol)
+    d2 = th.tensor(norms[2].item()) / h0
+    h1 = th.max(th.tensor(1e-6), h0 * 1e-3) if (d1 <= 1e-15 and d2 <= 1e-15) else (0.01 / max(d1, d2)) ** (1.0 / 5.0)
+    dt = th.min(100 * h0, h1).to(th.float32)
+    y, f_cur, t_lo, t_hi = y0, f0, t0, t0
+    coeff = None                                                             # [e, d, c, b, a] of the last accepted step
+    out = [y0.clone()]
+    steps = rejected = 0
+    for t_next in tt[1:]:
+        while t_next > t_hi:
+            ks = [f_cur]                                                     # _runge_kutta_step
+            for alpha_i, beta_i in zip(_DP_ALPHA, _DP_BETA):
+                ti = t_hi + dt if alpha_i == 1.0 else t_hi + alpha_i * dt
+                yi = lincomb(y, 1.0, ks, [b * dt for b in beta_i])
+                ks.append(func(ti, yi))
+            y1, f_new = yi, ks[-1]                                           # c_sol == beta[-1] (first-same-as-last)
+            err = lincomb(y, 0.0, ks, [c * dt for c in _DP_C_ERROR])
+            rms(0, y); rms(1, y1); rms(2, err)
+            ny, ny1, nerr = norms.tolist()                                   # the one host synchronisation of the step
+            ratio = nerr / (atol + rtol * max(ny, ny1))
+            steps += 1
+            if ratio <= 1:
+                y_mid = lincomb(y, 1.0, ks, [c * dt for c in _DP_C_MID])
+                fa, fb = ks[0], ks[-1]                                       # _interp_fit
+                pa = lincomb(y, -8.0, [y1, y_mid, fa, fb], [-8.0, 16.0, -2 * dt, 2 * dt])
+                pb = lincomb(y, 18.0, [y1, y_mid, fa, fb], [14.0, -32.0, 5 * dt, -3 * dt])
+                pc = lincomb(y, -11.0, [y1, y_mid, fa, fb], [-5.0, 16.0, -4 * dt, dt])
+                pd = lincomb(fa, dt, [], [])
+                coeff = [y, pd, pc, pb, pa]
+                t_lo, t_hi = t_hi, t_hi + dt
+                y, f_cur = y1, f_new
+            else:
+                rejected += 1
+            if ratio == 0:                                                   # _optimal_step_size
+                dt = dt * 10.0
+            else:
+                dt = dt * min(10.0, max(0.9 / ratio ** 0.2, 1.0 if ratio < 1 else 0.2))
+        x = (t_next - t_lo) / (t_hi - t_lo)                                  # _interp_evaluate
+        out.append(lincomb(coeff[0], 1.0, coeff[1:], [x, x * x, x * x * x, x * x * x * x]))
+    stats.clear()
+    stats.update(nfe=nfe, steps=steps, rejected=rejected)
+    return out
+
+
 class Sampler:
     """transport.py:230-401."""
 
     def __init__(self, transport: Transport):
         self.transport = transport
+        self.last_ode_stats = {}                       # dopri5: network evaluations / steps / rejected steps of the last call
 
     # ------------------------------------------------------------------ SDE
     def sample_sde(self, *, sampling_method="Euler", diffusion_form="SBDM", diffusion_norm=1.0, last_step="Mean",
@@ -211,9 +304,8 @@ class Sampler:
         """transport.py:358-401 with the fixed-grid methods of ``torchdiffeq.odeint`` on ``linspace(t0, t1, num_steps)``
         (integrators.py:95-116); returns the solution at every grid point.  ``atol`` / ``rtol`` are accepted for signature
         compatibility (fixed-grid solvers ignore them, as in torchdiffeq)."""
-        if sampling_method not in _ODE_FIXED:
-            raise NotImplementedError(f"ODE method {sampling_method!r}: the fixed-grid solvers {_ODE_FIXED} are built; adaptive solvers "
-                                      "(dopri5, ...) have a data-dependent number of network evaluations and are out of scope")
+        if sampling_method not in _ODE_FIXED + ("dopri5",):
+            raise NotImplementedError(f"ODE method {sampling_method!r}: built are the fixed-grid solvers {_ODE_FIXED} and the adaptive 'dopri5'")
         tr = self.transport
         t0, t1 = tr.check_interval(tr.train_eps, tr.sample_eps, sde=False, eval=True, reverse=reverse, last_step_size=0.0)
         ts = th.linspace(t0, t1, num_steps)
@@ -230,6 +322,10 @@ class Sampler:
                 if reverse:
                     tv = th.ones_like(tv) * (1 - tv)                             # transport.py:376-377
                 return _check_state(model(state, tv.to(dev), **model_kwargs), "model output")
+
+            if sampling_method == "dopri5":
+                with th.cuda.device(dev), th.no_grad():
+                    return _dopri5(f, y, ts, float(rtol), float(atol), self.last_ode_stats)
 
             with th.cuda.device(dev), th.no_grad():
                 st = _stream(dev)

@@ -203,6 +203,15 @@ int fitv2_tweedie(float* out, const float* x, const float* v, const float* coef_
 int fitv2_rk_stage(float* out, const float* y, const float* k1, const float* k2, const float* k3, const float* k4,
                    const float* s_dev, int mode, int64_t n, void* stream);
 
+/* Adaptive Dormand-Prince 5(4) ("dopri5", the reference's DEFAULT --ode-sampling-method: fit/utils/sit_eval_utils.py:20 ->
+ * torchdiffeq.odeint, integrators.py:109-116).  The step-size controller runs on the host (fitv2_b200/transport.py restates
+ * torchdiffeq's published rk_common.py / dopri5.py / interp.py); the device side is two kernels:
+ *   fitv2_lincomb:    out = c[0]*y + sum_{i<nk} c[1+i]*k[i]   (nk <= 7; c_dev: 1 + nk device floats; separately rounded, in order)
+ *   fitv2_scaled_rms: out_dev[0] = sqrt(mean(((a - b) / (atol + rtol*|s|))^2)), b and s nullable (plain RMS norm when both are
+ *                     NULL); one block, fixed summation order (deterministic). */
+int fitv2_lincomb(float* out, const float* y, const float* const* k, const float* c_dev, int nk, int64_t n, void* stream);
+int fitv2_scaled_rms(float* out_dev, const float* a, const float* b, const float* s, float atol, float rtol, int64_t n, void* stream);
+
 /* ---- after the trajectory (sample_fitv2_ddp.py:319-324) ----
  * Replaces FiT.unpatchify (fit_model.py:171-187, use_sit layout) fused with the latent scaling `samples / vae.config.scaling_factor`:
  *   z (batch, hp*wp, channels*patch*patch) fp32 -> out (batch, channels, hp*patch, wp*patch) fp32, out = unpatchify(z) / scaling_factor

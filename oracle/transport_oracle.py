@@ -172,8 +172,8 @@ def sample_sde(model: Callable, init: th.Tensor, *, sampling_method="Euler", dif
 # ------------------------------------------------------------------------------------------------
 # ODE (transport.py:358-401, integrators.py:77-116): fixed-grid methods of torchdiffeq.odeint
 # ------------------------------------------------------------------------------------------------
-def sample_ode(model: Callable, x: th.Tensor, *, sampling_method="euler", num_steps=50, reverse=False,
-               **model_kwargs) -> List[th.Tensor]:
+def sample_ode(model: Callable, x: th.Tensor, *, sampling_method="euler", num_steps=50, reverse=False, atol=1e-6, rtol=1e-3,
+               stats: Optional[dict] = None, **model_kwargs) -> List[th.Tensor]:
     """Returns the solution at every grid point (odeint returns a (num_steps, ...) tensor; the script takes [-1])."""
     t0, t1 = check_interval(0, sde=False, reverse=reverse)
     ts = th.linspace(t0, t1, num_steps)
@@ -184,6 +184,8 @@ def sample_ode(model: Callable, x: th.Tensor, *, sampling_method="euler", num_st
             tv = th.ones_like(tv) * (1 - tv)
         return model(y, tv, **model_kwargs)
 
+    if sampling_method == "dopri5":
+        return dopri5_integrate(f, x, ts, rtol=rtol, atol=atol, stats=stats)
     ys = [x]
     y = x
     for i in range(num_steps - 1):
@@ -221,3 +223,95 @@ def toy_velocity_model(x, t, **kw):
     """Polynomial stand-in for the network (+, -, * only: bit-reproducible on any CPU); used by the golden vectors."""
     tt = expand_t_like_x(t, x)
     return 0.5 * x * (1 + tt) - 0.125 * x * x * x + 0.3 * tt
+
+
+# ------------------------------------------------------------------------------------------------
+# adaptive dopri5 (the reference's DEFAULT ODE method, fit/utils/sit_eval_utils.py:20 -> torchdiffeq.odeint(method="dopri5"))
+# ------------------------------------------------------------------------------------------------
+# torchdiffeq is an un-vendored, uninstalled dependency ("parity unpinned"): the constants and the control flow below restate its
+# published _impl/dopri5.py (Dormand-Prince-Shampine tableau, DPS_C_MID), _impl/rk_common.py (_runge_kutta_step, _adaptive_step,
+# RKAdaptiveStepsizeODESolver._before_integrate / _advance), _impl/misc.py (_select_initial_step, _compute_error_ratio,
+# _optimal_step_size with safety 0.9, ifactor 10, dfactor 0.2, _rms_norm) and _impl/interp.py (_interp_fit, _interp_evaluate).
+DP_ALPHA = [1 / 5, 3 / 10, 4 / 5, 8 / 9, 1.0, 1.0]
+DP_BETA = [
+    [1 / 5],
+    [3 / 40, 9 / 40],
+    [44 / 45, -56 / 15, 32 / 9],
+    [19372 / 6561, -25360 / 2187, 64448 / 6561, -212 / 729],
+    [9017 / 3168, -355 / 33, 46732 / 5247, 49 / 176, -5103 / 18656],
+    [35 / 384, 0, 500 / 1113, 125 / 192, -2187 / 6784, 11 / 84],
+]
+DP_C_SOL = [35 / 384, 0, 500 / 1113, 125 / 192, -2187 / 6784, 11 / 84, 0]
+DP_C_ERROR = [35 / 384 - 1951 / 21600, 0, 500 / 1113 - 22642 / 50085, 125 / 192 - 451 / 720, -2187 / 6784 - -12231 / 42400,
+              11 / 84 - 649 / 6300, -1.0 / 60.0]
+DP_C_MID = [6025192743 / 30085553152 / 2, 0, 51252292925 / 65400821598 / 2, -2691868925 / 45128329728 / 2,
+            187940372067 / 1594534317056 / 2, -1776094331 / 19743644256 / 2, 11237099 / 235043384 / 2]
+
+
+def _rms(x):
+    return x.abs().pow(2).mean().sqrt()
+
+
+def dopri5_integrate(f: Callable, y0: th.Tensor, ts: th.Tensor, rtol=1e-3, atol=1e-6, stats: Optional[dict] = None) -> List[th.Tensor]:
+    """Solution at every time of ``ts`` (increasing or decreasing grid), torchdiffeq's adaptive dopri5 semantics: the solver
+    walks its own step sequence from ts[0] and evaluates a 4th-order dense-output polynomial at the requested times."""
+    sign = 1.0 if float(ts[-1]) >= float(ts[0]) else -1.0                 # torchdiffeq flips time for decreasing grids
+    tt = ts * sign
+    func = (lambda t, y: f(t, y)) if sign > 0 else (lambda t, y: -f(-t, y))
+    nfe = 0
+    t0 = tt[0]
+    f0 = func(t0, y0); nfe += 1
+    # _select_initial_step (order = 4)
+    scale = atol + y0.abs() * rtol
+    d0, d1 = _rms(y0 / scale), _rms(f0 / scale)
+    h0 = th.tensor(1e-6, dtype=tt.dtype) if (d0 < 1e-5 or d1 < 1e-5) else 0.01 * d0 / d1
+    f1 = func(t0 + h0, y0 + h0 * f0); nfe += 1
+    d2 = _rms((f1 - f0) / scale) / h0
+    h1 = th.max(th.tensor(1e-6, dtype=tt.dtype), h0 * 1e-3) if (d1 <= 1e-15 and d2 <= 1e-15) else (0.01 / max(d1, d2)) ** (1.0 / 5.0)
+    dt = th.min(100 * h0, h1).to(tt.dtype)
+    y, f_cur, t_lo, t_hi = y0, f0, t0, t0
+    coeff = [y0] * 5
+    out = [y0]
+    steps = rejected = 0
+    for t_next in tt[1:]:
+        while t_next > t_hi:
+            # _runge_kutta_step
+            ks = [f_cur]
+            for alpha_i, beta_i in zip(DP_ALPHA, DP_BETA):
+                ti = t_hi + dt if alpha_i == 1.0 else t_hi + alpha_i * dt
+                yi = y + sum(k * (b * dt) for k, b in zip(ks, beta_i))
+                ks.append(func(ti, yi)); nfe += 1
+            y1 = yi                                                          # c_sol[:-1] == beta[-1] and c_sol[-1] == 0
+            f_new = ks[-1]
+            err = sum(k * (c * dt) for k, c in zip(ks, DP_C_ERROR))
+            tol = atol + rtol * th.max(_rms(y), _rms(y1))
+            ratio = _rms(err) / tol
+            steps += 1
+            if ratio <= 1:
+                y_mid = y + sum(k * (c * dt) for k, c in zip(ks, DP_C_MID))
+                fa, fb = ks[0], ks[-1]
+                a = 2 * dt * (fb - fa) - 8 * (y1 + y) + 16 * y_mid          # _interp_fit
+                b = dt * (5 * fa - 3 * fb) + 18 * y + 14 * y1 - 32 * y_mid
+                c = dt * (fb - 4 * fa) - 11 * y - 5 * y1 + 16 * y_mid
+                coeff = [y, dt * fa, c, b, a]
+                t_lo, t_hi = t_hi, t_hi + dt
+                y, f_cur = y1, f_new
+            else:
+                rejected += 1
+            # _optimal_step_size
+            if ratio == 0:
+                dt = dt * 10.0
+            else:
+                dfactor = 1.0 if ratio < 1 else 0.2
+                factor = min(10.0, max(0.9 / float(ratio) ** 0.2, dfactor))
+                dt = dt * factor
+        x = (t_next - t_lo) / (t_hi - t_lo)                                 # _interp_evaluate
+        total = coeff[0] + x * coeff[1]
+        xp = x
+        for cf in coeff[2:]:
+            xp = xp * x
+            total = total + xp * cf
+        out.append(total)
+    if stats is not None:
+        stats.update(nfe=nfe, steps=steps, rejected=rejected)
+    return out

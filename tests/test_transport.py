@@ -50,7 +50,28 @@ def test_oracle_ode_fixed_grid(kat):
     assert th.equal(T.sample_ode(T.toy_velocity_model, o["init"], sampling_method="euler", num_steps=o["num_steps"])[-1], o["euler_final"])
     assert th.equal(T.sample_ode(T.toy_velocity_model, o["init"], sampling_method="midpoint", num_steps=o["num_steps"])[-1], o["midpoint_final"])
     with pytest.raises(NotImplementedError):
-        T.sample_ode(T.toy_velocity_model, o["init"], sampling_method="dopri5")
+        T.sample_ode(T.toy_velocity_model, o["init"], sampling_method="dopri8")
+
+
+def test_oracle_dopri5_meets_its_tolerance():
+    """The adaptive dopri5 restatement (torchdiffeq is not installed: unpinned) integrates to within its tolerance of a fine
+    fixed-grid solution, at the requested grid times as well (dense output), forwards and on a decreasing grid."""
+    x0 = th.linspace(-1.0, 1.0, 32, dtype=th.float64).reshape(2, 4, 4)
+    model = lambda x, t, **kw: T.toy_velocity_model(x, t.to(x.dtype))
+    th.set_default_dtype(th.float64)
+    try:
+        fine = T.sample_ode(model, x0, sampling_method="rk4", num_steps=2049)
+        for rtol, bound in ((1e-3, 2e-4), (1e-6, 1e-5)):       # the dense output is 4th order: its error, not the step error, shows at 1e-6
+            st = {}
+            ys = T.sample_ode(model, x0, sampling_method="dopri5", num_steps=9, rtol=rtol, atol=1e-8, stats=st)
+            assert len(ys) == 9 and st["nfe"] == 2 + 6 * st["steps"]
+            for i in (4, 8):
+                assert float((ys[i] - fine[i * 256]).abs().max()) < bound, (rtol, i, st)
+        back = T.sample_ode(model, fine[-1], sampling_method="dopri5", num_steps=5, rtol=1e-6, atol=1e-8, reverse=True)
+        ref_back = T.sample_ode(model, fine[-1], sampling_method="rk4", num_steps=2049, reverse=True)[-1]
+        assert float((back[-1] - ref_back).abs().max()) < 1e-5
+    finally:
+        th.set_default_dtype(th.float32)
 
 
 def test_oracle_rk_tableaus_have_their_published_order():
@@ -90,7 +111,7 @@ def test_create_transport_and_intervals():
         create_transport(snr_type="bogus")
     s = Sampler(tr)
     with pytest.raises(NotImplementedError):
-        s.sample_ode(sampling_method="dopri5")
+        s.sample_ode(sampling_method="dopri8")
     with pytest.raises(NotImplementedError):
         s.sample_sde(sampling_method="Midpoint")
     with pytest.raises(NotImplementedError):
@@ -149,6 +170,14 @@ def test_ode_kernels_bit_exact(kat, built_lib):
         ys = s.sample_ode(sampling_method=m, num_steps=o["num_steps"])(o["init"].cuda(), _gpu_toy)
         ref = T.sample_ode(T.toy_velocity_model, o["init"], sampling_method=m, num_steps=o["num_steps"])
         assert len(ys) == o["num_steps"] and all(th.equal(a.cpu(), b) for a, b in zip(ys, ref)), m
+    # adaptive dopri5 (the reference default): same controller as the oracle restatement; the norms are reduced in another order,
+    # so results agree to rounding and the step sequences coincide away from accept / reject ties
+    for kw in (dict(), dict(rtol=1e-5, atol=1e-7), dict(reverse=True)):
+        st = {}
+        ref = T.sample_ode(T.toy_velocity_model, o["init"], sampling_method="dopri5", num_steps=7, stats=st, **kw)
+        ys = s.sample_ode(sampling_method="dopri5", num_steps=7, **kw)(o["init"].cuda(), _gpu_toy)
+        assert len(ys) == 7 and s.last_ode_stats == st, (s.last_ode_stats, st)
+        assert max(float((a.cpu() - b).abs().max()) for a, b in zip(ys, ref)) < 2e-5
     yr = s.sample_ode(sampling_method="euler", num_steps=5, reverse=True)(o["init"].cuda(), _gpu_toy)
     assert th.equal(yr[-1].cpu(), T.sample_ode(T.toy_velocity_model, o["init"], sampling_method="euler", num_steps=5, reverse=True)[-1])
 
