@@ -128,14 +128,37 @@ def _check_state(x: th.Tensor, what: str) -> th.Tensor:
     return x.contiguous()
 
 
-def _dopri5(f: Callable, y0: th.Tensor, ts: th.Tensor, rtol: float, atol: float, stats: dict) -> List[th.Tensor]:
-    """torchdiffeq's adaptive dopri5 (RKAdaptiveStepsizeODESolver: _before_integrate, _advance, _adaptive_step, _runge_kutta_step;
-    misc._select_initial_step / _compute_error_ratio / _optimal_step_size with safety 0.9, ifactor 10, dfactor 0.2, RMS norm;
-    interp._interp_fit / _interp_evaluate) on device tensors: the solution at every time of ``ts``.  The step size and the times live
-    on the host in fp32 like torchdiffeq's 0-dim tensors; per step the device reports three norms."""
+def _device_ops(y0: th.Tensor):
+    """The two device-side operations of the adaptive solver, bound to the C ABI for tensors shaped like ``y0``."""
     lib = _lib.load()
     dev, n = y0.device, y0.numel()
     st = _stream(dev)
+    norms = th.empty(4, dtype=th.float32, device=dev)
+
+    def lincomb(base: th.Tensor, cy, ks, cs) -> th.Tensor:
+        out = th.empty_like(base)
+        c = th.stack([_f32(cy)] + [_f32(v) for v in cs]).to(dev)
+        ptrs = (C.c_void_p * max(len(ks), 1))(*[k.data_ptr() for k in ks])
+        _lib.check(lib.fitv2_lincomb(_p(out), _p(base), ptrs, _p(c), len(ks), n, st), "fitv2_lincomb")
+        return out
+
+    def rms_norms(items) -> List[float]:
+        """items: up to 4 tuples (a, b, s, atol, rtol) -> [sqrt(mean(((a - b) / (atol + rtol |s|))^2))]; ONE host read for all."""
+        for slot, (a, b, s_, at, rt) in enumerate(items):
+            _lib.check(lib.fitv2_scaled_rms(C.c_void_p(norms.data_ptr() + 4 * slot), _p(a), _p(b), _p(s_), float(at), float(rt), n, st),
+                       "fitv2_scaled_rms")
+        return norms[:len(items)].tolist()
+
+    return lincomb, rms_norms
+
+
+def _dopri5(f: Callable, y0: th.Tensor, ts: th.Tensor, rtol: float, atol: float, stats: dict, ops=None, max_steps: int = 100000) -> List[th.Tensor]:
+    """torchdiffeq's adaptive dopri5 (RKAdaptiveStepsizeODESolver: _before_integrate, _advance, _adaptive_step, _runge_kutta_step;
+    misc._select_initial_step / _compute_error_ratio / _optimal_step_size with safety 0.9, ifactor 10, dfactor 0.2, RMS norm;
+    interp._interp_fit / _interp_evaluate): the solution at every time of ``ts``.  The step size and the times live on the host in
+    fp32 like torchdiffeq's 0-dim tensors; per step the device reports three norms.  ``ops`` = (lincomb, rms_norms): the CUDA kernels
+    by default; the CPU tests inject torch implementations to exercise this controller without a GPU."""
+    lincomb, rms_norms = ops if ops is not None else _device_ops(y0)
     sign = 1.0 if float(ts[-1]) >= float(ts[0]) else -1.0                    # decreasing grids: integrate -f(-t, y) forwards
     tt = ts * sign
     nfe = 0
@@ -144,37 +167,27 @@ def _dopri5(f: Callable, y0: th.Tensor, ts: th.Tensor, rtol: float, atol: float,
         nonlocal nfe
         nfe += 1
         out = f(t * sign, state)
-        return out if sign > 0 else -out
-
-    def lincomb(base: th.Tensor, cy, ks, cs, out: Optional[th.Tensor] = None) -> th.Tensor:
-        out = th.empty_like(base) if out is None else out
-        c = th.stack([_f32(cy)] + [_f32(v) for v in cs]).to(dev)
-        ptrs = (C.c_void_p * max(len(ks), 1))(*[k.data_ptr() for k in ks])
-        _lib.check(lib.fitv2_lincomb(_p(out), _p(base), ptrs, _p(c), len(ks), n, st), "fitv2_lincomb")
-        return out
-
-    norms = th.empty(3, dtype=th.float32, device=dev)
-
-    def rms(slot: int, a, b=None, s=None, at=0.0, rt=0.0):
-        _lib.check(lib.fitv2_scaled_rms(C.c_void_p(norms.data_ptr() + 4 * slot), _p(a), _p(b), _p(s), at, rt, n, st), "fitv2_scaled_rms")
+        return out if sign > 0 else lincomb(out, -1.0, [], [])
 
     t0 = tt[0]
     f0 = func(t0, y0)
     # ---- _select_initial_step (order 4) ----
-    rms(0, y0, None, y0, atol, rtol); rms(1, f0, None, y0, atol, rtol)
-    d0, d1 = [th.tensor(v) for v in norms[:2].tolist()]
+    d0, d1 = [th.tensor(v) for v in rms_norms([(y0, None, y0, atol, rtol), (f0, None, y0, atol, rtol)])]
     h0 = th.tensor(1e-6) if (d0 < 1e-5 or d1 < 1e-5) else 0.01 * d0 / d1
     f1 = func(t0 + h0, lincomb(y0, 1.0, [f0], [h0]))
-    rms(2, f1, f0, y0, atol, rtol)
-    d2 = th.tensor(norms[2].item()) / h0
+    d2 = th.tensor(rms_norms([(f1, f0, y0, atol, rtol)])[0]) / h0
     h1 = th.max(th.tensor(1e-6), h0 * 1e-3) if (d1 <= 1e-15 and d2 <= 1e-15) else (0.01 / max(d1, d2)) ** (1.0 / 5.0)
     dt = th.min(100 * h0, h1).to(th.float32)
     y, f_cur, t_lo, t_hi = y0, f0, t0, t0
     coeff = None                                                             # [e, d, c, b, a] of the last accepted step
     out = [y0.clone()]
     steps = rejected = 0
+    hist = []                                                                # (t, dt, error ratio) of every attempted step
     for t_next in tt[1:]:
         while t_next > t_hi:
+            if steps >= max_steps or not bool(th.isfinite(dt)) or float(dt) <= 0.0:
+                raise RuntimeError(f"dopri5: no progress after {steps} steps (dt = {float(dt)}, t = {float(t_hi) * sign}): the model output is "
+                                   "not finite or the tolerance cannot be met")
             ks = [f_cur]                                                     # _runge_kutta_step
             for alpha_i, beta_i in zip(_DP_ALPHA, _DP_BETA):
                 ti = t_hi + dt if alpha_i == 1.0 else t_hi + alpha_i * dt
@@ -182,10 +195,10 @@ def _dopri5(f: Callable, y0: th.Tensor, ts: th.Tensor, rtol: float, atol: float,
                 ks.append(func(ti, yi))
             y1, f_new = yi, ks[-1]                                           # c_sol == beta[-1] (first-same-as-last)
             err = lincomb(y, 0.0, ks, [c * dt for c in _DP_C_ERROR])
-            rms(0, y); rms(1, y1); rms(2, err)
-            ny, ny1, nerr = norms.tolist()                                   # the one host synchronisation of the step
-            ratio = nerr / (atol + rtol * max(ny, ny1))
+            ny, ny1, nerr = rms_norms([(y, None, None, 0.0, 0.0), (y1, None, None, 0.0, 0.0), (err, None, None, 0.0, 0.0)])
+            ratio = nerr / (atol + rtol * max(ny, ny1))                      # the one host synchronisation of the step
             steps += 1
+            hist.append((float(t_hi) * sign, float(dt), float(ratio)))
             if ratio <= 1:
                 y_mid = lincomb(y, 1.0, ks, [c * dt for c in _DP_C_MID])
                 fa, fb = ks[0], ks[-1]                                       # _interp_fit
@@ -200,13 +213,34 @@ def _dopri5(f: Callable, y0: th.Tensor, ts: th.Tensor, rtol: float, atol: float,
                 rejected += 1
             if ratio == 0:                                                   # _optimal_step_size
                 dt = dt * 10.0
+            elif ratio != ratio:                                             # NaN error norm: shrink like a rejected step
+                dt = dt * 0.2
             else:
                 dt = dt * min(10.0, max(0.9 / ratio ** 0.2, 1.0 if ratio < 1 else 0.2))
         x = (t_next - t_lo) / (t_hi - t_lo)                                  # _interp_evaluate
         out.append(lincomb(coeff[0], 1.0, coeff[1:], [x, x * x, x * x * x, x * x * x * x]))
     stats.clear()
-    stats.update(nfe=nfe, steps=steps, rejected=rejected)
+    stats.update(nfe=nfe, steps=steps, rejected=rejected, history=hist)
     return out
+
+
+def _torch_ops():
+    """CPU stand-ins for the two kernels (tests of the controller logic only; the product path never uses them)."""
+    def lincomb(base, cy, ks, cs):
+        acc = _f32(cy) * base
+        for k, c in zip(ks, cs):
+            acc = acc + _f32(c) * k
+        return acc
+
+    def rms_norms(items):
+        out = []
+        for a, b, s_, at, rt in items:
+            v = a - b if b is not None else a
+            if s_ is not None:
+                v = v / (at + rt * s_.abs())
+            out.append(float(v.double().pow(2).mean().sqrt()))
+        return out
+    return lincomb, rms_norms
 
 
 class Sampler:

@@ -252,7 +252,8 @@ def _rms(x):
     return x.abs().pow(2).mean().sqrt()
 
 
-def dopri5_integrate(f: Callable, y0: th.Tensor, ts: th.Tensor, rtol=1e-3, atol=1e-6, stats: Optional[dict] = None) -> List[th.Tensor]:
+def dopri5_integrate(f: Callable, y0: th.Tensor, ts: th.Tensor, rtol=1e-3, atol=1e-6, stats: Optional[dict] = None,
+                     max_steps: int = 100000) -> List[th.Tensor]:
     """Solution at every time of ``ts`` (increasing or decreasing grid), torchdiffeq's adaptive dopri5 semantics: the solver
     walks its own step sequence from ts[0] and evaluates a 4th-order dense-output polynomial at the requested times."""
     sign = 1.0 if float(ts[-1]) >= float(ts[0]) else -1.0                 # torchdiffeq flips time for decreasing grids
@@ -273,8 +274,11 @@ def dopri5_integrate(f: Callable, y0: th.Tensor, ts: th.Tensor, rtol=1e-3, atol=
     coeff = [y0] * 5
     out = [y0]
     steps = rejected = 0
+    hist = []
     for t_next in tt[1:]:
         while t_next > t_hi:
+            if steps >= max_steps or not bool(th.isfinite(dt)) or float(dt) <= 0.0:   # (torchdiffeq's own guard is max_num_steps = 2**31 - 1)
+                raise RuntimeError(f"dopri5: no progress after {steps} steps (dt = {float(dt)}): solution blow-up or unreachable tolerance")
             # _runge_kutta_step
             ks = [f_cur]
             for alpha_i, beta_i in zip(DP_ALPHA, DP_BETA):
@@ -287,6 +291,7 @@ def dopri5_integrate(f: Callable, y0: th.Tensor, ts: th.Tensor, rtol=1e-3, atol=
             tol = atol + rtol * th.max(_rms(y), _rms(y1))
             ratio = _rms(err) / tol
             steps += 1
+            hist.append((float(t_hi) * sign, float(dt), float(ratio)))
             if ratio <= 1:
                 y_mid = y + sum(k * (c * dt) for k, c in zip(ks, DP_C_MID))
                 fa, fb = ks[0], ks[-1]
@@ -313,5 +318,5 @@ def dopri5_integrate(f: Callable, y0: th.Tensor, ts: th.Tensor, rtol=1e-3, atol=
             total = total + xp * cf
         out.append(total)
     if stats is not None:
-        stats.update(nfe=nfe, steps=steps, rejected=rejected)
+        stats.update(nfe=nfe, steps=steps, rejected=rejected, history=hist)
     return out
