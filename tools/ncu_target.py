@@ -34,4 +34,12 @@ for i in range(2):
 fn = Sampler(create_transport()).sample_sde(diffusion_form="sigma", num_steps=3)
 xs = fn(torch.randn(R, N, 16, device="cuda"), lambda xx, tt, **k: xx * 0.5)
 torch.cuda.synchronize()
-print("ok", float(out.abs().max()), float(z.abs().max()), float(xs[-1].abs().max()))
+# the kernels of the model variants: FiTv1 configuration (no q/k norm -> generic QKV epilogue + online-max attention, adaLN 'normal',
+# learn_sigma, (B, C, N) layout transposes) at depth 1, same row count
+torch.manual_seed(0)
+m1 = FiT(hidden_size=1152, depth=1, num_heads=16, learn_sigma=True, use_swiglu=True, use_swiglu_large=True).randomize_zero_init_(1).cuda().eval()
+o1 = m1(x.transpose(1, 2).contiguous(), t, y, grid, mask)
+# adaptive dopri5 pieces (fitv2_lincomb / fitv2_scaled_rms) on the headline state size
+ys = Sampler(create_transport()).sample_ode(sampling_method="dopri5", num_steps=2)(torch.randn(n, N, 16, device="cuda") * 0.3, lambda xx, tt, **k: -xx)
+torch.cuda.synchronize()
+print("ok", float(out.abs().max()), float(z.abs().max()), float(xs[-1].abs().max()), float(o1.abs().max()), float(ys[-1].abs().max()))
