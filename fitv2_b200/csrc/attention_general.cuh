@@ -54,7 +54,7 @@ template <int DH> struct AttnGenCfg {
 };
 
 template <typename OT, int DH>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(256, 2)
 attention_general_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_qt,
                  const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_kt,
                  const __grid_constant__ CUtensorMap map_v,

@@ -145,7 +145,9 @@ int fitv2_bind_weight(fitv2_handle* h, int slot, const void* dev_ptr, int64_t nu
  * ROPE_FREQS_H/W vectors by the following forward calls (which must use the same `rows`).  NULL, NULL switches back. */
 int fitv2_set_online_rope(fitv2_handle* h, const float* freqs_h_rows, const float* freqs_w_rows, int rows);
 
-/* Bytes of scratch the forward needs for (rows = batch incl. CFG duplication, tokens per row). */
+/* Bytes of scratch the forward needs for (rows = batch incl. CFG duplication, tokens per row).  Between calls the contents of
+ * the workspace belong to the handle (it keeps derived data there, e.g. the fp16 copy of the final-layer weight): a caller that
+ * reuses the memory for something else announces it again with fitv2_set_workspace before the next forward. */
 int64_t fitv2_workspace_bytes(const fitv2_handle* h, int rows, int tokens);
 int fitv2_set_workspace(fitv2_handle* h, void* dev_ptr, int64_t bytes);
 

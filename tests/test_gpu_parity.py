@@ -781,6 +781,9 @@ def test_workspace_bounds_canary(lib, width, depth, R, hp, wp, extra):
     ref = m(*a).cpu()                                                        # sizes the workspace
     ws = m._workspace
     ws.fill_(0xA5)
+    # the workspace belongs to the handle between calls (it caches the fp16 copy of the final weight there): re-announce it so that
+    # the handle re-derives its cached contents after the fill above
+    _lib.check(lib.fitv2_set_workspace(m._handle, _p(ws), ws.numel()))
     N = hp * wp
     frame = torch.full((R * N * 16 + 2048,), float("nan"), device="cuda")    # output in the middle of a NaN frame
     out = frame[1024:1024 + R * N * 16].view(R, N, 16)
