@@ -69,7 +69,9 @@ def measured_peaks():
 
 def ncu_traffic(workload):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu --set full summary."""
-    p = os.path.join(ROOT, "profiles", "r1_gateup_ncu_full.json")
+    p = os.path.join(ROOT, "profiles", "r2_gateup_ncu_full.json")
+    if not os.path.exists(p):
+        p = os.path.join(ROOT, "profiles", "r1_gateup_ncu_full.json")
     if workload != "xl256" or not os.path.exists(p):
         return None
     with open(p) as f:

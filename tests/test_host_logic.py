@@ -368,3 +368,20 @@ def test_missing_extension_fails_loudly():
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd=root,
                          env={**os.environ, "FITV2_B200_LIB": "/nonexistent/libfitv2_b200.so"})
     assert out.returncode == 0 and out.stdout.strip().endswith("LOUD True"), out.stdout + out.stderr[-1000:]
+
+
+def test_deepcopy_and_option_forwarding_are_per_instance():
+    """A copied module owns its own (lazily created) C handle and workspace; the environment -> option table only names options
+    the library declares in its header."""
+    import copy
+    torch.manual_seed(0)
+    m = FiT(**KW, **XL1)
+    m._handle, m._packed = object(), {"x": 1}                  # pretend the original has run
+    c = copy.deepcopy(m)
+    assert c._handle is None and c._packed is None and c._workspace is None
+    assert all(torch.equal(a, b) and a.data_ptr() != b.data_ptr() for a, b in zip(m.state_dict().values(), c.state_dict().values()))
+    m._handle = None                                           # (the fake handle must not reach fitv2_destroy)
+    with open(os.path.join(ROOT, "include", "fitv2_b200.h")) as f:
+        hdr = f.read()
+    declared = set(re.findall(r'"([a-z0-9_]+)" \(', hdr.split("fitv2_set_option")[0].split("Per-handle tuning switches")[1]))
+    assert {name for name, _ in _lib._ENV_OPTIONS.values()} <= declared, ({name for name, _ in _lib._ENV_OPTIONS.values()} - declared)
