@@ -442,6 +442,8 @@ class FiT(nn.Module):
         xf = x.to(torch.float32).contiguous()
         if xf.is_cuda:
             self._set_online_rope(size, x.shape[0])
+            if _MODELS.get(id(self)) is not self:                           # e.g. a module restored by pickle (no __init__ ran)
+                _MODELS[id(self)] = self
             out = torch.ops.fitv2_b200.forward(xf, t, y, grid, mask, id(self), x.shape[0])
         else:
             out = self._run(xf, t, y, grid, mask, rows=x.shape[0])          # raises: no CPU path
