@@ -47,7 +47,7 @@ def norm_code(name, weight: bool = False) -> int:
 # fitv2_set_option names <- FITV2_* environment variables (read when a handle is created, so tests / A/B tools can still use
 # the environment; the library itself never calls getenv)
 _ENV_OPTIONS = {
-    "FITV2_PDL": ("pdl", int), "FITV2_ATTN": ("attn", lambda v: {"tm": 1, "ws": 2, "general": 3, "v1": 3}.get(v, 0)),
+    "FITV2_PDL": ("pdl", int), "FITV2_ATTN": ("attn", lambda v: {"tm": 1, "ws": 2, "general": 3, "v1": 3, "tm1": 4}.get(v, 0)),
     "FITV2_ATTN_EARLY": ("attn_early", int), "FITV2_LN_THREADS": ("ln_threads", int),
     "FITV2_LN_WIDE_SINGLE": ("ln_wide_single", int), "FITV2_BN_RESID": ("bn_resid", int), "FITV2_QKV": ("qkv_heads", int),
     "FITV2_RESID_T": ("resid_t", int), "FITV2_BN_RESID_T": ("bn_resid_t", int),

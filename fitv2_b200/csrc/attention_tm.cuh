@@ -16,7 +16,9 @@
 
 namespace fitv2 {
 
-template <int DH> struct AttnTmCfg {
+// TPR = softmax threads per query row: 2 (eight warps per stream, 32 S columns per thread and sub-tile) or 1 (four warps
+// per stream, one thread owns the whole row: half as many barrier / TMEM round trips per exponential, no row-sum exchange).
+template <int DH, int TPR = 2> struct AttnTmCfg {
     using W = AttnWsCfg<DH>;
     static constexpr int kDHP = W::kDHP, kTail = W::kTail, kTailBytes = W::kTailBytes, kQMain = W::kQMain;
     static constexpr int kQKTile = W::kQKTile, kVPanel = W::kVPanel, kVTile = W::kVTile;
@@ -31,7 +33,8 @@ template <int DH> struct AttnTmCfg {
     static constexpr int kNumBars = 40;
     static constexpr int kOffSeg = kOffBar + ((kNumBars * 8 + 16 + 127) / 128) * 128;
     static constexpr uint32_t kQKBytes = W::kQKBytes, kVBytes = W::kVBytes;
-    static constexpr int kThreads = 32 * 19;
+    static constexpr int kSoftWarps = 4 * TPR;            // per stream
+    static constexpr int kThreads = 32 * (3 + 2 * kSoftWarps);
     static constexpr int smem_bytes(int tokens) { return kOffSeg + 2 * ((tokens + 127) / 128 * 128) * 4 + 1024; }
 };
 
@@ -51,15 +54,21 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v) {
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-template <typename OT, int DH>
-__global__ void __launch_bounds__(608, 1)
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* v) {
+    tmem_st16(taddr, v);
+    tmem_st16(taddr + 16, v + 16);
+}
+
+template <typename OT, int DH, int TPR = 2>
+__global__ void __launch_bounds__((AttnTmCfg<DH, TPR>::kThreads), 1)
 attention_tm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_qt,
                     const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_kt,
                     const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_o,
                     const float* __restrict__ seg, const int* __restrict__ seg_uniform,
                     int heads, int tokens, int num_items, float scale_log2e, float bound_log2e, int early)
 {
-    using C = AttnTmCfg<DH>;
+    using C = AttnTmCfg<DH, TPR>;
+    constexpr int SW = C::kSoftWarps, SOFT_THREADS = 32 * SW, COLS = 64 / TPR;   // per stream; S columns per thread and sub-tile
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kOffBar);
@@ -82,8 +91,8 @@ attention_tm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_qt); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_kt);
         tma_prefetch_desc(&map_v); tma_prefetch_desc(&map_o);
-        for (int i = 0; i < 4; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 8); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&o_full[i], 1); mbar_init(&o_free[i], 8); }
+        for (int i = 0; i < 4; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); mbar_init(&s_full[i], 1); mbar_init(&p_full[i], SW); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&o_full[i], 1); mbar_init(&o_free[i], SW); }
         for (int i = 0; i < C::kKStages; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 2); }
         for (int i = 0; i < C::kVStages; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 2); }
         mbar_fence_init();
@@ -196,8 +205,8 @@ attention_tm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                         const uint32_t a = t_x + b * 64, d = t_x + 128;
                         const uint64_t dv = umma_desc_kmajor(sm_v + pv.stage * C::kVTile + sub * C::kVPanel, 128);
 #pragma unroll
-                        for (int kk = 0; kk < 4; ++kk)                  // keys 0-31 live in columns [0,16), keys 32-63 in [32,48)
-                            umma_ts(d, a + (kk >> 1) * 32 + (kk & 1) * 8, dv + 2 * kk, idesc_o, (pv.j | kk) != 0);
+                        for (int kk = 0; kk < 4; ++kk)                  // TPR 2: keys 0-31 live in columns [0,16), keys 32-63 in [32,48);
+                            umma_ts(d, a + (TPR == 2 ? (kk >> 1) * 32 + (kk & 1) * 8 : kk * 8), dv + 2 * kk, idesc_o, (pv.j | kk) != 0);   // TPR 1: [0,32)
                         if (sub == 1) umma_commit(&v_empty[pv.stage]);
                         if (pv.j + 1 == sub_tiles) umma_commit(&o_full[x]);
                     }
@@ -216,9 +225,9 @@ attention_tm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         while (pv.item < num_items) { pv_step(); s_step(); }
     } else {
         // ------------------------------------- softmax warp groups -------------------------------------
-        const int x = (warp - 3) >> 3;
-        const int wl = (warp - 3) & 7;
-        const int half = wl >> 2;                                       // which 32 key columns of the sub-tile / output half
+        const int x = (warp - 3) / SW;
+        const int wl = (warp - 3) - x * SW;
+        const int half = wl >> 2;                                       // which 32 key columns of the sub-tile / output half (TPR 1: 0)
         const int quarter = warp & 3;
         const int row = quarter * 32 + lane;
         const int tid_wg = wl * 32 + lane;
@@ -239,7 +248,7 @@ attention_tm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
             }
         };
         fetch_meta(blockIdx.x);
-        uint32_t v[32];
+        uint32_t v[COLS];
         // One 64-key sub-tile of the softmax: S(k) out of TMEM buffer n_s % 2, P(k) back into its first 32 columns, hand-over to
         // the issuer.  Returns this thread's partial row sum.
         auto do_sub = [&](int j, bool uniform, float my_seg) -> float {
@@ -250,13 +259,14 @@ attention_tm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
             mbar_wait(&s_full[x * 2 + b], (n_s >> 1) & 1);
             tc_fence_after();
             tmem_ld32(t_x + b * 64 + half * 32, v);
+            if constexpr (TPR == 1) tmem_ld32(t_x + b * 64 + 32, v + 32);
             tmem_ld_wait();
-            uint32_t packed[16];
+            uint32_t packed[COLS / 2];
             float lsum = 0.f;
             auto soft32 = [&](auto mode_c) {
                 constexpr int kMode = decltype(mode_c)::value;
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
+                for (int i = 0; i < COLS / 2; ++i) {
                     float p0 = fast_exp2(fmaf(__uint_as_float(v[2 * i]), scale_log2e, -bound_log2e));
                     float p1 = fast_exp2(fmaf(__uint_as_float(v[2 * i + 1]), scale_log2e, -bound_log2e));
                     if constexpr (kMode != 0) {
@@ -276,7 +286,8 @@ attention_tm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
             if (mode == 0) soft32(std::integral_constant<int, 0>{});
             else if (mode == 1) soft32(std::integral_constant<int, 1>{});
             else soft32(std::integral_constant<int, 2>{});
-            tmem_st16(t_x + b * 64 + half * 32, packed);                // P(k) over the first 16 of this thread's own 32 S columns
+            if constexpr (TPR == 2) tmem_st16(t_x + b * 64 + half * 32, packed);   // P(k) over the first half of this thread's own S columns
+            else tmem_st32(t_x + b * 64, packed);
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
@@ -296,8 +307,8 @@ attention_tm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
             const int sample = bh / heads, head = bh - sample * heads;
             if (!uniform) {
                 const float* segb = seg + (size_t)sample * tokens;
-                for (int i = tid_wg; i < seg_pad; i += 256) seg_s[i] = i < tokens ? __ldg(segb + i) : 0.f;
-                named_bar_sync(1 + x, 256);
+                for (int i = tid_wg; i < seg_pad; i += SOFT_THREADS) seg_s[i] = i < tokens ? __ldg(segb + i) : 0.f;
+                named_bar_sync(1 + x, SOFT_THREADS);
             }
             float l_run = early_done ? l_early : 0.f;
             for (int j = early_done ? 1 : 0; j < sub_tiles; ++j) l_run += do_sub(j, uniform, my_seg);
@@ -315,24 +326,29 @@ attention_tm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
             }
 
             // ---- epilogue ----
-            l_part[half * 128 + row] = l_run;
+            if constexpr (TPR == 2) l_part[half * 128 + row] = l_run;
             if (store_pending) {                                        // the previous TMA store has read the staging tile
                 if (tid_wg == 0) tma_store_wait_read();
                 store_pending = false;
             }
             mbar_wait(&o_full[x], n_item & 1);
             tc_fence_after();
-            constexpr int OH = C::kDHP / 2;
+            constexpr int OH = C::kDHP / TPR;
             float o[OH];
             tmem_ld32(t_x + 128 + half * OH, reinterpret_cast<uint32_t*>(o));
             if constexpr (OH == 40) tmem_ld8(t_x + 128 + half * OH + 32, reinterpret_cast<uint32_t*>(o) + 32);
-            else tmem_ld16(t_x + 128 + half * OH + 32, reinterpret_cast<uint32_t*>(o) + 32);
+            else if constexpr (OH == 48) tmem_ld16(t_x + 128 + half * OH + 32, reinterpret_cast<uint32_t*>(o) + 32);
+            else {
+                static_assert(OH == 40 || OH == 48 || OH == 80, "output columns per thread");
+                tmem_ld32(t_x + 128 + 32, reinterpret_cast<uint32_t*>(o) + 32);
+                tmem_ld16(t_x + 128 + 64, reinterpret_cast<uint32_t*>(o) + 64);
+            }
             tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&o_free[x]);
-            named_bar_sync(1 + x, 256);                                 // row sums exchanged; staging tile free
-            const float l_tot = l_part[row] + l_part[row + 128];
+            named_bar_sync(1 + x, SOFT_THREADS);                        // row sums exchanged; staging tile free
+            const float l_tot = TPR == 2 ? l_part[row] + l_part[row + 128] : l_run;
             {
                 const float inv = (my_seg != 0.f && l_tot > 0.f) ? 1.0f / l_tot : 0.f;
                 const uint32_t dst = stage_sm + row * (DH * 2) + half * (OH * 2);
@@ -347,7 +363,7 @@ attention_tm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                 }
             }
             fence_proxy_async_smem();
-            named_bar_sync(1 + x, 256);
+            named_bar_sync(1 + x, SOFT_THREADS);
             if (tid_wg == 0) tma_store_4d(&map_o, stage_sm, 0, head, qt * 128, sample);
             store_pending = true;
             ++n_item;

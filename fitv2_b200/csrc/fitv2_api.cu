@@ -472,7 +472,7 @@ int launch_attention(fitv2_handle* h, const void* q, const void* k, const void* 
     int mode = h->opt.attn;
     if (!bounded || dbg_s || dbg_o) mode = 3;
     if (mode == 0) mode = (tokens <= 256 && c.head_dim == 72) ? 1 : 2;
-    if (mode == 1 && c.head_dim != 72) mode = 2;
+    if ((mode == 1 || mode == 4) && c.head_dim != 72) mode = 2;
     if (mode == 3) {
         const int num_items = ((tokens + 127) / 128) * c.num_heads * rows;      // (query tile, head, sample) work items
         const int grid = num_items < 2 * h->num_sms ? num_items : 2 * h->num_sms;   // persistent, two CTAs per SM
@@ -496,7 +496,15 @@ int launch_attention(fitv2_handle* h, const void* q, const void* k, const void* 
     const int items = q_pairs * c.num_heads * rows;
     const int g = items < h->num_sms ? items : h->num_sms;
     int rc;
-    if (mode == 1) {
+    if (mode == 4 && c.head_dim == 72) {                                        // experiment: one softmax thread per query row
+        using A = AttnTmCfg<72, 1>;
+        auto kern = attention_tm_kernel<OT, 72, 1>;
+        const int smem = A::smem_bytes(tokens);
+        if (smem > kSmemBudget) return fail(FITV2_E_INVALID, "tokens %d: attention shared memory %d exceeds %d", tokens, smem, kSmemBudget);
+        if ((rc = ensure_smem(h, kern, smem))) return rc;
+        CUDA_TRY(launch_k(kern, dim3(g), dim3(A::kThreads), smem, st, 1, am.mq, am.mqt, am.mk, am.mkt, am.mv, am.mo, seg, seg_uniform,
+                          c.num_heads, tokens, items, scale_log2e, bound_log2e, h->opt.attn_early));
+    } else if (mode == 1) {
         using A = AttnTmCfg<72>;
         auto kern = attention_tm_kernel<OT, 72>;
         const int smem = A::smem_bytes(tokens);
