@@ -561,6 +561,7 @@ int launch_ln_modulate(fitv2_handle* h, const float* x, const float* shift, cons
     }
     else if (nv <= 1) CUDA_TRY(launch_k(ln_modulate_kernel<OT, 1>, dim3(blocks), dim3(ln_threads), 0, st, 1, x, shift, scale, mod_ld, (OT*)out, M, D, tokens, norm_w));
     else if (nv <= 3) CUDA_TRY(launch_k(ln_modulate_kernel<OT, 3>, dim3(blocks), dim3(ln_threads), 0, st, 1, x, shift, scale, mod_ld, (OT*)out, M, D, tokens, norm_w));
+    else if (D == 1152) CUDA_TRY(launch_k(ln_modulate_kernel<OT, 9, 0, true>, dim3(blocks), dim3(ln_threads), 0, st, 1, x, shift, scale, mod_ld, (OT*)out, M, D, tokens, norm_w));
     else if (nv <= 9) CUDA_TRY(launch_k(ln_modulate_kernel<OT, 9>, dim3(blocks), dim3(ln_threads), 0, st, 1, x, shift, scale, mod_ld, (OT*)out, M, D, tokens, norm_w));
     else {                                                           // wide rows: one row per warp pair (4 rows per CTA)
         if (h->opt.ln_wide_single) CUDA_TRY(launch_k(ln_modulate_kernel<OT, 18>, dim3(blocks), dim3(ln_threads), 0, st, 1, x, shift, scale, mod_ld, (OT*)out, M, D, tokens, norm_w));

@@ -362,7 +362,7 @@ patch_embed_kernel(const float* __restrict__ xin, const float* __restrict__ w, c
 // ---------------------------------------------------------------------------------------------
 // MODE 0: affine-free LayerNorm (the FiTv2 configs); 1: LayerNorm * weight ('w_layernorm', norms.py:35-38);
 // 2: RMSNorm * weight ('rmsnorm', norms.py:53-77).  The weight vector (D floats, cache-resident) is fetched in the output loop.
-template <typename OT, int NV, int MODE = 0>
+template <typename OT, int NV, int MODE = 0, bool EXACT = false>   // EXACT: D == NV * 128, no tail guards
 __global__ void __launch_bounds__(256)
 ln_modulate_kernel(const float* __restrict__ x, const float* __restrict__ shift, const float* __restrict__ scale,
                    int mod_ld, OT* __restrict__ h, int M, int D, int tokens, const float* __restrict__ norm_w)
@@ -375,15 +375,16 @@ ln_modulate_kernel(const float* __restrict__ x, const float* __restrict__ shift,
     const int m = warp;
     const int nvec = D >> 2;
     const float4* xr = reinterpret_cast<const float4*>(x + (size_t)m * D);
-    const int sample = m / tokens;
+    const unsigned sample = (unsigned)m / (unsigned)tokens;
     const float4* sh = reinterpret_cast<const float4*>(shift + (size_t)sample * mod_ld);
     const float4* sc = reinterpret_cast<const float4*>(scale + (size_t)sample * mod_ld);
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     // every load of the row (x, shift, scale) is issued before the first use: 3*NV 128-bit requests in flight per lane
     float4 v[NV], a[NV], g[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
         const int j = lane + 32 * i;
-        v[i] = (j < nvec) ? ld_stream_f4(xr + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[i] = (EXACT || j < nvec) ? ld_stream_f4(xr + j) : zero4;
     }
     // wider rows (3B) would not fit the register file.  (Measured alternative: fetching shift / scale late, 64 registers and
     // twice the resident warps, is SLOWER: 35 vs 28 us per launch.)
@@ -392,40 +393,44 @@ ln_modulate_kernel(const float* __restrict__ x, const float* __restrict__ shift,
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
             const int j = lane + 32 * i;
-            a[i] = (j < nvec) ? __ldg(sh + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-            g[i] = (j < nvec) ? __ldg(sc + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            a[i] = (EXACT || j < nvec) ? __ldg(sh + j) : zero4;
+            g[i] = (EXACT || j < nvec) ? __ldg(sc + j) : zero4;
         }
     }
+    const float inv_d = 1.0f / (float)D;
     float mean = 0.f;
     if constexpr (MODE != 2) {
         float s = 0.f;
 #pragma unroll
         for (int i = 0; i < NV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-        mean = warp_sum(s) / (float)D;
+        mean = warp_sum(s) * inv_d;
     }
     float q = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
         const int j = lane + 32 * i;
-        if (j < nvec) {
+        if (EXACT || j < nvec) {
             const float d0 = v[i].x - mean, d1 = v[i].y - mean, d2 = v[i].z - mean, d3 = v[i].w - mean;
-            q += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+            q = fmaf(d0, d0, q); q = fmaf(d1, d1, q); q = fmaf(d2, d2, q); q = fmaf(d3, d3, q);
         }
     }
-    const float rstd = rsqrtf(warp_sum(q) / (float)D + 1e-6f);
+    const float rstd = rsqrtf(warp_sum(q) * inv_d + 1e-6f);
     uint2* hr = reinterpret_cast<uint2*>(h + (size_t)m * D);
     const float4* nw = reinterpret_cast<const float4*>(norm_w);
+    // The kernel is issue-bound as much as memory-bound (ncu: 712 SASS instructions per row, half of the launch in issue slots), so
+    // the output is three FMAs per element: (v - mean) * rstd * (1 + g) + a = v * A + B with A = rstd * (1 + g) [* w], B = a - mean * A
+    const float nmean = -mean;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
         const int j = lane + 32 * i;
-        if (j < nvec) {
+        if (EXACT || j < nvec) {
             if constexpr (!kEarlyMod) { a[i] = __ldg(sh + j); g[i] = __ldg(sc + j); }
-            float n0 = (v[i].x - mean) * rstd, n1 = (v[i].y - mean) * rstd, n2 = (v[i].z - mean) * rstd, n3 = (v[i].w - mean) * rstd;
-            if constexpr (MODE != 0) { const float4 w4 = __ldg(nw + j); n0 *= w4.x; n1 *= w4.y; n2 *= w4.z; n3 *= w4.w; }
-            const float o0 = n0 * (1.f + g[i].x) + a[i].x;
-            const float o1 = n1 * (1.f + g[i].y) + a[i].y;
-            const float o2 = n2 * (1.f + g[i].z) + a[i].z;
-            const float o3 = n3 * (1.f + g[i].w) + a[i].w;
+            float A0 = fmaf(rstd, g[i].x, rstd), A1 = fmaf(rstd, g[i].y, rstd), A2 = fmaf(rstd, g[i].z, rstd), A3 = fmaf(rstd, g[i].w, rstd);
+            if constexpr (MODE != 0) { const float4 w4 = __ldg(nw + j); A0 *= w4.x; A1 *= w4.y; A2 *= w4.z; A3 *= w4.w; }
+            const float o0 = fmaf(v[i].x, A0, fmaf(nmean, A0, a[i].x));
+            const float o1 = fmaf(v[i].y, A1, fmaf(nmean, A1, a[i].y));
+            const float o2 = fmaf(v[i].z, A2, fmaf(nmean, A2, a[i].z));
+            const float o3 = fmaf(v[i].w, A3, fmaf(nmean, A3, a[i].w));
             hr[j] = make_uint2(Op16<OT>::pack(o0, o1), Op16<OT>::pack(o2, o3));
         }
     }
@@ -489,10 +494,11 @@ ln_modulate_pair_kernel(const float* __restrict__ x, const float* __restrict__ s
     for (int i = 0; i < NV; ++i) {
         const int j = t + 64 * i;
         if (j < nvec) {
-            const float o0 = (v[i].x - mean) * rstd * (1.f + g[i].x) + a[i].x;
-            const float o1 = (v[i].y - mean) * rstd * (1.f + g[i].y) + a[i].y;
-            const float o2 = (v[i].z - mean) * rstd * (1.f + g[i].z) + a[i].z;
-            const float o3 = (v[i].w - mean) * rstd * (1.f + g[i].w) + a[i].w;
+            const float A0 = fmaf(rstd, g[i].x, rstd), A1 = fmaf(rstd, g[i].y, rstd), A2 = fmaf(rstd, g[i].z, rstd), A3 = fmaf(rstd, g[i].w, rstd);
+            const float o0 = fmaf(v[i].x, A0, fmaf(-mean, A0, a[i].x));     // = (v - mean) * rstd * (1 + g) + a, three FMAs per element
+            const float o1 = fmaf(v[i].y, A1, fmaf(-mean, A1, a[i].y));
+            const float o2 = fmaf(v[i].z, A2, fmaf(-mean, A2, a[i].z));
+            const float o3 = fmaf(v[i].w, A3, fmaf(-mean, A3, a[i].w));
             hr[j] = make_uint2(Op16<OT>::pack(o0, o1), Op16<OT>::pack(o2, o3));
         }
     }
