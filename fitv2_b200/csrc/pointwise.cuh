@@ -234,12 +234,22 @@ scaled_rms_kernel(float* __restrict__ out, const float* __restrict__ a, const fl
     pdl_wait();
     pdl_launch_dependents();
     __shared__ double red[32];
-    double acc = 0.0;
-    for (size_t i = threadIdx.x; i < n; i += blockDim.x) {
+    // one CTA (the result must not depend on a reduction order that changes from run to run); four independent element streams per
+    // thread keep 4-12 loads in flight instead of one dependent chain per iteration (ncu: 67 us at 131 k elements, 74 % long_scoreboard)
+    auto term = [&](size_t i) -> double {
         float v = b ? __fsub_rn(a[i], b[i]) : a[i];
         if (s) v = __fdiv_rn(v, __fadd_rn(atol, __fmul_rn(rtol, fabsf(s[i]))));
-        acc += (double)v * (double)v;
+        return (double)v * (double)v;
+    };
+    double acc4[4] = {0.0, 0.0, 0.0, 0.0};
+    const size_t B = blockDim.x;
+    size_t i = threadIdx.x;
+    for (; i + 3 * B < n; i += 4 * B) {
+        const double t0 = term(i), t1 = term(i + B), t2 = term(i + 2 * B), t3 = term(i + 3 * B);
+        acc4[0] += t0; acc4[1] += t1; acc4[2] += t2; acc4[3] += t3;
     }
+    for (; i < n; i += B) acc4[0] += term(i);
+    double acc = (acc4[0] + acc4[1]) + (acc4[2] + acc4[3]);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
