@@ -1245,7 +1245,7 @@ int fitv2_lincomb(float* out, const float* y, const float* const* k, const float
 
 int fitv2_scaled_rms(float* out_dev, const float* a, const float* b, const float* s, float atol, float rtol, int64_t n, void* stream) {
     if (!out_dev || !a || n <= 0) return fail(FITV2_E_INVALID, "bad scaled_rms argument");
-    CUDA_TRY(launch_k(scaled_rms_kernel, dim3(1), dim3(1024), 0, static_cast<cudaStream_t>(stream), 1, out_dev, a, b, s, atol, rtol, (size_t)n));
+    CUDA_TRY(launch_k(scaled_rms_kernel, dim3(kRmsCluster), dim3(1024), 0, static_cast<cudaStream_t>(stream), kRmsCluster, out_dev, a, b, s, atol, rtol, (size_t)n));
     return FITV2_OK;
 }
 

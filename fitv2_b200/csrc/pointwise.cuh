@@ -227,6 +227,11 @@ __global__ void lincomb_kernel(float* __restrict__ out, const float* __restrict_
     }
 }
 
+// One thread-block CLUSTER of kRmsCluster CTAs (grid = one cluster): every CTA reduces a contiguous slice, the partial sums meet in
+// CTA 0's shared memory through DSMEM and are added in rank order, so the result does not depend on scheduling (the dopri5
+// controller branches on it).  A single CTA was issue-bound on one SM: 67 us at 131 k elements (ncu), 31 us with four element
+// streams per thread.
+constexpr int kRmsCluster = 8;
 __global__ void __launch_bounds__(1024)
 scaled_rms_kernel(float* __restrict__ out, const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ s,
                   float atol, float rtol, size_t n)
@@ -234,8 +239,10 @@ scaled_rms_kernel(float* __restrict__ out, const float* __restrict__ a, const fl
     pdl_wait();
     pdl_launch_dependents();
     __shared__ double red[32];
-    // one CTA (the result must not depend on a reduction order that changes from run to run); four independent element streams per
-    // thread keep 4-12 loads in flight instead of one dependent chain per iteration (ncu: 67 us at 131 k elements, 74 % long_scoreboard)
+    __shared__ double part[kRmsCluster];
+    const uint32_t rank = cluster_ctarank();
+    const size_t per = (n + kRmsCluster - 1) / kRmsCluster;
+    const size_t lo = rank * per, hi = lo + per < n ? lo + per : n;
     auto term = [&](size_t i) -> double {
         float v = b ? __fsub_rn(a[i], b[i]) : a[i];
         if (s) v = __fdiv_rn(v, __fadd_rn(atol, __fmul_rn(rtol, fabsf(s[i]))));
@@ -243,12 +250,12 @@ scaled_rms_kernel(float* __restrict__ out, const float* __restrict__ a, const fl
     };
     double acc4[4] = {0.0, 0.0, 0.0, 0.0};
     const size_t B = blockDim.x;
-    size_t i = threadIdx.x;
-    for (; i + 3 * B < n; i += 4 * B) {
+    size_t i = lo + threadIdx.x;
+    for (; i + 3 * B < hi; i += 4 * B) {
         const double t0 = term(i), t1 = term(i + B), t2 = term(i + 2 * B), t3 = term(i + 3 * B);
         acc4[0] += t0; acc4[1] += t1; acc4[2] += t2; acc4[3] += t3;
     }
-    for (; i < n; i += B) acc4[0] += term(i);
+    for (; i < hi; i += B) acc4[0] += term(i);
     double acc = (acc4[0] + acc4[1]) + (acc4[2] + acc4[3]);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -257,6 +264,15 @@ scaled_rms_kernel(float* __restrict__ out, const float* __restrict__ a, const fl
     if (threadIdx.x == 0) {
         double t = 0.0;
         for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+        // part[rank] of CTA 0 (shared::cluster address of the same variable in the CTA of rank 0)
+        uint32_t remote;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(&part[rank])), "r"(0u));
+        asm volatile("st.shared::cluster.f64 [%0], %1;" :: "r"(remote), "d"(t) : "memory");
+    }
+    cluster_sync();                                                     // release / acquire: the eight stores are visible to CTA 0
+    if (rank == 0 && threadIdx.x == 0) {
+        double t = 0.0;
+        for (int r = 0; r < kRmsCluster; ++r) t += part[r];
         out[0] = (float)sqrt(t / (double)n);
     }
 }
