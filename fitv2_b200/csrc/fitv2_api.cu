@@ -629,7 +629,8 @@ int ensure_maps(fitv2_handle* h) {
         // five 256-channel groups, the last half empty): fc2 116 -> 110 us, proj 61 -> 63 us (proj is bound by the DRAM traffic of
         // the residual either way), so only fc2 uses it, and only where the normal orientation has no 256-wide tile.
         // Option resid_t = 0 / 1 forces it off / on for both.
-        h->fc2_t = o.resid_t < 0 ? h->bn_fc2 < 256 : o.resid_t == 1;
+        // Few token rows (batch 2: 1 024 rows = 20 transposed tiles for 74 clusters, 27 us per launch): the narrower normal-orientation
+        // tiles fill more clusters, decided by the same per-K-block cost model below.
         h->proj_t = o.resid_t == 1;
         if ((rc = make_map(&h->map_wproj_t, h->w[FITV2_W_PROJ_W], c.operand_dtype, L * D, D, D, 128))) return rc;
         {
@@ -655,6 +656,12 @@ int ensure_maps(fitv2_handle* h) {
                 if (best < 0 || cost < best) { best = cost; h->bn_resid_t = bn; }
             }
             if (o.bn_resid_t == 256 || o.bn_resid_t == 224) h->bn_resid_t = o.bn_resid_t;
+            auto kblock_clocks = [](long bn) { return 2L * bn > 256L + bn ? 2L * bn : 256L + bn; };
+            const long bt = h->bn_resid_t, bn = h->bn_fc2;
+            const long cost_t = ((groups * (((long)M + bt - 1) / bt) + clusters - 1) / clusters) * kblock_clocks(bt);
+            const long tiles_n = (((long)M + 2 * kGemmBM - 1) / (2 * kGemmBM)) * ((long)D / bn);
+            const long cost_n = ((tiles_n + clusters - 1) / clusters) * kblock_clocks(bn);
+            h->fc2_t = o.resid_t < 0 ? (h->bn_fc2 < 256 && cost_t <= cost_n) : o.resid_t == 1;
         }
         if ((rc = make_map(&h->map_ao_t, h->ws + l.ao, c.operand_dtype, M, D, D, h->bn_resid_t / kGemmCluster))) return rc;
         if ((rc = make_map(&h->map_hidden_t, h->ws + l.hidden, c.operand_dtype, M, Hm, Hm, h->bn_resid_t / kGemmCluster))) return rc;

@@ -310,7 +310,11 @@ def test_xl_config1_full_depth_and_sampler(lib, golden_dir):
     zb = torch.cat([fx["z"], torch.randn(30, N, 16, generator=g)])
     yb = torch.cat([fx["y"], torch.randint(0, 1000, (30,), generator=g)])
     zfull = euler_cfg_sample(m, zb.cuda(), yb.cuda(), make_grid(32, 16, 16).cuda(), torch.ones(32, N).cuda(), None, 250, 1.5, first_steps=2).cpu()
-    assert rel(zfull[:2], z2) < 1e-5 and bool(torch.isfinite(zfull).all())
+    # (1e-4, not bit-equal: the tile shapes follow M -- at 1 024 rows fc2 runs in the normal orientation, at 16 384 transposed with a
+    # TMA reduce-add -- so the fp32 residual update associates differently and a few 16-bit operand roundings flip; measured 1.6e-5)
+    d_full = rel(zfull[:2], z2)
+    print(f"[config 1] batch-32 rows 0-1 vs batch-2 run after two steps: {d_full:.2e}")
+    assert d_full < 1e-4 and bool(torch.isfinite(zfull).all())
 
 
 def test_trajectory_prefix_matches_oracle(lib):
