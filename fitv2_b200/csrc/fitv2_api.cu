@@ -203,7 +203,7 @@ struct Options {
     int ln_wide_single = 0;      // hidden 2304: one warp per row instead of a warp pair
     int bn_resid = 0;            // tile width of the proj / fc2 GEMMs in the normal orientation (0 = cost model)
     int qkv_heads = 3;           // heads per QKV tile at head_dim 72 (3 -> 224-wide tile, 2 -> 144)
-    int resid_t = -1;            // transposed residual GEMM + TMA reduce-add: -1 auto (fc2 only), 0 off, 1 proj and fc2
+    int resid_t = -1;            // transposed residual GEMM + TMA reduce-add: -1 auto (fc2 only, by cost model), 0 off, 1 proj and fc2, 2 fc2
     int bn_resid_t = 0;          // token rows per transposed tile (0 = cost model, 224, 256)
     int cond = 0;                // conditioning linears: 0 tensor pipe (tf32) where the shapes tile, 1 fp32 FMA kernels
     int l2_persist_mb = 0;       // persisting-L2 window on the fp32 residual stream (0 = off)
@@ -661,7 +661,7 @@ int ensure_maps(fitv2_handle* h) {
             const long cost_t = ((groups * (((long)M + bt - 1) / bt) + clusters - 1) / clusters) * kblock_clocks(bt);
             const long tiles_n = (((long)M + 2 * kGemmBM - 1) / (2 * kGemmBM)) * ((long)D / bn);
             const long cost_n = ((tiles_n + clusters - 1) / clusters) * kblock_clocks(bn);
-            h->fc2_t = o.resid_t < 0 ? (h->bn_fc2 < 256 && cost_t <= cost_n) : o.resid_t == 1;
+            h->fc2_t = o.resid_t < 0 ? (h->bn_fc2 < 256 && cost_t <= cost_n) : o.resid_t >= 1;     // 2: fc2 only, whatever the model says
         }
         if ((rc = make_map(&h->map_ao_t, h->ws + l.ao, c.operand_dtype, M, D, D, h->bn_resid_t / kGemmCluster))) return rc;
         if ((rc = make_map(&h->map_hidden_t, h->ws + l.hidden, c.operand_dtype, M, Hm, Hm, h->bn_resid_t / kGemmCluster))) return rc;
