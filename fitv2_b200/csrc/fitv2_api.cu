@@ -873,7 +873,7 @@ int forward_impl(fitv2_handle* h, const float* x_in, int x_rows, const float* t,
     // ---- patch embedding (modules.py:34-37); implicit cat([z, z]) when x_rows == rows / 2 ----
     prof_begin(h, PC_MISC, st);
     const int pe_threads = D / 4 >= 576 ? 576 : ((D / 4 + 31) / 32) * 32;   // more features than threads: the kernel loops
-    const int pe_groups = (M + kPatchRows - 1) / kPatchRows, pe_grid = pe_groups < 3 * h->num_sms ? pe_groups : 3 * h->num_sms;   // persistent: three 576-thread blocks per SM
+    const int pe_groups = (M + kPatchRows - 1) / kPatchRows, pe_grid = pe_groups < 2 * h->num_sms ? pe_groups : 2 * h->num_sms;   // persistent: two blocks are resident per SM (96 registers)
     CUDA_TRY(launch_k(patch_embed_kernel<16>, dim3(pe_grid), dim3(pe_threads), 0, st, 1, x, (const float*)h->w[FITV2_W_X_EMBED_W], (const float*)h->w[FITV2_W_X_EMBED_B],
                                                        x_res, M, D, x_rows * tokens));
     CUDA_TRY(cudaGetLastError());

@@ -326,9 +326,18 @@ __global__ void cfg_combine_kernel(float* __restrict__ out, const float* __restr
 // Launched with D / 4 threads (rounded up to a warp) so that one pass covers the row.
 // ---------------------------------------------------------------------------------------------
 constexpr int kPatchRows = 8;
-// Persistent blocks: a thread loads its 4 weight rows ONCE and then walks groups of kPatchRows token rows (grid-stride).  Measured
-// 36 us either way (32-row one-shot blocks: 34 us): 302 M FMAs are ~8 us and the kernel is bound by its 75 MB of pure writes at
-// 2.1 TB/s (write-only streams reach about a third of the copy rate here), not by the grid tail.
+// Persistent blocks: a thread loads its 4 weight rows ONCE and then walks groups of kPatchRows token rows (grid-stride).
+// The kernel is ISSUE-bound, not write-bound (a plain 75 MB fill runs at 5.6 TB/s = 14 us on this GPU; the scalar version took 36 us
+// for its 85 instructions per 16 output bytes): the 64 FMAs per float4 are 32 packed `fma.rn.f32x2` (two independent IEEE FMAs per
+// instruction, so the result is bit-identical to the scalar chain), the (x, x) operand pairs are pre-packed in shared memory, and the
+// next group's inputs are fetched into registers before the current group is computed.
+__device__ __forceinline__ uint64_t pack_f32x2(float a, float b) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
 template <int CIN>
 __global__ void __launch_bounds__(576)
 patch_embed_kernel(const float* __restrict__ xin, const float* __restrict__ w, const float* __restrict__ b,
@@ -336,45 +345,76 @@ patch_embed_kernel(const float* __restrict__ xin, const float* __restrict__ w, c
 {
     pdl_wait();
     pdl_launch_dependents();
-    __shared__ float sx[2][kPatchRows][CIN];
+    __shared__ __align__(16) uint64_t sx[2][kPatchRows][CIN];           // (x, x) pairs
+    constexpr int kGroupElems = kPatchRows * CIN, kPref = 4;            // up to kPref input elements per thread and group (>= 32 threads)
     const int groups = (M + kPatchRows - 1) / kPatchRows;
-    {
-        const int d0 = threadIdx.x * 4;                                 // launched with >= D / 4 threads (D <= 2304): one pass covers the row
-        const bool active = d0 < D;
-        float wr[4][CIN];
-        float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (active) {
+    const int d0 = threadIdx.x * 4;                                     // launched with >= D / 4 threads (D <= 2304): one pass covers the row
+    const bool active = d0 < D;
+    uint64_t wr[2][CIN];                                                // (w[d0][c], w[d0+1][c]) and (w[d0+2][c], w[d0+3][c])
+    float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (active) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
+        for (int c = 0; c < CIN; c += 4) {
+            float4 t[4];
 #pragma unroll
-                for (int c = 0; c < CIN; c += 4) {
-                    const float4 t = __ldg(reinterpret_cast<const float4*>(w + (size_t)(d0 + j) * CIN + c));
-                    wr[j][c] = t.x; wr[j][c + 1] = t.y; wr[j][c + 2] = t.z; wr[j][c + 3] = t.w;
-                }
-            bb = __ldg(reinterpret_cast<const float4*>(b + d0));
+            for (int j = 0; j < 4; ++j) t[j] = __ldg(reinterpret_cast<const float4*>(w + (size_t)(d0 + j) * CIN + c));
+            wr[0][c] = pack_f32x2(t[0].x, t[1].x); wr[0][c + 1] = pack_f32x2(t[0].y, t[1].y);
+            wr[0][c + 2] = pack_f32x2(t[0].z, t[1].z); wr[0][c + 3] = pack_f32x2(t[0].w, t[1].w);
+            wr[1][c] = pack_f32x2(t[2].x, t[3].x); wr[1][c + 1] = pack_f32x2(t[2].y, t[3].y);
+            wr[1][c + 2] = pack_f32x2(t[2].z, t[3].z); wr[1][c + 3] = pack_f32x2(t[2].w, t[3].w);
         }
-        int buf = 0;
-        for (int g = blockIdx.x; g < groups; g += gridDim.x, buf ^= 1) {
-            const int m0 = g * kPatchRows;
-            for (int i = threadIdx.x; i < kPatchRows * CIN; i += blockDim.x) {
-                const int r = i / CIN, c = i % CIN;
-                const int m = m0 + r;
-                sx[buf][r][c] = (m < M) ? xin[(size_t)(m % rows_in_tokens) * CIN + c] : 0.f;
-            }
-            __syncthreads();                                            // (double-buffered: the next group's fill does not race this group's reads)
-            if (active) {
+        bb = __ldg(reinterpret_cast<const float4*>(b + d0));
+    } else {
 #pragma unroll
-                for (int r = 0; r < kPatchRows; ++r) {
-                    if (m0 + r >= M) break;
-                    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int c = 0; c < CIN; ++c) wr[0][c] = wr[1][c] = 0ull;
+    }
+    float pre[kPref];
+    auto fetch = [&](int g) {
 #pragma unroll
-                    for (int c = 0; c < CIN; ++c) {
-                        const float xv = sx[buf][r][c];
+        for (int k = 0; k < kPref; ++k) {
+            const int i = threadIdx.x + k * blockDim.x;
+            const int m = g * kPatchRows + i / CIN;
+            pre[k] = (g < groups && i < kGroupElems && m < M) ? __ldg(xin + (size_t)(m % rows_in_tokens) * CIN + (i % CIN)) : 0.f;
+        }
+    };
+    fetch(blockIdx.x);
+    int buf = 0;
+    for (int g = blockIdx.x; g < groups; g += gridDim.x, buf ^= 1) {
+        const int m0 = g * kPatchRows;
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) acc[j] = fmaf(xv, wr[j][c], acc[j]);
+        for (int k = 0; k < kPref; ++k) {
+            const int i = threadIdx.x + k * blockDim.x;
+            if (i < kGroupElems) sx[buf][i / CIN][i % CIN] = pack_f32x2(pre[k], pre[k]);
+        }
+        __syncthreads();                                                // (double-buffered: the next group's fill does not race this group's reads)
+        fetch(g + gridDim.x);
+        if (active) {
+            // two rows at a time: four independent FMA chains per thread, the (x, x) pairs fetched two at a time (128-bit shared loads)
+#pragma unroll
+            for (int r = 0; r < kPatchRows; r += 2) {
+                if (m0 + r >= M) break;
+                uint64_t acc[2][2] = {{0ull, 0ull}, {0ull, 0ull}};
+#pragma unroll
+                for (int c = 0; c < CIN; c += 2) {
+                    const ulonglong2 xa = *reinterpret_cast<const ulonglong2*>(&sx[buf][r][c]);
+                    const ulonglong2 xb = *reinterpret_cast<const ulonglong2*>(&sx[buf][r + 1][c]);
+                    acc[0][0] = fma_f32x2(xa.x, wr[0][c], acc[0][0]);
+                    acc[0][1] = fma_f32x2(xa.x, wr[1][c], acc[0][1]);
+                    acc[1][0] = fma_f32x2(xb.x, wr[0][c], acc[1][0]);
+                    acc[1][1] = fma_f32x2(xb.x, wr[1][c], acc[1][1]);
+                    acc[0][0] = fma_f32x2(xa.y, wr[0][c + 1], acc[0][0]);
+                    acc[0][1] = fma_f32x2(xa.y, wr[1][c + 1], acc[0][1]);
+                    acc[1][0] = fma_f32x2(xb.y, wr[0][c + 1], acc[1][0]);
+                    acc[1][1] = fma_f32x2(xb.y, wr[1][c + 1], acc[1][1]);
+                }
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    if (m0 + r + q < M) {
+                        float a0, a1, a2, a3;
+                        unpack_f32x2(acc[q][0], a0, a1);
+                        unpack_f32x2(acc[q][1], a2, a3);
+                        *reinterpret_cast<float4*>(x + (size_t)(m0 + r + q) * D + d0) = make_float4(a0 + bb.x, a1 + bb.y, a2 + bb.z, a3 + bb.w);
                     }
-                    *reinterpret_cast<float4*>(x + (size_t)(m0 + r) * D + d0) =
-                        make_float4(acc[0] + bb.x, acc[1] + bb.y, acc[2] + bb.z, acc[3] + bb.w);
                 }
             }
         }
