@@ -1,9 +1,9 @@
 // Warp-specialised, software-pipelined masked flash attention (production kernel).
 //
-// Same math and reference lines as attention.cuh (fit/model/modules.py:176-204: segment-id mask, softmax, P V,
-// output * (mask != 0)); same operand layouts and the same bound-based single-pass softmax.  What changes is the
-// schedule.  attention.cuh runs  S-MMA -> softmax -> PV-MMA  strictly in sequence inside a CTA (ncu: 28 % issue
-// slots, stalls on barriers / TMEM loads, MUFU 32 %); here one persistent CTA per SM keeps TWO query tiles
+// Reference: fit/model/modules.py:176-204 (segment-id mask, softmax, P V, output * (mask != 0)).  Same operand layouts as
+// attention_general.cuh, but a bound-based single-pass softmax (no running maximum: q and k are affine-free-LayerNorm'ed)
+// and a different schedule.  attention_general.cuh runs  S-MMA -> softmax -> PV-MMA  strictly in sequence inside a CTA
+// (ncu: 28 % issue slots, stalls on barriers / TMEM loads, MUFU 32 %); here one persistent CTA per SM keeps TWO query tiles
 // ("streams" a and b, the two 128-row tiles of one (sample, head) pair at 256 tokens) in flight:
 //
 //   warp 0        TMA producer: Q_a, Q_b once per work item, K / V^T tiles through 2-stage rings; it runs ahead
