@@ -125,7 +125,7 @@ attention_general_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
         const int sample = bh / heads, head = bh - sample * heads;
         const int next_item = item + gridDim.x;
         const float* segb = seg + (size_t)sample * tokens;
-        const bool uniform = seg_uniform[sample] != 0;
+        const bool uniform = seg_uniform[sample] == tokens;            // key lengths < tokens (padded samples) take the compare path here
         const int qi = q0 + row;
         const bool q_ok = qi < tokens;
         const float my_seg = q_ok ? segb[qi] : 0.f;

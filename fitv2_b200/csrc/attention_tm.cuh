@@ -251,9 +251,10 @@ attention_tm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         uint32_t v[COLS];
         // One 64-key sub-tile of the softmax: S(k) out of TMEM buffer n_s % 2, P(k) back into its first 32 columns, hand-over to
         // the issuer.  Returns this thread's partial row sum.
-        auto do_sub = [&](int j, bool uniform, float my_seg) -> float {
+        auto do_sub = [&](int j, int klen, float my_seg) -> float {     // klen: key length of the sample (seg_uniform_kernel), 0 = compare ids
+            const bool uniform = klen != 0;
             const int kv0 = j * 64;
-            const int kv_valid = min(64, tokens - kv0);                 // may be <= 0 for the second half of a tail tile
+            const int kv_valid = min(64, (uniform ? klen : tokens) - kv0);   // may be <= 0 behind the last valid key
             const int mode = (uniform && kv_valid == 64) ? 0 : (uniform ? 1 : 2);
             const uint32_t b = n_s & 1;
             mbar_wait(&s_full[x * 2 + b], (n_s >> 1) & 1);
@@ -298,7 +299,8 @@ attention_tm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         bool early_done = false;                                        // sub-tile 0 of this item was already processed ...
         float l_early = 0.f;                                            // ... with this partial row sum
         for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-            const bool uniform = uni_nx != 0;
+            const int klen = uni_nx;
+            const bool uniform = klen != 0;
             const float my_seg = seg_nx;
             fetch_meta(item + gridDim.x);
             const int bh = item / q_pairs, qp = item - bh * q_pairs;
@@ -311,7 +313,7 @@ attention_tm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                 named_bar_sync(1 + x, SOFT_THREADS);
             }
             float l_run = early_done ? l_early : 0.f;
-            for (int j = early_done ? 1 : 0; j < sub_tiles; ++j) l_run += do_sub(j, uniform, my_seg);
+            for (int j = early_done ? 1 : 0; j < sub_tiles; ++j) l_run += do_sub(j, klen, my_seg);
             early_done = false;
             // The last P V of the item has only just been issued: instead of waiting for it (17 % of the warp samples sat in
             // the o_full wait below), the first sub-tile of the NEXT item -- its S was issued two sub-tiles ago -- is done now.
@@ -321,7 +323,7 @@ attention_tm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                 const int nxt = item + gridDim.x;
                 if (early && nxt < num_items && uni_nx != 0) {
                     const int bh_n = nxt / q_pairs;
-                    if (2 * (nxt - bh_n * q_pairs) + x < q_tiles) { l_early = do_sub(0, true, seg_nx); early_done = true; }
+                    if (2 * (nxt - bh_n * q_pairs) + x < q_tiles) { l_early = do_sub(0, uni_nx, seg_nx); early_done = true; }
                 }
             }
 

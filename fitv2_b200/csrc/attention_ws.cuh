@@ -297,7 +297,8 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         };
         fetch_meta(blockIdx.x);
         for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-            const bool uniform = uni_nx != 0;
+            const int klen = uni_nx;                                    // key length of the sample (seg_uniform_kernel), 0 = compare ids
+            const bool uniform = klen != 0;
             const float my_seg = seg_nx;
             fetch_meta(item + gridDim.x);
             const int bh = item / q_pairs, qp = item - bh * q_pairs;
@@ -313,7 +314,7 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
             float l_run = 0.f;
             for (int t = 0; t < kv_tiles; ++t, ++n_s) {
                 const int kv0 = t * 128;
-                const int kv_valid = min(128, tokens - kv0);
+                const int kv_valid = min(128, (uniform ? klen : tokens) - kv0);   // may be <= 0 behind the last valid key
                 const int mode = (uniform && kv_valid == 128) ? 0 : (uniform ? 1 : 2);   // dense / key-tail bound / segment compare
                 ATTN_TRACE(warp, 400 + t);
                 mbar_wait(&s_full[x], n_s & 1);

@@ -733,17 +733,34 @@ __global__ void rope_table_kernel(const long long* __restrict__ grid, const floa
     }
 }
 
-// Per-sample flag: 1 when every segment id of the sample is identical (attention skips the compares).
-__global__ void seg_uniform_kernel(const float* __restrict__ seg, int* __restrict__ flag, int tokens)
+// Per-sample KEY LENGTH for the attention kernels (they then skip the per-element segment compares):
+//   tokens      every segment id of the sample is identical (the sampling scripts: mask of ones);
+//   1..tokens-1 the ids are one non-zero value followed by zeros only (a padded sample of a mixed-aspect batch: n valid tokens, then
+//               padding).  Valid queries see exactly the first n keys; padded queries (id 0) may see anything, their output rows
+//               are zeroed (`* (mask != 0)`, fit/model/modules.py:204);
+//   0           anything else (packed sequences with several ids): the kernels compare ids per element.
+__global__ void seg_uniform_kernel(const float* __restrict__ seg, int* __restrict__ klen, int tokens)
 {
     pdl_wait();
     pdl_launch_dependents();
     const float* s = seg + (size_t)blockIdx.x * tokens;
     const float first = s[0];
-    int same = 1;
-    for (int i = threadIdx.x; i < tokens; i += blockDim.x) same &= (s[i] == first);
-    same = __syncthreads_and(same);
-    if (threadIdx.x == 0) flag[blockIdx.x] = same;
+    int n_first = 0, prefix_ok = 1;                                     // ids equal to the first one: contiguous from the start; the rest is 0
+    for (int i = threadIdx.x; i < tokens; i += blockDim.x) {
+        const float v = s[i];
+        if (v == first) { ++n_first; prefix_ok &= (i == 0 || s[i - 1] == first); }
+        else prefix_ok &= (v == 0.f);
+    }
+    __shared__ int cnt[32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) n_first += __shfl_xor_sync(0xffffffffu, n_first, o);
+    if ((threadIdx.x & 31) == 0) cnt[threadIdx.x >> 5] = n_first;
+    prefix_ok = __syncthreads_and(prefix_ok);
+    if (threadIdx.x == 0) {
+        int n = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) n += cnt[w];
+        klen[blockIdx.x] = prefix_ok ? n : 0;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -177,6 +177,60 @@ def test_attention_matches_oracle(lib, R, T, dh, H, masked, kernel):
     lib.fitv2_destroy(h)
 
 
+def _key_length(r):
+    """What seg_uniform_kernel must report for one row of segment ids: tokens when all ids are equal, n for n equal non-zero ids
+    followed by zeros only (a padded sample), 0 for anything else (the kernels then compare ids per element)."""
+    r = r.tolist()
+    n = 0
+    while n < len(r) and r[n] == r[0]:
+        n += 1
+    if n == len(r):
+        return len(r)
+    return n if r[0] != 0 and all(v == 0 for v in r[n:]) else 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("T", [200, 256, 520])
+def test_attention_key_length_paths(lib, T):
+    """Padded samples take the key-length path of the bounded kernels (no per-element id compares): every boundary position of the
+    valid length against the 64- / 128-key tiles, and the patterns that must NOT be classified as a prefix."""
+    H, dh = 16, 72
+    lens = [1, 63, 64, 65, 127, 128, 129, T - 1, T]
+    rows = []
+    for n in lens:
+        r = torch.zeros(T); r[:n] = 1; rows.append(r)
+    r = torch.zeros(T); r[:T // 2] = 7; rows.append(r)                       # non-unit id, still a prefix
+    rows.append(torch.zeros(T))                                              # all padding: output zero
+    r = torch.ones(T); r[T // 3: T // 2] = 0; rows.append(r)                 # hole in the middle: ids 1 | 0 | 1  -> compare path
+    r = torch.ones(T); r[: T // 4] = 0; rows.append(r)                       # padding in FRONT                  -> compare path
+    r = torch.ones(T); r[T // 2:] = 2; rows.append(r)                        # two packed images                 -> compare path
+    r = torch.ones(T); r[T // 2: T - 5] = 2; r[T - 5:] = 0; rows.append(r)   # two images + padding              -> compare path
+    mask = torch.stack(rows)
+    R = mask.shape[0]
+    h, ws = _handle(lib, 0, D=H * dh, H=H, dh=dh, Hm=3072, lora=288)
+    g = torch.Generator().manual_seed(T)
+    ln = lambda x: torch.nn.functional.layer_norm(x, (dh,))
+    q, k = [ln(torch.randn(R, H, T, dh, generator=g)).bfloat16() for _ in range(2)]
+    v = torch.randn(R, H, T, dh, generator=g).bfloat16()
+    tv = (T + 7) // 8 * 8
+    vt = torch.zeros(R, H, dh, tv, dtype=torch.bfloat16)
+    vt[..., :T] = v.transpose(-1, -2)
+    ref = _attention_oracle(q.float(), k.float(), v.float(), mask)
+    for attn in (1, 2, 4, 3):                                                # P in TMEM, shared-memory P, one thread per row, online max
+        _lib.check(lib.fitv2_set_option(h, b"attn", attn))
+        out = torch.full((R, T, H * dh), float("nan"), dtype=torch.bfloat16, device="cuda")
+        qd, kd, vd, md = q.cuda(), k.cuda(), vt.cuda(), mask.cuda()
+        _lib.check(lib.fitv2_debug_attention(h, _p(qd), _p(kd), _p(vd), _p(md), _p(out), R, T, None, None, None))
+        torch.cuda.synchronize()
+        err = rel(out, ref)
+        print(f"[key length] T={T} attn={attn}: {err:.2e}")
+        assert err < 6e-3
+        assert bool((out.float().cpu()[mask == 0] == 0).all())
+    lib.fitv2_destroy(h)
+    assert [_key_length(r) for r in mask][:len(lens)] == lens                # (the reference function of the tap test below)
+    assert [_key_length(r) for r in mask][len(lens):] == [T // 2, T, 0, 0, 0, 0]
+
+
 # ------------------------------------------------------------------------------------------------
 # FiT.forward / forward_with_cfg against the reference goldens and the oracle
 # ------------------------------------------------------------------------------------------------
@@ -197,7 +251,7 @@ def test_forward_golden_padded_mixed_aspect(xl2_padded, golden_dir):
     cos, sin = O.rope_cos_sin(cfg, fx["grid"])
     assert float((m.debug_tap("rope_cos").cpu() - cos[..., 0::2].permute(2, 0, 1)).abs().max()) < 1e-6   # pair-major table
     assert float((m.debug_tap("rope_sin").cpu() - sin[..., 0::2].permute(2, 0, 1)).abs().max()) < 1e-6
-    assert m.debug_tap("seg_uniform").cpu().tolist() == [int(bool((r == r[0]).all())) for r in fx["mask"]]
+    assert m.debug_tap("seg_uniform").cpu().tolist() == [_key_length(r) for r in fx["mask"]]
 
 
 def test_forward_invariants(xl2_padded, golden_dir):
