@@ -158,7 +158,10 @@ int fitv2_set_workspace(fitv2_handle* h, void* dev_ptr, int64_t bytes);
  *   t      fp32 (rows)               timesteps in [0, 1]
  *   y      int64 (rows)              class labels (num_classes = null class)
  *   grid   int64 (rows, 2, tokens)   [:,0] = w index, [:,1] = h index
- *   mask   fp32 (rows, tokens)       segment ids (0 = padding)
+ *   mask   fp32 (rows, tokens)       segment ids (0 = padding): tokens attend where the ids are equal (fit/model/modules.py:176-204).
+ *                                     All ids equal (the sampling scripts) and "n equal non-zero ids, then zeros" (a padded sample of a
+ *                                     mixed-aspect batch) are recognised on the device and run without per-element id compares;
+ *                                     any other pattern (several packed images per row) is compared element by element.
  *   out    fp32 (rows, tokens, C_out) velocity (or eps | sigma with learn_sigma); rows with mask 0 are exactly 0
  */
 int fitv2_forward(fitv2_handle* h, const float* x, int x_rows, const float* t, const int64_t* y,
