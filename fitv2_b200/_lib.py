@@ -21,12 +21,15 @@ WEIGHT_SLOTS = [
     "QKV_W", "QKV_B", "PROJ_W", "PROJ_B", "GATEUP_W", "GATEUP_B", "FC2_W", "FC2_B",
     "ROPE_FREQS_H", "ROPE_FREQS_W",
     "NORMAL_ADALN_W", "NORMAL_ADALN_B", "NORM1_W", "NORM2_W", "NORM_FINAL_W", "Q_NORM_W", "K_NORM_W",
+    "SG_G_W", "SG_G_B", "SG_X_W", "SG_X_B", "SG_FC2_W", "SG_FC2_B",
+    "FSG_G_W", "FSG_G_B", "FSG_X_W", "FSG_X_B", "FSG_FC2_W", "FSG_FC2_B",
 ]
 SLOT = {n: i for i, n in enumerate(WEIGHT_SLOTS)}
 OP16_SLOTS = {"QKV_W", "PROJ_W", "GATEUP_W", "FC2_W"}
 
 NORM_NONE, NORM_LAYERNORM, NORM_WLAYERNORM, NORM_RMSNORM = 0, 1, 2, 3       # FITV2_NORM_*
-ADALN_LORA, ADALN_NORMAL = 0, 1                                             # FITV2_ADALN_*
+ADALN_LORA, ADALN_NORMAL, ADALN_SWIGLU = 0, 1, 2                            # FITV2_ADALN_*
+MLP_SWIGLU, MLP_GELU = 0, 1                                                 # FITV2_MLP_*
 
 
 def norm_code(name, weight: bool = False) -> int:
@@ -77,13 +80,13 @@ class FitV2Config(C.Structure):
         ("num_embeddings", C.c_int32), ("operand_dtype", C.c_int32), ("time_shifting", C.c_float),
         ("rope_magnitude", C.c_float),
         ("out_channels", C.c_int32), ("adaln_type", C.c_int32), ("block_norm", C.c_int32), ("q_norm", C.c_int32),
-        ("k_norm", C.c_int32), ("channels_first", C.c_int32),
+        ("k_norm", C.c_int32), ("channels_first", C.c_int32), ("mlp_type", C.c_int32), ("rope_v", C.c_int32),
     ]
 
     def __init__(self, *a, **kw):
         # FiTv2 defaults for the variant fields (so that positional 11-field constructions keep meaning FiTv2)
         full = dict(out_channels=0, adaln_type=ADALN_LORA, block_norm=NORM_LAYERNORM, q_norm=NORM_LAYERNORM,
-                    k_norm=NORM_LAYERNORM, channels_first=0)
+                    k_norm=NORM_LAYERNORM, channels_first=0, mlp_type=MLP_SWIGLU, rope_v=0)
         full.update(kw)
         super().__init__(*a, **full)
 

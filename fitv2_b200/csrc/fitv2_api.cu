@@ -185,7 +185,8 @@ struct Layout {
     int rows = 0, tokens = 0, tokens_v = 0;
     int n_spans = 0;                                   // (offset, bytes) of every buffer, in allocation order (fitv2_debug_layout)
     size_t span_off[40], span_bytes[40];
-    size_t x_res, h, ao, q, k, vt, hidden, te, t0, c, sc, sc_split, lmid, lmid_split, gmod, mod, fmod, rope_cos, rope_sin, seg_uniform, cpart, xt, ot, wfin16, total;
+    size_t x_res, h, ao, q, k, vt, hidden, te, t0, c, sc, sc_split, lmid, lmid_split, gmod, mod, fmod, rope_cos, rope_sin, seg_uniform, cpart, xt, ot, wfin16,
+           sg_g, sg_s, sg_m, total;
 };
 
 }  // namespace
@@ -273,7 +274,8 @@ bool norm_has_weight(int mode) { return mode == FITV2_NORM_WLAYERNORM || mode ==
 // Element count of a weight slot for this configuration; 0 = the slot is not used (and need not be bound).
 int64_t expected_numel(const fitv2_config& c, int slot) {
     const int64_t D = c.hidden_size, L = c.depth, Hm = c.mlp_hidden, lora = c.lora_dim, C = c.token_channels, Co = out_channels(c);
-    const bool lora_mode = c.adaln_type == FITV2_ADALN_LORA;
+    const bool lora_mode = c.adaln_type == FITV2_ADALN_LORA, normal_mode = c.adaln_type == FITV2_ADALN_NORMAL, sg = c.adaln_type == FITV2_ADALN_SWIGLU;
+    const int64_t Hs = (D / 4) * 3, Hf = D / 2;                       // modules.py:266,285
     switch (slot) {
         case FITV2_W_X_EMBED_W: return D * C;
         case FITV2_W_X_EMBED_B: return D;
@@ -288,22 +290,30 @@ int64_t expected_numel(const fitv2_config& c, int slot) {
         case FITV2_W_LORA_A_B: return lora_mode ? L * lora : 0;
         case FITV2_W_LORA_B_W: return lora_mode ? L * 6 * D * lora : 0;
         case FITV2_W_LORA_B_B: return lora_mode ? L * 6 * D : 0;
-        case FITV2_W_FINAL_ADALN_W: return 2 * D * D;
-        case FITV2_W_FINAL_ADALN_B: return 2 * D;
+        case FITV2_W_FINAL_ADALN_W: return sg ? 0 : 2 * D * D;
+        case FITV2_W_FINAL_ADALN_B: return sg ? 0 : 2 * D;
         case FITV2_W_FINAL_LINEAR_W: return Co * D;
         case FITV2_W_FINAL_LINEAR_B: return Co;
         case FITV2_W_QKV_W: return L * 3 * D * D;
         case FITV2_W_QKV_B: return L * 3 * D;
         case FITV2_W_PROJ_W: return L * D * D;
         case FITV2_W_PROJ_B: return L * D;
-        case FITV2_W_GATEUP_W: return L * 2 * Hm * D;
-        case FITV2_W_GATEUP_B: return L * 2 * Hm;
+        case FITV2_W_GATEUP_W: return L * (c.mlp_type == FITV2_MLP_GELU ? 1 : 2) * Hm * D;    // GELU Mlp: fc1 alone
+        case FITV2_W_GATEUP_B: return L * (c.mlp_type == FITV2_MLP_GELU ? 1 : 2) * Hm;
         case FITV2_W_FC2_W: return L * D * Hm;
         case FITV2_W_FC2_B: return L * D;
         case FITV2_W_ROPE_FREQS_H: return c.head_dim / 4;
         case FITV2_W_ROPE_FREQS_W: return c.head_dim / 4;
-        case FITV2_W_NORMAL_ADALN_W: return lora_mode ? 0 : L * 6 * D * D;
-        case FITV2_W_NORMAL_ADALN_B: return lora_mode ? 0 : L * 6 * D;
+        case FITV2_W_NORMAL_ADALN_W: return normal_mode ? L * 6 * D * D : 0;
+        case FITV2_W_NORMAL_ADALN_B: return normal_mode ? L * 6 * D : 0;
+        case FITV2_W_SG_G_W: case FITV2_W_SG_X_W: return sg ? L * Hs * D : 0;
+        case FITV2_W_SG_G_B: case FITV2_W_SG_X_B: return sg ? L * Hs : 0;
+        case FITV2_W_SG_FC2_W: return sg ? L * 6 * D * Hs : 0;
+        case FITV2_W_SG_FC2_B: return sg ? L * 6 * D : 0;
+        case FITV2_W_FSG_G_W: case FITV2_W_FSG_X_W: return sg ? Hf * D : 0;
+        case FITV2_W_FSG_G_B: case FITV2_W_FSG_X_B: return sg ? Hf : 0;
+        case FITV2_W_FSG_FC2_W: return sg ? 2 * D * Hf : 0;
+        case FITV2_W_FSG_FC2_B: return sg ? 2 * D : 0;
         case FITV2_W_NORM1_W: return norm_has_weight(c.block_norm) ? L * D : 0;
         case FITV2_W_NORM2_W: return norm_has_weight(c.block_norm) ? L * D : 0;
         case FITV2_W_NORM_FINAL_W: return norm_has_weight(c.block_norm) ? D : 0;
@@ -354,6 +364,11 @@ Layout make_layout(const fitv2_config& c, int rows, int tokens, size_t guard = 0
     l.xt = take(c.channels_first ? M * c.token_channels * 4 : 0);
     l.ot = take(c.channels_first ? M * out_channels(c) * 4 : 0);
     l.wfin16 = take((size_t)out_channels(c) * D * 2);                   // fp16 copy of final_layer.linear.weight (tensor-pipe final layer)
+    // adaln_type 'swiglu': fc1_g(c), silu(fc1_g(c)) and the gated hidden of all blocks, (L, rows, (D/4)*3) fp32 each
+    const size_t sg_bytes = c.adaln_type == FITV2_ADALN_SWIGLU ? L * (size_t)rows * ((D / 4) * 3) * 4 : 0;
+    l.sg_g = take(sg_bytes);
+    l.sg_s = take(sg_bytes);
+    l.sg_m = take(sg_bytes);
     l.total = off;
     return l;
 }
@@ -616,13 +631,14 @@ int ensure_maps(fitv2_handle* h) {
         h->bn_proj = h->bn_fc2 = o.bn_resid;                        // tuning experiments only
     if (!h->bn_proj || !h->bn_fc2) return fail(FITV2_E_INVALID, "hidden_size %d has no supported tile width (multiple of 128/144/192/256)", (int)D);
     // q / k norm other than the affine-free LayerNorm of the FiTv2 configs: generic epilogue (two-head tile) + online-max attention
-    h->qkv_gen = !(c.q_norm == FITV2_NORM_LAYERNORM && c.k_norm == FITV2_NORM_LAYERNORM);
+    // (rope_v, the rotation of v, also lives in the generic epilogue; the attention kernel choice only follows the q / k norms)
+    h->qkv_gen = !(c.q_norm == FITV2_NORM_LAYERNORM && c.k_norm == FITV2_NORM_LAYERNORM) || c.rope_v != 0;
     // head_dim 72: three heads per 224-wide tile (option qkv_heads = 2 keeps the two-head 144-wide tile)
     h->qkv3 = c.head_dim == 72 && o.qkv_heads != 2 && !h->qkv_gen;
     if ((rc = make_map(&h->map_wqkv, h->w[FITV2_W_QKV_W], c.operand_dtype, L * 3 * D, D, D,
                        (h->qkv3 ? 3 * c.head_dim + 8 : 2 * c.head_dim) / kGemmCluster))) return rc;
     if ((rc = make_map(&h->map_wproj, h->w[FITV2_W_PROJ_W], c.operand_dtype, L * D, D, D, h->bn_proj / kGemmCluster))) return rc;
-    if ((rc = make_map(&h->map_wgu, h->w[FITV2_W_GATEUP_W], c.operand_dtype, L * 2 * Hm, D, D, 256 / kGemmCluster))) return rc;
+    if ((rc = make_map(&h->map_wgu, h->w[FITV2_W_GATEUP_W], c.operand_dtype, L * (c.mlp_type == FITV2_MLP_GELU ? 1 : 2) * Hm, D, D, 256 / kGemmCluster))) return rc;
     if ((rc = make_map(&h->map_wfc2, h->w[FITV2_W_FC2_W], c.operand_dtype, L * D, Hm, Hm, h->bn_fc2 / kGemmCluster))) return rc;
     {
         // Transposed residual GEMM (EPI_RESID_T): 256-token-wide tiles + TMA reduce-add into x.  Measured at XL/2 (hidden 1152,
@@ -671,7 +687,7 @@ int ensure_maps(fitv2_handle* h) {
     {
         const bool lora_mode = c.adaln_type == FITV2_ADALN_LORA;
         const uint64_t lora = lora_mode ? c.lora_dim : 0, split_rows = (uint64_t)((l.rows + kCondRows - 1) / kCondRows) * 128;
-        h->cond_tc = o.cond == 0 && D % 32 == 0 && (6 * D) % 48 == 0 && (2 * D) % 48 == 0 &&
+        h->cond_tc = o.cond == 0 && c.adaln_type != FITV2_ADALN_SWIGLU && D % 32 == 0 && (6 * D) % 48 == 0 && (2 * D) % 48 == 0 &&
                      (!lora_mode || (lora % 32 == 0 && (L * lora) % 48 == 0));
         if (h->cond_tc) {
             h->cond_bn_up = (6 * D) % 128 == 0 ? 128 : 48;
@@ -839,6 +855,31 @@ int forward_impl(fitv2_handle* h, const float* x_in, int x_rows, const float* t,
         if (h->cond_bn_up == 128) rc = launch_cond_tc<128>(h, h->map_sc_split, h->map_wnormal, h->map_wnormal, h->map_wnormal, u, st);
         else rc = launch_cond_tc<48>(h, h->map_sc_split, h->map_wnormal, h->map_wnormal, h->map_wnormal, u, st);
         if (rc) return rc;
+    } else if (c.adaln_type == FITV2_ADALN_SWIGLU) {
+        // modules.py:265-268,284-285: the modulation is a SwiGLU MLP on c ITSELF (no SiLU in front, no global term):
+        // g = Wg c + bg (+ silu(g)), m = (Wx c + bx) * silu(g), out = W2 m + b2; batched over the blocks, then once for the final layer
+        float* gb = (float*)(ws + l.sg_g);
+        float* sb = (float*)(ws + l.sg_s);
+        float* mb = (float*)(ws + l.sg_m);
+        auto sg_mlp = [&](int batches, int Hh, int Nout, int slot0, float* outp) -> int {
+            SmallLinear q;
+            memset(&q, 0, sizeof(q));
+            q.rows = rows; q.A = cc; q.lda = D; q.K = D; q.N = Hh; q.ldo = Hh; q.out_batch_stride = (size_t)rows * Hh;
+            q.W = (const float*)h->w[slot0]; q.w_batch_stride = (size_t)Hh * D; q.bias = (const float*)h->w[slot0 + 1]; q.bias_batch_stride = Hh;
+            q.out = gb; q.out_silu = sb;
+            int r2 = launch_small_linear(h, q, batches, st);
+            if (r2) return r2;
+            q.W = (const float*)h->w[slot0 + 2]; q.bias = (const float*)h->w[slot0 + 3];
+            q.out = mb; q.out_silu = nullptr; q.mul = sb; q.mul_batch_stride = (size_t)rows * Hh; q.ldm = Hh;
+            if ((r2 = launch_small_linear(h, q, batches, st))) return r2;
+            memset(&q, 0, sizeof(q));
+            q.rows = rows; q.A = mb; q.a_batch_stride = (size_t)rows * Hh; q.lda = Hh; q.K = Hh; q.N = Nout; q.ldo = Nout;
+            q.W = (const float*)h->w[slot0 + 4]; q.w_batch_stride = (size_t)Nout * Hh; q.bias = (const float*)h->w[slot0 + 5]; q.bias_batch_stride = Nout;
+            q.out = outp; q.out_batch_stride = (size_t)rows * Nout;
+            return launch_small_linear(h, q, batches, st);
+        };
+        if ((rc = sg_mlp(L, (D / 4) * 3, 6 * D, FITV2_W_SG_G_W, mod))) return rc;
+        if ((rc = sg_mlp(1, D / 2, 2 * D, FITV2_W_FSG_G_W, fmod))) return rc;
     } else {
         // final adaLN: fmod = Wf sc + bf   (shift | scale)
         p.A = sc; p.lda = D; p.K = D;
@@ -897,7 +938,7 @@ int forward_impl(fitv2_handle* h, const float* x_in, int x_rows, const float* t,
         ep.heads = H; ep.tokens_v = l.tokens_v;
         prof_begin(h, PC_QKV, st);
         if (h->qkv_gen) {
-            ep.q_norm = c.q_norm; ep.k_norm = c.k_norm;
+            ep.q_norm = c.q_norm; ep.k_norm = c.k_norm; ep.rope_v = c.rope_v;
             ep.q_norm_w = norm_has_weight(c.q_norm) ? (const float*)h->w[FITV2_W_Q_NORM_W] + (size_t)layer * DH : nullptr;
             ep.k_norm_w = norm_has_weight(c.k_norm) ? (const float*)h->w[FITV2_W_K_NORM_W] + (size_t)layer * DH : nullptr;
             if (DH == 72) rc = launch_gemm_t<144, EPI_QKV_GEN, OT, 72>(h, h->map_h, h->map_wqkv, M, 3 * D, D, layer * 3 * D, ep, st);
@@ -930,10 +971,16 @@ int forward_impl(fitv2_handle* h, const float* x_in, int x_rows, const float* t,
         x_kernels(false);
         prof_end(h, st);
         memset(&ep, 0, sizeof(ep));
-        ep.bias = (const float*)h->w[FITV2_W_GATEUP_B] + (size_t)layer * 2 * Hm;
         ep.tokens = tokens; ep.out16 = ws + l.hidden; ep.ld_out = Hm;
         prof_begin(h, PC_GATEUP, st);
-        if ((rc = launch_gemm_t<256, EPI_SWIGLU, OT, 0>(h, h->map_h, h->map_wgu, M, 2 * Hm, D, layer * 2 * Hm, ep, st))) return rc;
+        if (c.mlp_type == FITV2_MLP_GELU) {            // timm Mlp (modules.py:253): hidden = gelu_tanh(fc1(h)), plain 256-wide tiles
+            ep.bias = (const float*)h->w[FITV2_W_GATEUP_B] + (size_t)layer * Hm;
+            ep.act_gelu = 1;
+            if ((rc = launch_gemm_t<256, EPI_PLAIN, OT, 0>(h, h->map_h, h->map_wgu, M, Hm, D, layer * Hm, ep, st))) return rc;
+        } else {
+            ep.bias = (const float*)h->w[FITV2_W_GATEUP_B] + (size_t)layer * 2 * Hm;
+            if ((rc = launch_gemm_t<256, EPI_SWIGLU, OT, 0>(h, h->map_h, h->map_wgu, M, 2 * Hm, D, layer * 2 * Hm, ep, st))) return rc;
+        }
         prof_end(h, st);
         memset(&ep, 0, sizeof(ep));
         ep.bias = (const float*)h->w[FITV2_W_FC2_B] + (size_t)layer * D;
@@ -1016,11 +1063,15 @@ int fitv2_create(const fitv2_config* cfg, fitv2_handle** out) {
         return fail(FITV2_E_INVALID, "head_dim %d not supported (kernels are built for 72 and 96)", c.head_dim);
     if (c.num_heads % 2) return fail(FITV2_E_INVALID, "num_heads %d must be even (two heads per QKV tile)", c.num_heads);
     if (c.mlp_hidden % 128) return fail(FITV2_E_INVALID, "mlp_hidden %d must be a multiple of 128", c.mlp_hidden);
+    if (c.mlp_type != FITV2_MLP_SWIGLU && c.mlp_type != FITV2_MLP_GELU) return fail(FITV2_E_INVALID, "mlp_type %d unknown", c.mlp_type);
+    if (c.mlp_type == FITV2_MLP_GELU && c.mlp_hidden % 256) return fail(FITV2_E_INVALID, "mlp_hidden %d must be a multiple of 256 for the GELU Mlp", c.mlp_hidden);
+    if (c.rope_v != 0 && c.rope_v != 1) return fail(FITV2_E_INVALID, "rope_v %d must be 0 or 1", c.rope_v);
     if (c.hidden_size > 2304 || c.hidden_size % 16) return fail(FITV2_E_INVALID, "hidden_size %d must be a multiple of 16 and <= 2304", c.hidden_size);
     if (c.token_channels != 16) return fail(FITV2_E_INVALID, "token_channels %d not supported (p*p*C_in = 16)", c.token_channels);
     if (c.out_channels != 0 && c.out_channels != 16 && c.out_channels != 32)
         return fail(FITV2_E_INVALID, "out_channels %d not supported (16, or 32 with learn_sigma)", c.out_channels);
-    if (c.adaln_type != FITV2_ADALN_LORA && c.adaln_type != FITV2_ADALN_NORMAL) return fail(FITV2_E_INVALID, "adaln_type %d unknown", c.adaln_type);
+    if (c.adaln_type != FITV2_ADALN_LORA && c.adaln_type != FITV2_ADALN_NORMAL && c.adaln_type != FITV2_ADALN_SWIGLU)
+        return fail(FITV2_E_INVALID, "adaln_type %d unknown", c.adaln_type);
     if (c.adaln_type == FITV2_ADALN_LORA && (c.lora_dim <= 0 || c.lora_dim % 4)) return fail(FITV2_E_INVALID, "lora_dim %d must be a positive multiple of 4", c.lora_dim);
     if (c.block_norm < FITV2_NORM_LAYERNORM || c.block_norm > FITV2_NORM_RMSNORM) return fail(FITV2_E_INVALID, "block_norm %d unknown (layernorm / w_layernorm / rmsnorm)", c.block_norm);
     if (c.q_norm < FITV2_NORM_NONE || c.q_norm > FITV2_NORM_RMSNORM || c.k_norm < FITV2_NORM_NONE || c.k_norm > FITV2_NORM_RMSNORM)

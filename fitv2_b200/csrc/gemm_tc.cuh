@@ -67,7 +67,18 @@ struct GemmEpi {
     const float* k_norm_w;
     // EPI_PLAIN
     const float* row_scale;   // [M] or null: out = (acc + bias) * row_scale[m]  (final layer: fit_model.py:230)
+    int act_gelu;             // 1: out = gelu_tanh(acc + bias)  (timm Mlp fc1 + nn.GELU(approximate="tanh"), modules.py:253)
+    // EPI_QKV_GEN
+    int rope_v;               // 1: v is rotated like q / k (add_rel_pe_to_v, modules.py:171-172)
 };
+
+// nn.GELU(approximate="tanh"): 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3))); tanh(u) = 1 - 2 / (exp(2u) + 1), which is
+// the argument is clamped so that the exponential stays finite
+__device__ __forceinline__ float gelu_tanh(float x) {
+    const float u = fminf(fmaxf(0.7978845608028654f * fmaf(0.044715f * x, x * x, x), -30.0f), 30.0f);   // tanh(30) == 1 in fp32
+    const float th = 1.0f - 2.0f / (__expf(2.0f * u) + 1.0f);
+    return 0.5f * x * (1.0f + th);
+}
 
 constexpr int kGemmBM = 128;          // rows per CTA
 constexpr int kGemmBK = 64;
@@ -465,6 +476,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                         const float rs = ep.row_scale ? __ldg(ep.row_scale + m) : 1.0f;
 #pragma unroll
                         for (int j = 0; j < 8; ++j) o[j] = (__uint_as_float(v[j]) + __ldg(bias + c * 8 + j)) * rs;
+                        if (ep.act_gelu) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) o[j] = gelu_tanh(o[j]);
+                        }
                         if (ep.out16 != nullptr) {
                             OT* orow = reinterpret_cast<OT*>(ep.out16) + (size_t)m * ep.ld_out + n0 + half * HALF + c * 8;
                             *reinterpret_cast<uint4*>(orow) = make_uint4(Op16<OT>::pack(o[0], o[1]), Op16<OT>::pack(o[2], o[3]),
@@ -579,6 +594,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     }
                     __syncwarp();
                 } else {
+                    if constexpr (EPI == EPI_QKV_GEN) {
+                        if (ep.rope_v) {                                     // add_rel_pe_to_v: v * cos + rotate_half(v) * sin
+                            const float* cs = ep.rope_cos + (row_ok ? m : 0);
+                            const float* sn = ep.rope_sin + (row_ok ? m : 0);
+#pragma unroll
+                            for (int p = 0; p < DH / 2; ++p) {
+                                const float cc = __ldg(cs + (size_t)p * M), ss = __ldg(sn + (size_t)p * M);
+                                const float x0 = v[2 * p], x1 = v[2 * p + 1];
+                                v[2 * p] = x0 * cc - x1 * ss;
+                                v[2 * p + 1] = x1 * cc + x0 * ss;
+                            }
+                        }
+                    }
                     // V^T[sample, head, d, token]
                     if (one_sample && rows_valid == 32 && (token0 & 7) == 0) {
                         // transpose through the slab: [d][32 tokens] 16-bit, then 16-byte (8-token) stores

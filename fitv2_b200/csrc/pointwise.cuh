@@ -796,6 +796,7 @@ struct SmallLinear {
     const float* W; size_t w_batch_stride;
     const float* bias; size_t bias_batch_stride;
     const float* add;            // (rows, N) or null, shared by all batches
+    const float* mul; size_t mul_batch_stride; int ldm;   // optional: out = (acc + bias) * mul[batch][r][n]  (SwiGLU gate, adaln_type 'swiglu')
     const float* emb; const long long* labels;   // optional embedding-row add (label gather), ld = N
     int num_emb; int* err;       // rows of the table; labels outside [0, num_emb) set bit 0 of *err and read row 0 (the reference raises)
     float* out; size_t out_batch_stride; int ldo;
@@ -893,6 +894,7 @@ small_linear_kernel(SmallLinear p)
             if (n >= p.N) continue;
             float v = acc[i][j];
             if (bias) v += bias[n];
+            if (p.mul) v *= p.mul[z * p.mul_batch_stride + (size_t)r * p.ldm + n];
             if (p.add) v += p.add[(size_t)r * p.N + n];
             if (p.emb) {
                 long long lab = p.labels[r];
@@ -924,6 +926,7 @@ __global__ void small_linear_finalize_kernel(SmallLinear p)
     float v = 0.f;
     for (int s = 0; s < p.ksplit; ++s) v += part[(size_t)s * total];
     if (p.bias) v += p.bias[z * p.bias_batch_stride + n];
+    if (p.mul) v *= p.mul[z * p.mul_batch_stride + (size_t)r * p.ldm + n];
     if (p.add) v += p.add[(size_t)r * p.N + n];
     if (p.emb) {
         long long lab = p.labels[r];

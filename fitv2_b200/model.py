@@ -63,6 +63,13 @@ def _seq(*mods):
     return nn.Sequential(*mods)
 
 
+def _swiglu_holder(d: int, hidden: int, out: int) -> nn.Module:
+    """Parameters of a timm SwiGLU in its creation order (fc1_g, fc1_x, fc2)."""
+    m = _Holder()
+    m.fc1_g, m.fc1_x, m.fc2 = nn.Linear(d, hidden), nn.Linear(d, hidden), nn.Linear(hidden, out)
+    return m
+
+
 class FiT(nn.Module):
     """FiTv2 transformer (use_sit / SwiGLU / adaLN-LoRA / layernorm qk-norm / 2-D RoPE)."""
 
@@ -82,10 +89,8 @@ class FiT(nn.Module):
         # ---- reject what the kernels do not implement (no silent fallback) ----
         unsupported = []
         assert not (learn_sigma and use_sit)                                # fit_model.py:68
-        if not use_swiglu: unsupported.append("use_swiglu must be True (the GELU Mlp is not built)")
-        if adaln_type not in ("lora", "normal"): unsupported.append("adaln_type must be 'lora' or 'normal'")
+        if adaln_type not in ("lora", "normal", "swiglu"): unsupported.append("adaln_type must be 'lora', 'normal' or 'swiglu'")
         if adaln_type == "lora" and not adaln_lora_dim: unsupported.append("adaln_type='lora' needs adaln_lora_dim")
-        if (rel_pos_embed or "").lower() != "rope": unsupported.append("rel_pos_embed must be 'rope'")
         try:
             self.block_norm = _lib.norm_code(norm_type)
             self.q_norm_code = _lib.norm_code(q_norm, qk_norm_weight)
@@ -94,11 +99,12 @@ class FiT(nn.Module):
             unsupported.append(str(e))
             self.block_norm = self.q_norm_code = self.k_norm_code = _lib.NORM_LAYERNORM
         if self.block_norm == _lib.NORM_NONE: unsupported.append("norm_type must be 'layernorm', 'w_layernorm' or 'rmsnorm'")
-        if not (qkv_bias and ffn_bias and adaln_bias): unsupported.append("qkv_bias/ffn_bias/adaln_bias must be True")
+        # adaln_bias=False cannot be constructed in the reference either: initialize_weights calls nn.init.constant_ on the
+        # missing bias (fit_model.py:141-153), so there is no behaviour to reproduce
+        if not adaln_bias: unsupported.append("adaln_bias must be True (the reference constructor itself fails without it)")
         if online_rope and (custom_freqs.lower() not in _ONLINE_RULES or not isinstance(ori_max_pe_len, int)):
             unsupported.append("online_rope=True needs custom_freqs in ('linear', 'ntk-aware', 'ntk-by-parts') and ori_max_pe_len "
                                "(the reference's online mode has no 'normal' branch and never sets the yarn / ntk-aware-pro magnitudes)")
-        if add_rel_pe_to_v: unsupported.append("add_rel_pe_to_v=True")
         # use_checkpoint (activation checkpointing, fit_model.py:222-226) changes nothing in a no-grad forward: accepted, unused
         if finetune is not None or pretrain_ckpt is not None: unsupported.append("pretrain_ckpt/finetune (load weights with load_state_dict)")
         if save_attention: unsupported.append("save_attention=True")
@@ -117,9 +123,18 @@ class FiT(nn.Module):
         self.adaln_type, self.adaln_lora_dim = adaln_type, adaln_lora_dim
         self.online_rope, self.time_shifting, self.save_attention = online_rope, time_shifting, False
         self.head_dim = hidden_size // num_heads
-        self.use_swiglu_large = bool(use_swiglu_large)
-        self.mlp_hidden = int(hidden_size * mlp_ratio) if use_swiglu_large else (int(hidden_size * mlp_ratio) * 2) // 3   # modules.py:246-251
+        self.use_swiglu, self.use_swiglu_large = bool(use_swiglu), bool(use_swiglu_large)
+        if not use_swiglu:                                                  # modules.py:253: timm Mlp, fc2(GELU_tanh(fc1(x)))
+            self.mlp_hidden = int(hidden_size * mlp_ratio)
+            if self.mlp_hidden % 256: raise NotImplementedError(f"fitv2_b200.FiT: Mlp hidden {self.mlp_hidden} must be a multiple of 256")
+        else:
+            self.mlp_hidden = int(hidden_size * mlp_ratio) if use_swiglu_large else (int(hidden_size * mlp_ratio) * 2) // 3   # modules.py:246-251
         if self.mlp_hidden % 128: raise NotImplementedError(f"fitv2_b200.FiT: SwiGLU hidden {self.mlp_hidden} must be a multiple of 128")
+        # modules.py:153,170-174: q / k (and v with add_rel_pe_to_v) are rotated only for rel_pos_embed 'rope' / 'xpos' (lower-cased);
+        # anything else leaves them as they are -- here: zero frequencies (cos = 1, sin = 0 exactly) and magnitude 1
+        self.rel_pos_embed = None if rel_pos_embed is None else str(rel_pos_embed).lower()
+        self.rotates = self.rel_pos_embed in ("rope", "xpos")
+        self.add_rel_pe_to_v = bool(add_rel_pe_to_v)
         self.operand_dtype = operand_dtype
         self.rope_args = dict(head_dim=self.head_dim, custom_freqs=custom_freqs, theta=rope_theta,
                               max_pe_len_h=max_pe_len_h, max_pe_len_w=max_pe_len_w, decouple=decouple,
@@ -141,14 +156,19 @@ class FiT(nn.Module):
         for _ in range(depth):
             blk = _Holder()
             blk.norm1, blk.norm2 = wn(self.block_norm, D), wn(self.block_norm, D)
-            blk.attn = _Holder(); blk.attn.qkv = nn.Linear(D, 3 * D)
+            blk.attn = _Holder(); blk.attn.qkv = nn.Linear(D, 3 * D, bias=qkv_bias)
             blk.attn.q_norm, blk.attn.k_norm = wn(self.q_norm_code, self.head_dim), wn(self.k_norm_code, self.head_dim)
             blk.attn.proj = nn.Linear(D, D)
             blk.mlp = _Holder()
-            blk.mlp.fc1_g = nn.Linear(D, self.mlp_hidden); blk.mlp.fc1_x = nn.Linear(D, self.mlp_hidden)
-            blk.mlp.fc2 = nn.Linear(self.mlp_hidden, D)
+            if use_swiglu:
+                blk.mlp.fc1_g = nn.Linear(D, self.mlp_hidden, bias=ffn_bias); blk.mlp.fc1_x = nn.Linear(D, self.mlp_hidden, bias=ffn_bias)
+            else:
+                blk.mlp.fc1 = nn.Linear(D, self.mlp_hidden, bias=ffn_bias)
+            blk.mlp.fc2 = nn.Linear(self.mlp_hidden, D, bias=ffn_bias)
             if adaln_type == "lora":
                 blk.adaLN_modulation = _seq(nn.SiLU(), nn.Linear(D, adaln_lora_dim), nn.Linear(adaln_lora_dim, 6 * D))
+            elif adaln_type == "swiglu":                                    # modules.py:265-268: timm SwiGLU(D -> (D//4)*3 -> 6D)
+                blk.adaLN_modulation = _swiglu_holder(D, (D // 4) * 3, 6 * D)
             else:
                 blk.adaLN_modulation = _seq(nn.SiLU(), nn.Linear(D, 6 * D))
             blocks.append(blk)
@@ -156,7 +176,10 @@ class FiT(nn.Module):
         self.final_layer = _Holder()
         self.final_layer.norm_final = wn(self.block_norm, D)
         self.final_layer.linear = nn.Linear(D, patch_size * patch_size * self.out_channels)
-        self.final_layer.adaLN_modulation = _seq(nn.SiLU(), nn.Linear(D, 2 * D))
+        if adaln_type == "swiglu":                                          # modules.py:284-285
+            self.final_layer.adaLN_modulation = _swiglu_holder(D, D // 2, 2 * D)
+        else:
+            self.final_layer.adaLN_modulation = _seq(nn.SiLU(), nn.Linear(D, 2 * D))
         self.initialize_weights()
 
         self._handle = None
@@ -187,13 +210,14 @@ class FiT(nn.Module):
         nn.init.normal_(self.y_embedder.embedding_table.weight, std=0.02)
         nn.init.normal_(self.t_embedder.mlp[0].weight, std=0.02)
         nn.init.normal_(self.t_embedder.mlp[2].weight, std=0.02)
+        last = (lambda m: m.fc2) if self.adaln_type == "swiglu" else (lambda m: m[-1])   # fit_model.py:139-153
         for blk in self.blocks:
-            nn.init.constant_(blk.adaLN_modulation[-1].weight, 0)
-            nn.init.constant_(blk.adaLN_modulation[-1].bias, 0)
+            nn.init.constant_(last(blk.adaLN_modulation).weight, 0)
+            nn.init.constant_(last(blk.adaLN_modulation).bias, 0)
         if self.global_adaLN_modulation is not None:                        # fit_model.py:146-148 (adaln_type 'lora' only)
             nn.init.constant_(self.global_adaLN_modulation[-1].weight, 0)
             nn.init.constant_(self.global_adaLN_modulation[-1].bias, 0)
-        for lin in (self.final_layer.adaLN_modulation[-1], self.final_layer.linear):
+        for lin in (last(self.final_layer.adaLN_modulation), self.final_layer.linear):
             nn.init.constant_(lin.weight, 0)
             nn.init.constant_(lin.bias, 0)
 
@@ -260,11 +284,13 @@ class FiT(nn.Module):
                                        self.adaln_lora_dim or 0, self.in_channels * self.patch_size ** 2,
                                        self.y_embedder.embedding_table.weight.shape[0],
                                        _lib.OPERAND_FP16 if self.operand_dtype == "fp16" else _lib.OPERAND_BF16,
-                                       float(self.time_shifting), float(mag),
+                                       float(self.time_shifting), float(mag) if self.rotates else 1.0,
                                        out_channels=self.out_token_channels,
-                                       adaln_type=_lib.ADALN_LORA if self.adaln_type == "lora" else _lib.ADALN_NORMAL,
+                                       adaln_type={"lora": _lib.ADALN_LORA, "normal": _lib.ADALN_NORMAL, "swiglu": _lib.ADALN_SWIGLU}[self.adaln_type],
                                        block_norm=self.block_norm, q_norm=self.q_norm_code, k_norm=self.k_norm_code,
-                                       channels_first=0 if self.use_sit else 1)
+                                       channels_first=0 if self.use_sit else 1,
+                                       mlp_type=_lib.MLP_SWIGLU if self.use_swiglu else _lib.MLP_GELU,
+                                       rope_v=1 if (self.add_rel_pe_to_v and self.rotates) else 0)
                 h = C.c_void_p()
                 _lib.check(lib.fitv2_create(C.byref(cfg), C.byref(h)), "fitv2_create")
                 self._handle, self._handle_device = h, dev
@@ -305,10 +331,18 @@ class FiT(nn.Module):
         per-block weights stacked over depth, 16-bit GEMM operands, fc1_g/fc1_x interleaved in 128-row groups
         so that one 256-wide GEMM tile holds matching gate and up columns."""
         fh, fw, _ = rope_frequencies(**self.rope_args)
+        if not self.rotates:
+            fh, fw = torch.zeros_like(fh), torch.zeros_like(fw)
         op = torch.float16 if self.operand_dtype == "fp16" else torch.bfloat16
         f32 = lambda p: p.detach().to(device=dev, dtype=torch.float32).contiguous()
         blocks = self.blocks
         stack32 = lambda get: torch.stack([get(b).detach().to(device=dev, dtype=torch.float32) for b in blocks]).contiguous()
+
+        def bias32(get, n):
+            """Stacked bias of a per-block Linear; zeros for a bias-free one (qkv_bias / ffn_bias False)."""
+            if get(blocks[0]).bias is None:
+                return torch.zeros(len(blocks), n, dtype=torch.float32, device=dev)
+            return stack32(lambda b: get(b).bias)
 
         def tf32(w):
             # adaLN weights are tf32 operands of the tensor-pipe conditioning linears (csrc/cond_tc.cuh): round them to
@@ -320,6 +354,8 @@ class FiT(nn.Module):
         Hm = self.mlp_hidden
 
         def gateup(b, attr):
+            if getattr(b.mlp.fc1_g, attr) is None:                          # ffn_bias False
+                return torch.zeros(2 * Hm, dtype=torch.float32, device=dev)
             g = getattr(b.mlp.fc1_g, attr).detach().to(device=dev, dtype=torch.float32)
             u = getattr(b.mlp.fc1_x, attr).detach().to(device=dev, dtype=torch.float32)
             g = g.reshape(Hm // 128, 128, *g.shape[1:])
@@ -331,16 +367,18 @@ class FiT(nn.Module):
             "T_MLP0_W": f32(self.t_embedder.mlp[0].weight), "T_MLP0_B": f32(self.t_embedder.mlp[0].bias),
             "T_MLP2_W": f32(self.t_embedder.mlp[2].weight), "T_MLP2_B": f32(self.t_embedder.mlp[2].bias),
             "Y_TABLE": f32(self.y_embedder.embedding_table.weight),
-            "FINAL_ADALN_W": tf32(f32(self.final_layer.adaLN_modulation[1].weight)),
-            "FINAL_ADALN_B": f32(self.final_layer.adaLN_modulation[1].bias),
             "FINAL_LINEAR_W": f32(self.final_layer.linear.weight), "FINAL_LINEAR_B": f32(self.final_layer.linear.bias),
-            "QKV_W": stack16(lambda b: b.attn.qkv.weight), "QKV_B": stack32(lambda b: b.attn.qkv.bias),
+            "QKV_W": stack16(lambda b: b.attn.qkv.weight), "QKV_B": bias32(lambda b: b.attn.qkv, 3 * self.hidden_size),
             "PROJ_W": stack16(lambda b: b.attn.proj.weight), "PROJ_B": stack32(lambda b: b.attn.proj.bias),
-            "GATEUP_W": torch.stack([gateup(b, "weight").to(op) for b in blocks]).contiguous(),
-            "GATEUP_B": torch.stack([gateup(b, "bias") for b in blocks]).contiguous(),
-            "FC2_W": stack16(lambda b: b.mlp.fc2.weight), "FC2_B": stack32(lambda b: b.mlp.fc2.bias),
+            "FC2_W": stack16(lambda b: b.mlp.fc2.weight), "FC2_B": bias32(lambda b: b.mlp.fc2, self.hidden_size),
             "ROPE_FREQS_H": fh.to(dev).contiguous(), "ROPE_FREQS_W": fw.to(dev).contiguous(),
         }
+        if self.use_swiglu:
+            P["GATEUP_W"] = torch.stack([gateup(b, "weight").to(op) for b in blocks]).contiguous()
+            P["GATEUP_B"] = torch.stack([gateup(b, "bias") for b in blocks]).contiguous()
+        else:                                                               # GELU Mlp: the slots hold fc1 alone, no interleave
+            P["GATEUP_W"] = stack16(lambda b: b.mlp.fc1.weight)
+            P["GATEUP_B"] = bias32(lambda b: b.mlp.fc1, Hm)
         if self.adaln_type == "lora":
             P.update({
                 "GLOBAL_ADALN_W": tf32(f32(self.global_adaLN_modulation[1].weight)),
@@ -348,9 +386,18 @@ class FiT(nn.Module):
                 "LORA_A_W": tf32(stack32(lambda b: b.adaLN_modulation[1].weight)), "LORA_A_B": stack32(lambda b: b.adaLN_modulation[1].bias),
                 "LORA_B_W": tf32(stack32(lambda b: b.adaLN_modulation[2].weight)), "LORA_B_B": stack32(lambda b: b.adaLN_modulation[2].bias),
             })
-        else:                                                               # modules.py:254-258: one Linear(D -> 6D) per block
+        elif self.adaln_type == "normal":                                   # modules.py:254-258: one Linear(D -> 6D) per block
             P.update({"NORMAL_ADALN_W": tf32(stack32(lambda b: b.adaLN_modulation[1].weight)),
                       "NORMAL_ADALN_B": stack32(lambda b: b.adaLN_modulation[1].bias)})
+        if self.adaln_type == "swiglu":                                     # modules.py:265-268,284-285 (fp32 FMA kernels: no tf32 rounding)
+            fa = self.final_layer.adaLN_modulation
+            for tag, name in (("G", "fc1_g"), ("X", "fc1_x"), ("FC2", "fc2")):
+                P[f"SG_{tag}_W"] = stack32(lambda b: getattr(b.adaLN_modulation, name).weight)
+                P[f"SG_{tag}_B"] = stack32(lambda b: getattr(b.adaLN_modulation, name).bias)
+                P[f"FSG_{tag}_W"], P[f"FSG_{tag}_B"] = f32(getattr(fa, name).weight), f32(getattr(fa, name).bias)
+        else:
+            P.update({"FINAL_ADALN_W": tf32(f32(self.final_layer.adaLN_modulation[1].weight)),
+                      "FINAL_ADALN_B": f32(self.final_layer.adaLN_modulation[1].bias)})
         if self.block_norm != _lib.NORM_LAYERNORM:
             P.update({"NORM1_W": stack32(lambda b: b.norm1.weight), "NORM2_W": stack32(lambda b: b.norm2.weight),
                       "NORM_FINAL_W": f32(self.final_layer.norm_final.weight)})
@@ -417,7 +464,7 @@ class FiT(nn.Module):
         """online_rope (fit_model.py:212-214): per-sample frequencies from ``size`` (B,1,2).  The cache is keyed on the VALUES
         of ``size`` (a fresh tensor per batch usually reuses the freed allocation of the previous one, so a storage key would
         hand a new batch the old frequencies); a sampling loop should bind once through ``EulerCFGSampler(size=...)``."""
-        if not self.online_rope:
+        if not self.online_rope or not self.rotates:
             return
         if size is None:
             raise ValueError("online_rope=True needs `size` (B, 1, 2) = (h, w) patches per sample (fit_model.py:212-213)")

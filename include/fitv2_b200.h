@@ -43,6 +43,12 @@ extern "C" {
 
 #define FITV2_ADALN_LORA       0  /* global adaLN + per-block LoRA (modules.py:259-264): FiTv2      */
 #define FITV2_ADALN_NORMAL     1  /* per-block Linear(D -> 6D), no global term (modules.py:254-258): FiTv1 / DiT */
+#define FITV2_ADALN_SWIGLU     2  /* per-block SwiGLU(D -> (D/4)*3 -> 6D) and final SwiGLU(D -> D/2 -> 2D) applied to c itself,
+                                     no global term (modules.py:265-268,284-285); fp32 FMA kernels */
+
+#define FITV2_MLP_SWIGLU       0  /* fc2(silu(fc1_g(x)) * fc1_x(x)), hidden (int(D*mlp_ratio)*2)//3 or int(D*mlp_ratio) */
+#define FITV2_MLP_GELU         1  /* fc2(gelu_tanh(fc1(x))), hidden int(D*mlp_ratio) (a multiple of 256): use_swiglu = False,
+                                     the class default of fit_model.py:38; GATEUP_W / GATEUP_B then hold fc1 alone */
 
 /* Model geometry: the constructor contract of fit.model.fit_model.FiT (fit_model.py:25-65).  Zero-initialised trailing
  * fields select the FiTv2 family except for the three norm fields, which must be set (FITV2_NORM_LAYERNORM for FiTv2). */
@@ -64,6 +70,8 @@ typedef struct fitv2_config {
     int32_t q_norm;           /* FITV2_NORM_* of the per-head q norm (modules.py:146) */
     int32_t k_norm;           /* FITV2_NORM_* of the per-head k norm (modules.py:147) */
     int32_t channels_first;   /* 1: use_sit = False callers, x (B, C, N) -> out (B, C_out, N) (fit_model.py:204,231) */
+    int32_t mlp_type;         /* FITV2_MLP_*: 0 = timm SwiGLU (use_swiglu), 1 = timm Mlp with tanh-GELU (modules.py:253)   */
+    int32_t rope_v;           /* 1: add_rel_pe_to_v, v is rotated like q / k (modules.py:171-172)                          */
 } fitv2_config;
 
 typedef struct fitv2_handle fitv2_handle;
@@ -100,7 +108,8 @@ enum fitv2_weight {
     FITV2_W_PROJ_B,            /* fp32 (L, D)                                                        */
     FITV2_W_GATEUP_W,          /* OP16 (L, 2*Hm, D)     blocks.i.mlp.fc1_g / fc1_x interleaved in 128-row groups:
                                   rows [256t, 256t+128) = fc1_g rows [128t, 128t+128), next 128 = fc1_x rows */
-    FITV2_W_GATEUP_B,          /* fp32 (L, 2*Hm)        same interleave                               */
+    FITV2_W_GATEUP_B,          /* fp32 (L, 2*Hm)        same interleave.  FITV2_MLP_GELU: GATEUP_W = OP16 (L, Hm, D) blocks.i.mlp.fc1.weight,
+                                  GATEUP_B = fp32 (L, Hm) blocks.i.mlp.fc1.bias (no interleave)            */
     FITV2_W_FC2_W,             /* OP16 (L, D, Hm)       blocks.i.mlp.fc2.weight                       */
     FITV2_W_FC2_B,             /* fp32 (L, D)                                                        */
     FITV2_W_ROPE_FREQS_H,      /* fp32 (head_dim/4)     VisionRotaryEmbedding.freqs_h (rope.py:162)   */
@@ -113,6 +122,19 @@ enum fitv2_weight {
     FITV2_W_NORM_FINAL_W,      /* fp32 (D)              final_layer.norm_final.weight                   */
     FITV2_W_Q_NORM_W,          /* fp32 (L, head_dim)    blocks.i.attn.q_norm.weight                     */
     FITV2_W_K_NORM_W,          /* fp32 (L, head_dim)    blocks.i.attn.k_norm.weight                     */
+    /* adaln_type 'swiglu' (FITV2_ADALN_SWIGLU): Hs = (D/4)*3, Hf = D/2; FINAL_ADALN_* are then unused */
+    FITV2_W_SG_G_W,            /* fp32 (L, Hs, D)       blocks.i.adaLN_modulation.fc1_g.weight          */
+    FITV2_W_SG_G_B,            /* fp32 (L, Hs)                                                          */
+    FITV2_W_SG_X_W,            /* fp32 (L, Hs, D)       blocks.i.adaLN_modulation.fc1_x.weight          */
+    FITV2_W_SG_X_B,            /* fp32 (L, Hs)                                                          */
+    FITV2_W_SG_FC2_W,          /* fp32 (L, 6D, Hs)      blocks.i.adaLN_modulation.fc2.weight            */
+    FITV2_W_SG_FC2_B,          /* fp32 (L, 6D)                                                          */
+    FITV2_W_FSG_G_W,           /* fp32 (Hf, D)          final_layer.adaLN_modulation.fc1_g.weight       */
+    FITV2_W_FSG_G_B,           /* fp32 (Hf)                                                             */
+    FITV2_W_FSG_X_W,           /* fp32 (Hf, D)          final_layer.adaLN_modulation.fc1_x.weight       */
+    FITV2_W_FSG_X_B,           /* fp32 (Hf)                                                             */
+    FITV2_W_FSG_FC2_W,         /* fp32 (2D, Hf)         final_layer.adaLN_modulation.fc2.weight         */
+    FITV2_W_FSG_FC2_B,         /* fp32 (2D)                                                             */
     FITV2_W_COUNT
 };
 

@@ -77,6 +77,12 @@ class FiTConfig:
     q_norm: Optional[str] = "layernorm"
     k_norm: Optional[str] = "layernorm"
     qk_norm_weight: bool = False    # modules.py:141-144: promotes 'layernorm' to 'w_layernorm'
+    # the remaining constructor switches of fit_model.py:25-65 (no shipped config sets them; the class DEFAULTS do)
+    use_swiglu: bool = True         # modules.py:246-253: False = timm Mlp, fc2(GELU_tanh(fc1(x))), hidden int(D*mlp_ratio)
+    qkv_bias: bool = True           # modules.py:140
+    ffn_bias: bool = True           # modules.py:248-253
+    rel_pos_embed: Optional[str] = "rope"   # modules.py:153,170: q / k are rotated only for 'rope' / 'xpos' (lower-cased)
+    add_rel_pe_to_v: bool = False   # modules.py:171-172: v is rotated too
 
     @property
     def head_dim(self) -> int:
@@ -86,7 +92,19 @@ class FiTConfig:
     def mlp_hidden(self) -> int:
         # modules.py:246-251 : (int(hidden*mlp_ratio) * 2) // 3, or the full int(hidden*mlp_ratio) with swiglu_large
         full = int(self.hidden_size * self.mlp_ratio)
+        if not self.use_swiglu:
+            return full                                                  # modules.py:253 (timm Mlp)
         return full if self.use_swiglu_large else (full * 2) // 3
+
+    @property
+    def rotates(self) -> bool:
+        """modules.py:153,170: `rel_pos_embed.lower() in ['rope', 'xpos']`."""
+        return self.rel_pos_embed is not None and self.rel_pos_embed.lower() in ("rope", "xpos")
+
+    @property
+    def adaln_hidden(self) -> Tuple[int, int]:
+        """adaln_type 'swiglu': SwiGLU hidden of the block / final modulation (modules.py:265-268,285)."""
+        return (self.hidden_size // 4) * 3, self.hidden_size // 2
 
     @property
     def token_channels(self) -> int:
@@ -278,11 +296,19 @@ def rotate_half(x: torch.Tensor) -> torch.Tensor:
 # --------------------------------------------------------------------------- #
 class _SwiGLU(nn.Module):
     """Creation order of timm.layers.mlp.SwiGLU: fc1_g, fc1_x, fc2."""
-    def __init__(self, d, h):
+    def __init__(self, d, h, bias=True, out=None):
         super().__init__()
-        self.fc1_g = nn.Linear(d, h)
-        self.fc1_x = nn.Linear(d, h)
-        self.fc2 = nn.Linear(h, d)
+        self.fc1_g = nn.Linear(d, h, bias=bias)
+        self.fc1_x = nn.Linear(d, h, bias=bias)
+        self.fc2 = nn.Linear(h, out or d, bias=bias)
+
+
+class _Mlp(nn.Module):
+    """Creation order of timm.layers.mlp.Mlp: fc1, fc2 (act / drop / norm hold no parameters)."""
+    def __init__(self, d, h, bias=True):
+        super().__init__()
+        self.fc1 = nn.Linear(d, h, bias=bias)
+        self.fc2 = nn.Linear(h, d, bias=bias)
 
 
 class _Norm(nn.Module):
@@ -297,7 +323,7 @@ class _Attn(nn.Module):
     def __init__(self, cfg: "FiTConfig"):
         super().__init__()
         d = cfg.hidden_size
-        self.qkv = nn.Linear(d, 3 * d)      # modules.py:140
+        self.qkv = nn.Linear(d, 3 * d, bias=cfg.qkv_bias)      # modules.py:140
         self.q_norm = _Norm(cfg.norm_kind("q"), cfg.head_dim)   # modules.py:146-147
         self.k_norm = _Norm(cfg.norm_kind("k"), cfg.head_dim)
         self.proj = nn.Linear(d, d)         # modules.py:151
@@ -310,8 +336,13 @@ class _Block(nn.Module):
         self.norm1 = _Norm(cfg.norm_kind("block"), d)           # modules.py:239-240
         self.norm2 = _Norm(cfg.norm_kind("block"), d)
         self.attn = _Attn(cfg)                                  # modules.py:242-247
-        self.mlp = _SwiGLU(d, cfg.mlp_hidden)                   # modules.py:250
-        if cfg.adaln_type == "lora":
+        if cfg.use_swiglu:
+            self.mlp = _SwiGLU(d, cfg.mlp_hidden, cfg.ffn_bias)    # modules.py:247-251
+        else:
+            self.mlp = _Mlp(d, cfg.mlp_hidden, cfg.ffn_bias)       # modules.py:253
+        if cfg.adaln_type == "swiglu":                          # modules.py:265-268
+            self.adaLN_modulation = _SwiGLU(d, cfg.adaln_hidden[0], True, 6 * d)
+        elif cfg.adaln_type == "lora":
             self.adaLN_modulation = nn.Sequential(              # modules.py:259-264
                 nn.SiLU(), nn.Linear(d, cfg.adaln_lora_dim), nn.Linear(cfg.adaln_lora_dim, 6 * d))
         else:
@@ -324,7 +355,10 @@ class _Final(nn.Module):
         d = cfg.hidden_size
         self.norm_final = _Norm(cfg.norm_kind("block"), d)      # modules.py:282
         self.linear = nn.Linear(d, cfg.out_token_channels)      # modules.py:283
-        self.adaLN_modulation = nn.Sequential(nn.SiLU(), nn.Linear(d, 2 * d))  # modules.py:287-290
+        if cfg.adaln_type == "swiglu":                          # modules.py:284-285
+            self.adaLN_modulation = _SwiGLU(d, cfg.adaln_hidden[1], True, 2 * d)
+        else:
+            self.adaLN_modulation = nn.Sequential(nn.SiLU(), nn.Linear(d, 2 * d))  # modules.py:287-290
 
 
 class _Skeleton(nn.Module):
@@ -377,14 +411,15 @@ def reference_init_state_dict(cfg: FiTConfig, seed: int = 0) -> Dict[str, torch.
     nn.init.normal_(m.y_embedder.embedding_table.weight, std=0.02)
     nn.init.normal_(m.t_embedder.mlp[0].weight, std=0.02)
     nn.init.normal_(m.t_embedder.mlp[2].weight, std=0.02)
+    last = (lambda mod: mod.fc2) if cfg.adaln_type == "swiglu" else (lambda mod: mod[-1])   # fit_model.py:139-153
     for blk in m.blocks:
-        nn.init.constant_(blk.adaLN_modulation[-1].weight, 0)
-        nn.init.constant_(blk.adaLN_modulation[-1].bias, 0)
+        nn.init.constant_(last(blk.adaLN_modulation).weight, 0)
+        nn.init.constant_(last(blk.adaLN_modulation).bias, 0)
     if m.global_adaLN_modulation is not None:
         nn.init.constant_(m.global_adaLN_modulation[-1].weight, 0)
         nn.init.constant_(m.global_adaLN_modulation[-1].bias, 0)
-    nn.init.constant_(m.final_layer.adaLN_modulation[-1].weight, 0)
-    nn.init.constant_(m.final_layer.adaLN_modulation[-1].bias, 0)
+    nn.init.constant_(last(m.final_layer.adaLN_modulation).weight, 0)
+    nn.init.constant_(last(m.final_layer.adaLN_modulation).bias, 0)
     nn.init.constant_(m.final_layer.linear.weight, 0)
     nn.init.constant_(m.final_layer.linear.bias, 0)
     return {k: v.detach().clone() for k, v in m.state_dict().items()}
@@ -421,7 +456,12 @@ def _q(x: torch.Tensor, quant: Optional[str]) -> torch.Tensor:
 
 
 def _linear(x, sd, name, quant=None):
-    return F.linear(_q(x, quant), _q(sd[name + ".weight"], quant), sd[name + ".bias"])
+    return F.linear(_q(x, quant), _q(sd[name + ".weight"], quant), sd.get(name + ".bias"))   # bias-free linears: qkv_bias / ffn_bias False
+
+
+def _swiglu_mlp(x, sd, p, quant=None):
+    """timm SwiGLU: fc2(silu(fc1_g(x)) * fc1_x(x))."""
+    return _linear(F.silu(_linear(x, sd, p + ".fc1_g", quant)) * _linear(x, sd, p + ".fc1_x", quant), sd, p + ".fc2", quant)
 
 
 def timestep_embedding(t: torch.Tensor, dim: int = 256, max_period: int = 10000) -> torch.Tensor:
@@ -445,6 +485,8 @@ def block_modulation(cfg: FiTConfig, sd, c: torch.Tensor, i: int, global_adaln) 
     """modules.py:254-264,271 -> (B, 6D)."""
     s = F.silu(c)
     p = f"blocks.{i}.adaLN_modulation"
+    if cfg.adaln_type == "swiglu":                                       # modules.py:265-268: SwiGLU on c itself (no SiLU in front)
+        return _swiglu_mlp(c, sd, p) + global_adaln
     if cfg.adaln_type == "normal":
         return _linear(s, sd, p + ".1") + global_adaln
     return _linear(_linear(s, sd, p + ".1"), sd, p + ".2") + global_adaln
@@ -483,8 +525,11 @@ def attention(cfg: FiTConfig, sd, i: int, x, mask, cos, sin, quant=None, taps=No
     q, k, v = qkv.unbind(0)
     q = apply_norm(cfg.norm_kind("q"), q, sd, f"blocks.{i}.attn.q_norm")  # :168
     k = apply_norm(cfg.norm_kind("k"), k, sd, f"blocks.{i}.attn.k_norm")
-    q = q * cos + rotate_half(q) * sin                                   # :173
-    k = k * cos + rotate_half(k) * sin                                   # :174
+    if cfg.rotates:                                                      # :170
+        if cfg.add_rel_pe_to_v:
+            v = v * cos + rotate_half(v) * sin                           # :171-172
+        q = q * cos + rotate_half(q) * sin                               # :173
+        k = k * cos + rotate_half(k) * sin                               # :174
     if taps is not None:
         taps["q"], taps["k"], taps["v"] = q.clone(), k.clone(), v.clone()
     am = mask[:, None, None, :]
@@ -499,8 +544,10 @@ def attention(cfg: FiTConfig, sd, i: int, x, mask, cos, sin, quant=None, taps=No
 
 
 def swiglu(cfg: FiTConfig, sd, i: int, x, quant=None):
-    """timm SwiGLU: fc2(silu(fc1_g(x)) * fc1_x(x))."""
+    """timm SwiGLU: fc2(silu(fc1_g(x)) * fc1_x(x)); with use_swiglu=False timm Mlp: fc2(GELU_tanh(fc1(x))) (modules.py:253)."""
     p = f"blocks.{i}.mlp"
+    if not cfg.use_swiglu:
+        return _linear(F.gelu(_linear(x, sd, p + ".fc1", quant), approximate="tanh"), sd, p + ".fc2", quant)
     g = _linear(x, sd, p + ".fc1_g", quant)
     u = _linear(x, sd, p + ".fc1_x", quant)
     return _linear(F.silu(g) * u, sd, p + ".fc2", quant)
@@ -537,7 +584,10 @@ def forward(cfg: FiTConfig, sd, x, t, y, grid, mask, size=None, quant: Optional[
         h = h + g2.unsqueeze(1) * m                                      # modules.py:273
         if taps is not None and i == 0:
             taps["x1"] = h.clone()
-    shift, scale = _linear(F.silu(c), sd, "final_layer.adaLN_modulation.1").chunk(2, dim=1)
+    if cfg.adaln_type == "swiglu":
+        shift, scale = _swiglu_mlp(c, sd, "final_layer.adaLN_modulation").chunk(2, dim=1)
+    else:
+        shift, scale = _linear(F.silu(c), sd, "final_layer.adaLN_modulation.1").chunk(2, dim=1)
     out = _linear(modulate(apply_norm(bn, h, sd, "final_layer.norm_final"), shift, scale), sd, "final_layer.linear")  # modules.py:292-296
     out = out * maskf[..., None]                                         # fit_model.py:230
     return out if cfg.use_sit else out.transpose(1, 2)                   # :231-232 'B N C -> B C N'

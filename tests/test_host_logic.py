@@ -37,9 +37,9 @@ def test_constructor_contract_and_rejections():
             use_swiglu_large=False, use_checkpoint=False, qk_norm_weight=False, rel_pos_embed="rope", abs_pos_embed=None,
             custom_freqs="normal", online_rope=False)     # every key of configs/fitv2/config_fitv2_xl.yaml:26-47 + injected keys
     assert m.in_channels == 4 and m.dtype == torch.float32 and m.mlp_hidden == 3072 and m.head_dim == 72
-    for bad in (dict(adaln_type="swiglu"), dict(online_rope=True), dict(q_norm="batchnorm"), dict(norm_type="none"),
-                dict(use_swiglu=False), dict(num_heads=18), dict(operand_dtype="fp8"), dict(add_rel_pe_to_v=True),
-                dict(rel_pos_embed=None), dict(qkv_bias=False)):
+    for bad in (dict(adaln_type="bogus"), dict(online_rope=True), dict(q_norm="batchnorm"), dict(norm_type="none"),
+                dict(num_heads=18), dict(operand_dtype="fp8"), dict(adaln_bias=False), dict(save_attention=True),
+                dict(use_swiglu=False, mlp_ratio=3.9)):
         with pytest.raises(NotImplementedError):
             FiT(**{**KW, **XL1, **bad})
     with pytest.raises(AssertionError):                    # fit_model.py:68: assert not (learn_sigma and use_sit)
@@ -214,6 +214,55 @@ def test_variant_state_dict_keys_and_init_parity():
             assert "GLOBAL_ADALN_W" not in P and P["NORMAL_ADALN_W"].shape == (1, 6 * 1152, 1152) and P["FINAL_LINEAR_W"].shape == (32, 1152)
         else:
             assert P["NORM1_W"].shape == (1, 1152) and P["Q_NORM_W"].shape == (1, 72) and P["K_NORM_W"].shape == (1, 72)
+
+
+def test_ctor_variants_state_dict_init_and_packing(golden_dir):
+    """The remaining constructor switches of fit_model.py:25-65 (goldens of oracle/make_ctor_variant_goldens.py): parameter names
+    and the init under a seed equal the reference's, and the packed kernel-side weights reproduce the reference arithmetic."""
+    F = torch.nn.functional
+    cases = {c["name"]: c for c in torch.load(os.path.join(golden_dir, "ctor_variants_xl.pt"))}
+    models = {}
+    for name, c in cases.items():
+        torch.manual_seed(0)
+        m = FiT(**c["kwargs"])
+        ref = O.reference_init_state_dict(O.FiTConfig(**c["oracle_kwargs"]), 0)
+        sd = m.state_dict()
+        assert list(sd.keys()) == list(ref.keys()) == c["keys"], name
+        assert all(torch.equal(sd[k], ref[k]) for k in ref), name
+        m.randomize_zero_init_(1)
+        models[name] = (m, m.pack_weights(torch.device("cpu")))
+    D = 1152
+    # class defaults: timm Mlp, fc1 alone in the GATEUP slots (no interleave), hidden 4 D
+    m, P = models["defaults"]
+    assert not m.use_swiglu and m.mlp_hidden == 4 * D and not m.use_sit and m.learn_sigma and m.adaln_type == "normal"
+    assert P["GATEUP_W"].shape == (2, 4 * D, D) and P["GATEUP_B"].shape == (2, 4 * D) and P["FC2_W"].shape == (2, D, 4 * D)
+    assert torch.equal(P["GATEUP_W"][1].float(), m.blocks[1].mlp.fc1.weight.bfloat16().float()) and torch.equal(P["GATEUP_B"][1], m.blocks[1].mlp.fc1.bias)
+    assert "GLOBAL_ADALN_W" not in P and "NORMAL_ADALN_W" in P and "FINAL_ADALN_W" in P
+    # bias-free qkv / ffn: zero biases bound in their place; proj keeps its own; no rotation = zero frequencies
+    m, P = models["nobias_norope"]
+    assert m.blocks[0].attn.qkv.bias is None and m.blocks[0].mlp.fc1_g.bias is None and m.blocks[0].mlp.fc2.bias is None
+    for k in ("QKV_B", "GATEUP_B", "FC2_B", "ROPE_FREQS_H", "ROPE_FREQS_W"):
+        assert not bool(P[k].any()), k
+    assert P["QKV_B"].shape == (1, 3 * D) and P["GATEUP_B"].shape == (1, 2 * 3072) and P["FC2_B"].shape == (1, D)
+    assert bool(P["PROJ_B"].any()) and not m.rotates and m.rel_pos_embed is None
+    # rotation of v: 'XPOS' is lower-cased and rotates like 'rope' (modules.py:153,170)
+    m, P = models["rope_v"]
+    assert m.rotates and m.add_rel_pe_to_v and bool(P["ROPE_FREQS_H"].any())
+    # SwiGLU modulation MLPs: the launch sequence of the C side (g, silu(g); (x-linear) * silu(g); fc2) from the packed slots
+    m, P = models["adaln_swiglu"]
+    assert set(P) >= {"SG_G_W", "SG_X_B", "SG_FC2_W", "FSG_G_W", "FSG_FC2_B"} and not ({"FINAL_ADALN_W", "GLOBAL_ADALN_W", "NORMAL_ADALN_W"} & set(P))
+    assert P["SG_G_W"].shape == (1, 864, D) and P["SG_FC2_W"].shape == (1, 6 * D, 864) and P["FSG_X_W"].shape == (576, D) and P["FSG_FC2_W"].shape == (2 * D, 576)
+    cfg, sd = O.FiTConfig(**cases["adaln_swiglu"]["oracle_kwargs"]), {k: v.detach() for k, v in m.state_dict().items()}
+    c = torch.randn(3, D)
+    g = c @ P["SG_G_W"][0].t() + P["SG_G_B"][0]
+    mod = ((c @ P["SG_X_W"][0].t() + P["SG_X_B"][0]) * F.silu(g)) @ P["SG_FC2_W"][0].t() + P["SG_FC2_B"][0]
+    assert torch.allclose(mod, O.block_modulation(cfg, sd, c, 0, 0.0), atol=1e-6)
+    assert set(P) == set(_lib.WEIGHT_SLOTS) - {"GLOBAL_ADALN_W", "GLOBAL_ADALN_B", "LORA_A_W", "LORA_A_B", "LORA_B_W", "LORA_B_B", "FINAL_ADALN_W",
+                                               "FINAL_ADALN_B", "NORMAL_ADALN_W", "NORMAL_ADALN_B", "NORM1_W", "NORM2_W", "NORM_FINAL_W", "Q_NORM_W", "K_NORM_W"}
+    # a reference-default model: FiT() itself constructs (depth 28, GELU Mlp) -- only the meta device is touched here
+    with torch.device("meta"):
+        big = FiT()
+    assert big.depth == 28 and not big.use_swiglu and big.out_channels == 8
 
 
 def test_state_dict_keys_and_init_parity():

@@ -179,3 +179,24 @@ def test_swiglu_large_golden(golden_dir):
     R = fx["x"].shape[0]
     out = O.forward(cfg, sd, fx["x"], fx["t"], fx["y"], make_grid(R, fx["hp"], fx["wp"]), torch.ones(R, fx["hp"] * fx["wp"]))
     assert rel(out, fx["v_ref"]) < TOL
+
+
+def test_ctor_variant_goldens(golden_dir):
+    """The remaining constructor switches (oracle/make_ctor_variant_goldens.py, outputs of the REAL reference classes): the class
+    defaults (GELU Mlp, learn_sigma, (B,C,N), adaLN 'normal'), bias-free qkv / ffn without rotation, rotation of v under 'XPOS',
+    SwiGLU modulation MLPs.  The oracle regenerates the weights from the seeds and replays forward / forward_with_cfg."""
+    import hashlib
+    cases = torch.load(os.path.join(golden_dir, "ctor_variants_xl.pt"))
+    assert [c["name"] for c in cases] == ["defaults", "nobias_norope", "rope_v", "adaln_swiglu"]
+    for c in cases:
+        cfg = O.FiTConfig(**c["oracle_kwargs"])
+        sd = O.synthetic_state_dict(cfg)
+        assert list(sd.keys()) == c["keys"], c["name"]
+        a = (c["x"], c["t"], c["y"], c["grid"], c["mask"])
+        assert rel(O.forward(cfg, sd, *a), c["out"]) < TOL, c["name"]
+        assert rel(O.forward_with_cfg(cfg, sd, *a, None, 1.5), c["out_cfg"]) < TOL, c["name"]
+    d = {c["name"]: c for c in cases}
+    assert "blocks.0.mlp.fc1.weight" in d["defaults"]["keys"] and "blocks.0.mlp.fc1_g.weight" not in d["defaults"]["keys"]
+    assert "blocks.0.attn.qkv.bias" not in d["nobias_norope"]["keys"] and "blocks.0.mlp.fc2.bias" not in d["nobias_norope"]["keys"]
+    assert "blocks.0.attn.proj.bias" in d["nobias_norope"]["keys"]          # proj keeps its bias (modules.py:151)
+    assert "blocks.0.adaLN_modulation.fc1_g.weight" in d["adaln_swiglu"]["keys"] and "final_layer.adaLN_modulation.fc2.bias" in d["adaln_swiglu"]["keys"]
