@@ -704,35 +704,44 @@ def test_ctor_variant_goldens(lib, golden_dir):
     failures = []
     for c in torch.load(os.path.join(golden_dir, "ctor_variants_xl.pt")):
         name = c["name"]
-        torch.manual_seed(0)
-        m = FiT(**c["kwargs"]).randomize_zero_init_(1)
-        sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
-        _check_weights(sd, c)
-        cfg = O.FiTConfig(**c["oracle_kwargs"])
-        m = m.cuda().eval()
-        a = [c[k].cuda() for k in ("x", "t", "y", "grid", "mask")]
-        out = m(*a).cpu()
-        # taps of this forward against the oracle: conditioning vector, per-block modulation, final modulation, q / k / v of block 0
-        cvec = O.conditioning(cfg, sd, c["t"], c["y"])
-        mods = torch.stack([O.block_modulation(cfg, sd, cvec, i, 0.0 if cfg.adaln_type != "lora" else
-                                               O._linear(torch.nn.functional.silu(cvec), sd, "global_adaLN_modulation.1")) for i in range(cfg.depth)])
-        info = dict(c=rel(m.debug_tap("c"), cvec), mod=rel(m.debug_tap("mod"), mods))
-        if cfg.depth == 1:
-            taps = {}
-            O.forward(cfg, sd, c["x"], c["t"], c["y"], c["grid"], c["mask"], taps=taps)
-            valid = (c["mask"] != 0)[:, None, :, None]
-            info["q"] = rel(m.debug_tap("q").float().cpu() * valid, taps["q"] * valid)
-            info["k"] = rel(m.debug_tap("k").float().cpu() * valid, taps["k"] * valid)
-            info["v"] = rel(m.debug_tap("vt").float().cpu()[..., :256].transpose(2, 3) * valid, taps["v"] * valid)
-        e = rel(out, c["out"])
-        oc = m.forward_with_cfg(*a, None, 1.5).cpu()
-        ec = rel(oc, c["out_cfg"])
-        pad_ok = bool(((out if cfg.use_sit else out.transpose(1, 2))[c["mask"] == 0] == 0).all())
-        print(f"[parity] ctor variant {name}: forward {e:.2e}, forward_with_cfg {ec:.2e}, pad rows zero {pad_ok}, taps "
-              + ", ".join(f"{k} {v:.2e}" for k, v in info.items()))
-        if not (e < V_TOL and ec < V_TOL and pad_ok and out.shape == c["out"].shape):
+        try:
+            _run_ctor_variant(c, failures)
+        except Exception as exc:                                            # keep going: one log shows every case
+            print(f"[parity] ctor variant {name}: raised {type(exc).__name__}: {exc}")
             failures.append(name)
     assert not failures, failures
+
+
+def _run_ctor_variant(c, failures):
+    name = c["name"]
+    torch.manual_seed(0)
+    m = FiT(**c["kwargs"]).randomize_zero_init_(1)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    _check_weights(sd, c)
+    cfg = O.FiTConfig(**c["oracle_kwargs"])
+    m = m.cuda().eval()
+    a = [c[k].cuda() for k in ("x", "t", "y", "grid", "mask")]
+    out = m(*a).cpu()
+    # taps of this forward against the oracle: conditioning vector, per-block modulation, final modulation, q / k / v of block 0
+    cvec = O.conditioning(cfg, sd, c["t"], c["y"])
+    mods = torch.stack([O.block_modulation(cfg, sd, cvec, i, 0.0 if cfg.adaln_type != "lora" else
+                                           O._linear(torch.nn.functional.silu(cvec), sd, "global_adaLN_modulation.1")) for i in range(cfg.depth)])
+    info = dict(c=rel(m.debug_tap("c"), cvec), mod=rel(m.debug_tap("mod"), mods))
+    if cfg.depth == 1:
+        taps = {}
+        O.forward(cfg, sd, c["x"], c["t"], c["y"], c["grid"], c["mask"], taps=taps)
+        valid = (c["mask"] != 0)[:, None, :, None]
+        info["q"] = rel(m.debug_tap("q").float().cpu() * valid, taps["q"] * valid)
+        info["k"] = rel(m.debug_tap("k").float().cpu() * valid, taps["k"] * valid)
+        info["v"] = rel(m.debug_tap("vt").float().cpu()[..., :256].transpose(2, 3) * valid, taps["v"] * valid)
+    e = rel(out, c["out"])
+    oc = m.forward_with_cfg(*a, None, 1.5).cpu()
+    ec = rel(oc, c["out_cfg"])
+    pad_ok = bool(((out if cfg.use_sit else out.transpose(1, 2))[c["mask"] == 0] == 0).all())
+    print(f"[parity] ctor variant {name}: forward {e:.2e}, forward_with_cfg {ec:.2e}, pad rows zero {pad_ok}, taps "
+          + ", ".join(f"{k} {v:.2e}" for k, v in info.items()))
+    if not (e < V_TOL and ec < V_TOL and pad_ok and out.shape == c["out"].shape):
+        failures.append(name)
 
 
 # ------------------------------------------------------------------------------------------------
