@@ -71,7 +71,10 @@ def _swiglu_holder(d: int, hidden: int, out: int) -> nn.Module:
 
 
 class FiT(nn.Module):
-    """FiTv2 transformer (use_sit / SwiGLU / adaLN-LoRA / layernorm qk-norm / 2-D RoPE)."""
+    """FiT / FiTv2 transformer with the constructor contract of fit_model.py:25-65: the FiTv2 family (use_sit, SwiGLU, adaLN-LoRA,
+    layernorm q/k norm, 2-D RoPE) on the fast kernels, every other switch the reference class can be built with (FiTv1 layout,
+    GELU Mlp, adaLN 'normal' / 'swiglu', weighted / RMS / absent norms, bias-free qkv / ffn, no rotation, rotation of v) on their
+    generic variants."""
 
     def __init__(self, context_size: int = 256, patch_size: int = 2, in_channels: int = 4, hidden_size: int = 1152,
                  depth: int = 28, num_heads: int = 16, mlp_ratio: float = 4.0, class_dropout_prob: float = 0.1,
@@ -106,7 +109,8 @@ class FiT(nn.Module):
             unsupported.append("online_rope=True needs custom_freqs in ('linear', 'ntk-aware', 'ntk-by-parts') and ori_max_pe_len "
                                "(the reference's online mode has no 'normal' branch and never sets the yarn / ntk-aware-pro magnitudes)")
         # use_checkpoint (activation checkpointing, fit_model.py:222-226) changes nothing in a no-grad forward: accepted, unused
-        if finetune is not None or pretrain_ckpt is not None: unsupported.append("pretrain_ckpt/finetune (load weights with load_state_dict)")
+        # save_attention: the reference's own constructor raises on it (Attention.__init__ has no such keyword), and
+        # the attention kernels never materialise the attention matrix
         if save_attention: unsupported.append("save_attention=True")
         if patch_size ** 2 * in_channels != 16: unsupported.append("patch_size**2 * in_channels must be 16")
         if hidden_size % num_heads or hidden_size // num_heads not in (72, 96): unsupported.append("head_dim must be 72 or 96")
@@ -180,9 +184,12 @@ class FiT(nn.Module):
             self.final_layer.adaLN_modulation = _swiglu_holder(D, D // 2, 2 * D)
         else:
             self.final_layer.adaLN_modulation = _seq(nn.SiLU(), nn.Linear(D, 2 * D))
-        self.initialize_weights()
-
         self._handle = None
+        self._packed = None
+        self.initialize_weights(pretrain_ckpt=pretrain_ckpt, ignore=ignore_keys)
+        if finetune is not None:                                            # fit_model.py:114-115
+            self.finetune(type=finetune, unfreeze=ignore_keys)
+
         self._handle_device = None
         self._packed = None
         self._workspace = None
@@ -196,8 +203,9 @@ class FiT(nn.Module):
     # ------------------------------------------------------------------------------------------
     # weights
     # ------------------------------------------------------------------------------------------
-    def initialize_weights(self):
-        """Same scheme as fit_model.py:117-157 (xavier Linears, N(0,0.02) tables, zeroed adaLN/final)."""
+    def initialize_weights(self, pretrain_ckpt=None, ignore=None):
+        """Same scheme as fit_model.py:117-157 (xavier Linears, N(0,0.02) tables, zeroed adaLN/final); with ``pretrain_ckpt`` the
+        checkpoint is loaded on top (fit_model.py:159-170: every key that CONTAINS an ``ignore`` string is left at its init)."""
         def _basic_init(m):
             if isinstance(m, nn.Linear):
                 nn.init.xavier_uniform_(m.weight)
@@ -220,6 +228,23 @@ class FiT(nn.Module):
         for lin in (last(self.final_layer.adaLN_modulation), self.final_layer.linear):
             nn.init.constant_(lin.weight, 0)
             nn.init.constant_(lin.bias, 0)
+        if pretrain_ckpt is not None:
+            from .checkpoint import init_from_ckpt
+            keys = list(self.state_dict().keys())
+            ignore_keys = sorted({key for ign in (ignore or []) for key in keys if ign in key})
+            init_from_ckpt(self, pretrain_ckpt, ignore_keys, verbose=True)
+
+    def finetune(self, type, unfreeze):
+        """fit_model.py:291-299: 'full' leaves everything trainable; otherwise only parameters whose name contains one of the
+        ``unfreeze`` strings keep requires_grad (bookkeeping for the training scripts; the forward here never builds a graph)."""
+        if type == "full":
+            return
+        for _, p in self.named_parameters():
+            p.requires_grad = False
+        for unf in (unfreeze or []):
+            for name, p in self.named_parameters():
+                if unf in name:
+                    p.requires_grad = True
 
     @torch.no_grad()
     def randomize_zero_init_(self, seed: int = 1, std: float = 0.02):

@@ -388,6 +388,31 @@ def test_init_from_ckpt_rules(tmp_path):
     assert torch.equal(m3.x_embedder.proj.weight, sd["x_embedder.proj.weight"])
 
 
+def test_pretrain_ckpt_ignore_keys_and_finetune(tmp_path):
+    """fit_model.py:114-115,159-170,291-299: `pretrain_ckpt` loads a checkpoint on top of the init inside the constructor, skipping
+    every key that CONTAINS one of `ignore_keys`; `finetune` (anything but 'full') freezes all parameters except those whose name
+    contains one of the same strings."""
+    from safetensors.torch import save_file
+    torch.manual_seed(0)
+    a = FiT(**KW, **XL1).randomize_zero_init_(1)
+    path = str(tmp_path / "model_ema.safetensors")
+    save_file({k: v.detach().contiguous() for k, v in a.state_dict().items()}, path)
+    torch.manual_seed(5)
+    b = FiT(**KW, **XL1, pretrain_ckpt=path, ignore_keys=["final_layer.linear", "y_embedder"], finetune="partial")
+    sa, sb = a.state_dict(), b.state_dict()
+    for k in sa:
+        if "final_layer.linear" in k:
+            assert not bool(sb[k].any()), k                                  # left at its (zero) init
+        elif "y_embedder" in k:
+            assert not torch.equal(sa[k], sb[k]), k                          # left at its own N(0, 0.02) draw
+        else:
+            assert torch.equal(sa[k], sb[k]), k
+    grads = {n for n, p in b.named_parameters() if p.requires_grad}
+    assert grads == {n for n, _ in b.named_parameters() if "final_layer.linear" in n or "y_embedder" in n} and len(grads) == 3
+    c = FiT(**KW, **XL1, pretrain_ckpt=path, finetune="full")
+    assert all(p.requires_grad for p in c.parameters()) and all(torch.equal(sa[k], v) for k, v in c.state_dict().items())
+
+
 def test_bench_reference_arm_contract():
     """`bench.py --impl reference` (the CPU arm the driver runs beside ours): one JSON line on the same metric / unit, with
     `impl`, `cpu_baseline` and a zero-copy `e2e`, no GPU needed."""
