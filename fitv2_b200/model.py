@@ -184,16 +184,11 @@ class FiT(nn.Module):
             self.final_layer.adaLN_modulation = _swiglu_holder(D, D // 2, 2 * D)
         else:
             self.final_layer.adaLN_modulation = _seq(nn.SiLU(), nn.Linear(D, 2 * D))
-        self._handle = None
-        self._packed = None
+        # C handle, packed kernel-side weights and workspace are created lazily by the first CUDA forward
+        self._handle, self._handle_device, self._packed, self._workspace, self._ws_shape = None, None, None, None, None
         self.initialize_weights(pretrain_ckpt=pretrain_ckpt, ignore=ignore_keys)
         if finetune is not None:                                            # fit_model.py:114-115
             self.finetune(type=finetune, unfreeze=ignore_keys)
-
-        self._handle_device = None
-        self._packed = None
-        self._workspace = None
-        self._ws_shape = None
         _MODELS[id(self)] = self
 
     @property
