@@ -744,6 +744,30 @@ def _run_ctor_variant(c, failures):
         failures.append(name)
 
 
+def test_ctor_variants_combined_at_3b_width_fp16(lib):
+    """The switches of test_ctor_variant_goldens all at once, away from the golden shape: 3B/2 width (head_dim 96, Mlp hidden
+    9216, SwiGLU-modulation hidden 1728 / 1152), fp16 operands, 3 rows x 200 tokens (ragged tiles) with a padded sample, CUDA
+    graph capturable -- against the oracle (which the goldens pin to the real classes for each switch)."""
+    kw = dict(hidden_size=2304, depth=1, num_heads=24, learn_sigma=False, use_sit=True, use_swiglu=False, qkv_bias=False,
+              q_norm="layernorm", k_norm="layernorm", adaln_type="swiglu", add_rel_pe_to_v=True)
+    torch.manual_seed(0)
+    m = FiT(**kw, operand_dtype="fp16").randomize_zero_init_(1)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    cfg = O.FiTConfig(hidden_size=2304, depth=1, num_heads=24, adaln_lora_dim=0, use_swiglu=False, qkv_bias=False,
+                      adaln_type="swiglu", add_rel_pe_to_v=True)
+    assert list(sd.keys()) == list(O.reference_init_state_dict(cfg, 0).keys())
+    x, t, y, grid, mask = inputs(3, 10, 20)
+    mask[2, 150:] = 0
+    x[2, 150:] = 0
+    ref = O.forward(cfg, sd, x, t, y, grid, mask)
+    m = m.cuda().eval()
+    out = run(m, x, t, y, grid, mask)
+    e = rel(out, ref)
+    print(f"[parity] constructor switches combined at 3B width, fp16 operands, 3 x 200 tokens: {e:.2e}")
+    assert e < 2e-3 and bool((out[mask == 0] == 0).all())
+    assert torch.equal(run(m, x, t, y, grid, mask), out)
+
+
 # ------------------------------------------------------------------------------------------------
 # the boundary as the reference script uses it (sample_fitv2_ddp.py:172-213): wrappers + jit trace
 # ------------------------------------------------------------------------------------------------
