@@ -55,7 +55,7 @@ _ENV_OPTIONS = {
     "FITV2_LN_WIDE_SINGLE": ("ln_wide_single", int), "FITV2_BN_RESID": ("bn_resid", int), "FITV2_QKV": ("qkv_heads", int),
     "FITV2_RESID_T": ("resid_t", int), "FITV2_BN_RESID_T": ("bn_resid_t", int),
     "FITV2_COND": ("cond", lambda v: 1 if v == "simt" else 0), "FITV2_L2_PERSIST_MB": ("l2_persist_mb", int),
-    "FITV2_FINAL_TC": ("final_tc", int), "FITV2_VERBOSE": ("verbose", int),
+    "FITV2_FINAL_TC": ("final_tc", int), "FITV2_GELU_EPI": ("gelu_epi", int), "FITV2_VERBOSE": ("verbose", int),
 }
 
 

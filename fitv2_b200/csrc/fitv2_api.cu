@@ -210,6 +210,7 @@ struct Options {
     int l2_persist_mb = 0;       // persisting-L2 window on the fp32 residual stream (0 = off)
     int ws_guard = 0;            // bytes of guard padding behind every workspace buffer (bounds test)
     int final_tc = 1;            // final layer: 1 = LayerNorm+modulate kernel + skinny tcgen05 GEMM, 0 = fused fp32 SIMT kernel
+    int gelu_epi = 0;            // GELU Mlp fc1: 0 = slab-staged epilogue (EPI_GELU), 1 = plain epilogue with act_gelu (16-byte row stores)
     int verbose = 0;
 };
 
@@ -975,8 +976,13 @@ int forward_impl(fitv2_handle* h, const float* x_in, int x_rows, const float* t,
         prof_begin(h, PC_GATEUP, st);
         if (c.mlp_type == FITV2_MLP_GELU) {            // timm Mlp (modules.py:253): hidden = gelu_tanh(fc1(h)), plain 256-wide tiles
             ep.bias = (const float*)h->w[FITV2_W_GATEUP_B] + (size_t)layer * Hm;
-            ep.act_gelu = 1;
-            if ((rc = launch_gemm_t<256, EPI_PLAIN, OT, 0>(h, h->map_h, h->map_wgu, M, Hm, D, layer * Hm, ep, st))) return rc;
+            if (h->opt.gelu_epi == 1) {
+                ep.act_gelu = 1;
+                rc = launch_gemm_t<256, EPI_PLAIN, OT, 0>(h, h->map_h, h->map_wgu, M, Hm, D, layer * Hm, ep, st);
+            } else {
+                rc = launch_gemm_t<256, EPI_GELU, OT, 0>(h, h->map_h, h->map_wgu, M, Hm, D, layer * Hm, ep, st);
+            }
+            if (rc) return rc;
         } else {
             ep.bias = (const float*)h->w[FITV2_W_GATEUP_B] + (size_t)layer * 2 * Hm;
             if ((rc = launch_gemm_t<256, EPI_SWIGLU, OT, 0>(h, h->map_h, h->map_wgu, M, 2 * Hm, D, layer * 2 * Hm, ep, st))) return rc;
@@ -1115,7 +1121,7 @@ int fitv2_set_option(fitv2_handle* h, const char* name, int64_t value) {
     struct { const char* n; int* p; } tab[] = {
         {"pdl", &o.pdl}, {"attn", &o.attn}, {"attn_early", &o.attn_early}, {"ln_threads", &o.ln_threads},
         {"ln_wide_single", &o.ln_wide_single}, {"bn_resid", &o.bn_resid}, {"qkv_heads", &o.qkv_heads}, {"resid_t", &o.resid_t},
-        {"bn_resid_t", &o.bn_resid_t}, {"cond", &o.cond}, {"l2_persist_mb", &o.l2_persist_mb}, {"final_tc", &o.final_tc}, {"ws_guard", &o.ws_guard}, {"verbose", &o.verbose}};
+        {"bn_resid_t", &o.bn_resid_t}, {"cond", &o.cond}, {"l2_persist_mb", &o.l2_persist_mb}, {"final_tc", &o.final_tc}, {"gelu_epi", &o.gelu_epi}, {"ws_guard", &o.ws_guard}, {"verbose", &o.verbose}};
     for (auto& e : tab) {
         if (strcmp(e.n, name)) continue;
         *e.p = v;

@@ -36,7 +36,8 @@
 
 namespace fitv2 {
 
-enum { EPI_QKV = 0, EPI_RESID = 1, EPI_SWIGLU = 2, EPI_PLAIN = 3, EPI_RESID_T = 4, EPI_QKV_GEN = 5 };
+enum { EPI_QKV = 0, EPI_RESID = 1, EPI_SWIGLU = 2, EPI_PLAIN = 3, EPI_RESID_T = 4, EPI_QKV_GEN = 5, EPI_GELU = 6 };
+// EPI_GELU: hidden = gelu_tanh(acc + bias) -> 16-bit, staged through the warp slabs like EPI_SWIGLU (timm Mlp fc1, modules.py:253).
 // EPI_QKV_GEN: the QKV epilogue with a run-time q / k norm (none, LayerNorm with or without weight, RMSNorm with weight:
 // fit/model/norms.py:35-50) for the configurations outside the FiTv2 default (affine-free LayerNorm, EPI_QKV).
 __host__ __device__ constexpr bool epi_is_qkv(int epi) { return epi == EPI_QKV || epi == EPI_QKV_GEN; }
@@ -459,6 +460,42 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                         *reinterpret_cast<uint4*>(obase + (size_t)r * ep.ld_out + c * 8) = lds128(stg + slab_off(r, c));
                 }
                 __syncwarp();
+            } else if constexpr (EPI == EPI_GELU) {
+                // timm Mlp fc1 + nn.GELU(approximate="tanh") (modules.py:253).  Each warp owns 128 tile columns and passes them through
+                // its 4 KB slab in two 64-column halves: the staging and the 4 rows x 128 contiguous bytes store pattern of EPI_SWIGLU
+                static_assert(BN == 256, "GELU epilogue is written for 256-wide tiles");
+                constexpr int HALF = BN / 2;
+                const float* bias = ep.bias + n0 + half * HALF;
+                mbar_wait(&tfull_bar[acc], acc_phase);
+                tc_fence_after();
+#pragma unroll
+                for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        uint32_t g[16];
+                        tmem_ld16(t_row + half * HALF + pass * 64 + c * 16, g);
+                        tmem_ld_wait();
+                        if (pass == 1 && c == 3) release_acc(acc);
+                        uint32_t packed[8];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float4 b = __ldg(reinterpret_cast<const float4*>(bias + pass * 64 + c * 16 + j * 4));
+                            packed[2 * j] = Op16<OT>::pack(gelu_tanh(__uint_as_float(g[4 * j]) + b.x), gelu_tanh(__uint_as_float(g[4 * j + 1]) + b.y));
+                            packed[2 * j + 1] = Op16<OT>::pack(gelu_tanh(__uint_as_float(g[4 * j + 2]) + b.z), gelu_tanh(__uint_as_float(g[4 * j + 3]) + b.w));
+                        }
+                        sts128(stg + slab_off(lane, 2 * c), make_uint4(packed[0], packed[1], packed[2], packed[3]));
+                        sts128(stg + slab_off(lane, 2 * c + 1), make_uint4(packed[4], packed[5], packed[6], packed[7]));
+                    }
+                    __syncwarp();
+                    OT* obase = reinterpret_cast<OT*>(ep.out16) + (size_t)m_warp * ep.ld_out + n0 + half * HALF + pass * 64;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {                     // 4 rows x 128 contiguous bytes per warp instruction
+                        int r, c; slab_task<8>(i, lane, r, c);
+                        if (r < rows_valid)
+                            *reinterpret_cast<uint4*>(obase + (size_t)r * ep.ld_out + c * 8) = lds128(stg + slab_off(r, c));
+                    }
+                    __syncwarp();
+                }
             } else if constexpr (EPI == EPI_PLAIN) {
                 constexpr int HALF = BN / 2;
                 constexpr int NG = HALF / 8;

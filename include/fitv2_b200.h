@@ -149,7 +149,7 @@ void fitv2_destroy(fitv2_handle* h);
  * the environment when it creates a handle).  Names: "pdl" (1), "attn" (0 auto / 1 P-in-TMEM / 2 shared-memory-P / 3 online-max),
  * "attn_early" (1), "ln_threads" (64), "ln_wide_single" (0), "bn_resid" (0 = cost model),
  * "qkv_heads" (3), "resid_t" (-1 auto), "bn_resid_t" (0 = cost model), "cond" (0 tensor pipe / 1 fp32 FMA), "l2_persist_mb" (0),
- * "final_tc" (1), "ws_guard" (0), "verbose" (0).  Unknown names fail. */
+ * "final_tc" (1), "gelu_epi" (0 slab-staged GELU epilogue / 1 plain epilogue), "ws_guard" (0), "verbose" (0).  Unknown names fail. */
 int fitv2_set_option(fitv2_handle* h, const char* name, int64_t value);
 
 /* Device-side checks report through a sticky word in pinned host memory instead of trapping: returns FITV2_E_INVALID (and

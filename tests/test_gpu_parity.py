@@ -740,6 +740,14 @@ def _run_ctor_variant(c, failures):
     pad_ok = bool(((out if cfg.use_sit else out.transpose(1, 2))[c["mask"] == 0] == 0).all())
     print(f"[parity] ctor variant {name}: forward {e:.2e}, forward_with_cfg {ec:.2e}, pad rows zero {pad_ok}, taps "
           + ", ".join(f"{k} {v:.2e}" for k, v in info.items()))
+    if not cfg.use_swiglu:
+        # the two GELU epilogues (slab-staged EPI_GELU, the default, and the plain epilogue with act_gelu) are the same arithmetic
+        m.set_option("gelu_epi", 1)
+        same = torch.equal(m(*a).cpu(), out)
+        m.set_option("gelu_epi", 0)
+        print(f"[parity] ctor variant {name}: plain GELU epilogue bit-equal to the staged one: {same}")
+        if not same:
+            failures.append(name + " (gelu_epi)")
     if not (e < V_TOL and ec < V_TOL and pad_ok and out.shape == c["out"].shape):
         failures.append(name)
 

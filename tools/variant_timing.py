@@ -22,6 +22,7 @@ base = dict(hidden_size=1152, depth=depth, num_heads=16, learn_sigma=False, use_
 cases = {
     "fitv2_default": dict(use_swiglu=True, adaln_type="lora", adaln_lora_dim=288),
     "gelu_mlp": dict(use_swiglu=False, adaln_type="lora", adaln_lora_dim=288),
+    "gelu_mlp_plain_epilogue": dict(use_swiglu=False, adaln_type="lora", adaln_lora_dim=288),
     "adaln_swiglu": dict(use_swiglu=True, adaln_type="swiglu"),
     "rope_v": dict(use_swiglu=True, adaln_type="lora", adaln_lora_dim=288, add_rel_pe_to_v=True),
 }
@@ -29,6 +30,8 @@ out = {}
 for name, kw in cases.items():
     torch.manual_seed(0)
     m = FiT(**base, **kw).randomize_zero_init_(1).cuda().eval()
+    if name.endswith("plain_epilogue"):
+        m.set_option("gelu_epi", 1)
     for _ in range(3):
         m(x, t, y, grid, mask)
     m.profile("all")
