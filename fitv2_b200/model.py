@@ -564,6 +564,22 @@ class FiT(nn.Module):
         return x if scaling_factor == 1.0 else x / scaling_factor
 
     # ------------------------------------------------------------------------------------------
+    # attention-map API of the reference class (fit_model.py:301-330)
+    # ------------------------------------------------------------------------------------------
+    def get_attention_maps(self):
+        """fit_model.py:301-316: ``None`` unless save_attention is enabled -- which it never is here (the attention kernels keep
+        S and P in tensor / shared memory and never materialise the (B, H, N, N) matrix)."""
+        return None
+
+    def enable_attention_visualization(self):
+        raise NotImplementedError("fitv2_b200.FiT does not materialise attention maps (save_attention); use the reference model "
+                                  "for visualisation")
+
+    def disable_attention_visualization(self):
+        """fit_model.py:325-330: nothing to switch off."""
+        self.save_attention = False
+
+    # ------------------------------------------------------------------------------------------
     # introspection used by tests / bench
     # ------------------------------------------------------------------------------------------
     def kernel_launches(self) -> int:

@@ -37,6 +37,9 @@ def test_constructor_contract_and_rejections():
             use_swiglu_large=False, use_checkpoint=False, qk_norm_weight=False, rel_pos_embed="rope", abs_pos_embed=None,
             custom_freqs="normal", online_rope=False)     # every key of configs/fitv2/config_fitv2_xl.yaml:26-47 + injected keys
     assert m.in_channels == 4 and m.dtype == torch.float32 and m.mlp_hidden == 3072 and m.head_dim == 72
+    assert m.get_attention_maps() is None and m.disable_attention_visualization() is None     # fit_model.py:301-330 with save_attention off
+    with pytest.raises(NotImplementedError):
+        m.enable_attention_visualization()
     for bad in (dict(adaln_type="bogus"), dict(online_rope=True), dict(q_norm="batchnorm"), dict(norm_type="none"),
                 dict(num_heads=18), dict(operand_dtype="fp8"), dict(adaln_bias=False), dict(save_attention=True),
                 dict(use_swiglu=False, mlp_ratio=3.9)):
